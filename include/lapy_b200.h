@@ -1,0 +1,138 @@
+/*
+ * lapy_b200.h - C ABI of the B200-native backend for LaPy's FEM hot path.
+ *
+ * LaPy (Deep-MI/LaPy, pure Python) has no FFI of its own; the seam this library plugs into is
+ * the Python surface of lapy/solver.py, lapy/heat.py, lapy/diffgeo.py and lapy/shapedna.py
+ * (SURVEY.md §8b).  Each entry point below names the reference code it replaces (file:line,
+ * relative to the reference root).  INTEGRATION.md shows the ctypes stub a LaPy maintainer
+ * would add; lapy_b200/_lib.py is that stub in this repo.
+ *
+ * Conventions
+ *   - every function returns an int status (LB_OK == 0) and records a thread-local message
+ *     retrievable with lb_last_error();
+ *   - all array arguments are HOST pointers to C-contiguous memory, borrowed for the duration
+ *     of the call; outputs are written into caller-allocated arrays;
+ *   - device objects (lb_mesh, lb_mat, lb_amg) are opaque handles owned by the library,
+ *     released with the matching *_free; a context owns one CUDA stream and a stream-ordered
+ *     memory pool, calls on one context are serialised by the caller;
+ *   - there is no CPU fallback: lb_ctx_create fails when no CUDA device is usable.
+ *   - matrices are symmetric sparse matrices stored as canonical CSC == CSR: fp64 values,
+ *     int32 sorted unique indices, explicit zeros kept, exactly what
+ *     scipy.sparse.csc_matrix((data,(i,j))) yields for the reference.
+ */
+#ifndef LAPY_B200_H
+#define LAPY_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct lb_ctx lb_ctx;
+typedef struct lb_mesh lb_mesh;
+typedef struct lb_mat lb_mat;
+
+enum lb_status {
+    LB_OK = 0,
+    LB_ERR_ARG = 1,         /* -> ValueError in the Python shim            */
+    LB_ERR_CUDA = 2,        /* -> RuntimeError                             */
+    LB_ERR_NOCONV = 3,      /* -> ArpackNoConvergence-like / RuntimeError  */
+    LB_ERR_OOM = 4,         /* -> MemoryError                              */
+    LB_ERR_UNSUPPORTED = 5  /* -> NotImplementedError                      */
+};
+
+enum lb_dtype { LB_F32 = 0, LB_F64 = 1 };
+
+/* which operator an assembly call builds */
+enum lb_fem_kind {
+    LB_FEM_TRIA = 0,      /* Solver._fem_tria        lapy/solver.py:105-194 */
+    LB_FEM_TRIA_ANISO = 1,/* Solver._fem_tria_aniso  lapy/solver.py:196-308 */
+    LB_FEM_TRIA_MASS = 2, /* Solver.fem_tria_mass    lapy/solver.py:310-377 (B only) */
+    LB_FEM_TETRA = 3      /* Solver._fem_tetra       lapy/solver.py:379-533 */
+};
+
+/* iteration report filled by the solvers */
+typedef struct lb_info {
+    int32_t iterations;     /* outer iterations performed                         */
+    int32_t converged;      /* number of converged columns / eigenpairs           */
+    int32_t amg_levels;     /* levels of the preconditioner hierarchy (0 = Jacobi) */
+    int32_t reserved;
+    double residual;        /* max relative residual at exit                       */
+    double setup_ms;        /* device time of the preconditioner setup            */
+    double solve_ms;        /* device time of the iteration                       */
+} lb_info;
+
+/* ---- context ------------------------------------------------------------------------- */
+/* stream: a cudaStream_t to run on (e.g. torch.cuda.current_stream().cuda_stream) or NULL
+ * to let the context create its own non-blocking stream. */
+int lb_ctx_create(int device, void *stream, lb_ctx **out);
+int lb_ctx_destroy(lb_ctx *ctx);
+int lb_ctx_sync(lb_ctx *ctx);
+const char *lb_last_error(void);
+const char *lb_version(void);
+/* device-time stopwatch on the context's stream (CUDA events) */
+int lb_timer_start(lb_ctx *ctx);
+int lb_timer_stop(lb_ctx *ctx, double *ms);
+/* number of kernels this library has launched on ctx since creation */
+int lb_launch_count(lb_ctx *ctx, int64_t *count);
+
+/* ---- mesh upload: geometry.v / geometry.t as the reference's Solver reads them --------- */
+/* v: (nv,3) LB_F32|LB_F64; t: (nt,k) signed integers of t_itemsize 4|8 bytes, k = 3|4.
+ * Replaces the fancy-index gathers at lapy/solver.py:145-150, :418-425. */
+int lb_mesh_create(lb_ctx *ctx, const void *v, int v_dtype, int64_t nv, const void *t,
+                   int t_itemsize, int64_t nt, int k, lb_mesh **out);
+int lb_mesh_update_vertices(lb_mesh *mesh, const void *v, int v_dtype);
+int lb_mesh_free(lb_mesh *mesh);
+
+/* ---- assembly -------------------------------------------------------- */
+/* kind: lb_fem_kind.  lump != 0 -> diagonal mass.  u1,u2 (nt,3) and aniso_mat (nt,2) fp64 host
+ * arrays, only for LB_FEM_TRIA_ANISO.  a_out may be NULL (and is ignored for TRIA_MASS). */
+int lb_fem_assemble(lb_ctx *ctx, lb_mesh *mesh, int kind, int lump, const double *u1,
+                    const double *u2, const double *aniso_mat, lb_mat **a_out, lb_mat **b_out);
+
+/* ---- matrices --------------------------------------------------------------------------- */
+int lb_mat_info(lb_mat *m, int64_t *n, int64_t *nnz);
+int lb_mat_download(lb_mat *m, int32_t *indptr, int32_t *indices, double *data);
+/* user supplied matrix (e.g. ``fem.mass = sparse.eye(n)``, lapy/diffgeo.py:149) */
+int lb_mat_upload(lb_ctx *ctx, int64_t n, int64_t nnz, const int32_t *indptr,
+                  const int32_t *indices, const double *data, lb_mat **out);
+int lb_mat_free(lb_mat *m);
+/* y (n,m) row-major = M x (n,m) row-major; replaces csc_matvec(s) (lapy/solver.py:844-846) */
+int lb_spmm(lb_ctx *ctx, lb_mat *mat, const double *x, int64_t m, double *y);
+
+/* ---- solvers ------------------------------------------------------------------------------ */
+/* Solver.eigs (lapy/solver.py:667-716): k eigenpairs of A x = lambda B x nearest sigma (<= 0),
+ * ascending, B-orthonormal.  evals (k), evecs (n,k) row-major.  tol <= 0 / maxit <= 0 pick
+ * defaults (1e-9 relative residual, 200). */
+int lb_eigs(lb_ctx *ctx, lb_mat *a, lb_mat *b, int k, double sigma, double tol, int maxit,
+            double *evals, double *evecs, lb_info *info);
+
+/* Solve (alpha*A + beta*B) x = rhs for m right-hand sides with optional Dirichlet rows:
+ *   heat.diffusion    lapy/heat.py:208-227      alpha = t, beta = 1, B = lumped mass
+ *   Solver.poisson    lapy/solver.py:848-883    alpha = 1, beta = 0, fix = dtup
+ * rhs, x: (n,m) row-major.  fix_idx (nfix) rows are eliminated and x there set to
+ * fix_val (nfix) (broadcast over columns), the rhs is corrected with -A d like solver.py:846.
+ * project_nullspace != 0: the operator is singular with constant null space (closed mesh
+ * Poisson, lapy/diffgeo.py:156): rhs and iterates are kept orthogonal to constants. */
+int lb_solve(lb_ctx *ctx, lb_mat *a, double alpha, lb_mat *b, double beta, const double *rhs,
+             int64_t m, const int64_t *fix_idx, int64_t nfix, const double *fix_val, double tol,
+             int maxit, int project_nullspace, double *x, lb_info *info);
+
+/* ---- differential operators ---------------------------------------- */
+/* f (nv,nf) row-major -> g (nt,nf,3): tria_compute_gradient lapy/diffgeo.py:222-300,
+ * tet_compute_gradient :846-922 */
+int lb_gradient(lb_ctx *ctx, lb_mesh *mesh, const double *f, int64_t nf, double *g);
+/* x (nt,nf,3) -> d (nv,nf): tria_compute_divergence lapy/diffgeo.py:303-387,
+ * tet_compute_divergence :925-1006 */
+int lb_divergence(lb_ctx *ctx, lb_mesh *mesh, const double *x, int64_t nf, double *d);
+/* normalise g in place to unit length per (element, function); 0/0 -> 0 like
+ * np.nan_to_num at lapy/diffgeo.py:153-154 */
+int lb_normalize_field(lb_ctx *ctx, int64_t nrows, double *g_host_or_null);
+/* mean edge length of the unique edges: TriaMesh.avg_edge_length lapy/tria_mesh.py:735-748 */
+int lb_avg_edge_length(lb_ctx *ctx, lb_mesh *mesh, double *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LAPY_B200_H */

@@ -1,0 +1,269 @@
+"""ctypes binding of liblapyb200.so (include/lapy_b200.h) - the only way host Python reaches
+the device code.  There is NO CPU fallback: if the shared library is missing or no CUDA device
+is usable, importing / first use fails loudly (``ImportError`` / ``RuntimeError``).
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "liblapyb200.so")
+
+OK, ERR_ARG, ERR_CUDA, ERR_NOCONV, ERR_OOM, ERR_UNSUPPORTED = range(6)
+F32, F64 = 0, 1
+FEM_TRIA, FEM_TRIA_ANISO, FEM_TRIA_MASS, FEM_TETRA = range(4)
+
+
+class NoConvergence(RuntimeError):
+    """Iterative solver did not reach its tolerance (cf. scipy ArpackNoConvergence)."""
+
+
+class Info(C.Structure):
+    _fields_ = [
+        ("iterations", C.c_int32),
+        ("converged", C.c_int32),
+        ("amg_levels", C.c_int32),
+        ("reserved", C.c_int32),
+        ("residual", C.c_double),
+        ("setup_ms", C.c_double),
+        ("solve_ms", C.c_double),
+    ]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
+
+
+_vp, _i64, _int, _dbl = C.c_void_p, C.c_int64, C.c_int, C.c_double
+_pp = C.POINTER(C.c_void_p)
+
+# name -> argtypes; every function returns int status except the two string getters
+SIGNATURES = {
+    "lb_ctx_create": [_int, _vp, _pp],
+    "lb_ctx_destroy": [_vp],
+    "lb_ctx_sync": [_vp],
+    "lb_timer_start": [_vp],
+    "lb_timer_stop": [_vp, C.POINTER(_dbl)],
+    "lb_launch_count": [_vp, C.POINTER(_i64)],
+    "lb_mesh_create": [_vp, _vp, _int, _i64, _vp, _int, _i64, _int, _pp],
+    "lb_mesh_update_vertices": [_vp, _vp, _int],
+    "lb_mesh_drop_cache": [_vp],
+    "lb_mesh_free": [_vp],
+    "lb_fem_assemble": [_vp, _vp, _int, _int, _vp, _vp, _vp, _pp, _pp],
+    "lb_mat_info": [_vp, C.POINTER(_i64), C.POINTER(_i64)],
+    "lb_mat_download": [_vp, _vp, _vp, _vp],
+    "lb_mat_upload": [_vp, _i64, _i64, _vp, _vp, _vp, _pp],
+    "lb_mat_free": [_vp],
+}
+STRING_GETTERS = ("lb_last_error", "lb_version")
+
+_lib = None
+_lock = threading.Lock()
+
+
+def lib():
+    """The loaded shared library (loaded once)."""
+    global _lib
+    if _lib is None:
+        with _lock:
+            if _lib is None:
+                if not os.path.exists(LIB_PATH):
+                    raise ImportError(
+                        f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; "
+                        "g.build()'` (nvcc, sm_100a). lapy_b200 has no CPU fallback."
+                    )
+                handle = C.CDLL(LIB_PATH)
+                for name, argtypes in SIGNATURES.items():
+                    fn = getattr(handle, name)
+                    fn.argtypes = argtypes
+                    fn.restype = C.c_int
+                for name in STRING_GETTERS:
+                    getattr(handle, name).restype = C.c_char_p
+                    getattr(handle, name).argtypes = []
+                _lib = handle
+    return _lib
+
+
+def check(status: int):
+    if status == OK:
+        return
+    msg = lib().lb_last_error().decode("utf-8", "replace")
+    if status == ERR_ARG:
+        raise ValueError(msg)
+    if status == ERR_NOCONV:
+        raise NoConvergence(msg)
+    if status == ERR_OOM:
+        raise MemoryError(msg)
+    if status == ERR_UNSUPPORTED:
+        raise NotImplementedError(msg)
+    raise RuntimeError(msg)
+
+
+def ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class Context:
+    """One CUDA stream + memory pool on one device (lb_ctx)."""
+
+    def __init__(self, device: int = 0, stream: int | None = None):
+        h = C.c_void_p()
+        check(lib().lb_ctx_create(int(device), C.c_void_p(stream) if stream else None, C.byref(h)))
+        self.handle = h
+        self.device = int(device)
+
+    def close(self):
+        if getattr(self, "handle", None):
+            lib().lb_ctx_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def sync(self):
+        check(lib().lb_ctx_sync(self.handle))
+
+    def timer_start(self):
+        check(lib().lb_timer_start(self.handle))
+
+    def timer_stop(self) -> float:
+        ms = C.c_double()
+        check(lib().lb_timer_stop(self.handle, C.byref(ms)))
+        return ms.value
+
+    def launch_count(self) -> int:
+        n = C.c_int64()
+        check(lib().lb_launch_count(self.handle, C.byref(n)))
+        return n.value
+
+
+_default_ctx: dict[int, Context] = {}
+
+
+def default_context(device: int | None = None) -> Context:
+    """Process-wide context per device; device defaults to $LAPY_B200_DEVICE, $LOCAL_RANK or 0."""
+    if device is None:
+        device = int(os.environ.get("LAPY_B200_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+    if device not in _default_ctx:
+        _default_ctx[device] = Context(device)
+    return _default_ctx[device]
+
+
+class DeviceMesh:
+    """geometry.v / geometry.t resident on the device (lb_mesh)."""
+
+    def __init__(self, ctx: Context, v: np.ndarray, t: np.ndarray):
+        v = np.asarray(v)
+        t = np.asarray(t)
+        if v.ndim != 2 or v.shape[1] != 3:
+            raise ValueError("vertices must have shape (n, 3)")
+        if t.ndim != 2 or t.shape[1] not in (3, 4):
+            raise ValueError("elements must have shape (m, 3) or (m, 4)")
+        if v.dtype != np.float32:
+            v = v.astype(np.float64, copy=False)
+        if t.dtype.kind not in "iu":
+            raise ValueError("element indices must be integers")
+        if t.dtype.itemsize not in (4, 8) or t.dtype.kind == "u" or not t.dtype.isnative:
+            t = t.astype(np.int64)  # big-endian FreeSurfer '>i4', uint*, int16 ...
+        v = np.ascontiguousarray(v)  # TriaMesh may hand over a transposed view
+        t = np.ascontiguousarray(t)
+        self.ctx = ctx
+        self.nv, self.nt, self.k = v.shape[0], t.shape[0], t.shape[1]
+        self.v_dtype = v.dtype
+        h = C.c_void_p()
+        check(
+            lib().lb_mesh_create(
+                ctx.handle, ptr(v), F32 if v.dtype == np.float32 else F64, self.nv,
+                ptr(t), t.dtype.itemsize, self.nt, self.k, C.byref(h),
+            )
+        )  # fmt: skip
+        self.handle = h
+
+    def drop_cache(self):
+        check(lib().lb_mesh_drop_cache(self.handle))
+
+    def close(self):
+        if getattr(self, "handle", None):
+            lib().lb_mesh_free(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class DeviceMatrix:
+    """Symmetric sparse matrix in canonical CSC==CSR on the device (lb_mat)."""
+
+    def __init__(self, ctx: Context, handle):
+        self.ctx = ctx
+        self.handle = handle
+        n, nnz = C.c_int64(), C.c_int64()
+        check(lib().lb_mat_info(handle, C.byref(n), C.byref(nnz)))
+        self.n, self.nnz = n.value, nnz.value
+
+    @classmethod
+    def from_scipy(cls, ctx: Context, m):
+        from scipy import sparse
+
+        m = sparse.csc_matrix(m)
+        if m.shape[0] != m.shape[1]:
+            raise ValueError("matrix must be square")
+        if not m.has_canonical_format:
+            m = m.copy()
+            m.sum_duplicates()
+        indptr = np.ascontiguousarray(m.indptr, dtype=np.int32)
+        indices = np.ascontiguousarray(m.indices, dtype=np.int32)
+        data = np.ascontiguousarray(m.data, dtype=np.float64)
+        h = C.c_void_p()
+        check(lib().lb_mat_upload(ctx.handle, m.shape[0], m.nnz, ptr(indptr), ptr(indices), ptr(data), C.byref(h)))
+        return cls(ctx, h)
+
+    def to_scipy(self):
+        from scipy import sparse
+
+        indptr = np.empty(self.n + 1, np.int32)
+        indices = np.empty(self.nnz, np.int32)
+        data = np.empty(self.nnz, np.float64)
+        check(lib().lb_mat_download(self.handle, ptr(indptr), ptr(indices), ptr(data)))
+        m = sparse.csc_matrix((data, indices, indptr), shape=(self.n, self.n))
+        m.has_canonical_format = True
+        return m
+
+    def close(self):
+        if getattr(self, "handle", None):
+            lib().lb_mat_free(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def assemble(ctx: Context, mesh: DeviceMesh, kind: int, lump: bool, aniso=None, want_a: bool = True):
+    """lb_fem_assemble -> (DeviceMatrix A | None, DeviceMatrix B)."""
+    u1 = u2 = am = None
+    if kind == FEM_TRIA_ANISO:
+        u1, u2, am = (np.ascontiguousarray(x, dtype=np.float64) for x in aniso)
+        if u1.shape != (mesh.nt, 3) or u2.shape != (mesh.nt, 3) or am.shape != (mesh.nt, 2):
+            raise ValueError("u1, u2 must have shape (n_triangles, 3) and aniso_mat (n_triangles, 2)")
+    ha, hb = C.c_void_p(), C.c_void_p()
+    check(
+        lib().lb_fem_assemble(
+            ctx.handle, mesh.handle, kind, int(bool(lump)), ptr(u1), ptr(u2), ptr(am),
+            C.byref(ha) if want_a else None, C.byref(hb),
+        )
+    )  # fmt: skip
+    a = DeviceMatrix(ctx, ha) if (want_a and ha.value) else None
+    return a, DeviceMatrix(ctx, hb)

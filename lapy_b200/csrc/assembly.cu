@@ -1,0 +1,786 @@
+// assembly.cu - linear-FEM stiffness / mass assembly on the device.
+//
+// Replaces lapy/solver.py:105-194 (_fem_tria), :196-308 (_fem_tria_aniso), :310-377
+// (fem_tria_mass), :379-533 (_fem_tetra) and the SciPy COO->CSC conversion they end in.
+//
+// Pipeline (all on the context's stream, one host read-back for nnz):
+//   1. element pass      one thread per element: gather 3|4 vertices (one 32 B sector each),
+//                        local cot / volume entries in the dtype of the caller's vertices with
+//                        unfused IEEE ops, one 32 B (tria) / 96 B (tet) record per element,
+//                        deterministic block partial sums of vol (for the degenerate clamp,
+//                        solver.py:158-159) and the per-vertex incidence histogram.
+//   2. incidence build   scan + fill + per-vertex sort: vertex -> (element*4 + corner), ascending.
+//                        This IS the reference's triplet order restricted to one column.
+//   3. row count         one thread per row: sorted unique neighbour keys in shared memory.
+//   4. scan -> indptr; nnz read back; exact-size outputs allocated.
+//   5. row fill          one thread per row accumulates (key, A, B) in COO input order into a
+//                        shared-memory image of the block's contiguous CSR segment, which the
+//                        block then streams out fully coalesced.  Every output byte is written
+//                        exactly once; no atomics on values -> bit-reproducible.
+// No sort of the 9T / 16T triplets is ever materialised (SURVEY.md §7 "Hard parts").
+#include <climits>
+
+#include "common.cuh"
+
+namespace lb {
+
+constexpr int kRowThreads = 128;  // rows per block in the row kernels
+
+// ---- upload / conversion ----------------------------------------------------------------
+template <class TIn>
+__global__ void convert_vertices(const TIn *__restrict__ raw, int64_t nv, D4 *__restrict__ v4,
+                                 float4 *__restrict__ v4f) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nv) return;
+    TIn x = raw[3 * i], y = raw[3 * i + 1], z = raw[3 * i + 2];
+    st_d4(v4 + i, (double)x, (double)y, (double)z, 0.0);
+    if (v4f) v4f[i] = make_float4((float)x, (float)y, (float)z, 0.f);
+}
+
+template <class TIn>
+__global__ void convert_elements(const TIn *__restrict__ raw, int64_t nt, int k, int4 *__restrict__ t4,
+                                 long long *__restrict__ minmax) {
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    long long lo = LLONG_MAX, hi = LLONG_MIN;
+    if (e < nt) {
+        long long a = raw[k * e], b = raw[k * e + 1], c = raw[k * e + 2];
+        long long d = k == 4 ? (long long)raw[k * e + 3] : -1;
+        lo = min(a, min(b, c));
+        hi = max(a, max(b, c));
+        if (k == 4) {
+            lo = min(lo, d);
+            hi = max(hi, d);
+        }
+        t4[e] = make_int4((int)a, (int)b, (int)c, (int)d);
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    if ((threadIdx.x & 31) == 0 && lo != LLONG_MAX) {
+        atomicMin(minmax, lo);
+        atomicMax(minmax + 1, hi);
+    }
+}
+
+// ---- deterministic block sum ------------------------------------------------------------
+__device__ __forceinline__ double block_sum(double x) {
+    __shared__ double ws[32];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = x;
+    __syncthreads();
+    double s = 0;
+    if (threadIdx.x < 32) {
+        s = threadIdx.x < ((blockDim.x + 31) >> 5) ? ws[threadIdx.x] : 0.0;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    }
+    return s;  // valid in thread 0
+}
+
+// ---- element records --------------------------------------------------------------------
+// triangle record (D4): a12, a23, a31, bii        (final fp64 values)
+//   degenerate (vol < eps before the clamp): d12, d23, d31 numerators, w = -1
+// tet record (3 x D4): a12 a13 a14 a23 | a24 a34 a11 a22 | a33 a44 bii lump   (A already /6)
+//   degenerate: the six numerators in slots 0..5, bii = -1
+enum { MODE_FEM = 0, MODE_ANISO = 1, MODE_MASS = 2 };
+
+struct ElemConsts {
+    double vol_mean;  // clamp value in the element dtype, widened
+    double bii_deg;   // bii of a clamped element
+    double lump_deg;  // lumped mass contribution of a clamped element (tets)
+};
+
+template <class T, int MODE>
+__global__ void __launch_bounds__(256) tria_element_kernel(
+    const typename Ex<T>::V4 *__restrict__ v4, const int4 *__restrict__ t4, int64_t nt,
+    const double *__restrict__ u1, const double *__restrict__ u2, const double *__restrict__ am,
+    D4 *__restrict__ rec, int32_t *__restrict__ deg, double *__restrict__ partial) {
+    using E = Ex<T>;
+    using ED = Ex<double>;
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    double vol_d = 0.0;
+    if (e < nt) {
+        int4 ti = __ldg(t4 + e);
+        Vec3<T> p1 = load_vertex<T>(v4, ti.x), p2 = load_vertex<T>(v4, ti.y), p3 = load_vertex<T>(v4, ti.z);
+        Vec3<T> ec = vsub(p2, p1), ea = vsub(p3, p2), eb = vsub(p1, p3);  // v2mv1, v3mv2, v1mv3
+        Vec3<T> cr = vcross(ea, eb);
+        T s = E::sqrt(vdot(cr, cr));
+        T vol = MODE == MODE_MASS ? E::mul((T)0.5, s) : E::mul((T)2, s);
+        vol_d = (double)vol;
+        bool degen = vol < E::eps();
+        double q12, q23, q31;
+        if (MODE == MODE_FEM) {
+            T d12 = vdot(ea, eb), d23 = vdot(eb, ec), d31 = vdot(ec, ea);
+            if (!degen) {
+                d12 = E::div(d12, vol);
+                d23 = E::div(d23, vol);
+                d31 = E::div(d31, vol);
+            }
+            q12 = (double)d12; q23 = (double)d23; q31 = (double)d31;
+        } else if (MODE == MODE_ANISO) {
+            // projections and the weighted dot run in fp64 (u1, u2, aniso_mat are fp64 arrays)
+            Vec3<double> a = vwiden(ea), b = vwiden(eb), c = vwiden(ec);
+            Vec3<double> w1 = {u1[3 * e], u1[3 * e + 1], u1[3 * e + 2]};
+            Vec3<double> w2 = {u2[3 * e], u2[3 * e + 1], u2[3 * e + 2]};
+            double m0 = am[2 * e], m1 = am[2 * e + 1];
+            double a0 = vdot(w1, a), a1 = vdot(w2, a), b0 = vdot(w1, b), b1 = vdot(w2, b);
+            double c0 = vdot(w1, c), c1 = vdot(w2, c);
+            auto adot = [&](double x0, double x1, double y0, double y1) {
+                return ED::add(ED::mul(ED::mul(x0, m0), y0), ED::mul(ED::mul(x1, m1), y1));
+            };
+            q12 = adot(a0, a1, b0, b1);
+            q23 = adot(b0, b1, c0, c1);
+            q31 = adot(c0, c1, a0, a1);
+            if (!degen) {
+                q12 = ED::div(q12, vol_d);
+                q23 = ED::div(q23, vol_d);
+                q31 = ED::div(q31, vol_d);
+            }
+        } else {
+            q12 = q23 = q31 = 0.0;
+        }
+        double bii = degen ? -1.0 : (double)E::div(vol, MODE == MODE_MASS ? (T)6 : (T)24);
+        st_d4(rec + e, q12, q23, q31, bii);
+        if (deg) {
+            atomicAdd(deg + ti.x, 1);
+            atomicAdd(deg + ti.y, 1);
+            atomicAdd(deg + ti.z, 1);
+        }
+    }
+    double s = block_sum(vol_d);
+    if (threadIdx.x == 0) partial[blockIdx.x] = s;
+}
+
+template <class T>
+__global__ void __launch_bounds__(256) tet_element_kernel(
+    const typename Ex<T>::V4 *__restrict__ v4, const int4 *__restrict__ t4, int64_t nt,
+    D4 *__restrict__ rec, int32_t *__restrict__ deg, double *__restrict__ partial) {
+    using E = Ex<T>;
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    double vol_d = 0.0;
+    if (e < nt) {
+        int4 ti = __ldg(t4 + e);
+        Vec3<T> p1 = load_vertex<T>(v4, ti.x), p2 = load_vertex<T>(v4, ti.y);
+        Vec3<T> p3 = load_vertex<T>(v4, ti.z), p4 = load_vertex<T>(v4, ti.w);
+        Vec3<T> e1 = vsub(p2, p1), e2 = vsub(p3, p2), e3 = vsub(p1, p3);
+        Vec3<T> e4 = vsub(p4, p1), e5 = vsub(p4, p2), e6 = vsub(p4, p3);
+        T vol = fabs(vdot(e4, vcross(e1, e3)));
+        vol_d = (double)vol;
+        bool degen = vol < E::eps();
+        T e11 = vdot(e1, e1), e22 = vdot(e2, e2), e33 = vdot(e3, e3);
+        T e44 = vdot(e4, e4), e55 = vdot(e5, e5), e66 = vdot(e6, e6);
+        T e12 = vdot(e1, e2), e13 = vdot(e1, e3), e14 = vdot(e1, e4), e15 = vdot(e1, e5);
+        T e23 = vdot(e2, e3), e25 = vdot(e2, e5), e26 = vdot(e2, e6);
+        T e34 = vdot(e3, e4), e36 = vdot(e3, e6);
+        T a12 = E::add(E::mul(-e36, e26), E::mul(e23, e66));
+        T a13 = E::add(E::mul(-e15, e25), E::mul(e12, e55));
+        T a14 = E::sub(E::mul(e23, e26), E::mul(e36, e22));
+        T a23 = E::add(E::mul(-e14, e34), E::mul(e13, e44));
+        T a24 = E::sub(E::mul(e13, e34), E::mul(e14, e33));
+        T a34 = E::add(E::mul(-e14, e13), E::mul(e11, e34));
+        D4 *r = rec + 3 * e;
+        if (degen) {
+            st_d4(r, (double)a12, (double)a13, (double)a14, (double)a23);
+            st_d4(r + 1, (double)a24, (double)a34, 0.0, 0.0);
+            st_d4(r + 2, 0.0, 0.0, -1.0, 0.0);
+        } else {
+            a12 = E::div(a12, vol); a13 = E::div(a13, vol); a14 = E::div(a14, vol);
+            a23 = E::div(a23, vol); a24 = E::div(a24, vol); a34 = E::div(a34, vol);
+            T a11 = E::sub(E::sub(-a12, a13), a14);
+            T a22 = E::sub(E::sub(-a12, a23), a24);
+            T a33 = E::sub(E::sub(-a13, a23), a34);
+            T a44 = E::sub(E::sub(-a14, a24), a34);
+            const T six = (T)6;
+            st_d4(r, (double)E::div(a12, six), (double)E::div(a13, six), (double)E::div(a14, six),
+                  (double)E::div(a23, six));
+            st_d4(r + 1, (double)E::div(a24, six), (double)E::div(a34, six), (double)E::div(a11, six),
+                  (double)E::div(a22, six));
+            st_d4(r + 2, (double)E::div(a33, six), (double)E::div(a44, six), (double)E::div(vol, (T)60),
+                  (double)E::div(vol, (T)24));
+        }
+        if (deg) {
+            atomicAdd(deg + ti.x, 1);
+            atomicAdd(deg + ti.y, 1);
+            atomicAdd(deg + ti.z, 1);
+            atomicAdd(deg + ti.w, 1);
+        }
+    }
+    double s = block_sum(vol_d);
+    if (threadIdx.x == 0) partial[blockIdx.x] = s;
+}
+
+// vol_mean = max(1e-4 * mean(vol), eps) in the element dtype (solver.py:158, :357, :436)
+template <class T>
+__global__ void finalize_consts(const double *__restrict__ partial, int nblocks, int64_t nt, int kind,
+                                ElemConsts *__restrict__ out) {
+    using E = Ex<T>;
+    double s = 0;
+    for (int i = threadIdx.x; i < nblocks; i += blockDim.x) s += partial[i];
+    s = block_sum(s);
+    if (threadIdx.x == 0) {
+        T mean = (T)(s / (double)nt);
+        T vm = E::mul((T)0.0001, mean);
+        if (!((double)vm > kEps)) vm = (T)kEps;  // python max(a, eps): a if a > eps else eps
+        out->vol_mean = (double)vm;
+        if (kind == LB_FEM_TETRA) {
+            out->bii_deg = (double)E::div(vm, (T)60);
+            out->lump_deg = (double)E::div(vm, (T)24);
+        } else {
+            out->bii_deg = (double)E::div(vm, kind == LB_FEM_TRIA_MASS ? (T)6 : (T)24);
+            out->lump_deg = 2.0 * out->bii_deg;
+        }
+    }
+}
+
+// ---- incidence ----------------------------------------------------------------------------
+__global__ void incidence_fill(const int4 *__restrict__ t4, int64_t nt, int k,
+                               const int32_t *__restrict__ inc_ptr, int32_t *__restrict__ cursor,
+                               int32_t *__restrict__ inc) {
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= nt) return;
+    int4 ti = __ldg(t4 + e);
+    int code = (int)e * 4;
+    inc[inc_ptr[ti.x] + atomicAdd(cursor + ti.x, 1)] = code;
+    inc[inc_ptr[ti.y] + atomicAdd(cursor + ti.y, 1)] = code + 1;
+    inc[inc_ptr[ti.z] + atomicAdd(cursor + ti.z, 1)] = code + 2;
+    if (k == 4) inc[inc_ptr[ti.w] + atomicAdd(cursor + ti.w, 1)] = code + 3;
+}
+
+// per-vertex insertion sort of the (atomically ordered) incidence codes -> deterministic
+__global__ void incidence_sort(const int32_t *__restrict__ inc_ptr, int32_t *__restrict__ inc, int64_t n) {
+    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    int beg = inc_ptr[r], end = inc_ptr[r + 1];
+    for (int i = beg + 1; i < end; i++) {
+        int key = inc[i];
+        int j = i - 1;
+        while (j >= beg && inc[j] > key) {
+            inc[j + 1] = inc[j];
+            j--;
+        }
+        inc[j + 1] = key;
+    }
+}
+
+// ---- sorted small-set helpers (thread-private slices of shared or global memory) ----------
+__device__ __forceinline__ int find_slot(const int32_t *keys, int cnt, int key) {
+    // rows hold ~7 (tria) / ~15 (tet) keys: a backwards linear scan beats a binary search
+    int pos = cnt;
+    while (pos > 0 && keys[pos - 1] >= key) pos--;
+    return pos;  // first position with keys[pos] >= key
+}
+
+__device__ __forceinline__ void insert_key(int32_t *keys, int &cnt, int key) {
+    int pos = find_slot(keys, cnt, key);
+    if (pos < cnt && keys[pos] == key) return;
+    for (int q = cnt; q > pos; q--) keys[q] = keys[q - 1];
+    keys[pos] = key;
+    cnt++;
+}
+
+__device__ __forceinline__ void accumulate(int32_t *keys, double *av, double *bv, int &cnt, int key,
+                                           double a, double b, bool want_a, bool want_b) {
+    int pos = find_slot(keys, cnt, key);
+    if (pos < cnt && keys[pos] == key) {
+        if (want_a) av[pos] = __dadd_rn(av[pos], a);
+        if (want_b) bv[pos] = __dadd_rn(bv[pos], b);
+        return;
+    }
+    for (int q = cnt; q > pos; q--) {
+        keys[q] = keys[q - 1];
+        if (want_a) av[q] = av[q - 1];
+        if (want_b) bv[q] = bv[q - 1];
+    }
+    keys[pos] = key;
+    if (want_a) av[pos] = a;  // first addend itself, like csr_sum_duplicates (keeps -0.0)
+    if (want_b) bv[pos] = b;
+    cnt++;
+}
+
+// ---- row count ----------------------------------------------------------------------------
+// dynamic smem: cap int32 keys.  Blocks whose upper bound exceeds cap use the global scratch.
+template <int K>
+__global__ void __launch_bounds__(kRowThreads) row_count_kernel(
+    const int4 *__restrict__ t4, const int32_t *__restrict__ inc_ptr, const int32_t *__restrict__ inc,
+    int64_t n, int cap, int32_t *__restrict__ scratch, int32_t *__restrict__ row_nnz,
+    int32_t *__restrict__ row_has) {
+    extern __shared__ int32_t skeys[];
+    __shared__ int s_total;
+    int64_t r = (int64_t)blockIdx.x * kRowThreads + threadIdx.x;
+    int beg = 0, end = 0;
+    if (r < n) {
+        beg = inc_ptr[r];
+        end = inc_ptr[r + 1];
+    }
+    int ninc = end - beg;
+    int ub = ninc ? ninc * (K - 1) + 1 : 0;
+    // block exclusive scan of ub
+    __shared__ int wsum[kRowThreads / 32];
+    int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int incl = ub;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        int y = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += y;
+    }
+    if (lane == 31) wsum[wid] = incl;
+    __syncthreads();
+    int base = 0;
+    for (int w = 0; w < wid; w++) base += wsum[w];
+    if (threadIdx.x == kRowThreads - 1) s_total = base + incl;
+    __syncthreads();
+    int off = base + incl - ub;
+    int32_t *keys = (s_total <= cap) ? skeys + off : scratch + ((int64_t)beg * (K - 1) + r);
+    int cnt = 0;
+    for (int p = beg; p < end; p++) {
+        int4 ti = __ldg(t4 + (inc[p] >> 2));
+        insert_key(keys, cnt, ti.x);
+        insert_key(keys, cnt, ti.y);
+        insert_key(keys, cnt, ti.z);
+        if (K == 4) insert_key(keys, cnt, ti.w);
+    }
+    if (r < n) {
+        row_nnz[r] = cnt;
+        row_has[r] = ninc > 0;
+    }
+}
+
+// ---- row fill -----------------------------------------------------------------------------
+struct RowOut {
+    const int32_t *indptr;
+    int32_t *a_idx;
+    double *a_val;  // may be NULL (mass only)
+    int32_t *b_idx;
+    double *b_val;  // may be NULL (lumped)
+    const int32_t *lump_ptr;  // lumped mass: indptr of the diagonal matrix, or NULL
+    int32_t *lump_idx;
+    double *lump_val;
+};
+
+template <int K>
+__global__ void __launch_bounds__(kRowThreads) row_fill_kernel(
+    const int4 *__restrict__ t4, const D4 *__restrict__ rec, const int32_t *__restrict__ inc_ptr,
+    const int32_t *__restrict__ inc, int64_t n, int cap, const ElemConsts *__restrict__ consts,
+    int degen_div_f32, RowOut out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *s_a = reinterpret_cast<double *>(smem_raw);
+    double *s_b = s_a + cap;
+    int32_t *s_k = reinterpret_cast<int32_t *>(s_b + cap);
+
+    const int64_t r0 = (int64_t)blockIdx.x * kRowThreads;
+    const int64_t r = r0 + threadIdx.x;
+    const int64_t rlast = min(r0 + (int64_t)kRowThreads, n);
+    const int blk_beg = out.indptr[r0], blk_end = out.indptr[rlast];
+    const int blk_nnz = blk_end - blk_beg;
+    const bool want_a = out.a_val != nullptr, want_b = out.b_val != nullptr;
+    const bool want_pat = want_a || want_b;
+    const bool use_smem = want_pat && blk_nnz <= cap;
+
+    if (r < n) {
+        const int rbeg = out.indptr[r];
+        int32_t *keys;
+        double *av, *bv;
+        if (use_smem) {
+            keys = s_k + (rbeg - blk_beg);
+            av = s_a + (rbeg - blk_beg);
+            bv = s_b + (rbeg - blk_beg);
+        } else {  // oversized block (very high valence): accumulate straight into the output
+            keys = (want_a ? out.a_idx : out.b_idx) + rbeg;
+            av = out.a_val + rbeg;
+            bv = out.b_val + rbeg;
+        }
+        int cnt = 0;
+        double lump = 0.0;
+        const int beg = inc_ptr[r], end = inc_ptr[r + 1];
+        for (int p = beg; p < end; p++) {
+            const int code = inc[p];
+            const int e = code >> 2, c = code & 3;
+            const int4 ti = __ldg(t4 + e);
+            if (K == 3) {
+                D4 q = ldg_d4(rec + e);
+                double a12 = q.x, a23 = q.y, a31 = q.z, bii = q.w;
+                if (bii < 0.0) {  // clamped element (solver.py:159): divide by the global mean
+                    const double vm = consts->vol_mean;
+                    if (degen_div_f32) {
+                        a12 = (double)__fdiv_rn((float)a12, (float)vm);
+                        a23 = (double)__fdiv_rn((float)a23, (float)vm);
+                        a31 = (double)__fdiv_rn((float)a31, (float)vm);
+                    } else {
+                        a12 = __ddiv_rn(a12, vm);
+                        a23 = __ddiv_rn(a23, vm);
+                        a31 = __ddiv_rn(a31, vm);
+                    }
+                    bii = consts->bii_deg;
+                }
+                const double bij = 0.5 * bii;
+                lump += 2.0 * bii;  // vol/12 (vol/3 for fem_tria_mass) == 2*bii exactly
+                int k0, k1;
+                double x0, x1, xd;
+                // column = corner c; rows in the reference's triplet order (solver.py:171-175)
+                if (c == 0) {
+                    k0 = ti.y; x0 = a12; k1 = ti.z; x1 = a31; xd = __dsub_rn(-a12, a31);
+                } else if (c == 1) {
+                    k0 = ti.x; x0 = a12; k1 = ti.z; x1 = a23; xd = __dsub_rn(-a12, a23);
+                } else {
+                    k0 = ti.y; x0 = a23; k1 = ti.x; x1 = a31; xd = __dsub_rn(-a31, a23);
+                }
+                if (want_pat) {
+                    accumulate(keys, av, bv, cnt, k0, x0, bij, want_a, want_b);
+                    accumulate(keys, av, bv, cnt, k1, x1, bij, want_a, want_b);
+                    accumulate(keys, av, bv, cnt, (int)r, xd, bii, want_a, want_b);
+                }
+            } else {
+                const D4 *rp = rec + 3 * (int64_t)e;
+                D4 q0 = ldg_d4(rp), q1 = ldg_d4(rp + 1), q2 = ldg_d4(rp + 2);
+                double a12 = q0.x, a13 = q0.y, a14 = q0.z, a23 = q0.w, a24 = q1.x, a34 = q1.y;
+                double a11 = q1.z, a22 = q1.w, a33 = q2.x, a44 = q2.y, bii = q2.z, lmp = q2.w;
+                if (bii < 0.0) {
+                    const double vm = consts->vol_mean;
+                    if (degen_div_f32) {
+                        const float vf = (float)vm;
+                        float f12 = __fdiv_rn((float)a12, vf), f13 = __fdiv_rn((float)a13, vf);
+                        float f14 = __fdiv_rn((float)a14, vf), f23 = __fdiv_rn((float)a23, vf);
+                        float f24 = __fdiv_rn((float)a24, vf), f34 = __fdiv_rn((float)a34, vf);
+                        a11 = (double)__fdiv_rn(__fsub_rn(__fsub_rn(-f12, f13), f14), 6.f);
+                        a22 = (double)__fdiv_rn(__fsub_rn(__fsub_rn(-f12, f23), f24), 6.f);
+                        a33 = (double)__fdiv_rn(__fsub_rn(__fsub_rn(-f13, f23), f34), 6.f);
+                        a44 = (double)__fdiv_rn(__fsub_rn(__fsub_rn(-f14, f24), f34), 6.f);
+                        a12 = (double)__fdiv_rn(f12, 6.f); a13 = (double)__fdiv_rn(f13, 6.f);
+                        a14 = (double)__fdiv_rn(f14, 6.f); a23 = (double)__fdiv_rn(f23, 6.f);
+                        a24 = (double)__fdiv_rn(f24, 6.f); a34 = (double)__fdiv_rn(f34, 6.f);
+                    } else {
+                        double f12 = __ddiv_rn(a12, vm), f13 = __ddiv_rn(a13, vm), f14 = __ddiv_rn(a14, vm);
+                        double f23 = __ddiv_rn(a23, vm), f24 = __ddiv_rn(a24, vm), f34 = __ddiv_rn(a34, vm);
+                        a11 = __ddiv_rn(__dsub_rn(__dsub_rn(-f12, f13), f14), 6.0);
+                        a22 = __ddiv_rn(__dsub_rn(__dsub_rn(-f12, f23), f24), 6.0);
+                        a33 = __ddiv_rn(__dsub_rn(__dsub_rn(-f13, f23), f34), 6.0);
+                        a44 = __ddiv_rn(__dsub_rn(__dsub_rn(-f14, f24), f34), 6.0);
+                        a12 = __ddiv_rn(f12, 6.0); a13 = __ddiv_rn(f13, 6.0); a14 = __ddiv_rn(f14, 6.0);
+                        a23 = __ddiv_rn(f23, 6.0); a24 = __ddiv_rn(f24, 6.0); a34 = __ddiv_rn(f34, 6.0);
+                    }
+                    bii = consts->bii_deg;
+                    lmp = consts->lump_deg;
+                }
+                const double bij = 0.5 * bii;
+                lump += lmp;
+                int k0, k1, k2;
+                double x0, x1, x2, xd;
+                // column = corner c; rows in the reference's triplet order (solver.py:472-497)
+                if (c == 0) {
+                    k0 = ti.y; x0 = a12; k1 = ti.z; x1 = a13; k2 = ti.w; x2 = a14; xd = a11;
+                } else if (c == 1) {
+                    k0 = ti.x; x0 = a12; k1 = ti.z; x1 = a23; k2 = ti.w; x2 = a24; xd = a22;
+                } else if (c == 2) {
+                    k0 = ti.y; x0 = a23; k1 = ti.x; x1 = a13; k2 = ti.w; x2 = a34; xd = a33;
+                } else {
+                    k0 = ti.x; x0 = a14; k1 = ti.y; x1 = a24; k2 = ti.z; x2 = a34; xd = a44;
+                }
+                if (want_pat) {
+                    accumulate(keys, av, bv, cnt, k0, x0, bij, want_a, want_b);
+                    accumulate(keys, av, bv, cnt, k1, x1, bij, want_a, want_b);
+                    accumulate(keys, av, bv, cnt, k2, x2, bij, want_a, want_b);
+                    accumulate(keys, av, bv, cnt, (int)r, xd, bii, want_a, want_b);
+                }
+            }
+        }
+        if (out.lump_ptr && end > beg) {
+            const int lp = out.lump_ptr[r];
+            out.lump_idx[lp] = (int)r;
+            out.lump_val[lp] = lump;
+        }
+        if (!use_smem && want_a && want_b) {
+            for (int q = 0; q < cnt; q++) out.b_idx[rbeg + q] = keys[q];
+        }
+    }
+    if (use_smem) {
+        __syncthreads();
+        for (int q = threadIdx.x; q < blk_nnz; q += kRowThreads) {
+            const int key = s_k[q];
+            if (want_a) {
+                out.a_idx[blk_beg + q] = key;
+                out.a_val[blk_beg + q] = s_a[q];
+            }
+            if (want_b) {
+                out.b_idx[blk_beg + q] = key;
+                out.b_val[blk_beg + q] = s_b[q];
+            }
+        }
+    }
+}
+
+// ---- host side ----------------------------------------------------------------------------
+static void build_incidence(lb_mesh *mesh, DBuf<int32_t> &deg) {
+    // deg holds the per-vertex incidence histogram (from the element pass)
+    lb_ctx *c = mesh->ctx;
+    const int64_t nv = mesh->nv, nt = mesh->nt;
+    mesh->inc_ptr.alloc(c, nv + 1);
+    mesh->inc.alloc(c, (size_t)mesh->k * nt);
+    exclusive_scan_i32(c, deg.p, mesh->inc_ptr.p, nv);
+    deg.zero();
+    LB_LAUNCH(c, incidence_fill, cdiv(nt, 256), 256, 0, mesh->t4.p, nt, mesh->k, mesh->inc_ptr.p, deg.p,
+              mesh->inc.p);
+    LB_LAUNCH(c, incidence_sort, cdiv(nv, 128), 128, 0, mesh->inc_ptr.p, mesh->inc.p, nv);
+    mesh->has_inc = true;
+}
+
+template <class T>
+static void run_element_pass(lb_mesh *mesh, int kind, const double *u1, const double *u2, const double *am,
+                             D4 *rec, int32_t *deg, ElemConsts *consts) {
+    lb_ctx *c = mesh->ctx;
+    const int64_t nt = mesh->nt;
+    const int nblocks = cdiv(nt, 256);
+    DBuf<double> partial(c, nblocks);
+    const typename Ex<T>::V4 *v4;
+    if constexpr (sizeof(T) == 4) v4 = mesh->v4f.p;
+    else v4 = mesh->v4.p;
+    switch (kind) {
+        case LB_FEM_TRIA: {
+            auto kern = tria_element_kernel<T, MODE_FEM>;
+            LB_LAUNCH(c, kern, nblocks, 256, 0, v4, mesh->t4.p, nt, u1, u2, am, rec, deg, partial.p);
+            break;
+        }
+        case LB_FEM_TRIA_ANISO: {
+            auto kern = tria_element_kernel<T, MODE_ANISO>;
+            LB_LAUNCH(c, kern, nblocks, 256, 0, v4, mesh->t4.p, nt, u1, u2, am, rec, deg, partial.p);
+            break;
+        }
+        case LB_FEM_TRIA_MASS: {
+            auto kern = tria_element_kernel<T, MODE_MASS>;
+            LB_LAUNCH(c, kern, nblocks, 256, 0, v4, mesh->t4.p, nt, u1, u2, am, rec, deg, partial.p);
+            break;
+        }
+        default: {
+            auto kern = tet_element_kernel<T>;
+            LB_LAUNCH(c, kern, nblocks, 256, 0, v4, mesh->t4.p, nt, rec, deg, partial.p);
+        }
+    }
+    auto fin = finalize_consts<T>;
+    LB_LAUNCH(c, fin, 1, 256, 0, partial.p, nblocks, nt, kind, consts);
+}
+
+static lb_mat *new_mat(lb_ctx *c, int64_t n, int64_t nnz) {
+    lb_mat *m = new lb_mat();
+    m->ctx = c;
+    m->n = n;
+    m->nnz = nnz;
+    m->indptr.alloc(c, n + 1);
+    m->indices.alloc(c, nnz);
+    m->data.alloc(c, nnz);
+    return m;
+}
+
+template <int K>
+static void run_rows(lb_mesh *mesh, const D4 *rec, const ElemConsts *consts, bool want_a, bool lump,
+                     bool degen_f32, lb_mat **a_out, lb_mat **b_out) {
+    lb_ctx *c = mesh->ctx;
+    const int64_t n = mesh->n_ref;
+    const int nblocks = cdiv(n, kRowThreads);
+    // --- count
+    const int cap_keys = K == 3 ? 4096 : 12288;  // int32 keys of shared memory per block
+    DBuf<int32_t> row_nnz(c, n), row_has(c, n);
+    DBuf<int32_t> scratch(c, (size_t)mesh->k * mesh->nt * (K - 1) + n);
+    if (cap_keys * 4 > 48 * 1024)
+        LB_CUDA(cudaFuncSetAttribute(row_count_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap_keys * 4));
+    LB_LAUNCH(c, row_count_kernel<K>, nblocks, kRowThreads, cap_keys * 4, mesh->t4.p, mesh->inc_ptr.p, mesh->inc.p,
+              n, cap_keys, scratch.p, row_nnz.p, row_has.p);
+    const bool full_b = !lump;
+    lb_mat *A = nullptr, *B = nullptr;
+    DBuf<int32_t> indptr(c, n + 1), lump_ptr;
+    exclusive_scan_i32(c, row_nnz.p, indptr.p, n);
+    int32_t totals[2] = {0, 0};
+    if (lump) {
+        lump_ptr.alloc(c, n + 1);
+        exclusive_scan_i32(c, row_has.p, lump_ptr.p, n);
+        read_back(c, &totals[1], lump_ptr.p + n, 1);
+    }
+    read_back(c, &totals[0], indptr.p + n, 1);
+    const int64_t nnz = totals[0];
+    try {
+        RowOut out{};
+        out.indptr = indptr.p;
+        if (want_a) {
+            A = new_mat(c, n, nnz);
+            d2d(c, A->indptr.p, indptr.p, (n + 1) * sizeof(int32_t));
+            out.a_idx = A->indices.p;
+            out.a_val = A->data.p;
+        }
+        if (full_b) {
+            B = new_mat(c, n, nnz);
+            d2d(c, B->indptr.p, indptr.p, (n + 1) * sizeof(int32_t));
+            out.b_idx = B->indices.p;
+            out.b_val = B->data.p;
+        } else {
+            B = new_mat(c, n, totals[1]);
+            B->diagonal = true;
+            d2d(c, B->indptr.p, lump_ptr.p, (n + 1) * sizeof(int32_t));
+            out.lump_ptr = lump_ptr.p;
+            out.lump_idx = B->indices.p;
+            out.lump_val = B->data.p;
+        }
+        if (want_a || full_b) {
+            const int cap = K == 3 ? 1792 : 3072;  // CSR entries of shared memory per block
+            const int smem = cap * 20;
+            if (smem > 48 * 1024)
+                LB_CUDA(cudaFuncSetAttribute(row_fill_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            LB_LAUNCH(c, row_fill_kernel<K>, nblocks, kRowThreads, smem, mesh->t4.p, rec, mesh->inc_ptr.p,
+                      mesh->inc.p, n, cap, consts, (int)degen_f32, out);
+        } else {
+            // mass only + lumped: no CSR pattern needed, but the same kernel does the sums
+            const int cap = 0;
+            LB_LAUNCH(c, row_fill_kernel<K>, nblocks, kRowThreads, 16, mesh->t4.p, rec, mesh->inc_ptr.p,
+                      mesh->inc.p, n, cap, consts, (int)degen_f32, out);
+        }
+    } catch (...) {
+        delete A;
+        delete B;
+        throw;
+    }
+    if (a_out) *a_out = A;
+    else delete A;
+    *b_out = B;
+}
+
+}  // namespace lb
+
+using namespace lb;
+
+extern "C" {
+
+int lb_mesh_create(lb_ctx *c, const void *v, int v_dtype, int64_t nv, const void *t, int t_itemsize,
+                   int64_t nt, int k, lb_mesh **out) {
+    LB_API_BEGIN
+    LB_REQUIRE(c && v && t && out, "lb_mesh_create: NULL argument");
+    LB_REQUIRE(k == 3 || k == 4, "elements must have 3 or 4 vertices, got %d", k);
+    LB_REQUIRE(v_dtype == LB_F32 || v_dtype == LB_F64, "vertex dtype must be float32 or float64");
+    LB_REQUIRE(t_itemsize == 4 || t_itemsize == 8, "element indices must be int32 or int64");
+    LB_REQUIRE(nv > 0 && nt > 0, "empty mesh");
+    LB_REQUIRE(nv < (1ll << 31) - 1 && nt < (1ll << 29), "mesh too large for int32 indexing");
+    DeviceGuard g(c->device);
+    lb_mesh *m = new lb_mesh();
+    try {
+        m->ctx = c;
+        m->nv = nv;
+        m->nt = nt;
+        m->k = k;
+        m->v_dtype = v_dtype;
+        m->v4.alloc(c, nv);
+        m->t4.alloc(c, nt);
+        if (v_dtype == LB_F32) m->v4f.alloc(c, nv);
+        const size_t vbytes = (size_t)nv * 3 * (v_dtype == LB_F32 ? 4 : 8);
+        const size_t tbytes = (size_t)nt * k * t_itemsize;
+        DBuf<unsigned char> raw_v(c, vbytes), raw_t(c, tbytes);
+        DBuf<long long> minmax(c, 2);
+        long long init[2] = {LLONG_MAX, LLONG_MIN};
+        std::memcpy(c->pinned, init, sizeof(init));
+        h2d(c, minmax.p, c->pinned, sizeof(init));
+        h2d(c, raw_v.p, v, vbytes);
+        h2d(c, raw_t.p, t, tbytes);
+        if (v_dtype == LB_F32)
+            LB_LAUNCH(c, convert_vertices<float>, cdiv(nv, 256), 256, 0, (const float *)raw_v.p, nv, m->v4.p, m->v4f.p);
+        else
+            LB_LAUNCH(c, convert_vertices<double>, cdiv(nv, 256), 256, 0, (const double *)raw_v.p, nv, m->v4.p,
+                      (float4 *)nullptr);
+        if (t_itemsize == 4)
+            LB_LAUNCH(c, convert_elements<int32_t>, cdiv(nt, 256), 256, 0, (const int32_t *)raw_t.p, nt, k, m->t4.p,
+                      minmax.p);
+        else
+            LB_LAUNCH(c, convert_elements<int64_t>, cdiv(nt, 256), 256, 0, (const int64_t *)raw_t.p, nt, k, m->t4.p,
+                      minmax.p);
+        long long mm[2];
+        read_back(c, mm, minmax.p, 2);
+        LB_REQUIRE(mm[0] >= 0, "negative vertex index %lld in elements", mm[0]);
+        LB_REQUIRE(mm[1] < nv, "Max index exceeds number of vertices");
+        m->n_ref = mm[1] + 1;
+    } catch (...) {
+        delete m;
+        throw;
+    }
+    *out = m;
+    LB_API_END
+}
+
+int lb_mesh_update_vertices(lb_mesh *m, const void *v, int v_dtype) {
+    LB_API_BEGIN
+    LB_REQUIRE(m && v, "NULL argument");
+    LB_REQUIRE(v_dtype == LB_F32 || v_dtype == LB_F64, "vertex dtype must be float32 or float64");
+    lb_ctx *c = m->ctx;
+    DeviceGuard g(c->device);
+    const size_t vbytes = (size_t)m->nv * 3 * (v_dtype == LB_F32 ? 4 : 8);
+    DBuf<unsigned char> raw_v(c, vbytes);
+    h2d(c, raw_v.p, v, vbytes);
+    m->v_dtype = v_dtype;
+    if (v_dtype == LB_F32) {
+        if (!m->v4f.p) m->v4f.alloc(c, m->nv);
+        LB_LAUNCH(c, convert_vertices<float>, cdiv(m->nv, 256), 256, 0, (const float *)raw_v.p, m->nv, m->v4.p,
+                  m->v4f.p);
+    } else {
+        LB_LAUNCH(c, convert_vertices<double>, cdiv(m->nv, 256), 256, 0, (const double *)raw_v.p, m->nv, m->v4.p,
+                  (float4 *)nullptr);
+    }
+    sync(c);  // raw_v is borrowed from the caller until here
+    LB_API_END
+}
+
+int lb_mesh_drop_cache(lb_mesh *m) {
+    LB_API_BEGIN
+    LB_REQUIRE(m, "mesh is NULL");
+    DeviceGuard g(m->ctx->device);
+    m->inc_ptr.release();
+    m->inc.release();
+    m->has_inc = false;
+    LB_API_END
+}
+
+int lb_mesh_free(lb_mesh *m) {
+    LB_API_BEGIN
+    if (!m) return LB_OK;
+    DeviceGuard g(m->ctx->device);
+    delete m;
+    LB_API_END
+}
+
+int lb_fem_assemble(lb_ctx *c, lb_mesh *mesh, int kind, int lump, const double *u1, const double *u2,
+                    const double *aniso_mat, lb_mat **a_out, lb_mat **b_out) {
+    LB_API_BEGIN
+    LB_REQUIRE(c && mesh && b_out, "lb_fem_assemble: NULL argument");
+    LB_REQUIRE(mesh->ctx == c, "mesh belongs to another context");
+    LB_REQUIRE(kind >= LB_FEM_TRIA && kind <= LB_FEM_TETRA, "unknown operator kind %d", kind);
+    LB_REQUIRE((kind == LB_FEM_TETRA) == (mesh->k == 4), "operator kind does not match element type");
+    if (kind == LB_FEM_TRIA_ANISO) LB_REQUIRE(u1 && u2 && aniso_mat, "anisotropic operator needs u1, u2, aniso_mat");
+    DeviceGuard g(c->device);
+    const int64_t nt = mesh->nt;
+    const bool want_a = kind != LB_FEM_TRIA_MASS && a_out != nullptr;
+    DBuf<D4> rec(c, (size_t)nt * (mesh->k == 4 ? 3 : 1));
+    DBuf<ElemConsts> consts(c, 1);
+    DBuf<double> d_u1, d_u2, d_am;
+    if (kind == LB_FEM_TRIA_ANISO) {
+        d_u1.alloc(c, 3 * nt);
+        d_u2.alloc(c, 3 * nt);
+        d_am.alloc(c, 2 * nt);
+        h2d(c, d_u1.p, u1, 3 * nt * sizeof(double));
+        h2d(c, d_u2.p, u2, 3 * nt * sizeof(double));
+        h2d(c, d_am.p, aniso_mat, 2 * nt * sizeof(double));
+    }
+    DBuf<int32_t> deg;
+    if (!mesh->has_inc) {
+        deg.alloc(c, mesh->nv);
+        deg.zero();
+    }
+    if (mesh->v_dtype == LB_F32)
+        run_element_pass<float>(mesh, kind, d_u1.p, d_u2.p, d_am.p, rec.p, deg.p, consts.p);
+    else
+        run_element_pass<double>(mesh, kind, d_u1.p, d_u2.p, d_am.p, rec.p, deg.p, consts.p);
+    if (!mesh->has_inc) build_incidence(mesh, deg);
+    if (a_out) *a_out = nullptr;
+    // clamped elements: the aniso numerators are fp64 even for fp32 meshes (solver.py:278-280)
+    const bool degen_f32 = mesh->v_dtype == LB_F32 && kind != LB_FEM_TRIA_ANISO;
+    if (mesh->k == 3) run_rows<3>(mesh, rec.p, consts.p, want_a, lump != 0, degen_f32, a_out, b_out);
+    else run_rows<4>(mesh, rec.p, consts.p, want_a, lump != 0, degen_f32, a_out, b_out);
+    sync(c);  // u1/u2/aniso_mat are borrowed host buffers
+    LB_API_END
+}
+
+}  // extern "C"

@@ -1,0 +1,188 @@
+// common.cuh - context, error handling, device buffers and small device primitives shared by
+// all translation units of liblapyb200.so (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/lapy_b200.h"
+#include "exact.cuh"
+
+namespace lb {
+
+constexpr int kSMs = 148;          // B200: 2 dies x 74 SMs
+constexpr double kEps = 2.220446049250313e-16;  // sys.float_info.epsilon (lapy/solver.py:158)
+
+void set_error(const char *fmt, ...);
+
+struct Error {
+    int code;
+};
+
+#define LB_CUDA(expr)                                                                          \
+    do {                                                                                       \
+        cudaError_t _e = (expr);                                                               \
+        if (_e != cudaSuccess) {                                                               \
+            lb::set_error("CUDA error %s at %s:%d: %s", cudaGetErrorName(_e), __FILE__,        \
+                          __LINE__, cudaGetErrorString(_e));                                   \
+            throw lb::Error{_e == cudaErrorMemoryAllocation ? LB_ERR_OOM : LB_ERR_CUDA};       \
+        }                                                                                      \
+    } while (0)
+
+#define LB_REQUIRE(cond, ...)                                                                  \
+    do {                                                                                       \
+        if (!(cond)) {                                                                         \
+            lb::set_error(__VA_ARGS__);                                                        \
+            throw lb::Error{LB_ERR_ARG};                                                       \
+        }                                                                                      \
+    } while (0)
+
+// wraps an extern "C" body: C++ exceptions never cross the ABI
+#define LB_API_BEGIN try {
+#define LB_API_END                                                                             \
+    }                                                                                          \
+    catch (const lb::Error &e) { return e.code; }                                              \
+    catch (const std::bad_alloc &) {                                                           \
+        lb::set_error("host allocation failed");                                               \
+        return LB_ERR_OOM;                                                                     \
+    }                                                                                          \
+    catch (...) {                                                                              \
+        lb::set_error("unknown internal error");                                               \
+        return LB_ERR_CUDA;                                                                    \
+    }                                                                                          \
+    return LB_OK;
+
+}  // namespace lb
+
+struct lb_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int64_t launches = 0;
+    void *pinned = nullptr;  // small pinned staging area for scalar read-backs
+    size_t pinned_bytes = 0;
+    void *cusolver = nullptr;  // cusolverDnHandle_t, created lazily (dense Rayleigh-Ritz only)
+};
+
+namespace lb {
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+// stream-ordered device buffer (cudaMallocAsync pool of the context's device)
+template <class T>
+struct DBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    lb_ctx *ctx = nullptr;
+    DBuf() = default;
+    DBuf(lb_ctx *c, size_t count) { alloc(c, count); }
+    DBuf(const DBuf &) = delete;
+    DBuf &operator=(const DBuf &) = delete;
+    DBuf(DBuf &&o) noexcept : p(o.p), n(o.n), ctx(o.ctx) { o.p = nullptr; o.n = 0; }
+    DBuf &operator=(DBuf &&o) noexcept {
+        if (this != &o) {
+            release();
+            p = o.p; n = o.n; ctx = o.ctx;
+            o.p = nullptr; o.n = 0;
+        }
+        return *this;
+    }
+    void alloc(lb_ctx *c, size_t count) {
+        release();
+        ctx = c;
+        n = count;
+        if (count == 0) { p = nullptr; return; }
+        LB_CUDA(cudaMallocAsync((void **)&p, count * sizeof(T), c->stream));
+    }
+    void zero() {
+        if (n) LB_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), ctx->stream));
+    }
+    void release() {
+        if (p) cudaFreeAsync(p, ctx->stream);
+        p = nullptr;
+        n = 0;
+    }
+    ~DBuf() { release(); }
+    T *get() const { return p; }
+    operator T *() const { return p; }
+};
+
+inline void h2d(lb_ctx *c, void *dst, const void *src, size_t bytes) {
+    if (bytes) LB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream));
+}
+inline void d2h(lb_ctx *c, void *dst, const void *src, size_t bytes) {
+    if (bytes) LB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream));
+}
+inline void d2d(lb_ctx *c, void *dst, const void *src, size_t bytes) {
+    if (bytes) LB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, c->stream));
+}
+inline void sync(lb_ctx *c) { LB_CUDA(cudaStreamSynchronize(c->stream)); }
+
+// read back a few scalars (stream-ordered, then wait)
+template <class T>
+inline void read_back(lb_ctx *c, T *host, const T *dev, size_t count) {
+    LB_REQUIRE(count * sizeof(T) <= c->pinned_bytes, "read_back too large");
+    LB_CUDA(cudaMemcpyAsync(c->pinned, dev, count * sizeof(T), cudaMemcpyDeviceToHost, c->stream));
+    sync(c);
+    std::memcpy(host, c->pinned, count * sizeof(T));
+}
+
+inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// kernel launch with bookkeeping (gpu_launches in bench.py is this counter)
+#define LB_LAUNCH(ctx, kernel, grid, block, smem, ...)                                         \
+    do {                                                                                       \
+        kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);                       \
+        (ctx)->launches++;                                                                     \
+        LB_CUDA(cudaGetLastError());                                                           \
+    } while (0)
+
+void destroy_dense_handles(lb_ctx *ctx);  // dense.cu
+
+// exclusive prefix sum of int32 counts: out[0..n] (n+1 entries, out[n] = total)
+void exclusive_scan_i32(lb_ctx *ctx, const int32_t *in, int32_t *out, int64_t n);
+
+}  // namespace lb
+
+// ---- device objects ---------------------------------------------------------------------
+struct lb_mesh {
+    lb_ctx *ctx = nullptr;
+    int64_t nv = 0, nt = 0;
+    int k = 3;              // vertices per element
+    int v_dtype = LB_F64;   // dtype of the caller's vertices: element math runs in it
+    lb::DBuf<lb::D4> v4;    // (nv) fp64 xyz + pad: one 32-byte sector per gathered vertex
+    lb::DBuf<float4> v4f;   // (nv) fp32 xyz + pad, only when v_dtype == LB_F32
+    lb::DBuf<int4> t4;      // (nt) int32 x4, triangles padded with -1: one 16-byte load
+    // vertex -> (element, corner) incidence, built on first use: code = element*4 + corner,
+    // ascending per vertex (== COO input order of the reference's triplets)
+    lb::DBuf<int32_t> inc_ptr;  // (nv+1)
+    lb::DBuf<int32_t> inc;      // (k*nt)
+    int64_t n_ref = 0;          // max referenced vertex + 1 (matrix dimension)
+    bool has_inc = false;
+};
+
+struct lb_mat {
+    lb_ctx *ctx = nullptr;
+    int64_t n = 0, nnz = 0;
+    lb::DBuf<int32_t> indptr;   // (n+1)
+    lb::DBuf<int32_t> indices;  // (nnz) sorted, unique per row
+    lb::DBuf<double> data;      // (nnz)
+    bool diagonal = false;      // every stored entry is on the diagonal (lumped mass / identity)
+};

@@ -1,0 +1,295 @@
+// ctx.cu - context life cycle, error reporting, prefix sums, matrix upload / download.
+#include "common.cuh"
+
+namespace lb {
+
+static thread_local char g_err[1024] = "";
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+// ---- exclusive scan (int32) ---------------------------------------------------------------
+// Three small kernels (tile reduce -> scan of tile sums -> tile scan + offset).  Inputs are at
+// most a few tens of MB (per-vertex / per-row counts), so this is launch-latency, not
+// bandwidth dominated; every pass is fully coalesced.
+constexpr int kScanThreads = 256;
+constexpr int kScanItems = 8;  // per thread
+constexpr int kScanTile = kScanThreads * kScanItems;
+
+__device__ __forceinline__ int warp_incl_scan(int x) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        int y = __shfl_up_sync(0xffffffffu, x, d);
+        if (lane >= d) x += y;
+    }
+    return x;
+}
+
+// block-wide exclusive scan of one int per thread; returns exclusive prefix, total in *total
+__device__ __forceinline__ int block_excl_scan(int x, int *total) {
+    __shared__ int warp_sums[32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int incl = warp_incl_scan(x);
+    if (lane == 31) warp_sums[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+        int nw = (blockDim.x + 31) >> 5;
+        int s = lane < nw ? warp_sums[lane] : 0;
+        s = warp_incl_scan(s);
+        warp_sums[lane] = s;
+    }
+    __syncthreads();
+    int base = wid ? warp_sums[wid - 1] : 0;
+    *total = warp_sums[((blockDim.x + 31) >> 5) - 1];
+    __syncthreads();
+    return base + incl - x;
+}
+
+__global__ void scan_tile_reduce(const int32_t *__restrict__ in, int32_t *__restrict__ tile_sums,
+                                 int64_t n) {
+    int64_t base = (int64_t)blockIdx.x * kScanTile;
+    int s = 0;
+#pragma unroll
+    for (int i = 0; i < kScanItems; i++) {
+        int64_t idx = base + (int64_t)i * kScanThreads + threadIdx.x;
+        if (idx < n) s += in[idx];
+    }
+    int total;
+    block_excl_scan(s, &total);
+    if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
+}
+
+__global__ void scan_tile_sums(int32_t *tile_sums, int ntiles, int32_t *grand_total) {
+    // single block, loops over the tile sums in chunks of blockDim.x
+    __shared__ int carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < ntiles; base += blockDim.x) {
+        int i = base + threadIdx.x;
+        int x = i < ntiles ? tile_sums[i] : 0;
+        int total;
+        int ex = block_excl_scan(x, &total);
+        int c = carry;
+        if (i < ntiles) tile_sums[i] = ex + c;
+        __syncthreads();
+        if (threadIdx.x == 0) carry = c + total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *grand_total = carry;
+}
+
+__global__ void scan_tile_apply(const int32_t *__restrict__ in, const int32_t *__restrict__ tile_sums,
+                                int32_t *__restrict__ out, int64_t n) {
+    // each thread owns kScanItems CONSECUTIVE items (blocked arrangement) staged through smem
+    __shared__ int32_t buf[kScanTile];
+    int64_t base = (int64_t)blockIdx.x * kScanTile;
+#pragma unroll
+    for (int i = 0; i < kScanItems; i++) {
+        int l = i * kScanThreads + threadIdx.x;
+        int64_t idx = base + l;
+        buf[l] = idx < n ? in[idx] : 0;
+    }
+    __syncthreads();
+    int v[kScanItems];
+    int s = 0;
+#pragma unroll
+    for (int i = 0; i < kScanItems; i++) {
+        v[i] = buf[threadIdx.x * kScanItems + i];
+        s += v[i];
+    }
+    int total;
+    int ex = block_excl_scan(s, &total) + tile_sums[blockIdx.x];
+#pragma unroll
+    for (int i = 0; i < kScanItems; i++) {
+        buf[threadIdx.x * kScanItems + i] = ex;
+        ex += v[i];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < kScanItems; i++) {
+        int l = i * kScanThreads + threadIdx.x;
+        int64_t idx = base + l;
+        if (idx < n) out[idx] = buf[l];
+    }
+}
+
+void exclusive_scan_i32(lb_ctx *ctx, const int32_t *in, int32_t *out, int64_t n) {
+    if (n == 0) {
+        LB_CUDA(cudaMemsetAsync(out, 0, sizeof(int32_t), ctx->stream));
+        return;
+    }
+    int ntiles = cdiv(n, kScanTile);
+    DBuf<int32_t> tile_sums(ctx, ntiles);
+    LB_LAUNCH(ctx, scan_tile_reduce, ntiles, kScanThreads, 0, in, tile_sums.p, n);
+    LB_LAUNCH(ctx, scan_tile_sums, 1, 1024, 0, tile_sums.p, ntiles, out + n);
+    LB_LAUNCH(ctx, scan_tile_apply, ntiles, kScanThreads, 0, in, tile_sums.p, out, n);
+}
+
+}  // namespace lb
+
+using namespace lb;
+
+extern "C" {
+
+const char *lb_last_error(void) { return g_err; }
+const char *lb_version(void) { return "lapy_b200 0.1 (sm_100a)"; }
+
+int lb_ctx_create(int device, void *stream, lb_ctx **out) {
+    LB_API_BEGIN
+    LB_REQUIRE(out != nullptr, "lb_ctx_create: out is NULL");
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        set_error("lb_ctx_create: no CUDA device available (%s); this library has no CPU fallback",
+                  e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+        return LB_ERR_CUDA;
+    }
+    LB_REQUIRE(device >= 0 && device < count, "lb_ctx_create: device %d out of range [0,%d)", device, count);
+    DeviceGuard g(device);
+    lb_ctx *c = new lb_ctx();
+    c->device = device;
+    if (stream) {
+        c->stream = (cudaStream_t)stream;
+    } else {
+        LB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        c->own_stream = true;
+    }
+    LB_CUDA(cudaEventCreate(&c->ev0));
+    LB_CUDA(cudaEventCreate(&c->ev1));
+    c->pinned_bytes = 1 << 16;
+    LB_CUDA(cudaMallocHost(&c->pinned, c->pinned_bytes));
+    // keep freed blocks in the pool: assembly / solver workspaces are re-used across calls
+    cudaMemPool_t pool;
+    LB_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+    uint64_t thresh = UINT64_MAX;
+    LB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh));
+    *out = c;
+    LB_API_END
+}
+
+
+int lb_ctx_destroy(lb_ctx *c) {
+    LB_API_BEGIN
+    if (!c) return LB_OK;
+    DeviceGuard g(c->device);
+    cudaStreamSynchronize(c->stream);
+    lb::destroy_dense_handles(c);
+    cudaEventDestroy(c->ev0);
+    cudaEventDestroy(c->ev1);
+    cudaFreeHost(c->pinned);
+    if (c->own_stream) cudaStreamDestroy(c->stream);
+    delete c;
+    LB_API_END
+}
+
+int lb_ctx_sync(lb_ctx *c) {
+    LB_API_BEGIN
+    LB_REQUIRE(c, "ctx is NULL");
+    DeviceGuard g(c->device);
+    sync(c);
+    LB_API_END
+}
+
+int lb_timer_start(lb_ctx *c) {
+    LB_API_BEGIN
+    LB_REQUIRE(c, "ctx is NULL");
+    DeviceGuard g(c->device);
+    LB_CUDA(cudaEventRecord(c->ev0, c->stream));
+    LB_API_END
+}
+
+int lb_timer_stop(lb_ctx *c, double *ms) {
+    LB_API_BEGIN
+    LB_REQUIRE(c && ms, "ctx/ms is NULL");
+    DeviceGuard g(c->device);
+    LB_CUDA(cudaEventRecord(c->ev1, c->stream));
+    LB_CUDA(cudaEventSynchronize(c->ev1));
+    float f = 0;
+    LB_CUDA(cudaEventElapsedTime(&f, c->ev0, c->ev1));
+    *ms = f;
+    LB_API_END
+}
+
+int lb_launch_count(lb_ctx *c, int64_t *count) {
+    LB_API_BEGIN
+    LB_REQUIRE(c && count, "ctx/count is NULL");
+    *count = c->launches;
+    LB_API_END
+}
+
+// ---- matrices ---------------------------------------------------------------------------
+int lb_mat_info(lb_mat *m, int64_t *n, int64_t *nnz) {
+    LB_API_BEGIN
+    LB_REQUIRE(m, "matrix is NULL");
+    if (n) *n = m->n;
+    if (nnz) *nnz = m->nnz;
+    LB_API_END
+}
+
+int lb_mat_download(lb_mat *m, int32_t *indptr, int32_t *indices, double *data) {
+    LB_API_BEGIN
+    LB_REQUIRE(m, "matrix is NULL");
+    lb_ctx *c = m->ctx;
+    DeviceGuard g(c->device);
+    if (indptr) d2h(c, indptr, m->indptr.p, (m->n + 1) * sizeof(int32_t));
+    if (indices) d2h(c, indices, m->indices.p, m->nnz * sizeof(int32_t));
+    if (data) d2h(c, data, m->data.p, m->nnz * sizeof(double));
+    sync(c);
+    LB_API_END
+}
+
+__global__ void check_diagonal_kernel(const int32_t *__restrict__ indptr, const int32_t *__restrict__ indices,
+                                      int64_t n, int *not_diag) {
+    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    for (int p = indptr[r]; p < indptr[r + 1]; p++)
+        if (indices[p] != r) *not_diag = 1;
+}
+
+int lb_mat_upload(lb_ctx *c, int64_t n, int64_t nnz, const int32_t *indptr, const int32_t *indices,
+                  const double *data, lb_mat **out) {
+    LB_API_BEGIN
+    LB_REQUIRE(c && out, "ctx/out is NULL");
+    LB_REQUIRE(n >= 0 && nnz >= 0 && n < INT32_MAX && nnz < INT32_MAX, "matrix too large for int32 indices");
+    LB_REQUIRE(indptr && (nnz == 0 || (indices && data)), "NULL array");
+    LB_REQUIRE(indptr[0] == 0 && indptr[n] == nnz, "indptr does not match nnz");
+    DeviceGuard g(c->device);
+    lb_mat *m = new lb_mat();
+    m->ctx = c;
+    m->n = n;
+    m->nnz = nnz;
+    try {
+        m->indptr.alloc(c, n + 1);
+        m->indices.alloc(c, nnz);
+        m->data.alloc(c, nnz);
+        h2d(c, m->indptr.p, indptr, (n + 1) * sizeof(int32_t));
+        h2d(c, m->indices.p, indices, nnz * sizeof(int32_t));
+        h2d(c, m->data.p, data, nnz * sizeof(double));
+        DBuf<int> flag(c, 1);
+        flag.zero();
+        if (n) LB_LAUNCH(c, check_diagonal_kernel, cdiv(n, 256), 256, 0, m->indptr.p, m->indices.p, n, flag.p);
+        int h = 0;
+        read_back(c, &h, flag.p, 1);
+        m->diagonal = (h == 0);
+    } catch (...) {
+        delete m;
+        throw;
+    }
+    *out = m;
+    LB_API_END
+}
+
+int lb_mat_free(lb_mat *m) {
+    LB_API_BEGIN
+    if (!m) return LB_OK;
+    DeviceGuard g(m->ctx->device);
+    delete m;
+    LB_API_END
+}
+
+}  // extern "C"
