@@ -420,13 +420,16 @@ __global__ void __launch_bounds__(kRowThreads) row_fill_kernel(
                 int k0, k1;
                 double x0, x1, xd;
                 // column = corner c; rows in the reference's triplet order (solver.py:171-175)
+                // the diagonal (row sum = 0, solver.py:167-169) is formed in the element dtype
+                double m0, m1;
                 if (c == 0) {
-                    k0 = ti.y; x0 = a12; k1 = ti.z; x1 = a31; xd = __dsub_rn(-a12, a31);
+                    k0 = ti.y; x0 = a12; k1 = ti.z; x1 = a31; m0 = a12; m1 = a31;
                 } else if (c == 1) {
-                    k0 = ti.x; x0 = a12; k1 = ti.z; x1 = a23; xd = __dsub_rn(-a12, a23);
+                    k0 = ti.x; x0 = a12; k1 = ti.z; x1 = a23; m0 = a12; m1 = a23;
                 } else {
-                    k0 = ti.y; x0 = a23; k1 = ti.x; x1 = a31; xd = __dsub_rn(-a31, a23);
+                    k0 = ti.y; x0 = a23; k1 = ti.x; x1 = a31; m0 = a31; m1 = a23;
                 }
+                xd = degen_div_f32 ? (double)__fsub_rn(-(float)m0, (float)m1) : __dsub_rn(-m0, m1);
                 if (want_pat) {
                     accumulate(keys, av, bv, cnt, k0, x0, bij, want_a, want_b);
                     accumulate(keys, av, bv, cnt, k1, x1, bij, want_a, want_b);
@@ -582,7 +585,7 @@ static void run_rows(lb_mesh *mesh, const D4 *rec, const ElemConsts *consts, boo
     const int cap_keys = K == 3 ? 4096 : 12288;  // int32 keys of shared memory per block
     DBuf<int32_t> row_nnz(c, n), row_has(c, n);
     DBuf<int32_t> scratch(c, (size_t)mesh->k * mesh->nt * (K - 1) + n);
-    if (cap_keys * 4 > 48 * 1024)
+    if (cap_keys * 4 > 40 * 1024)
         LB_CUDA(cudaFuncSetAttribute(row_count_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap_keys * 4));
     LB_LAUNCH(c, row_count_kernel<K>, nblocks, kRowThreads, cap_keys * 4, mesh->t4.p, mesh->inc_ptr.p, mesh->inc.p,
               n, cap_keys, scratch.p, row_nnz.p, row_has.p);
@@ -623,7 +626,7 @@ static void run_rows(lb_mesh *mesh, const D4 *rec, const ElemConsts *consts, boo
         if (want_a || full_b) {
             const int cap = K == 3 ? 1792 : 3072;  // CSR entries of shared memory per block
             const int smem = cap * 20;
-            if (smem > 48 * 1024)
+            if (smem > 40 * 1024)
                 LB_CUDA(cudaFuncSetAttribute(row_fill_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
             LB_LAUNCH(c, row_fill_kernel<K>, nblocks, kRowThreads, smem, mesh->t4.p, rec, mesh->inc_ptr.p,
                       mesh->inc.p, n, cap, consts, (int)degen_f32, out);
