@@ -83,6 +83,8 @@ int lb_launch_count(lb_ctx *ctx, int64_t *count);
 int lb_mesh_create(lb_ctx *ctx, const void *v, int v_dtype, int64_t nv, const void *t,
                    int t_itemsize, int64_t nt, int k, lb_mesh **out);
 int lb_mesh_update_vertices(lb_mesh *mesh, const void *v, int v_dtype);
+/* forget the cached vertex->element incidence (rebuilt by the next assembly; benchmarking aid) */
+int lb_mesh_drop_cache(lb_mesh *mesh);
 int lb_mesh_free(lb_mesh *mesh);
 
 /* ---- assembly -------------------------------------------------------- */
@@ -126,12 +128,6 @@ int lb_gradient(lb_ctx *ctx, lb_mesh *mesh, const double *f, int64_t nf, double 
 /* x (nt,nf,3) -> d (nv,nf): tria_compute_divergence lapy/diffgeo.py:303-387,
  * tet_compute_divergence :925-1006 */
 int lb_divergence(lb_ctx *ctx, lb_mesh *mesh, const double *x, int64_t nf, double *d);
-/* normalise g in place to unit length per (element, function); 0/0 -> 0 like
- * np.nan_to_num at lapy/diffgeo.py:153-154 */
-int lb_normalize_field(lb_ctx *ctx, int64_t nrows, double *g_host_or_null);
-/* mean edge length of the unique edges: TriaMesh.avg_edge_length lapy/tria_mesh.py:735-748 */
-int lb_avg_edge_length(lb_ctx *ctx, lb_mesh *mesh, double *out);
-
 #ifdef __cplusplus
 }
 #endif

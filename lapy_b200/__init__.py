@@ -6,7 +6,7 @@ else of LaPy (mesh toolboxes, IO, plotting) is out of scope and keeps working wi
 Importing the package does not need a GPU; the first device call does (no CPU fallback).
 """
 
-from . import mesh  # noqa: F401
+from . import diffgeo, heat, mesh, shapedna  # noqa: F401
 from .mesh import TetMesh, TriaMesh  # noqa: F401
 from .solver import Solver  # noqa: F401
 

@@ -58,6 +58,11 @@ SIGNATURES = {
     "lb_mat_download": [_vp, _vp, _vp, _vp],
     "lb_mat_upload": [_vp, _i64, _i64, _vp, _vp, _vp, _pp],
     "lb_mat_free": [_vp],
+    "lb_spmm": [_vp, _vp, _vp, _i64, _vp],
+    "lb_eigs": [_vp, _vp, _vp, _int, _dbl, _dbl, _int, _vp, _vp, C.POINTER(Info)],
+    "lb_solve": [_vp, _vp, _dbl, _vp, _dbl, _vp, _i64, _vp, _i64, _vp, _dbl, _int, _int, _vp, C.POINTER(Info)],
+    "lb_gradient": [_vp, _vp, _vp, _i64, _vp],
+    "lb_divergence": [_vp, _vp, _vp, _i64, _vp],
 }
 STRING_GETTERS = ("lb_last_error", "lb_version")
 
@@ -267,3 +272,60 @@ def assemble(ctx: Context, mesh: DeviceMesh, kind: int, lump: bool, aniso=None, 
     )  # fmt: skip
     a = DeviceMatrix(ctx, ha) if (want_a and ha.value) else None
     return a, DeviceMatrix(ctx, hb)
+
+
+def spmm(ctx: Context, mat: DeviceMatrix, x: np.ndarray) -> np.ndarray:
+    """y = M x for x (n,) or (n, m) (lb_spmm)."""
+    x = np.asarray(x, dtype=np.float64)
+    one_d = x.ndim == 1
+    x2 = np.ascontiguousarray(x.reshape(mat.n, -1))
+    y = np.empty_like(x2)
+    check(lib().lb_spmm(ctx.handle, mat.handle, ptr(x2), x2.shape[1], ptr(y)))
+    return y[:, 0] if one_d else y
+
+
+def eigs(ctx: Context, a: DeviceMatrix, b: DeviceMatrix, k: int, sigma: float, tol: float = 0.0, maxit: int = 0):
+    """lb_eigs -> (evals (k,), evecs (n,k), info dict)."""
+    evals = np.empty(k, np.float64)
+    evecs = np.empty((a.n, k), np.float64)
+    info = Info()
+    check(lib().lb_eigs(ctx.handle, a.handle, b.handle, int(k), float(sigma), float(tol), int(maxit),
+                        ptr(evals), ptr(evecs), C.byref(info)))  # fmt: skip
+    return evals, evecs, info.as_dict()
+
+
+def solve(ctx: Context, a: DeviceMatrix, alpha: float, b: DeviceMatrix | None, beta: float, rhs: np.ndarray,
+          fix_idx=None, fix_val=None, tol: float = 0.0, maxit: int = 0, project_nullspace: bool = False):
+    """lb_solve: (alpha*A + beta*B) x = rhs, rhs (n, m) -> (x (n, m), info dict)."""
+    rhs = np.ascontiguousarray(rhs, dtype=np.float64)
+    if rhs.ndim != 2 or rhs.shape[0] != a.n:
+        raise ValueError("rhs must have shape (n, m)")
+    x = np.empty_like(rhs)
+    nfix = 0
+    if fix_idx is not None and len(fix_idx):
+        fix_idx = np.ascontiguousarray(fix_idx, dtype=np.int64)
+        fix_val = np.ascontiguousarray(fix_val, dtype=np.float64)
+        nfix = len(fix_idx)
+    else:
+        fix_idx = fix_val = None
+    info = Info()
+    check(lib().lb_solve(ctx.handle, a.handle, float(alpha), b.handle if b is not None else None, float(beta),
+                         ptr(rhs), rhs.shape[1], ptr(fix_idx), nfix, ptr(fix_val), float(tol), int(maxit),
+                         int(bool(project_nullspace)), ptr(x), C.byref(info)))  # fmt: skip
+    return x, info.as_dict()
+
+
+def gradient(ctx: Context, mesh: DeviceMesh, f: np.ndarray) -> np.ndarray:
+    """f (nv, nf) -> (nt, nf, 3) (lb_gradient)."""
+    f = np.ascontiguousarray(f, dtype=np.float64)
+    g = np.empty((mesh.nt, f.shape[1], 3), np.float64)
+    check(lib().lb_gradient(ctx.handle, mesh.handle, ptr(f), f.shape[1], ptr(g)))
+    return g
+
+
+def divergence(ctx: Context, mesh: DeviceMesh, x: np.ndarray) -> np.ndarray:
+    """x (nt, nf, 3) -> (nv, nf) (lb_divergence)."""
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    d = np.empty((mesh.nv, x.shape[1]), np.float64)
+    check(lib().lb_divergence(ctx.handle, mesh.handle, ptr(x), x.shape[1], ptr(d)))
+    return d

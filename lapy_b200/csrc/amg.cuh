@@ -1,0 +1,54 @@
+// amg.cuh - smoothed-aggregation AMG hierarchy built and applied on the device.
+//
+// Replaces the sparse factorisation of the reference (SuperLU splu / CHOLMOD, lapy/solver.py:707,
+// :876, lapy/heat.py:226) as the "inverse" used by the eigensolver and the linear solves: one
+// V-cycle is the preconditioner of block LOBPCG / block PCG.  Setup is deterministic (hash
+// priorities, fixed summation orders) and runs entirely on the GPU.
+#pragma once
+#include <memory>
+
+#include "blockvec.cuh"
+
+namespace lb {
+
+struct AmgLevel {
+    std::unique_ptr<lb_mat> K;   // operator of this level (level 0: a private copy alpha*A + beta*B)
+    std::unique_ptr<lb_mat> P;   // (n_l, n_{l+1}) smoothed prolongator, CSR
+    std::unique_ptr<lb_mat> R;   // P^T, CSR
+    DBuf<double> dinv;           // 1 / diag(K)
+    double rho = 2.0;            // upper bound of the spectral radius of D^-1 K (Gershgorin)
+    // V-cycle work blocks (n_l, mcap): solution, right-hand side, residual, Chebyshev direction
+    DBuf<double> x, b, r, d;
+};
+
+struct Amg {
+    lb_ctx *ctx = nullptr;
+    std::vector<AmgLevel> levels;
+    DBuf<double> coarse_chol;  // dense Cholesky factor of the coarsest operator
+    int coarse_n = 0;
+    int cheb_deg = 2;
+    int mcap = 0;  // block width the work arrays are sized for
+    double setup_ms = 0;
+};
+
+struct AmgOptions {
+    double theta = 0.0;      // strength-of-connection threshold (0: every off-diagonal is strong)
+    int max_coarse = 2000;   // dense coarse solve at or below this size
+    int max_levels = 16;
+    int cheb_deg = 2;
+};
+
+// K is consumed (moved into level 0).  mcap: max number of simultaneous right-hand sides.
+std::unique_ptr<Amg> amg_setup(lb_ctx *c, std::unique_ptr<lb_mat> K, int mcap, const AmgOptions &opt);
+// z (n,m) = V-cycle(r (n,m)); r is not modified
+void amg_apply(Amg &amg, const double *r, int ldr, double *z, int ldz, int m);
+
+// C = alpha*A + beta*B for matrices with identical pattern or diagonal B (new matrix)
+std::unique_ptr<lb_mat> mat_axpby(lb_ctx *c, const lb_mat *a, double alpha, const lb_mat *b, double beta);
+// general sparse product C = A * B (CSR, deterministic, sorted columns)
+std::unique_ptr<lb_mat> spgemm(lb_ctx *c, const lb_mat *a, const lb_mat *b);
+std::unique_ptr<lb_mat> transpose(lb_ctx *c, const lb_mat *a);
+// dinv[i] = d[i] > 0 ? 1/d[i] : 0
+void launch_diag_inverse(lb_ctx *c, int64_t n, const double *d, double *dinv);
+
+}  // namespace lb

@@ -529,6 +529,26 @@ static void build_incidence(lb_mesh *mesh, DBuf<int32_t> &deg) {
     mesh->has_inc = true;
 }
 
+__global__ void degree_count(const int4 *__restrict__ t4, int64_t nt, int k, int32_t *__restrict__ deg) {
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= nt) return;
+    int4 ti = __ldg(t4 + e);
+    atomicAdd(deg + ti.x, 1);
+    atomicAdd(deg + ti.y, 1);
+    atomicAdd(deg + ti.z, 1);
+    if (k == 4) atomicAdd(deg + ti.w, 1);
+}
+
+// vertex -> element incidence without an assembly (used by the divergence gather)
+void ensure_incidence(lb_mesh *mesh) {
+    if (mesh->has_inc) return;
+    lb_ctx *c = mesh->ctx;
+    DBuf<int32_t> deg(c, mesh->nv);
+    deg.zero();
+    LB_LAUNCH(c, degree_count, cdiv(mesh->nt, 256), 256, 0, mesh->t4.p, mesh->nt, mesh->k, deg.p);
+    build_incidence(mesh, deg);
+}
+
 template <class T>
 static void run_element_pass(lb_mesh *mesh, int kind, const double *u1, const double *u2, const double *am,
                              D4 *rec, int32_t *deg, ElemConsts *consts) {
@@ -589,6 +609,7 @@ static void run_rows(lb_mesh *mesh, const D4 *rec, const ElemConsts *consts, boo
         LB_CUDA(cudaFuncSetAttribute(row_count_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap_keys * 4));
     LB_LAUNCH(c, row_count_kernel<K>, nblocks, kRowThreads, cap_keys * 4, mesh->t4.p, mesh->inc_ptr.p, mesh->inc.p,
               n, cap_keys, scratch.p, row_nnz.p, row_has.p);
+    phase(c, "row count");
     const bool full_b = !lump;
     lb_mat *A = nullptr, *B = nullptr;
     DBuf<int32_t> indptr(c, n + 1), lump_ptr;
@@ -601,6 +622,7 @@ static void run_rows(lb_mesh *mesh, const D4 *rec, const ElemConsts *consts, boo
     }
     read_back(c, &totals[0], indptr.p + n, 1);
     const int64_t nnz = totals[0];
+    phase(c, "scan + nnz readback");
     try {
         RowOut out{};
         out.indptr = indptr.p;
@@ -623,6 +645,7 @@ static void run_rows(lb_mesh *mesh, const D4 *rec, const ElemConsts *consts, boo
             out.lump_idx = B->indices.p;
             out.lump_val = B->data.p;
         }
+        phase(c, "alloc outputs");
         if (want_a || full_b) {
             const int cap = K == 3 ? 1792 : 3072;  // CSR entries of shared memory per block
             const int smem = cap * 20;
@@ -754,6 +777,7 @@ int lb_fem_assemble(lb_ctx *c, lb_mesh *mesh, int kind, int lump, const double *
     LB_REQUIRE((kind == LB_FEM_TETRA) == (mesh->k == 4), "operator kind does not match element type");
     if (kind == LB_FEM_TRIA_ANISO) LB_REQUIRE(u1 && u2 && aniso_mat, "anisotropic operator needs u1, u2, aniso_mat");
     DeviceGuard g(c->device);
+    phase(c, "(enter assemble)");
     const int64_t nt = mesh->nt;
     const bool want_a = kind != LB_FEM_TRIA_MASS && a_out != nullptr;
     DBuf<D4> rec(c, (size_t)nt * (mesh->k == 4 ? 3 : 1));
@@ -776,13 +800,16 @@ int lb_fem_assemble(lb_ctx *c, lb_mesh *mesh, int kind, int lump, const double *
         run_element_pass<float>(mesh, kind, d_u1.p, d_u2.p, d_am.p, rec.p, deg.p, consts.p);
     else
         run_element_pass<double>(mesh, kind, d_u1.p, d_u2.p, d_am.p, rec.p, deg.p, consts.p);
+    phase(c, "element pass");
     if (!mesh->has_inc) build_incidence(mesh, deg);
+    phase(c, "incidence");
     if (a_out) *a_out = nullptr;
     // clamped elements: the aniso numerators are fp64 even for fp32 meshes (solver.py:278-280)
     const bool degen_f32 = mesh->v_dtype == LB_F32 && kind != LB_FEM_TRIA_ANISO;
     if (mesh->k == 3) run_rows<3>(mesh, rec.p, consts.p, want_a, lump != 0, degen_f32, a_out, b_out);
     else run_rows<4>(mesh, rec.p, consts.p, want_a, lump != 0, degen_f32, a_out, b_out);
     sync(c);  // u1/u2/aniso_mat are borrowed host buffers
+    phase(c, "rows");
     LB_API_END
 }
 

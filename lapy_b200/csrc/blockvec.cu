@@ -1,0 +1,288 @@
+// blockvec.cu - CSR x block-vector products and block BLAS-1 kernels (all HBM-bound).
+//
+// Replaces scipy's cs*_matvec(s) (lapy/solver.py:844-846, ARPACK's M/OPinv callbacks) and the
+// NumPy vector arithmetic inside ARPACK / SuperLU solves with kernels that keep every block
+// vector resident on the device.  Reductions are two-stage with a fixed tree -> bit-reproducible.
+#include "blockvec.cuh"
+
+namespace lb {
+
+// ---- SpMM: a group of G lanes per row, lanes over columns -------------------------------------
+// Each nonzero (j, a) is broadcast to the group; the group streams row j of X as one contiguous
+// segment (8*m bytes), so X traffic is fully coalesced; matrix entries are read once per row.
+template <int G>
+__global__ void __launch_bounds__(256) spmm_kernel(int64_t n, const int32_t *__restrict__ indptr,
+                                                   const int32_t *__restrict__ indices,
+                                                   const double *__restrict__ val, const double *__restrict__ x,
+                                                   int ldx, double *y, int ldy, int m, int mode,
+                                                   const double *b, int ldb) {
+    const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const int lane = threadIdx.x % G;
+    if (row >= n) return;
+    const int beg = indptr[row], end = indptr[row + 1];
+    for (int c0 = 0; c0 < m; c0 += 2 * G) {
+        const int ca = c0 + lane, cb = ca + G;
+        const bool ha = ca < m, hb = cb < m;
+        double s0 = 0.0, s1 = 0.0;
+        int p = beg;
+        for (; p + 1 < end; p += 2) {
+            const int j0 = __ldg(indices + p), j1 = __ldg(indices + p + 1);
+            const double a0 = __ldg(val + p), a1 = __ldg(val + p + 1);
+            const double *x0 = x + (int64_t)j0 * ldx, *x1 = x + (int64_t)j1 * ldx;
+            double u0 = ha ? __ldg(x0 + ca) : 0.0, u1 = hb ? __ldg(x0 + cb) : 0.0;
+            double w0 = ha ? __ldg(x1 + ca) : 0.0, w1 = hb ? __ldg(x1 + cb) : 0.0;
+            s0 = fma(a0, u0, s0);
+            s1 = fma(a0, u1, s1);
+            s0 = fma(a1, w0, s0);
+            s1 = fma(a1, w1, s1);
+        }
+        if (p < end) {
+            const int j0 = __ldg(indices + p);
+            const double a0 = __ldg(val + p);
+            const double *x0 = x + (int64_t)j0 * ldx;
+            if (ha) s0 = fma(a0, __ldg(x0 + ca), s0);
+            if (hb) s1 = fma(a0, __ldg(x0 + cb), s1);
+        }
+        if (mode == 1) {
+            if (ha) s0 = b[row * ldb + ca] - s0;
+            if (hb) s1 = b[row * ldb + cb] - s1;
+        } else if (mode == 2) {
+            if (ha) s0 = b[row * ldb + ca] + s0;
+            if (hb) s1 = b[row * ldb + cb] + s1;
+        }
+        if (ha) y[row * ldy + ca] = s0;
+        if (hb) y[row * ldy + cb] = s1;
+    }
+}
+
+// ---- SpMV for 1-2 columns: 8 lanes per row, lanes over nonzeros, fixed shuffle tree -------------
+__global__ void __launch_bounds__(256) spmv_kernel(int64_t n, const int32_t *__restrict__ indptr,
+                                                   const int32_t *__restrict__ indices,
+                                                   const double *__restrict__ val, const double *__restrict__ x,
+                                                   int ldx, double *y, int ldy, int m, int mode,
+                                                   const double *b, int ldb) {
+    constexpr int G = 8;
+    const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const int lane = threadIdx.x % G;
+    double s0 = 0.0, s1 = 0.0;
+    if (row < n) {
+        const int beg = indptr[row], end = indptr[row + 1];
+        for (int p = beg + lane; p < end; p += G) {
+            const int j = __ldg(indices + p);
+            const double a = __ldg(val + p);
+            s0 = fma(a, __ldg(x + (int64_t)j * ldx), s0);
+            if (m > 1) s1 = fma(a, __ldg(x + (int64_t)j * ldx + 1), s1);
+        }
+    }
+#pragma unroll
+    for (int o = G / 2; o; o >>= 1) {
+        s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    }
+    if (row < n && lane == 0) {
+        if (mode == 1) {
+            s0 = b[row * ldb] - s0;
+            if (m > 1) s1 = b[row * ldb + 1] - s1;
+        } else if (mode == 2) {
+            s0 = b[row * ldb] + s0;
+            if (m > 1) s1 = b[row * ldb + 1] + s1;
+        }
+        y[row * ldy] = s0;
+        if (m > 1) y[row * ldy + 1] = s1;
+    }
+}
+
+// diagonal matrix (lumped mass, identity): entries only on the diagonal, possibly missing rows
+__global__ void diag_spmm_kernel(int64_t n, const int32_t *__restrict__ indptr, const double *__restrict__ val,
+                                 const double *__restrict__ x, int ldx, double *y, int ldy, int m,
+                                 int mode, const double *b, int ldb) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * m) return;
+    const int64_t row = t / m;
+    const int col = (int)(t - row * m);
+    const int beg = indptr[row], end = indptr[row + 1];
+    double s = end > beg ? val[beg] * x[row * ldx + col] : 0.0;
+    if (mode == 1) s = b[row * ldb + col] - s;
+    else if (mode == 2) s = b[row * ldb + col] + s;
+    y[row * ldy + col] = s;
+}
+
+void spmm(lb_ctx *c, const lb_mat *a, const double *x, int ldx, double *y, int ldy, int m, int mode, const double *b,
+          int ldb) {
+    const int64_t n = a->n;
+    if (n == 0 || m == 0) return;
+    if (a->diagonal) {
+        LB_LAUNCH(c, diag_spmm_kernel, cdiv(n * m, 256), 256, 0, n, a->indptr.p, a->data.p, x, ldx, y, ldy, m, mode, b,
+                  ldb);
+        return;
+    }
+    const int32_t *ip = a->indptr.p, *ix = a->indices.p;
+    const double *v = a->data.p;
+    if (m <= 2) {
+        LB_LAUNCH(c, spmv_kernel, cdiv(n * 8, 256), 256, 0, n, ip, ix, v, x, ldx, y, ldy, m, mode, b, ldb);
+    } else if (m <= 8) {
+        LB_LAUNCH(c, spmm_kernel<4>, cdiv(n * 4, 256), 256, 0, n, ip, ix, v, x, ldx, y, ldy, m, mode, b, ldb);
+    } else if (m <= 16) {
+        LB_LAUNCH(c, spmm_kernel<8>, cdiv(n * 8, 256), 256, 0, n, ip, ix, v, x, ldx, y, ldy, m, mode, b, ldb);
+    } else if (m <= 32) {
+        LB_LAUNCH(c, spmm_kernel<16>, cdiv(n * 16, 256), 256, 0, n, ip, ix, v, x, ldx, y, ldy, m, mode, b, ldb);
+    } else {
+        LB_LAUNCH(c, spmm_kernel<32>, cdiv(n * 32, 256), 256, 0, n, ip, ix, v, x, ldx, y, ldy, m, mode, b, ldb);
+    }
+}
+
+// ---- column dots ------------------------------------------------------------------------------
+constexpr int kDotBlocks = kSMs * 4;
+constexpr int kDotCW = 32;  // columns per pass
+constexpr int kDotRY = 8;   // row lanes per block (block = 32 x 8 threads)
+
+__global__ void __launch_bounds__(kDotCW *kDotRY) col_dots_partial(int64_t n, int cols, const double *__restrict__ x,
+                                                                   int ldx, const double *__restrict__ y, int ldy,
+                                                                   double *__restrict__ partial) {
+    __shared__ double red[kDotRY][kDotCW + 1];
+    const int tx = threadIdx.x % kDotCW, ty = threadIdx.x / kDotCW;
+    const int64_t chunk = (n + gridDim.x - 1) / gridDim.x;
+    const int64_t r0 = (int64_t)blockIdx.x * chunk, r1 = min(n, r0 + chunk);
+    for (int c0 = 0; c0 < cols; c0 += kDotCW) {
+        const int col = c0 + tx;
+        double s = 0.0;
+        if (col < cols)
+            for (int64_t r = r0 + ty; r < r1; r += kDotRY) s = fma(x[r * ldx + col], y ? y[r * ldy + col] : 1.0, s);
+        red[ty][tx] = s;
+        __syncthreads();
+        if (ty == 0 && col < cols) {
+            double t = 0.0;
+#pragma unroll
+            for (int k = 0; k < kDotRY; k++) t += red[k][tx];
+            partial[(int64_t)blockIdx.x * cols + col] = t;
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void col_dots_final(int nblocks, int cols, const double *__restrict__ partial, double *__restrict__ out) {
+    const int col = blockIdx.x * blockDim.x + threadIdx.x;
+    if (col >= cols) return;
+    double s = 0.0;
+    for (int b = 0; b < nblocks; b++) s += partial[(int64_t)b * cols + col];
+    out[col] = s;
+}
+
+void col_dots(lb_ctx *c, int64_t n, int cols, const double *x, int ldx, const double *y, int ldy, double *out) {
+    if (cols == 0) return;
+    const int nb = (int)std::min<int64_t>(kDotBlocks, std::max<int64_t>(1, n / 64));
+    DBuf<double> partial(c, (size_t)nb * cols);
+    LB_LAUNCH(c, col_dots_partial, nb, kDotCW * kDotRY, 0, n, cols, x, ldx, y, ldy, partial.p);
+    LB_LAUNCH(c, col_dots_final, cdiv(cols, 64), 64, 0, nb, cols, partial.p, out);
+}
+
+// ---- elementwise block kernels -------------------------------------------------------------------
+__global__ void axpby_cols_kernel(int64_t n, int cols, const double *__restrict__ a, double a_const,
+                                  const double *__restrict__ x, int ldx, const double *__restrict__ b, double b_const,
+                                  double *__restrict__ y, int ldy) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * cols) return;
+    const int64_t row = t / cols;
+    const int col = (int)(t - row * cols);
+    const double av = a ? a[col] : a_const, bv = b ? b[col] : b_const;
+    const double xv = x[row * ldx + col];
+    double *yp = y + row * ldy + col;
+    *yp = bv == 0.0 ? av * xv : fma(av, xv, bv * *yp);
+}
+
+void axpby_cols(lb_ctx *c, int64_t n, int cols, const double *a, double a_const, const double *x, int ldx,
+                const double *b, double b_const, double *y, int ldy) {
+    if (n * cols == 0) return;
+    LB_LAUNCH(c, axpby_cols_kernel, cdiv(n * cols, 256), 256, 0, n, cols, a, a_const, x, ldx, b, b_const, y, ldy);
+}
+
+__global__ void residual_cols_kernel(int64_t n, int ncols, const int *__restrict__ idx, const double *__restrict__ lam,
+                                     const double *__restrict__ ax, int ldax, const double *__restrict__ mx, int ldmx,
+                                     double *__restrict__ out, int ldout) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * ncols) return;
+    const int64_t row = t / ncols;
+    const int a = (int)(t - row * ncols);
+    const int col = idx[a];
+    out[row * ldout + a] = fma(-lam[col], mx[row * ldmx + col], ax[row * ldax + col]);
+}
+
+void residual_cols(lb_ctx *c, int64_t n, int ncols, const int *idx, const double *lam, const double *ax, int ldax,
+                   const double *mx, int ldmx, double *out, int ldout) {
+    if (n * ncols == 0) return;
+    LB_LAUNCH(c, residual_cols_kernel, cdiv(n * ncols, 256), 256, 0, n, ncols, idx, lam, ax, ldax, mx, ldmx, out, ldout);
+}
+
+void copy_cols(lb_ctx *c, int64_t n, int cols, const double *x, int ldx, double *y, int ldy) {
+    if (n * cols == 0) return;
+    LB_CUDA(cudaMemcpy2DAsync(y, (size_t)ldy * 8, x, (size_t)ldx * 8, (size_t)cols * 8, n, cudaMemcpyDeviceToDevice,
+                              c->stream));
+}
+
+__global__ void scale_rows_kernel(int64_t n, int cols, const double *__restrict__ d, const double *__restrict__ x,
+                                  int ldx, double *__restrict__ y, int ldy) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * cols) return;
+    const int64_t row = t / cols;
+    const int col = (int)(t - row * cols);
+    y[row * ldy + col] = d[row] * x[row * ldx + col];
+}
+
+void scale_rows(lb_ctx *c, int64_t n, int cols, const double *d, const double *x, int ldx, double *y, int ldy) {
+    if (n * cols == 0) return;
+    LB_LAUNCH(c, scale_rows_kernel, cdiv(n * cols, 256), 256, 0, n, cols, d, x, ldx, y, ldy);
+}
+
+__global__ void sub_means_kernel(int64_t n, int cols, const double *__restrict__ sums, double *__restrict__ x,
+                                 int ldx) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * cols) return;
+    const int64_t row = t / cols;
+    const int col = (int)(t - row * cols);
+    x[row * ldx + col] -= sums[col] / (double)n;
+}
+
+void remove_col_means(lb_ctx *c, int64_t n, int cols, double *x, int ldx) {
+    if (n * cols == 0) return;
+    DBuf<double> sums(c, cols);
+    col_dots(c, n, cols, x, ldx, nullptr, 0, sums.p);  // y == NULL: dots with ones = column sums
+    LB_LAUNCH(c, sub_means_kernel, cdiv(n * cols, 256), 256, 0, n, cols, sums.p, x, ldx);
+}
+
+__device__ __forceinline__ uint64_t splitmix64(uint64_t z) {
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+__global__ void fill_random_kernel(int64_t n, int cols, double *__restrict__ x, int ldx, uint64_t seed) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * cols) return;
+    const int64_t row = t / cols;
+    const int col = (int)(t - row * cols);
+    const uint64_t h = splitmix64(splitmix64(seed + (uint64_t)col) ^ (uint64_t)row);
+    x[row * ldx + col] = (double)(h >> 11) * (2.0 / 9007199254740992.0) - 1.0;  // uniform [-1,1)
+}
+
+void fill_random(lb_ctx *c, int64_t n, int cols, double *x, int ldx, uint64_t seed) {
+    if (n * cols == 0) return;
+    LB_LAUNCH(c, fill_random_kernel, cdiv(n * cols, 256), 256, 0, n, cols, x, ldx, seed);
+}
+
+__global__ void extract_diag_kernel(int64_t n, const int32_t *__restrict__ indptr, const int32_t *__restrict__ indices,
+                                    const double *__restrict__ val, double *__restrict__ d) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    double s = 0.0;
+    for (int p = indptr[r]; p < indptr[r + 1]; p++)
+        if (indices[p] == r) s = val[p];
+    d[r] = s;
+}
+
+void extract_diagonal(lb_ctx *c, const lb_mat *a, double *d) {
+    if (a->n == 0) return;
+    LB_LAUNCH(c, extract_diag_kernel, cdiv(a->n, 256), 256, 0, a->n, a->indptr.p, a->indices.p, a->data.p, d);
+}
+
+}  // namespace lb

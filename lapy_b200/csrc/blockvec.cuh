@@ -1,0 +1,56 @@
+// blockvec.cuh - sparse x block-vector products, block BLAS-1 and the dense tall-skinny products.
+//
+// Block vectors are row-major (n, cols) fp64 arrays with a leading dimension ld >= cols: the
+// layout the reference returns eigenvectors in (lapy/solver.py:713, C-order (n, k)) and the one
+// that makes CSR x block products coalesced (a row of X is one contiguous 8*cols-byte segment).
+#pragma once
+#include "common.cuh"
+
+namespace lb {
+
+// Y(n,m) = A X                       (mode 0)
+// Y(n,m) = B - A X                   (mode 1, residual; B may alias Y)
+// Y(n,m) = B + A X                   (mode 2; B may alias Y)
+void spmm(lb_ctx *c, const lb_mat *a, const double *x, int ldx, double *y, int ldy, int m, int mode = 0,
+          const double *b = nullptr, int ldb = 0);
+
+// out[j] = sum_i X[i,j] * Y[i,j], j < cols  (deterministic two-stage reduction), device output
+void col_dots(lb_ctx *c, int64_t n, int cols, const double *x, int ldx, const double *y, int ldy, double *out);
+
+// Y[:,j] = a[j]*X[:,j] + b[j]*Y[:,j]; a / b device arrays or NULL (then a_const / b_const)
+void axpby_cols(lb_ctx *c, int64_t n, int cols, const double *a, double a_const, const double *x, int ldx,
+                const double *b, double b_const, double *y, int ldy);
+
+// Y[:, j] = X[:, idx[j]] - lam[idx[j]] * Z[:, idx[j]]   (compacting gather of active columns)
+void residual_cols(lb_ctx *c, int64_t n, int ncols, const int *idx, const double *lam, const double *ax, int ldax,
+                   const double *mx, int ldmx, double *out, int ldout);
+
+void copy_cols(lb_ctx *c, int64_t n, int cols, const double *x, int ldx, double *y, int ldy);
+void scale_rows(lb_ctx *c, int64_t n, int cols, const double *d, const double *x, int ldx, double *y, int ldy);
+// subtract from every column its mean (constant null-space projection, lapy/diffgeo.py:156 solve)
+void remove_col_means(lb_ctx *c, int64_t n, int cols, double *x, int ldx);
+void fill_random(lb_ctx *c, int64_t n, int cols, double *x, int ldx, uint64_t seed);
+void extract_diagonal(lb_ctx *c, const lb_mat *a, double *d);  // d[i] = A[i,i] (0 if not stored)
+
+// ---- dense tall-skinny products (row-major blocks) -----------------------------------------
+// C(p,q) row-major = X(n,p)^T Y(n,q)
+void gram(lb_ctx *c, int64_t n, int p, const double *x, int ldx, int q, const double *y, int ldy, double *cmat);
+// Y(n,q) = alpha * X(n,p) C(p,q) + beta * Y;  X must not alias Y
+void update(lb_ctx *c, int64_t n, int p, const double *x, int ldx, int q, const double *cmat, int ldc, double alpha,
+            double beta, double *y, int ldy);
+// W(n,q) <- W L^-T  with L (q,q) row-major lower Cholesky factor (in place)
+void trsm_right_lt(lb_ctx *c, int64_t n, int q, const double *l, double *w, int ldw);
+
+// ---- small dense (device, cuSOLVER) ------------------------------------------------------------
+// in-place lower Cholesky of the row-major (q,q) SPD matrix g; returns LAPACK info (0 = ok)
+int chol_lower(lb_ctx *c, int q, double *g);
+// eigen-decomposition of the symmetric row-major (s,s) matrix g: on return row j of g holds the
+// j-th eigenvector (ascending), evals (s) device
+int sym_eig(lb_ctx *c, int s, double *g, double *evals);
+// solve G X = B for SPD row-major G (q,q), B (q, nrhs) row-major ... used for the coarsest level:
+// stores the Cholesky factor in g
+void dense_chol_solve_prepare(lb_ctx *c, int q, double *g);
+// X(q,m) row-major <- G^-1 X with the factor l from dense_chol_solve_prepare
+void dense_chol_solve(lb_ctx *c, int q, const double *l, int m, double *x, int ldx);
+
+}  // namespace lb

@@ -69,6 +69,9 @@ struct lb_ctx {
     void *pinned = nullptr;  // small pinned staging area for scalar read-backs
     size_t pinned_bytes = 0;
     void *cusolver = nullptr;  // cusolverDnHandle_t, created lazily (dense Rayleigh-Ritz only)
+    void *cublas = nullptr;    // cublasHandle_t, created lazily (bring-up path of the dense block products)
+    bool trace = false;        // LAPY_B200_TRACE=1: per-phase wall clock (synchronising!) on stderr
+    double trace_t0 = 0;
 };
 
 namespace lb {
@@ -144,6 +147,16 @@ inline void read_back(lb_ctx *c, T *host, const T *dev, size_t count) {
     std::memcpy(host, c->pinned, count * sizeof(T));
 }
 
+double wall_ms();
+// development aid: prints the wall time since the previous phase mark (after a stream sync)
+inline void phase(lb_ctx *c, const char *name) {
+    if (!c->trace) return;
+    cudaStreamSynchronize(c->stream);
+    double t = wall_ms();
+    fprintf(stderr, "[lb trace] %-28s %9.3f ms\n", name, t - c->trace_t0);
+    c->trace_t0 = wall_ms();
+}
+
 inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
 // kernel launch with bookkeeping (gpu_launches in bench.py is this counter)
@@ -180,7 +193,8 @@ struct lb_mesh {
 
 struct lb_mat {
     lb_ctx *ctx = nullptr;
-    int64_t n = 0, nnz = 0;
+    int64_t n = 0, nnz = 0;     // n = number of rows
+    int64_t ncols = -1;         // -1: square (n); prolongators / restrictors are rectangular CSR
     lb::DBuf<int32_t> indptr;   // (n+1)
     lb::DBuf<int32_t> indices;  // (nnz) sorted, unique per row
     lb::DBuf<double> data;      // (nnz)

@@ -1,9 +1,17 @@
 // ctx.cu - context life cycle, error reporting, prefix sums, matrix upload / download.
+#include <chrono>
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace lb {
 
 static thread_local char g_err[1024] = "";
+
+double wall_ms() {
+    using namespace std::chrono;
+    return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
+}
 
 void set_error(const char *fmt, ...) {
     va_list ap;
@@ -168,10 +176,11 @@ int lb_ctx_create(int device, void *stream, lb_ctx **out) {
     LB_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
     uint64_t thresh = UINT64_MAX;
     LB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh));
+    const char *tr = getenv("LAPY_B200_TRACE");
+    c->trace = tr && tr[0] == '1';
     *out = c;
     LB_API_END
 }
-
 
 int lb_ctx_destroy(lb_ctx *c) {
     LB_API_BEGIN

@@ -1,0 +1,354 @@
+// eigs.cu - block LOBPCG on the pencil (A, B) with an AMG V-cycle preconditioner (lb_eigs).
+//
+// Replaces Solver.eigs (lapy/solver.py:667-716): splu(A - sigma*B) + ARPACK shift-invert Lanczos.
+// For sigma <= 0 "the k eigenvalues nearest sigma" are the k smallest, which is what a
+// preconditioned block eigensolver delivers; the reference's shift enters as the SPD operator
+// K = A - sigma*B the preconditioner approximates the inverse of (the same operator SuperLU
+// factorises at solver.py:707).
+//
+// Algorithm (Knyazev's LOBPCG in the robust basis form of Duersch/Shao/Yang/Gu 2018):
+//   S = [X | P | W] kept B-orthonormal; W = B-orthonormalised, X- and P-orthogonalised
+//   preconditioned residuals of the not yet converged columns (soft locking); Rayleigh-Ritz on
+//   S^T A S (<= 3m x 3m, cuSOLVER syevd); new X = S Cx, new P = S Cp with Cp the W/P part of Cx
+//   re-orthonormalised against Cx in coefficient space.  All n-sized work is SpMM / tall-skinny
+//   block products on the device; the host only handles <= 3m x 3m coefficient matrices.
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <numeric>
+
+#include <cusolverDn.h>
+
+#include "amg.cuh"
+
+namespace lb {
+
+__global__ void set_column(int64_t n, double *x, int ld, int col, double v) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) x[i * ld + col] = v;
+}
+
+// Cholesky-QR of W (n, q) in the B inner product, repeated twice; falls back to an eigen-based
+// whitening (SVQB) when the Gram matrix is numerically singular.  On return bw = B w.
+// Returns the number of columns kept (columns with negligible norm are dropped by SVQB).
+static int b_orthonormalize(lb_ctx *c, const lb_mat *B, int64_t n, int q, double *w, int ldw, double *bw, int ldbw,
+                            double *tmp /* n x q scratch, ld = q */) {
+    DBuf<double> G(c, (size_t)q * q), ev(c, q);
+    int kept = q;
+    for (int rep = 0; rep < 2; rep++) {
+        spmm(c, B, w, ldw, bw, ldbw, kept);
+        gram(c, n, kept, w, ldw, kept, bw, ldbw, G.p);
+        DBuf<double> Gc(c, (size_t)kept * kept);
+        d2d(c, Gc.p, G.p, (size_t)kept * kept * sizeof(double));
+        int info = chol_lower(c, kept, Gc.p);
+        if (info == 0) {
+            trsm_right_lt(c, n, kept, Gc.p, w, ldw);
+            continue;
+        }
+        // SVQB: G = V diag(e) V^T; W <- W V diag(e)^-1/2 over the columns with e > eps * e_max
+        std::vector<double> hV((size_t)kept * kept), hE(kept);
+        info = sym_eig(c, kept, G.p, ev.p);
+        LB_REQUIRE(info == 0, "whitening eigen-decomposition failed (info=%d)", info);
+        d2h(c, hV.data(), G.p, hV.size() * sizeof(double));
+        d2h(c, hE.data(), ev.p, kept * sizeof(double));
+        sync(c);
+        const double emax = std::max(hE[kept - 1], 0.0);
+        std::vector<double> T;  // (kept, newq) row-major
+        int newq = 0;
+        for (int j = kept - 1; j >= 0; j--)
+            if (hE[j] > 1e-13 * emax && hE[j] > 0.0) newq++;
+        if (newq == 0) return 0;
+        T.assign((size_t)kept * newq, 0.0);
+        int col = 0;
+        for (int j = kept - 1; j >= 0 && col < newq; j--, col++) {
+            const double s = 1.0 / std::sqrt(hE[j]);
+            for (int i = 0; i < kept; i++) T[(size_t)i * newq + col] = hV[(size_t)j * kept + i] * s;  // row j = evec j
+        }
+        DBuf<double> dT(c, T.size());
+        h2d(c, dT.p, T.data(), T.size() * sizeof(double));
+        update(c, n, kept, w, ldw, newq, dT.p, newq, 1.0, 0.0, tmp, q);
+        copy_cols(c, n, newq, tmp, q, w, ldw);
+        sync(c);
+        kept = newq;
+    }
+    spmm(c, B, w, ldw, bw, ldbw, kept);
+    return kept;
+}
+
+// ---- host-side small dense helpers (column-major-free: everything row-major) ------------------
+// orthonormalise the columns of Q (s x q, row-major) against the orthonormal columns of C
+// (s x m) and among themselves (modified Gram-Schmidt, twice); drops dependent columns
+static int host_orth(int s, int m, const std::vector<double> &C, int q, std::vector<double> &Q) {
+    std::vector<double> col(s);
+    int kept = 0;
+    for (int j = 0; j < q; j++) {
+        for (int i = 0; i < s; i++) col[i] = Q[(size_t)i * q + j];
+        double n0 = 0;
+        for (int i = 0; i < s; i++) n0 += col[i] * col[i];
+        n0 = std::sqrt(n0);
+        if (!(n0 > 0)) continue;
+        for (int rep = 0; rep < 2; rep++) {
+            for (int k = 0; k < m; k++) {
+                double d = 0;
+                for (int i = 0; i < s; i++) d += C[(size_t)i * m + k] * col[i];
+                for (int i = 0; i < s; i++) col[i] -= d * C[(size_t)i * m + k];
+            }
+            for (int k = 0; k < kept; k++) {
+                double d = 0;
+                for (int i = 0; i < s; i++) d += Q[(size_t)i * q + k] * col[i];
+                for (int i = 0; i < s; i++) col[i] -= d * Q[(size_t)i * q + k];
+            }
+        }
+        double n1 = 0;
+        for (int i = 0; i < s; i++) n1 += col[i] * col[i];
+        n1 = std::sqrt(n1);
+        if (n1 < 1e-8 * n0 || n1 < 1e-14) continue;
+        for (int i = 0; i < s; i++) Q[(size_t)i * q + kept] = col[i] / n1;
+        kept++;
+    }
+    return kept;
+}
+
+struct EigStats {
+    int iterations = 0, converged = 0, levels = 0, block = 0;
+    double residual = 0, setup_ms = 0, solve_ms = 0;
+};
+
+static EigStats lobpcg(lb_ctx *c, const lb_mat *A, const lb_mat *B, int k, double sigma, double tol, int maxit,
+                       double *h_evals, double *h_evecs) {
+    const int64_t n = A->n;
+    EigStats st;
+    int m = ((k + std::max(6, (k + 3) / 4) + 7) / 8) * 8;
+    if (const char *e = getenv("LAPY_B200_BLOCK")) m = std::max(k + 1, atoi(e));
+    const int ld = 3 * m;
+    st.block = m;
+
+    // preconditioner on K = A - sigma*B (SPD for sigma < 0)
+    const double shift = sigma < 0 ? -sigma : 1e-2;
+    AmgOptions opt;
+    if (const char *e = getenv("LAPY_B200_CHEB")) opt.cheb_deg = std::max(1, atoi(e));
+    auto amg = amg_setup(c, mat_axpby(c, A, 1.0, B, shift), m, opt);
+    st.levels = (int)amg->levels.size();
+    st.setup_ms = amg->setup_ms;
+
+    cudaEvent_t e0, e1;
+    LB_CUDA(cudaEventCreate(&e0));
+    LB_CUDA(cudaEventCreate(&e1));
+    LB_CUDA(cudaEventRecord(e0, c->stream));
+
+    const size_t blk = (size_t)n * ld;
+    DBuf<double> S[2] = {DBuf<double>(c, blk), DBuf<double>(c, blk)};
+    DBuf<double> AS[2] = {DBuf<double>(c, blk), DBuf<double>(c, blk)};
+    DBuf<double> BS[2] = {DBuf<double>(c, blk), DBuf<double>(c, blk)};
+    DBuf<double> Rbuf(c, (size_t)n * m), tmp(c, (size_t)n * m);
+    DBuf<double> G(c, (size_t)ld * ld), evd(c, ld), lam_d(c, m), coef(c, (size_t)ld * 2 * m), dots(c, 2 * m);
+    DBuf<int> idx_d(c, m);
+    std::vector<double> lam(m), hG, hC, hQ, coefh, rr(2 * m);
+    std::vector<int> act(m), idx(m);
+    int cur = 0;
+
+    // ---- initial block: constants + pseudo-random, B-orthonormalised, one Rayleigh-Ritz
+    fill_random(c, n, m, S[0].p, ld, 0x1234567ull);
+    LB_LAUNCH(c, set_column, cdiv(n, 256), 256, 0, n, S[0].p, ld, 0, 1.0);
+    int kept = b_orthonormalize(c, B, n, m, S[0].p, ld, BS[0].p, ld, tmp.p);
+    LB_REQUIRE(kept == m, "initial block is rank deficient");
+    spmm(c, A, S[0].p, ld, AS[0].p, ld, m);
+    auto rayleigh_ritz = [&](int s, int mp_hint, const std::vector<int> &active_cols, int &mp_new) {
+        // G = S^T A S (s x s); eigenvectors -> Cx; Cp from the active columns
+        gram(c, n, s, S[cur].p, ld, s, AS[cur].p, ld, G.p);
+        int info = sym_eig(c, s, G.p, evd.p);
+        LB_REQUIRE(info == 0, "Rayleigh-Ritz eigen-decomposition failed (info=%d)", info);
+        hG.resize((size_t)m * s);
+        d2h(c, hG.data(), G.p, hG.size() * sizeof(double));  // rows 0..m-1 = the m smallest eigenvectors
+        d2h(c, lam.data(), evd.p, m * sizeof(double));
+        sync(c);
+        hC.assign((size_t)s * m, 0.0);  // Cx (s x m) row-major
+        for (int j = 0; j < m; j++)
+            for (int i = 0; i < s; i++) hC[(size_t)i * m + j] = hG[(size_t)j * s + i];
+        const int q = (int)active_cols.size();
+        mp_new = 0;
+        if (s > m && q > 0) {
+            hQ.assign((size_t)s * q, 0.0);
+            for (int a = 0; a < q; a++)
+                for (int i = m; i < s; i++) hQ[(size_t)i * q + a] = hC[(size_t)i * m + active_cols[a]];
+            mp_new = host_orth(s, m, hC, q, hQ);
+        }
+        const int w = m + mp_new;
+        coefh.assign((size_t)s * w, 0.0);
+        for (int i = 0; i < s; i++) {
+            for (int j = 0; j < m; j++) coefh[(size_t)i * w + j] = hC[(size_t)i * m + j];
+            for (int j = 0; j < mp_new; j++) coefh[(size_t)i * w + m + j] = hQ[(size_t)i * q + j];
+        }
+        h2d(c, coef.p, coefh.data(), coefh.size() * sizeof(double));
+        const int nxt = cur ^ 1;
+        update(c, n, s, S[cur].p, ld, w, coef.p, w, 1.0, 0.0, S[nxt].p, ld);
+        update(c, n, s, AS[cur].p, ld, w, coef.p, w, 1.0, 0.0, AS[nxt].p, ld);
+        update(c, n, s, BS[cur].p, ld, w, coef.p, w, 1.0, 0.0, BS[nxt].p, ld);
+        h2d(c, lam_d.p, lam.data(), m * sizeof(double));
+        sync(c);  // coefh / lam are host buffers
+        cur = nxt;
+        (void)mp_hint;
+    };
+    int mp = 0;
+    {
+        std::vector<int> none;
+        rayleigh_ritz(m, 0, none, mp);
+    }
+
+    double worst = 0.0;
+    int nconv_k = 0;
+    for (int it = 0; it < maxit; it++) {
+        st.iterations = it;
+        // ---- residual norms of all m columns
+        std::iota(idx.begin(), idx.end(), 0);
+        h2d(c, idx_d.p, idx.data(), m * sizeof(int));
+        residual_cols(c, n, m, idx_d.p, lam_d.p, AS[cur].p, ld, BS[cur].p, ld, Rbuf.p, m);
+        col_dots(c, n, m, Rbuf.p, m, Rbuf.p, m, dots.p);
+        col_dots(c, n, m, BS[cur].p, ld, BS[cur].p, ld, dots.p + m);
+        read_back(c, rr.data(), dots.p, 2 * m);
+        double lam_mean = 0;
+        for (int j = 0; j < k; j++) lam_mean += std::fabs(lam[j]);
+        lam_mean /= k;
+        if (!(lam_mean > 0)) lam_mean = 1.0;
+        worst = 0.0;
+        nconv_k = 0;
+        int ma = 0;
+        for (int j = 0; j < m; j++) {
+            const double scale = std::max(std::fabs(lam[j]), lam_mean);
+            const double rel = std::sqrt(rr[j]) / (scale * std::sqrt(rr[m + j]));
+            const bool conv = rel <= tol;
+            act[j] = !conv;
+            if (j < k) {
+                nconv_k += conv;
+                worst = std::max(worst, std::isfinite(rel) ? rel : INFINITY);
+            }
+            if (!conv) idx[ma++] = j;
+        }
+        if (c->trace)
+            fprintf(stderr, "[lb trace] lobpcg it %3d: max res(first k) %.3e, converged %d/%d, active %d, P %d\n", it,
+                    worst, nconv_k, k, ma, mp);
+        if (nconv_k == k || !std::isfinite(worst)) break;
+        if (it == maxit - 1) break;
+        // ---- W = precond(R_active), orthogonalised against [X P], B-orthonormalised
+        std::vector<int> active_cols(idx.begin(), idx.begin() + ma);
+        h2d(c, idx_d.p, idx.data(), ma * sizeof(int));
+        residual_cols(c, n, ma, idx_d.p, lam_d.p, AS[cur].p, ld, BS[cur].p, ld, Rbuf.p, ma);
+        const int w0 = m + mp;
+        double *W = S[cur].p + w0, *AW = AS[cur].p + w0, *BW = BS[cur].p + w0;
+        amg_apply(*amg, Rbuf.p, ma, W, ld, ma);
+        for (int rep = 0; rep < 2; rep++) {
+            gram(c, n, w0, BS[cur].p, ld, ma, W, ld, G.p);                        // (w0 x ma)
+            update(c, n, w0, S[cur].p, ld, ma, G.p, ma, -1.0, 1.0, W, ld);        // W -= [X P] G
+        }
+        const int mw = b_orthonormalize(c, B, n, ma, W, ld, BW, ld, tmp.p);
+        if (mw == 0) break;  // nothing left to add: stagnation
+        spmm(c, A, W, ld, AW, ld, mw);
+        // ---- Rayleigh-Ritz on [X P W]
+        rayleigh_ritz(w0 + mw, mp, active_cols, mp);
+    }
+    st.iterations += 1;
+    st.converged = nconv_k;
+    st.residual = worst;
+
+    LB_CUDA(cudaEventRecord(e1, c->stream));
+    LB_CUDA(cudaEventSynchronize(e1));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    st.solve_ms = ms;
+
+    for (int j = 0; j < k; j++) h_evals[j] = lam[j];
+    LB_CUDA(cudaMemcpy2DAsync(h_evecs, (size_t)k * 8, S[cur].p, (size_t)ld * 8, (size_t)k * 8, n,
+                              cudaMemcpyDeviceToHost, c->stream));
+    sync(c);
+    return st;
+}
+
+// ---- dense path for tiny problems (n too small for a 3m-wide basis) -----------------------------
+__global__ void densify_sym(int64_t n, const int32_t *__restrict__ ptr, const int32_t *__restrict__ idx,
+                            const double *__restrict__ val, double *__restrict__ dense) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    for (int p = ptr[i]; p < ptr[i + 1]; p++) dense[i * n + idx[p]] = val[p];
+}
+
+static void dense_eigs(lb_ctx *c, const lb_mat *A, const lb_mat *B, int k, double *h_evals, double *h_evecs) {
+    const int n = (int)A->n;
+    DBuf<double> dA(c, (size_t)n * n), dB(c, (size_t)n * n), w(c, n);
+    dA.zero();
+    dB.zero();
+    LB_LAUNCH(c, densify_sym, cdiv(n, 128), 128, 0, (int64_t)n, A->indptr.p, A->indices.p, A->data.p, dA.p);
+    LB_LAUNCH(c, densify_sym, cdiv(n, 128), 128, 0, (int64_t)n, B->indptr.p, B->indices.p, B->data.p, dB.p);
+    if (!c->cusolver) {
+        DBuf<double> dummy(c, 1), e(c, 1);
+        dummy.zero();
+        sym_eig(c, 1, dummy.p, e.p);  // creates the handle
+    }
+    cusolverDnHandle_t h = (cusolverDnHandle_t)c->cusolver;
+    int lwork = 0;
+    cusolverStatus_t s = cusolverDnDsygvd_bufferSize(h, CUSOLVER_EIG_TYPE_1, CUSOLVER_EIG_MODE_VECTOR,
+                                                     CUBLAS_FILL_MODE_UPPER, n, dA.p, n, dB.p, n, w.p, &lwork);
+    LB_REQUIRE(s == CUSOLVER_STATUS_SUCCESS, "cusolver sygvd buffer query failed (%d)", (int)s);
+    DBuf<double> work(c, lwork);
+    DBuf<int> info(c, 1);
+    s = cusolverDnDsygvd(h, CUSOLVER_EIG_TYPE_1, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_UPPER, n, dA.p, n, dB.p, n,
+                         w.p, work.p, lwork, info.p);
+    c->launches++;
+    LB_REQUIRE(s == CUSOLVER_STATUS_SUCCESS, "cusolver sygvd failed (%d)", (int)s);
+    int hinfo = 0;
+    read_back(c, &hinfo, info.p, 1);
+    if (hinfo != 0) {
+        set_error("dense generalized eigensolve failed (info=%d): mass matrix not positive definite?", hinfo);
+        throw Error{LB_ERR_NOCONV};
+    }
+    d2h(c, h_evals, w.p, k * sizeof(double));
+    // eigenvector j = column j column-major = row j row-major: transpose the first k rows into (n,k)
+    std::vector<double> rows((size_t)k * n);
+    d2h(c, rows.data(), dA.p, rows.size() * sizeof(double));
+    sync(c);
+    for (int j = 0; j < k; j++)
+        for (int i = 0; i < n; i++) h_evecs[(size_t)i * k + j] = rows[(size_t)j * n + i];
+}
+
+}  // namespace lb
+
+using namespace lb;
+
+extern "C" int lb_eigs(lb_ctx *c, lb_mat *a, lb_mat *b, int k, double sigma, double tol, int maxit, double *evals,
+                       double *evecs, lb_info *info) {
+    LB_API_BEGIN
+    LB_REQUIRE(c && a && b && evals && evecs, "lb_eigs: NULL argument");
+    LB_REQUIRE(a->n == b->n, "stiffness and mass must have the same dimension");
+    LB_REQUIRE(k >= 1 && k < a->n, "k must satisfy 1 <= k < n (n = %lld)", (long long)a->n);
+    if (sigma > 0) {
+        set_error("sigma > 0 (interior eigenvalues) is not supported by the block eigensolver; use sigma <= 0");
+        return LB_ERR_UNSUPPORTED;
+    }
+    DeviceGuard g(c->device);
+    if (tol <= 0) tol = 1e-9;
+    if (maxit <= 0) maxit = 200;
+    EigStats st;
+    const int m = ((k + std::max(6, (k + 3) / 4) + 7) / 8) * 8;
+    if (a->n <= std::max<int64_t>(4 * m, 600)) {
+        dense_eigs(c, a, b, k, evals, evecs);
+        st.converged = k;
+    } else {
+        st = lobpcg(c, a, b, k, sigma, tol, maxit, evals, evecs);
+    }
+    if (info) {
+        info->iterations = st.iterations;
+        info->converged = st.converged;
+        info->amg_levels = st.levels;
+        info->reserved = st.block;
+        info->residual = st.residual;
+        info->setup_ms = st.setup_ms;
+        info->solve_ms = st.solve_ms;
+    }
+    if (st.converged < k) {
+        set_error("LOBPCG did not converge: %d of %d eigenpairs, max scaled residual %.3e after %d iterations",
+                  st.converged, k, st.residual, st.iterations);
+        return LB_ERR_NOCONV;
+    }
+    LB_API_END
+}

@@ -1,0 +1,290 @@
+// solve.cu - block preconditioned CG behind heat.diffusion / Solver.poisson (lb_solve) and the
+// public SpMM entry point.
+//
+// Replaces splu(hmat).solve(b0) (lapy/heat.py:226-227) and the Dirichlet elimination + splu solve
+// of Solver.poisson (lapy/solver.py:848-883).  No factorisation: the operator alpha*A + beta*B is
+// applied matrix-free to all right-hand sides at once (CSR SpMM); the preconditioner is Jacobi
+// when the operator is strongly diagonally dominant (backward-Euler heat matrix: mass dominated)
+// and one smoothed-aggregation V-cycle otherwise (Poisson).
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+
+#include "amg.cuh"
+
+namespace lb {
+
+// ---- Dirichlet handling -----------------------------------------------------------------------
+__global__ void mark_fixed(int64_t nfix, const int64_t *__restrict__ idx, const double *__restrict__ val,
+                           int *__restrict__ is_fixed, double *__restrict__ dval) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nfix) return;
+    is_fixed[idx[t]] = 1;
+    dval[idx[t]] = val[t];
+}
+
+__global__ void broadcast_cols(int64_t n, int m, const double *__restrict__ d, double *__restrict__ out) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * m) return;
+    out[t] = d[t / m];
+}
+
+// rows / columns of fixed vertices -> identity (keeps the pattern, explicit zeros)
+__global__ void mask_matrix(int64_t n, const int32_t *__restrict__ ptr, const int32_t *__restrict__ idx,
+                            double *__restrict__ val, const int *__restrict__ is_fixed) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    const int fr = is_fixed[r];
+    for (int p = ptr[r]; p < ptr[r + 1]; p++) {
+        const int j = idx[p];
+        if (fr || is_fixed[j]) val[p] = (j == r) ? 1.0 : 0.0;
+    }
+}
+
+__global__ void set_fixed_rows(int64_t n, int m, const int *__restrict__ is_fixed, const double *__restrict__ d,
+                               double *__restrict__ x) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * m) return;
+    const int64_t r = t / m;
+    if (is_fixed[r]) x[t] = d[r];
+}
+
+// min over rows of (K_ii - sum_{j!=i} |K_ij|) / K_ii  (diagonal dominance margin)
+__global__ void dominance_margin(int64_t n, const int32_t *__restrict__ ptr, const int32_t *__restrict__ idx,
+                                 const double *__restrict__ val, unsigned long long *__restrict__ out_neg) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    double worst = 0.0;  // we track max of (1 - margin) >= 0
+    if (i < n && ptr[i + 1] > ptr[i]) {
+        double d = 0.0, off = 0.0;
+        for (int p = ptr[i]; p < ptr[i + 1]; p++) {
+            if (idx[p] == i) d = val[p];
+            else off += fabs(val[p]);
+        }
+        worst = d > 0.0 ? off / d : 1e300;
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) worst = fmax(worst, __shfl_xor_sync(0xffffffffu, worst, o));
+    if ((threadIdx.x & 31) == 0 && worst > 0.0) atomicMax(out_neg, (unsigned long long)__double_as_longlong(worst));
+}
+
+__global__ void add_diag_shift(int64_t n, const int32_t *__restrict__ ptr, const int32_t *__restrict__ idx,
+                               double *__restrict__ val, double eps) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    for (int p = ptr[r]; p < ptr[r + 1]; p++)
+        if (idx[p] == r) val[p] *= (1.0 + eps);
+}
+
+// ---- PCG scalar kernels -------------------------------------------------------------------------
+__global__ void pcg_alpha(int m, const double *__restrict__ rz, const double *__restrict__ pq,
+                          const int *__restrict__ active, double *__restrict__ alpha, double *__restrict__ neg_alpha) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= m) return;
+    const double a = (active[j] && pq[j] > 0.0) ? rz[j] / pq[j] : 0.0;
+    alpha[j] = a;
+    neg_alpha[j] = -a;
+}
+
+__global__ void pcg_beta(int m, double *__restrict__ rz, const double *__restrict__ rz_new,
+                         const int *__restrict__ active, double *__restrict__ beta) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= m) return;
+    beta[j] = (active[j] && rz[j] != 0.0) ? rz_new[j] / rz[j] : 0.0;
+    rz[j] = rz_new[j];
+}
+
+struct SolveStats {
+    int iterations = 0, converged = 0, levels = 0;
+    double residual = 0, setup_ms = 0, solve_ms = 0;
+};
+
+// Solves K x = rhs (all device, (n,m) row-major with ld = m). K SPD (or PSD with constant null
+// space when project != 0).  x is overwritten (initial guess 0).
+static SolveStats block_pcg(lb_ctx *c, lb_mat *K, const double *rhs, double *x, int m, double tol, int maxit,
+                            bool project, int force_prec) {
+    const int64_t n = K->n;
+    SolveStats st;
+    // ---- preconditioner choice
+    DBuf<unsigned long long> dom(c, 1);
+    dom.zero();
+    LB_LAUNCH(c, dominance_margin, cdiv(n, 256), 256, 0, n, K->indptr.p, K->indices.p, K->data.p, dom.p);
+    unsigned long long bits = 0;
+    read_back(c, &bits, dom.p, 1);
+    double off_ratio;
+    std::memcpy(&off_ratio, &bits, 8);
+    bool use_amg = !(off_ratio < 0.95);  // kappa(D^-1 K) <= (1+r)/(1-r) < 39
+    if (force_prec == 1) use_amg = false;
+    if (force_prec == 2) use_amg = true;
+    std::unique_ptr<Amg> amg;
+    DBuf<double> dinv;
+    if (use_amg) {
+        auto Kp = mat_axpby(c, K, 1.0, nullptr, 0.0);
+        if (project) LB_LAUNCH(c, add_diag_shift, cdiv(n, 256), 256, 0, n, Kp->indptr.p, Kp->indices.p, Kp->data.p, 1e-6);
+        AmgOptions opt;
+        amg = amg_setup(c, std::move(Kp), m, opt);
+        st.levels = (int)amg->levels.size();
+        st.setup_ms = amg->setup_ms;
+    } else {
+        DBuf<double> diag(c, n);
+        extract_diagonal(c, K, diag.p);
+        dinv.alloc(c, n);
+        launch_diag_inverse(c, n, diag.p, dinv.p);
+    }
+    auto precond = [&](const double *r, double *z) {
+        if (use_amg) amg_apply(*amg, r, m, z, m, m);
+        else scale_rows(c, n, m, dinv.p, r, m, z, m);
+        if (project) remove_col_means(c, n, m, z, m);
+    };
+
+    cudaEvent_t e0, e1;
+    LB_CUDA(cudaEventCreate(&e0));
+    LB_CUDA(cudaEventCreate(&e1));
+    LB_CUDA(cudaEventRecord(e0, c->stream));
+
+    DBuf<double> r(c, (size_t)n * m), z(c, (size_t)n * m), p(c, (size_t)n * m), q(c, (size_t)n * m);
+    DBuf<double> rz(c, m), rz_new(c, m), pq(c, m), rr(c, m), alpha(c, m), nalpha(c, m), beta(c, m);
+    DBuf<int> active(c, m);
+    std::vector<double> h_rr(m), h_bb(m);
+    std::vector<int> h_active(m, 1);
+
+    d2d(c, r.p, rhs, (size_t)n * m * sizeof(double));
+    if (project) remove_col_means(c, n, m, r.p, m);
+    LB_CUDA(cudaMemsetAsync(x, 0, (size_t)n * m * sizeof(double), c->stream));
+    col_dots(c, n, m, r.p, m, r.p, m, rr.p);
+    read_back(c, h_bb.data(), rr.p, m);
+    int nact = 0;
+    for (int j = 0; j < m; j++) {
+        h_active[j] = h_bb[j] > 0.0;
+        nact += h_active[j];
+    }
+    h2d(c, active.p, h_active.data(), m * sizeof(int));
+    sync(c);
+    double worst = 0.0;
+    if (nact) {
+        precond(r.p, z.p);
+        d2d(c, p.p, z.p, (size_t)n * m * sizeof(double));
+        col_dots(c, n, m, r.p, m, z.p, m, rz.p);
+        for (int it = 0; it < maxit; it++) {
+            st.iterations = it + 1;
+            spmm(c, K, p.p, m, q.p, m, m);
+            col_dots(c, n, m, p.p, m, q.p, m, pq.p);
+            LB_LAUNCH(c, pcg_alpha, cdiv(m, 64), 64, 0, m, rz.p, pq.p, active.p, alpha.p, nalpha.p);
+            axpby_cols(c, n, m, alpha.p, 0.0, p.p, m, nullptr, 1.0, x, m);
+            axpby_cols(c, n, m, nalpha.p, 0.0, q.p, m, nullptr, 1.0, r.p, m);
+            col_dots(c, n, m, r.p, m, r.p, m, rr.p);
+            read_back(c, h_rr.data(), rr.p, m);
+            worst = 0.0;
+            nact = 0;
+            for (int j = 0; j < m; j++) {
+                if (h_bb[j] <= 0.0) continue;
+                const double rel = std::sqrt(h_rr[j] / h_bb[j]);
+                if (!(rel <= tol)) {
+                    nact++;
+                    worst = std::max(worst, rel);
+                    if (!std::isfinite(rel)) worst = INFINITY;
+                } else {
+                    h_active[j] = 0;
+                }
+            }
+            if (nact == 0 || !std::isfinite(worst)) break;
+            h2d(c, active.p, h_active.data(), m * sizeof(int));
+            precond(r.p, z.p);
+            col_dots(c, n, m, r.p, m, z.p, m, rz_new.p);
+            LB_LAUNCH(c, pcg_beta, cdiv(m, 64), 64, 0, m, rz.p, rz_new.p, active.p, beta.p);
+            axpby_cols(c, n, m, nullptr, 1.0, z.p, m, beta.p, 0.0, p.p, m);
+        }
+    }
+    if (project) remove_col_means(c, n, m, x, m);
+    LB_CUDA(cudaEventRecord(e1, c->stream));
+    LB_CUDA(cudaEventSynchronize(e1));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    st.solve_ms = ms;
+    st.residual = worst;
+    st.converged = m - nact;
+    return st;
+}
+
+}  // namespace lb
+
+using namespace lb;
+
+extern "C" {
+
+int lb_spmm(lb_ctx *c, lb_mat *mat, const double *x, int64_t m, double *y) {
+    LB_API_BEGIN
+    LB_REQUIRE(c && mat && x && y, "lb_spmm: NULL argument");
+    LB_REQUIRE(m >= 1 && m <= 4096, "lb_spmm: bad column count");
+    DeviceGuard g(c->device);
+    const int64_t n = mat->n;
+    DBuf<double> dx(c, (size_t)n * m), dy(c, (size_t)n * m);
+    h2d(c, dx.p, x, (size_t)n * m * sizeof(double));
+    spmm(c, mat, dx.p, (int)m, dy.p, (int)m, (int)m);
+    d2h(c, y, dy.p, (size_t)n * m * sizeof(double));
+    sync(c);
+    LB_API_END
+}
+
+int lb_solve(lb_ctx *c, lb_mat *a, double alpha, lb_mat *b, double beta, const double *rhs, int64_t m,
+             const int64_t *fix_idx, int64_t nfix, const double *fix_val, double tol, int maxit, int project_nullspace,
+             double *x, lb_info *info) {
+    LB_API_BEGIN
+    LB_REQUIRE(c && a && rhs && x, "lb_solve: NULL argument");
+    LB_REQUIRE(m >= 1 && m <= 1024, "lb_solve: number of right-hand sides must be in [1, 1024]");
+    LB_REQUIRE(nfix == 0 || (fix_idx && fix_val), "lb_solve: Dirichlet arrays missing");
+    DeviceGuard g(c->device);
+    const int64_t n = a->n;
+    if (tol <= 0) tol = 1e-12;
+    if (maxit <= 0) maxit = 2000;
+    const int mm = (int)m;
+    for (int64_t i = 0; i < nfix; i++)
+        LB_REQUIRE(fix_idx[i] >= 0 && fix_idx[i] < n, "Dirichlet index %lld out of range", (long long)fix_idx[i]);
+    auto K = mat_axpby(c, a, alpha, beta != 0.0 ? b : nullptr, beta);
+    DBuf<double> d_rhs(c, (size_t)n * mm), d_x(c, (size_t)n * mm);
+    h2d(c, d_rhs.p, rhs, (size_t)n * mm * sizeof(double));
+    DBuf<int> is_fixed;
+    DBuf<double> dval;
+    if (nfix > 0) {
+        is_fixed.alloc(c, n);
+        is_fixed.zero();
+        dval.alloc(c, n);
+        dval.zero();
+        DBuf<int64_t> d_idx(c, nfix);
+        DBuf<double> d_val(c, nfix);
+        h2d(c, d_idx.p, fix_idx, nfix * sizeof(int64_t));
+        h2d(c, d_val.p, fix_val, nfix * sizeof(double));
+        LB_LAUNCH(c, mark_fixed, cdiv(nfix, 256), 256, 0, nfix, d_idx.p, d_val.p, is_fixed.p, dval.p);
+        // rhs <- rhs - K d  (solver.py:846), then eliminate: identity rows/cols, rhs_fixed = d
+        DBuf<double> dblock(c, (size_t)n * mm);
+        LB_LAUNCH(c, broadcast_cols, cdiv(n * mm, 256), 256, 0, n, mm, dval.p, dblock.p);
+        spmm(c, K.get(), dblock.p, mm, d_rhs.p, mm, mm, 1, d_rhs.p, mm);
+        LB_LAUNCH(c, mask_matrix, cdiv(n, 256), 256, 0, n, K->indptr.p, K->indices.p, K->data.p, is_fixed.p);
+        LB_LAUNCH(c, set_fixed_rows, cdiv(n * mm, 256), 256, 0, n, mm, is_fixed.p, dval.p, d_rhs.p);
+    }
+    int force = 0;
+    if (const char *e = getenv("LAPY_B200_PREC")) force = !strcmp(e, "jacobi") ? 1 : !strcmp(e, "amg") ? 2 : 0;
+    const bool project = project_nullspace != 0 && nfix == 0;
+    SolveStats st = block_pcg(c, K.get(), d_rhs.p, d_x.p, mm, tol, maxit, project, force);
+    if (nfix > 0) LB_LAUNCH(c, set_fixed_rows, cdiv(n * mm, 256), 256, 0, n, mm, is_fixed.p, dval.p, d_x.p);
+    d2h(c, x, d_x.p, (size_t)n * mm * sizeof(double));
+    sync(c);
+    if (info) {
+        info->iterations = st.iterations;
+        info->converged = st.converged;
+        info->amg_levels = st.levels;
+        info->reserved = 0;
+        info->residual = st.residual;
+        info->setup_ms = st.setup_ms;
+        info->solve_ms = st.solve_ms;
+    }
+    if (st.converged < mm) {
+        set_error("PCG did not converge: %d of %d right-hand sides, max relative residual %.3e after %d iterations",
+                  st.converged, mm, st.residual, st.iterations);
+        return LB_ERR_NOCONV;
+    }
+    LB_API_END
+}
+
+}  // extern "C"

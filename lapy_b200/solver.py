@@ -148,3 +148,89 @@ class Solver:
     @staticmethod
     def _fem_tetra(tetra, lump: bool = False, dtype=np.float64):
         return tuple(Solver._assemble_static(tetra, _lib.FEM_TETRA, lump, dtype))
+
+    # -- Solver.eigs (lapy/solver.py:667-716) ----------------------------------------------------
+    def eigs(self, k: int = 10, sigma: float = -0.01, *, tol: float = 0.0, maxit: int = 0):
+        """k eigenpairs of ``A x = lambda B x`` nearest ``sigma`` (sigma <= 0: the k smallest).
+
+        Returns ``(eigenvalues (k,), eigenvectors (n, k))``, ascending, B-orthonormal like ARPACK's.
+        ``tol`` / ``maxit`` (extensions) bound the block-LOBPCG iteration; ``self.last_info`` holds
+        the iteration report.  sigma > 0 raises ``NotImplementedError``.
+        """
+        n = self._shape0()
+        if k >= n:  # SciPy ARPACK wrapper raises the same for sparse input (arpack.py:1691-1699)
+            raise TypeError(f"Cannot use scipy.linalg.eigh for sparse A with k >= N. k={k}, N={n}")
+        if k <= 0:
+            raise ValueError(f"k must be greater than 0. k={k}")
+        logger.info("Solver: block LOBPCG + smoothed-aggregation AMG on the GPU ...")
+        evals, evecs, info = _lib.eigs(self._ctx, self._device("a"), self._device("b"), k, sigma, tol, maxit)
+        self.last_info = info
+        return evals, evecs
+
+    eigensystem = eigs  # name used by README.md:51 / BASELINE.json
+
+    def _shape0(self):
+        for which in "ab":
+            if self._dev[which] is not None:
+                return self._dev[which].n
+        return self._host["a"].shape[0]
+
+    # -- Solver.poisson (lapy/solver.py:718-889) -----------------------------------------------------
+    def poisson(self, h=0.0, dtup=(), ntup=(), *, tol: float = 0.0, maxit: int = 0):
+        """Solve ``A x = B (h - n) - A d`` with Dirichlet (``dtup``) / Neumann (``ntup``) data.
+
+        Same argument checks, broadcasting and return shapes as the reference.  The solve is an
+        AMG-preconditioned block CG over all right-hand sides; without Dirichlet data the operator
+        is singular (constants) and the zero-mean solution is returned (the reference returns the
+        LU solution, defined up to the same constant).
+        """
+        a_dev = self._device("a")
+        dim = a_dev.n
+        b_dev = self._device("b")
+        if b_dev.n != dim:
+            raise ValueError("Error: Square input matrices should have same number of rows and columns.")
+        dtype = np.float64
+        if np.isscalar(h):
+            h = np.full((dim, 1), h, dtype=dtype)
+        else:
+            h = np.asarray(h, dtype=dtype)
+            if h.ndim == 1:
+                if h.size != dim:
+                    raise ValueError("h should be either scalar or column vector with row num of A")
+                h = h[:, np.newaxis]
+            elif h.ndim == 2:
+                if h.shape[0] != dim:
+                    raise ValueError("h should be either scalar or array with first dim matching A")
+            else:
+                raise ValueError("h should be either scalar or 1-D/2-D array")
+        n_rhs = h.shape[1]
+        scalar_rhs = n_rhs == 1
+        didx, ddat = [], []
+        if dtup:
+            if len(dtup) != 2:
+                raise ValueError("dtup should contain index and data arrays")
+            didx, ddat = dtup[0], dtup[1]
+            if np.unique(didx).size != len(didx):
+                raise ValueError("dtup indices need to be unique")
+            if not (len(didx) > 0 and len(didx) == len(ddat)):
+                raise ValueError("dtup should contain index and data arrays (same lengths > 0)")
+        if ntup:
+            if len(ntup) != 2:
+                raise ValueError("ntup should contain index and data arrays")
+            nidx, ndat = ntup[0], ntup[1]
+            if not (len(nidx) > 0 and len(nidx) == len(ndat)):
+                raise ValueError("ntup should contain index and data arrays (same lengths > 0)")
+            h = h.copy()
+            np.subtract.at(h, (np.asarray(nidx), slice(None)), np.asarray(ndat, dtype=dtype)[:, None])
+        logger.info("Solver: AMG-preconditioned block CG on the GPU ...")
+        rhs = _lib.spmm(self._ctx, b_dev, h)  # b = M (h - n)
+        x, info = _lib.solve(
+            self._ctx, a_dev, 1.0, None, 0.0, rhs,
+            fix_idx=np.asarray(didx) if len(didx) else None,
+            fix_val=np.asarray(ddat, dtype=dtype) if len(didx) else None,
+            tol=tol, maxit=maxit, project_nullspace=len(didx) == 0,
+        )  # fmt: skip
+        self.last_info = info
+        if scalar_rhs:
+            return np.squeeze(np.array(x))
+        return np.array(x)
