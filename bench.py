@@ -1,15 +1,19 @@
 #!/usr/bin/env python
-"""bench.py - the driver's benchmark contract for lapy_b200 (see DESIGN.md "Measurement").
+"""bench.py - the driver's benchmark contract for lapy_b200 (DESIGN.md "Measurement").
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload NAME]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload NAME] [--k 50]
 
-N=1 workload = BASELINE.json configs[1]: synthetic level-9 icosphere (2,621,442 vertices,
-5,242,880 triangles), one "step" = one pass of the hot path over one mesh.  With N>1 (torchrun,
-one rank per GPU) every rank processes its own mesh per step (mesh-parallel batch, no data-path
-collective) -> "scaling": "weak"; value = meshes all ranks processed / max-over-ranks device time.
+N=1 workload = BASELINE.json configs[1]: ShapeDNA k=50 of the synthetic level-9 icosphere
+(2,621,442 vertices / 5,242,880 triangles).  One "step" = one pass of the hot path over one mesh:
+FEM assembly of stiffness + mass (incl. the vertex->element incidence) and the generalized
+eigensolve, from a mesh already resident in HBM to eigenvalues / eigenvectors in host NumPy arrays.
+With N>1 (torchrun, one rank per GPU) every rank processes its own mesh per step (mesh-parallel
+batch as in BrainPrint, no data-path collective) -> "scaling": "weak"; value = meshes all ranks
+processed / max-over-ranks device time.
 
-Prints ONE JSON line (rank 0).  `--impl reference` times the reference's CPU implementation of
-the same path (the oracle: NumPy element math + SciPy COO->CSC / SuperLU / ARPACK) on the host.
+Prints ONE JSON line (rank 0).  `--impl reference` times the reference's CPU algorithm for the
+same path (the oracle: NumPy element math + SciPy COO->CSC + SuperLU + ARPACK, sequential) on a
+bounded sample.
 """
 
 from __future__ import annotations
@@ -17,7 +21,6 @@ from __future__ import annotations
 import argparse
 import json
 import os
-import subprocess
 import sys
 import threading
 import time
@@ -28,6 +31,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 PEAK_FALLBACK_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
+METRIC = "shapedna_k50_meshes_per_s"
 
 
 def measured_peak():
@@ -41,94 +45,113 @@ def measured_peak():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
-
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")  # fmt: skip
+    """SM clock / throttle reasons sampled through NVML during the timed region."""
 
     def __init__(self, index):
-        self.index, self.rows, self._stop = index, [], threading.Event()
+        self.index, self.sm, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop = threading.Event()
         self.t = threading.Thread(target=self._run, daemon=True)
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
 
     def _run(self):
+        nv = self.nv
+        names = {
+            "hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+            "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+            "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+            "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4),
+        }
         while not self._stop.is_set():
             try:
-                out = subprocess.run(
-                    ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
-                    capture_output=True, text=True, timeout=5,
-                ).stdout.strip()  # fmt: skip
-                if out:
-                    self.rows.append([x.strip() for x in out.split(",")])
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                get = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+                mask = int(get(self.h))
+                for k, bit in names.items():
+                    if mask & bit:
+                        self.reasons.add(k)
             except Exception:
                 pass
             self._stop.wait(0.2)
 
     def __enter__(self):
-        self.t.start()
+        if self.nv:
+            self.t.start()
         return self
 
     def __exit__(self, *a):
         self._stop.set()
-        self.t.join(timeout=6)
+        if self.nv:
+            self.t.join(timeout=3)
 
     def summary(self):
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for r in self.rows for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
         return {
-            "sm_mhz": float(np.median(sm)) if sm else None,
-            "sm_max_mhz": max(mx) if mx else None,
-            "reasons": reasons,
-            "samples": len(sm),
+            "sm_mhz": float(np.median(self.sm)) if self.sm else None,
+            "sm_max_mhz": self.max_mhz,
+            "reasons": sorted(self.reasons),
+            "samples": len(self.sm),
         }
 
 
-def make_workload(name, rank):
+def make_workload(name, rank=0):
     from lapy_b200 import mesh as M
 
     if name == "icosphere9":
-        return M.icosphere(9), "level-9 icosphere, 2,621,442 v / 5,242,880 tris (BASELINE.json configs[1])"
+        return M.icosphere(9), "level-9 icosphere, 2,621,442 v / 5,242,880 tris, ShapeDNA k=50 (BASELINE.json configs[1])"
     if name.startswith("icosphere"):
         lvl = int(name[len("icosphere"):])
         return M.icosphere(lvl), f"level-{lvl} icosphere (reduced size: NOT the headline config)"
+    if name.startswith("brain"):  # BrainPrint-like batch surface (config 5)
+        return M.perturbed_sphere(7, seed=rank), "level-7 perturbed sphere, 163,842 v (BASELINE.json configs[4] unit)"
     if name.startswith("cube"):
         n = int(name[len("cube"):])
         return M.cube_tets(n), f"structured tet cube n={n}"
     raise SystemExit(f"unknown workload {name}")
 
 
-def algorithmic_bytes(mesh, nnz):
-    """read t and v once, write A and B once (fp64 values, int32 indices)."""
-    nt, k = mesh.t.shape
-    nv = mesh.v.shape[0]
-    return 4 * k * nt + 24 * nv + 2 * (12 * nnz + 4 * (nv + 1))
+def cpu_reference(args, full_mesh):
+    """The reference's algorithm on the host (oracle), bounded sample: ShapeDNA k of a level-7
+    icosphere (the full level-9 mesh costs ~26 min / 27 GB of SuperLU), scaled
+    linearly in the vertex count to one workload mesh (an under-estimate of the CPU time:
+    SuperLU fill grows ~n^1.4)."""
+    from lapy_b200 import mesh as M
+    from oracle import solve as osolve
+
+    nv_full = full_mesh.v.shape[0]
+    lvl = 7 if nv_full > 200000 else None
+    sample = M.icosphere(lvl) if lvl else full_mesh
+    t0 = time.perf_counter()
+    osolve.shapedna(sample, k=args.k)
+    dt = time.perf_counter() - t0
+    scale = nv_full / sample.v.shape[0]
+    what = (
+        f"1 ShapeDNA k={args.k} of a level-7 icosphere (163,842 v) = {dt:.1f} s, scaled x{scale:.0f} (linear in vertices, "
+        "optimistic for the CPU) to one workload mesh; survey-measured full-size reference: 1557 s/mesh"
+        if lvl
+        else f"1 ShapeDNA k={args.k} of the workload mesh = {dt:.1f} s"
+    )
+    return 1.0 / (dt * scale), dt * scale, what
 
 
-def run_reference(args, rank, world):
-    """CPU arm: the reference's algorithm (oracle) on the host cores, bounded sample."""
+def run_reference(args, rank):
     if rank != 0:
         return
-    from oracle import fem as ofem
-
-    mesh, desc = make_workload(args.workload, 0)
-    nt = mesh.t.shape[0]
-    for _ in range(max(args.warmup, 1) if args.steps > 1 else 1):
-        ofem.fem(mesh)
-    t0 = time.perf_counter()
-    steps = max(1, min(args.steps, 3))
-    for _ in range(steps):
-        a, b = ofem.fem(mesh)
-    dt = (time.perf_counter() - t0) / steps
-    val = nt / dt / 1e9
+    mesh, desc = make_workload(args.workload)
+    val, sec, what = cpu_reference(args, mesh)
     line = {
-        "impl": "reference", "metric": "fem_assembly_gelem_per_s", "value": val, "unit": "Gelem/s",
-        "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": desc, "step": "Solver(mesh): stiffness + full mass assembly to CSC"},
-        "cpu_baseline": {"value": val, "unit": "Gelem/s", "cores": 1, "kind": "port",
-                         "sample": f"{steps} full assemblies of the same mesh (NumPy + SciPy COO->CSC, sequential)"},
-        "e2e": {"value": val, "unit": "Gelem/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "meshes/s", "n_gpus": args.gpus, "steps": 1,
+        "warmup": 0, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": desc, "step": "Solver(mesh) + eigs(k): assembly + generalized eigensolve", "k": args.k},
+        "cpu_baseline": {"value": val, "unit": "meshes/s", "cores": 1, "kind": "port", "sample": what},
+        "e2e": {"value": val, "unit": "meshes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }  # fmt: skip
     print(json.dumps(line), flush=True)
 
@@ -136,27 +159,29 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="icosphere9")
+    ap.add_argument("--k", type=int, default=50)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
 
     if args.impl == "reference":
-        run_reference(args, rank, world)
+        run_reference(args, rank)
         return
+    args.warmup = max(args.warmup, 3)
 
     import torch
     import torch.distributed as dist
 
     import lapy_b200
     from lapy_b200 import _lib
+    from lapy_b200.shapedna import compute_shapedna
 
     torch.cuda.set_device(local_rank)
     if world > 1:
@@ -164,14 +189,16 @@ def main():
     ctx = _lib.Context(local_rank)
 
     mesh, desc = make_workload(args.workload, rank)
-    nt = mesh.t.shape[0]
+    nt, nv = mesh.t.shape[0], mesh.v.shape[0]
     kind = _lib.FEM_TETRA if mesh.t.shape[1] == 4 else _lib.FEM_TRIA
     dmesh = _lib.DeviceMesh(ctx, mesh.v, mesh.t)  # inputs resident in HBM before the timed region
+    asm_ms = []
 
     def step():
         dmesh.drop_cache()  # the vertex->element incidence is part of the assembly work
         a, b = _lib.assemble(ctx, dmesh, kind, False)
-        return a, b
+        ev, evec, info = _lib.eigs(ctx, a, b, args.k, -0.01)
+        return ev, evec, info, a.nnz
 
     def barrier():
         ctx.sync()
@@ -180,18 +207,26 @@ def main():
             dist.barrier()
 
     for _ in range(args.warmup):
-        a, b = step()
-    nnz = a.nnz
+        ev, evec, info, nnz = step()
     barrier()
     l0 = ctx.launch_count()
+    ctx.profile_enable(True)
     with ClockSampler(local_rank) as clk:
-        ctx.timer_start()
+        ctx.timer_start()  # CUDA events on the library's stream (the stream every kernel runs on)
         for _ in range(args.steps):
-            a, b = step()
-        ms = ctx.timer_stop()
+            ev, evec, info, nnz = step()
+        dev_ms = ctx.timer_stop()
+    prof = ctx.profile_report()
+    ctx.profile_enable(False)
     launches = ctx.launch_count() - l0
     barrier()
-    t_ms = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    # assembly alone (device time), outside the timed region
+    for _ in range(5):
+        dmesh.drop_cache()
+        ctx.timer_start()
+        _lib.assemble(ctx, dmesh, kind, False)
+        asm_ms.append(ctx.timer_stop())
+    t_ms = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
     ms_step = float(t_ms.item()) / args.steps
@@ -200,53 +235,62 @@ def main():
     vpin = torch.from_numpy(np.ascontiguousarray(mesh.v)).pin_memory().numpy()
     tpin = torch.from_numpy(np.ascontiguousarray(mesh.t)).pin_memory().numpy()
     hmesh = type(mesh)(vpin, tpin)
-    e2e_steps = max(2, min(args.steps, 5))
+    e2e_steps = max(1, min(args.steps, 3))
 
     def e2e_step():
         hmesh.__dict__.pop("_lb_device_mesh", None)
-        fem = lapy_b200.Solver(hmesh, ctx=ctx)
-        return fem.stiffness, fem.mass
+        return compute_shapedna(hmesh, k=args.k)
 
     e2e_step()
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        sa, sb = e2e_step()
+        sd = e2e_step()
     barrier()
     e2e_s = torch.tensor([(time.perf_counter() - t0) / e2e_steps], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_s = float(e2e_s.item())
     h2d = vpin.nbytes + tpin.nbytes
-    d2h = 2 * (sa.data.nbytes + sa.indices.nbytes + sa.indptr.nbytes)
+    d2h = sd["Eigenvalues"].nbytes + sd["Eigenvectors"].nbytes
 
     if rank == 0:
         peak, peak_kind = measured_peak()
-        abytes = algorithmic_bytes(mesh, nnz)
-        achieved = abytes / (ms_step * 1e-3) / 1e9
+        sp = prof.get("spmm", {"launches": 0, "ms": 0.0, "work": 0.0})
+        achieved = sp["work"] / (sp["ms"] * 1e-3) / 1e9 if sp["ms"] else 0.0
+        total_prof_ms = sum(v["ms"] for v in prof.values())
+        classes = {
+            k: {"launches": v["launches"], "ms_per_step": v["ms"] / args.steps,
+                "rate": v["work"] / (v["ms"] * 1e-3) / 1e9 if v["ms"] else None,
+                "rate_unit": "GB/s" if k in ("spmm", "col_dots") else "GFLOP/s"}
+            for k, v in prof.items()
+        }  # fmt: skip
+        asm = float(np.median(asm_ms)) if asm_ms else None
         line = {
-            "metric": "fem_assembly_gelem_per_s", "value": world * nt / (ms_step * 1e-3) / 1e9, "unit": "Gelem/s",
-            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": desc, "step": "Solver(mesh): stiffness + full mass assembly to CSC",
-                       "l2": "inputs+outputs per step (629 MB) exceed the 126 MB L2", "parallelism": f"mesh-parallel x{world}"},
+            "metric": METRIC, "value": world / (ms_step * 1e-3), "unit": "meshes/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": desc, "step": "FEM assembly (A, B full) + block-LOBPCG/AMG eigensolve, mesh resident in HBM",
+                       "k": args.k, "sigma": -0.01, "tol": "1e-9 scaled residual", "parallelism": f"mesh-parallel x{world}",
+                       "l2": "working set per step (S/AS/BS blocks 24 GB at level 9) exceeds the 126 MB L2"},
+            "s_per_mesh": ms_step * 1e-3,
+            "assembly": {"ms": asm, "gelem_per_s": nt / (asm * 1e-3) / 1e9 if asm else None,
+                         "roofline_frac": (4 * mesh.t.shape[1] * nt + 24 * nv + 2 * (12 * nnz + 4 * (nv + 1))) / (asm * 1e-3) / 1e9 / peak if asm else None},
+            "eigs": {"iterations": info["iterations"], "amg_levels": info["amg_levels"], "residual": info["residual"],
+                     "amg_setup_ms": info["setup_ms"], "lobpcg_ms": info["solve_ms"]},
             "gpu_launches": int(launches),
-            "e2e": {"value": world * nt / e2e_s / 1e9, "unit": "Gelem/s", "h2d_bytes_per_step": int(h2d),
-                    "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_s * 1e3},
+            "e2e": {"value": world / e2e_s, "unit": "meshes/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "ms_per_step": e2e_s * 1e3},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_kind": peak_kind, "kernel": "assembly pipeline (all kernels of one step)",
-                         "algorithmic_bytes": int(abytes)},
+                         "traffic": None, "peak_kind": peak_kind, "kernel": "spmm_kernel (CSR x block vectors), all launches of the timed region",
+                         "launches": sp["launches"], "ms_per_step": sp["ms"] / args.steps,
+                         "share_of_profiled_device_time": sp["ms"] / total_prof_ms if total_prof_ms else None},
+            "kernel_classes": classes,
             "clocks": clk.summary(),
         }  # fmt: skip
         if not args.no_cpu_baseline:
-            from oracle import fem as ofem
-
-            ofem.fem(mesh)
-            t0 = time.perf_counter()
-            ofem.fem(mesh)
-            dt = time.perf_counter() - t0
-            line["cpu_baseline"] = {"value": nt / dt / 1e9, "unit": "Gelem/s", "cores": 1, "kind": "port",
-                                    "sample": "1 full assembly of the same mesh (NumPy + SciPy COO->CSC, sequential)"}  # fmt: skip
+            val, sec, what = cpu_reference(args, mesh)
+            line["cpu_baseline"] = {"value": val, "unit": "meshes/s", "cores": 1, "kind": "port", "sample": what}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -49,6 +49,8 @@ SIGNATURES = {
     "lb_timer_start": [_vp],
     "lb_timer_stop": [_vp, C.POINTER(_dbl)],
     "lb_launch_count": [_vp, C.POINTER(_i64)],
+    "lb_profile_enable": [_vp, _int],
+    "lb_profile_report": [_vp, _vp, _vp, _vp],
     "lb_mesh_create": [_vp, _vp, _int, _i64, _vp, _int, _i64, _int, _pp],
     "lb_mesh_update_vertices": [_vp, _vp, _int],
     "lb_mesh_drop_cache": [_vp],
@@ -142,6 +144,23 @@ class Context:
         ms = C.c_double()
         check(lib().lb_timer_stop(self.handle, C.byref(ms)))
         return ms.value
+
+    PROFILE_CLASSES = ("spmm", "gram", "update", "trsm", "col_dots", "reserved")
+
+    def profile_enable(self, on: bool = True):
+        check(lib().lb_profile_enable(self.handle, int(on)))
+
+    def profile_report(self) -> dict:
+        """{class: {launches, ms, work}} since profile_enable(True); work = bytes or flops."""
+        cnt = np.zeros(6, np.int64)
+        ms = np.zeros(6, np.float64)
+        work = np.zeros(6, np.float64)
+        check(lib().lb_profile_report(self.handle, ptr(cnt), ptr(ms), ptr(work)))
+        return {
+            name: {"launches": int(cnt[i]), "ms": float(ms[i]), "work": float(work[i])}
+            for i, name in enumerate(self.PROFILE_CLASSES)
+            if cnt[i]
+        }
 
     def launch_count(self) -> int:
         n = C.c_int64()

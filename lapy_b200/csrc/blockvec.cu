@@ -111,6 +111,9 @@ void spmm(lb_ctx *c, const lb_mat *a, const double *x, int ldx, double *y, int l
           int ldb) {
     const int64_t n = a->n;
     if (n == 0 || m == 0) return;
+    const int64_t xrows = a->ncols < 0 ? a->n : a->ncols;
+    // algorithmic bytes: matrix once, X once, Y once (+ B once for the residual modes)
+    ProfScope prof(c, PROF_SPMM, 12.0 * a->nnz + 4.0 * (n + 1) + 8.0 * m * (xrows + n * (mode ? 2 : 1)));
     if (a->diagonal) {
         LB_LAUNCH(c, diag_spmm_kernel, cdiv(n * m, 256), 256, 0, n, a->indptr.p, a->data.p, x, ldx, y, ldy, m, mode, b,
                   ldb);
@@ -170,6 +173,7 @@ __global__ void col_dots_final(int nblocks, int cols, const double *__restrict__
 
 void col_dots(lb_ctx *c, int64_t n, int cols, const double *x, int ldx, const double *y, int ldy, double *out) {
     if (cols == 0) return;
+    ProfScope prof(c, PROF_DOTS, 8.0 * n * cols * (y && y != x ? 2 : 1));
     const int nb = (int)std::min<int64_t>(kDotBlocks, std::max<int64_t>(1, n / 64));
     DBuf<double> partial(c, (size_t)nb * cols);
     LB_LAUNCH(c, col_dots_partial, nb, kDotCW * kDotRY, 0, n, cols, x, ldx, y, ldy, partial.p);

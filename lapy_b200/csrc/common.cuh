@@ -72,6 +72,15 @@ struct lb_ctx {
     void *cublas = nullptr;    // cublasHandle_t, created lazily (bring-up path of the dense block products)
     bool trace = false;        // LAPY_B200_TRACE=1: per-phase wall clock (synchronising!) on stderr
     double trace_t0 = 0;
+    // per-kernel-class device timing (lb_profile_enable): event pairs around the hot launches
+    bool profile = false;
+    struct ProfRec {
+        int cls;
+        cudaEvent_t e0, e1;
+        double work;  // algorithmic bytes (HBM-bound classes) or flops (dense classes)
+    };
+    std::vector<ProfRec> prof;
+    std::vector<cudaEvent_t> prof_pool;
 };
 
 namespace lb {
@@ -168,6 +177,15 @@ inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
     } while (0)
 
 void destroy_dense_handles(lb_ctx *ctx);  // dense.cu
+
+// kernel classes of the profile report
+enum ProfClass { PROF_SPMM = 0, PROF_GRAM, PROF_UPDATE, PROF_TRSM, PROF_DOTS, PROF_ELEMENTWISE, PROF_NCLASS };
+struct ProfScope {
+    lb_ctx *c;
+    int idx = -1;
+    ProfScope(lb_ctx *ctx, int cls, double work);
+    ~ProfScope();
+};
 
 // exclusive prefix sum of int32 counts: out[0..n] (n+1 entries, out[n] = total)
 void exclusive_scan_i32(lb_ctx *ctx, const int32_t *in, int32_t *out, int64_t n);

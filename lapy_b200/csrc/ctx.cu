@@ -20,6 +20,30 @@ void set_error(const char *fmt, ...) {
     va_end(ap);
 }
 
+// ---- per-class device timing ------------------------------------------------------------------
+static cudaEvent_t prof_event(lb_ctx *c) {
+    if (!c->prof_pool.empty()) {
+        cudaEvent_t e = c->prof_pool.back();
+        c->prof_pool.pop_back();
+        return e;
+    }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+}
+
+ProfScope::ProfScope(lb_ctx *ctx, int cls, double work) : c(ctx) {
+    if (!c->profile) return;
+    lb_ctx::ProfRec r{cls, prof_event(c), prof_event(c), work};
+    cudaEventRecord(r.e0, c->stream);
+    idx = (int)c->prof.size();
+    c->prof.push_back(r);
+}
+
+ProfScope::~ProfScope() {
+    if (idx >= 0) cudaEventRecord(c->prof[idx].e1, c->stream);
+}
+
 // ---- exclusive scan (int32) ---------------------------------------------------------------
 // Three small kernels (tile reduce -> scan of tile sums -> tile scan + offset).  Inputs are at
 // most a few tens of MB (per-vertex / per-row counts), so this is launch-latency, not
@@ -188,6 +212,11 @@ int lb_ctx_destroy(lb_ctx *c) {
     DeviceGuard g(c->device);
     cudaStreamSynchronize(c->stream);
     lb::destroy_dense_handles(c);
+    for (auto &r : c->prof) {
+        cudaEventDestroy(r.e0);
+        cudaEventDestroy(r.e1);
+    }
+    for (auto e : c->prof_pool) cudaEventDestroy(e);
     cudaEventDestroy(c->ev0);
     cudaEventDestroy(c->ev1);
     cudaFreeHost(c->pinned);
@@ -221,6 +250,37 @@ int lb_timer_stop(lb_ctx *c, double *ms) {
     float f = 0;
     LB_CUDA(cudaEventElapsedTime(&f, c->ev0, c->ev1));
     *ms = f;
+    LB_API_END
+}
+
+int lb_profile_enable(lb_ctx *c, int on) {
+    LB_API_BEGIN
+    LB_REQUIRE(c, "ctx is NULL");
+    DeviceGuard g(c->device);
+    sync(c);
+    for (auto &r : c->prof) {
+        c->prof_pool.push_back(r.e0);
+        c->prof_pool.push_back(r.e1);
+    }
+    c->prof.clear();
+    c->profile = on != 0;
+    LB_API_END
+}
+
+// per class: launches, total device ms, total work (bytes or flops); arrays of PROF_NCLASS = 6
+int lb_profile_report(lb_ctx *c, int64_t *count, double *ms, double *work) {
+    LB_API_BEGIN
+    LB_REQUIRE(c && count && ms && work, "NULL argument");
+    DeviceGuard g(c->device);
+    sync(c);
+    for (int k = 0; k < PROF_NCLASS; k++) count[k] = 0, ms[k] = 0, work[k] = 0;
+    for (auto &r : c->prof) {
+        float t = 0;
+        cudaEventElapsedTime(&t, r.e0, r.e1);
+        count[r.cls]++;
+        ms[r.cls] += t;
+        work[r.cls] += r.work;
+    }
     LB_API_END
 }
 

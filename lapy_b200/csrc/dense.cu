@@ -59,6 +59,7 @@ void destroy_dense_handles(lb_ctx *c) {
 // Row-major (n,p) with leading dimension ld is column-major (p,n) with the same ld.
 void gram(lb_ctx *c, int64_t n, int p, const double *x, int ldx, int q, const double *y, int ldy, double *cmat) {
     if (p == 0 || q == 0) return;
+    ProfScope prof(c, PROF_GRAM, 2.0 * n * p * q);
     const double one = 1.0, zero = 0.0;
     // C_rm(p,q) = X^T Y  <=>  C_cm(q,p) = Y_cm(q,n) * X_cm(p,n)^T
     LB_CUBLAS(cublasDgemm(blas(c), CUBLAS_OP_N, CUBLAS_OP_T, q, p, (int)n, &one, y, ldy, x, ldx, &zero, cmat, q));
@@ -68,6 +69,7 @@ void gram(lb_ctx *c, int64_t n, int p, const double *x, int ldx, int q, const do
 void update(lb_ctx *c, int64_t n, int p, const double *x, int ldx, int q, const double *cmat, int ldc, double alpha,
             double beta, double *y, int ldy) {
     if (q == 0 || n == 0) return;
+    ProfScope prof(c, PROF_UPDATE, 2.0 * n * p * q);
     // Y_cm(q,n) = alpha * C_cm(q,p) * X_cm(p,n) + beta * Y_cm
     LB_CUBLAS(cublasDgemm(blas(c), CUBLAS_OP_N, CUBLAS_OP_N, q, (int)n, p, &alpha, cmat, ldc, x, ldx, &beta, y, ldy));
     c->launches++;
@@ -75,6 +77,7 @@ void update(lb_ctx *c, int64_t n, int p, const double *x, int ldx, int q, const 
 
 void trsm_right_lt(lb_ctx *c, int64_t n, int q, const double *l, double *w, int ldw) {
     if (q == 0 || n == 0) return;
+    ProfScope prof(c, PROF_TRSM, 1.0 * n * q * q);
     const double one = 1.0;
     // W_rm <- W_rm L^-T  <=>  W_cm <- L^-1 W_cm; row-major lower L is column-major upper U = L^T
     LB_CUBLAS(cublasDtrsm(blas(c), CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_UPPER, CUBLAS_OP_T, CUBLAS_DIAG_NON_UNIT, q,

@@ -109,6 +109,25 @@ static int host_orth(int s, int m, const std::vector<double> &C, int q, std::vec
     return kept;
 }
 
+struct PhaseTimer {
+    lb_ctx *c;
+    double t0 = 0;
+    double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    explicit PhaseTimer(lb_ctx *ctx) : c(ctx) {}
+    void start() {
+        if (!c->trace) return;
+        cudaStreamSynchronize(c->stream);
+        t0 = wall_ms();
+    }
+    void stop(int slot) {
+        if (!c->trace) return;
+        cudaStreamSynchronize(c->stream);
+        const double t = wall_ms();
+        acc[slot] += t - t0;
+        t0 = t;
+    }
+};
+
 struct EigStats {
     int iterations = 0, converged = 0, levels = 0, block = 0;
     double residual = 0, setup_ms = 0, solve_ms = 0;
@@ -197,8 +216,12 @@ static EigStats lobpcg(lb_ctx *c, const lb_mat *A, const lb_mat *B, int k, doubl
 
     double worst = 0.0;
     int nconv_k = 0;
+    PhaseTimer pt(c);
+    int vcycles = 1;
+    if (const char *e = getenv("LAPY_B200_VCYCLES")) vcycles = std::max(1, atoi(e));
     for (int it = 0; it < maxit; it++) {
         st.iterations = it;
+        pt.start();
         // ---- residual norms of all m columns
         std::iota(idx.begin(), idx.end(), 0);
         h2d(c, idx_d.p, idx.data(), m * sizeof(int));
@@ -227,6 +250,7 @@ static EigStats lobpcg(lb_ctx *c, const lb_mat *A, const lb_mat *B, int k, doubl
         if (c->trace)
             fprintf(stderr, "[lb trace] lobpcg it %3d: max res(first k) %.3e, converged %d/%d, active %d, P %d\n", it,
                     worst, nconv_k, k, ma, mp);
+        pt.stop(0);
         if (nconv_k == k || !std::isfinite(worst)) break;
         if (it == maxit - 1) break;
         // ---- W = precond(R_active), orthogonalised against [X P], B-orthonormalised
@@ -236,16 +260,31 @@ static EigStats lobpcg(lb_ctx *c, const lb_mat *A, const lb_mat *B, int k, doubl
         const int w0 = m + mp;
         double *W = S[cur].p + w0, *AW = AS[cur].p + w0, *BW = BS[cur].p + w0;
         amg_apply(*amg, Rbuf.p, ma, W, ld, ma);
+        for (int vc = 1; vc < vcycles; vc++) {
+            // second cycle on the residual of the first: W += V(R - K W)
+            spmm(c, amg->levels[0].K.get(), W, ld, tmp.p, ma, ma, 1, Rbuf.p, ma);
+            amg_apply(*amg, tmp.p, ma, Rbuf.p, ma, ma);  // Rbuf is free to overwrite only after use below
+            axpby_cols(c, n, ma, nullptr, 1.0, Rbuf.p, ma, nullptr, 1.0, W, ld);
+            residual_cols(c, n, ma, idx_d.p, lam_d.p, AS[cur].p, ld, BS[cur].p, ld, Rbuf.p, ma);
+        }
+        pt.stop(1);
         for (int rep = 0; rep < 2; rep++) {
             gram(c, n, w0, BS[cur].p, ld, ma, W, ld, G.p);                        // (w0 x ma)
             update(c, n, w0, S[cur].p, ld, ma, G.p, ma, -1.0, 1.0, W, ld);        // W -= [X P] G
         }
+        pt.stop(2);
         const int mw = b_orthonormalize(c, B, n, ma, W, ld, BW, ld, tmp.p);
         if (mw == 0) break;  // nothing left to add: stagnation
+        pt.stop(3);
         spmm(c, A, W, ld, AW, ld, mw);
+        pt.stop(4);
         // ---- Rayleigh-Ritz on [X P W]
         rayleigh_ritz(w0 + mw, mp, active_cols, mp);
+        pt.stop(5);
     }
+    if (c->trace)
+        fprintf(stderr, "[lb trace] lobpcg phases (ms): residual %.1f | precond %.1f | ortho-vs-XP %.1f | B-orthonormalize %.1f | A*W %.1f | Rayleigh-Ritz+update %.1f\n",
+                pt.acc[0], pt.acc[1], pt.acc[2], pt.acc[3], pt.acc[4], pt.acc[5]);
     st.iterations += 1;
     st.converged = nconv_k;
     st.residual = worst;
@@ -327,6 +366,7 @@ extern "C" int lb_eigs(lb_ctx *c, lb_mat *a, lb_mat *b, int k, double sigma, dou
     }
     DeviceGuard g(c->device);
     if (tol <= 0) tol = 1e-9;
+    if (const char *e = getenv("LAPY_B200_TOL")) tol = atof(e);
     if (maxit <= 0) maxit = 200;
     EigStats st;
     const int m = ((k + std::max(6, (k + 3) / 4) + 7) / 8) * 8;

@@ -167,6 +167,9 @@ static SolveStats block_pcg(lb_ctx *c, lb_mat *K, const double *rhs, double *x, 
         for (int it = 0; it < maxit; it++) {
             st.iterations = it + 1;
             spmm(c, K, p.p, m, q.p, m, m);
+            // singular case: iterate with P K P (P = I - 11^T/n) so that residuals stay in range(K)
+            // even when K 1 != 0 by rounding (fp32-assembled operators, lambda_0 ~ -1e-6)
+            if (project) remove_col_means(c, n, m, q.p, m);
             col_dots(c, n, m, p.p, m, q.p, m, pq.p);
             LB_LAUNCH(c, pcg_alpha, cdiv(m, 64), 64, 0, m, rz.p, pq.p, active.p, alpha.p, nalpha.p);
             axpby_cols(c, n, m, alpha.p, 0.0, p.p, m, nullptr, 1.0, x, m);

