@@ -109,6 +109,14 @@ int lb_mat_free(lb_mat *m);
 /* y (n,m) row-major = M x (n,m) row-major; replaces csc_matvec(s) (lapy/solver.py:844-846) */
 int lb_spmm(lb_ctx *ctx, lb_mat *mat, const double *x, int64_t m, double *y);
 
+/* dense tall-skinny block products on the fp64 tensor cores (hand-written DMMA kernels), the
+ * contractions LAPACK performs inside ARPACK for the reference (lapy/solver.py:713); row-major:
+ * C(p,q) = X(n,p)^T Y(n,q)   and   Y(n,q) = alpha X(n,p) C(p,q) + beta Y */
+int lb_block_gram(lb_ctx *ctx, int64_t n, int64_t p, const double *x, int64_t q, const double *y,
+                  double *cmat);
+int lb_block_update(lb_ctx *ctx, int64_t n, int64_t p, const double *x, int64_t q,
+                    const double *cmat, double alpha, double beta, double *y);
+
 /* ---- solvers ------------------------------------------------------------------------------ */
 /* Solver.eigs (lapy/solver.py:667-716): k eigenpairs of A x = lambda B x nearest sigma (<= 0),
  * ascending, B-orthonormal.  evals (k), evecs (n,k) row-major.  tol <= 0 / maxit <= 0 pick

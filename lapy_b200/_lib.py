@@ -61,6 +61,8 @@ SIGNATURES = {
     "lb_mat_upload": [_vp, _i64, _i64, _vp, _vp, _vp, _pp],
     "lb_mat_free": [_vp],
     "lb_spmm": [_vp, _vp, _vp, _i64, _vp],
+    "lb_block_gram": [_vp, _i64, _i64, _vp, _i64, _vp, _vp],
+    "lb_block_update": [_vp, _i64, _i64, _vp, _i64, _vp, _dbl, _dbl, _vp],
     "lb_eigs": [_vp, _vp, _vp, _int, _dbl, _dbl, _int, _vp, _vp, C.POINTER(Info)],
     "lb_solve": [_vp, _vp, _dbl, _vp, _dbl, _vp, _i64, _vp, _i64, _vp, _dbl, _int, _int, _vp, C.POINTER(Info)],
     "lb_gradient": [_vp, _vp, _vp, _i64, _vp],
@@ -348,3 +350,22 @@ def divergence(ctx: Context, mesh: DeviceMesh, x: np.ndarray) -> np.ndarray:
     d = np.empty((mesh.nv, x.shape[1]), np.float64)
     check(lib().lb_divergence(ctx.handle, mesh.handle, ptr(x), x.shape[1], ptr(d)))
     return d
+
+
+def block_gram(ctx: Context, x: np.ndarray, y: np.ndarray) -> np.ndarray:
+    """x^T y for tall-skinny row-major blocks (lb_block_gram)."""
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    y = np.ascontiguousarray(y, dtype=np.float64)
+    out = np.empty((x.shape[1], y.shape[1]), np.float64)
+    check(lib().lb_block_gram(ctx.handle, x.shape[0], x.shape[1], ptr(x), y.shape[1], ptr(y), ptr(out)))
+    return out
+
+
+def block_update(ctx: Context, x: np.ndarray, cmat: np.ndarray, alpha=1.0, beta=0.0, y=None) -> np.ndarray:
+    """alpha * x @ cmat + beta * y (lb_block_update)."""
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    cmat = np.ascontiguousarray(cmat, dtype=np.float64)
+    out = np.zeros((x.shape[0], cmat.shape[1])) if y is None else np.array(y, dtype=np.float64, order="C")
+    check(lib().lb_block_update(ctx.handle, x.shape[0], x.shape[1], ptr(x), cmat.shape[1], ptr(cmat),
+                                float(alpha), float(beta), ptr(out)))  # fmt: skip
+    return out

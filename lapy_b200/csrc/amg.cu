@@ -82,6 +82,59 @@ std::unique_ptr<lb_mat> mat_axpby(lb_ctx *c, const lb_mat *a, double alpha, cons
     return out;
 }
 
+// ---- symmetric permutation P A P^T (locality renumbering; column order inside rows is kept) -----
+__global__ void perm_row_len(int64_t n, const int32_t *__restrict__ ptr, const int32_t *__restrict__ order,
+                             int32_t *__restrict__ len) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < n) {
+        const int o = order[r];
+        len[r] = ptr[o + 1] - ptr[o];
+    }
+}
+
+__global__ void perm_copy_rows(int64_t n, const int32_t *__restrict__ ptr, const int32_t *__restrict__ idx,
+                               const double *__restrict__ val, const int32_t *__restrict__ order,
+                               const int32_t *__restrict__ inv, const int32_t *__restrict__ nptr,
+                               int32_t *__restrict__ nidx, double *__restrict__ nval) {
+    // 8 lanes per row
+    const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+    const int lane = threadIdx.x & 7;
+    if (r >= n) return;
+    const int o = order[r];
+    const int src = ptr[o], len = ptr[o + 1] - src, dst = nptr[r];
+    for (int q = lane; q < len; q += 8) {
+        nidx[dst + q] = inv[idx[src + q]];
+        nval[dst + q] = val[src + q];
+    }
+}
+
+std::unique_ptr<lb_mat> permute_symmetric(lb_ctx *c, const lb_mat *a, const int32_t *order, const int32_t *inv) {
+    const int64_t n = a->n;
+    auto out = make_mat(c, n, -1, a->nnz);
+    out->diagonal = a->diagonal;
+    DBuf<int32_t> len(c, n);
+    LB_LAUNCH(c, perm_row_len, cdiv(n, 256), 256, 0, n, a->indptr.p, order, len.p);
+    exclusive_scan_i32(c, len.p, out->indptr.p, n);
+    LB_LAUNCH(c, perm_copy_rows, cdiv(n * 8, 256), 256, 0, n, a->indptr.p, a->indices.p, a->data.p, order, inv,
+              out->indptr.p, out->indices.p, out->data.p);
+    return out;
+}
+
+__global__ void gather_rows_kernel(int64_t n, int cols, const int32_t *__restrict__ map, const double *__restrict__ x,
+                                   int ldx, double *__restrict__ y, int ldy) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * cols) return;
+    const int64_t row = t / cols;
+    const int col = (int)(t - row * cols);
+    y[row * ldy + col] = x[(int64_t)map[row] * ldx + col];
+}
+
+// y[i, :] = x[map[i], :]
+void gather_rows(lb_ctx *c, int64_t n, int cols, const int32_t *map, const double *x, int ldx, double *y, int ldy) {
+    if (n * cols == 0) return;
+    LB_LAUNCH(c, gather_rows_kernel, cdiv(n * cols, 256), 256, 0, n, cols, map, x, ldx, y, ldy);
+}
+
 // ---- sorted accumulate into a thread-private slice of global memory ----------------------------
 __device__ __forceinline__ void acc_insert(int32_t *keys, double *vals, int &cnt, int key, double v) {
     int pos = cnt;
@@ -425,6 +478,7 @@ std::unique_ptr<Amg> amg_setup(lb_ctx *c, std::unique_ptr<lb_mat> K0, int mcap, 
     auto amg = std::make_unique<Amg>();
     amg->ctx = c;
     amg->cheb_deg = opt.cheb_deg;
+    amg->gamma = opt.gamma;
     amg->mcap = mcap;
     cudaEvent_t e0, e1;
     LB_CUDA(cudaEventCreate(&e0));
@@ -561,7 +615,10 @@ static void smooth(Amg &amg, int l, double *x, int ldx, const double *b, int ldb
     }
 }
 
-static void vcycle(Amg &amg, int l, const double *b, int ldb, double *x, int ldx, int m) {
+// one multigrid cycle on level l: x <- x + cycle(b - K x) (x = 0 on entry when zero_guess).
+// amg.gamma = 1: V-cycle; 2: W-cycle (the coarse problem is visited twice - cheap, levels shrink
+// ~10x - which keeps the convergence factor level-independent for MIS-2 aggregates)
+static void cycle(Amg &amg, int l, const double *b, int ldb, double *x, int ldx, int m, bool zero_guess) {
     lb_ctx *c = amg.ctx;
     AmgLevel &L = amg.levels[l];
     if (l == (int)amg.levels.size() - 1) {
@@ -570,17 +627,19 @@ static void vcycle(Amg &amg, int l, const double *b, int ldb, double *x, int ldx
         return;
     }
     AmgLevel &C = amg.levels[l + 1];
-    smooth(amg, l, x, ldx, b, ldb, m, true);
+    smooth(amg, l, x, ldx, b, ldb, m, zero_guess);
     spmm(c, L.K.get(), x, ldx, L.r.p, m, m, 1, b, ldb);       // r = b - K x
     spmm(c, L.R.get(), L.r.p, m, C.b.p, m, m, 0);             // b_c = R r
-    vcycle(amg, l + 1, C.b.p, m, C.x.p, m, m);
+    const bool coarsest_next = l + 1 == (int)amg.levels.size() - 1;
+    const int visits = coarsest_next ? 1 : amg.gamma;
+    for (int g = 0; g < visits; g++) cycle(amg, l + 1, C.b.p, m, C.x.p, m, m, g == 0);
     spmm(c, L.P.get(), C.x.p, m, x, ldx, m, 2, x, ldx);       // x += P x_c
     smooth(amg, l, x, ldx, b, ldb, m, false);
 }
 
 void amg_apply(Amg &amg, const double *r, int ldr, double *z, int ldz, int m) {
     LB_REQUIRE(m <= amg.mcap, "AMG applied to %d columns but sized for %d", m, amg.mcap);
-    vcycle(amg, 0, r, ldr, z, ldz, m);
+    cycle(amg, 0, r, ldr, z, ldz, m, true);
 }
 
 }  // namespace lb

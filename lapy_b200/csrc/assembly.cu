@@ -549,6 +549,105 @@ void ensure_incidence(lb_mesh *mesh) {
     build_incidence(mesh, deg);
 }
 
+// ---- locality ordering ----------------------------------------------------------------------------
+// Vertices are binned into a 128^3 grid over the bounding box; bins are ordered along the Morton
+// curve, vertices inside a bin by index.  Counting sort (histogram, scan, fill, per-bin sort), the
+// same pattern as the incidence build; deterministic.
+__global__ void bbox_kernel(const D4 *__restrict__ v4, int64_t n, double *__restrict__ out /* 6 x gridDim */) {
+    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        D4 p = ldg_d4(v4 + i);
+        lo[0] = fmin(lo[0], p.x); hi[0] = fmax(hi[0], p.x);
+        lo[1] = fmin(lo[1], p.y); hi[1] = fmax(hi[1], p.y);
+        lo[2] = fmin(lo[2], p.z); hi[2] = fmax(hi[2], p.z);
+    }
+    __shared__ double red[6][256];
+    for (int k = 0; k < 3; k++) {
+        red[k][threadIdx.x] = lo[k];
+        red[3 + k][threadIdx.x] = hi[k];
+    }
+    __syncthreads();
+    for (int s = 128; s; s >>= 1) {
+        if (threadIdx.x < s)
+            for (int k = 0; k < 3; k++) {
+                red[k][threadIdx.x] = fmin(red[k][threadIdx.x], red[k][threadIdx.x + s]);
+                red[3 + k][threadIdx.x] = fmax(red[3 + k][threadIdx.x], red[3 + k][threadIdx.x + s]);
+            }
+        __syncthreads();
+    }
+    if (threadIdx.x < 6) out[threadIdx.x * gridDim.x + blockIdx.x] = red[threadIdx.x][0];
+}
+
+__device__ __forceinline__ unsigned spread3(unsigned x) {  // 7 bits -> every third bit
+    x &= 0x7f;
+    x = (x | (x << 8)) & 0x0000700f;
+    x = (x | (x << 4)) & 0x000430c3;
+    x = (x | (x << 2)) & 0x00049249;
+    return x;
+}
+
+__global__ void morton_cell_kernel(const D4 *__restrict__ v4, int64_t n, double ox, double oy, double oz, double sx,
+                                   double sy, double sz, int32_t *__restrict__ cell, int32_t *__restrict__ hist) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    D4 p = ldg_d4(v4 + i);
+    const unsigned ix = min(127, max(0, (int)((p.x - ox) * sx)));
+    const unsigned iy = min(127, max(0, (int)((p.y - oy) * sy)));
+    const unsigned iz = min(127, max(0, (int)((p.z - oz) * sz)));
+    const int cid = (int)(spread3(ix) | (spread3(iy) << 1) | (spread3(iz) << 2));
+    cell[i] = cid;
+    atomicAdd(hist + cid, 1);
+}
+
+__global__ void order_fill_kernel(int64_t n, const int32_t *__restrict__ cell, const int32_t *__restrict__ cptr,
+                                  int32_t *__restrict__ cursor, int32_t *__restrict__ order) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int cid = cell[i];
+    order[cptr[cid] + atomicAdd(cursor + cid, 1)] = (int)i;
+}
+
+__global__ void invert_order_kernel(int64_t n, const int32_t *__restrict__ order, int32_t *__restrict__ inv) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) inv[order[i]] = (int)i;
+}
+
+void ensure_order(lb_mesh *mesh) {
+    if (mesh->order) return;
+    lb_ctx *c = mesh->ctx;
+    const int64_t n = mesh->n_ref;
+    constexpr int kCells = 128 * 128 * 128;
+    const int nb = 256;
+    DBuf<double> box(c, 6 * nb);
+    LB_LAUNCH(c, bbox_kernel, nb, 256, 0, mesh->v4.p, n, box.p);
+    std::vector<double> h(6 * nb);
+    read_back(c, h.data(), box.p, h.size());
+    double lo[3], hi[3];
+    for (int k = 0; k < 3; k++) {
+        lo[k] = 1e300;
+        hi[k] = -1e300;
+        for (int b = 0; b < nb; b++) {
+            lo[k] = std::min(lo[k], h[k * nb + b]);
+            hi[k] = std::max(hi[k], h[(3 + k) * nb + b]);
+        }
+    }
+    double sc[3];
+    for (int k = 0; k < 3; k++) sc[k] = hi[k] > lo[k] ? 127.999 / (hi[k] - lo[k]) : 0.0;
+    DBuf<int32_t> cell(c, n), hist(c, kCells), cptr(c, kCells + 1);
+    hist.zero();
+    LB_LAUNCH(c, morton_cell_kernel, cdiv(n, 256), 256, 0, mesh->v4.p, n, lo[0], lo[1], lo[2], sc[0], sc[1], sc[2],
+              cell.p, hist.p);
+    exclusive_scan_i32(c, hist.p, cptr.p, kCells);
+    hist.zero();
+    auto order = std::make_shared<DBuf<int32_t>>(c, (size_t)n);
+    auto inv = std::make_shared<DBuf<int32_t>>(c, (size_t)n);
+    LB_LAUNCH(c, order_fill_kernel, cdiv(n, 256), 256, 0, n, cell.p, cptr.p, hist.p, order->p);
+    LB_LAUNCH(c, incidence_sort, cdiv(kCells, 128), 128, 0, cptr.p, order->p, (int64_t)kCells);
+    LB_LAUNCH(c, invert_order_kernel, cdiv(n, 256), 256, 0, n, order->p, inv->p);
+    mesh->order = order;
+    mesh->order_inv = inv;
+}
+
 template <class T>
 static void run_element_pass(lb_mesh *mesh, int kind, const double *u1, const double *u2, const double *am,
                              D4 *rec, int32_t *deg, ElemConsts *consts) {
@@ -757,6 +856,8 @@ int lb_mesh_drop_cache(lb_mesh *m) {
     m->inc_ptr.release();
     m->inc.release();
     m->has_inc = false;
+    m->order.reset();
+    m->order_inv.reset();
     LB_API_END
 }
 
@@ -808,6 +909,15 @@ int lb_fem_assemble(lb_ctx *c, lb_mesh *mesh, int kind, int lump, const double *
     const bool degen_f32 = mesh->v_dtype == LB_F32 && kind != LB_FEM_TRIA_ANISO;
     if (mesh->k == 3) run_rows<3>(mesh, rec.p, consts.p, want_a, lump != 0, degen_f32, a_out, b_out);
     else run_rows<4>(mesh, rec.p, consts.p, want_a, lump != 0, degen_f32, a_out, b_out);
+    if (mesh->nv >= 20000) {  // locality hint for the solvers (internal renumbering)
+        ensure_order(mesh);
+        if (a_out && *a_out) {
+            (*a_out)->order = mesh->order;
+            (*a_out)->order_inv = mesh->order_inv;
+        }
+        (*b_out)->order = mesh->order;
+        (*b_out)->order_inv = mesh->order_inv;
+    }
     sync(c);  // u1/u2/aniso_mat are borrowed host buffers
     phase(c, "rows");
     LB_API_END

@@ -34,12 +34,21 @@ void extract_diagonal(lb_ctx *c, const lb_mat *a, double *d);  // d[i] = A[i,i] 
 
 // ---- dense tall-skinny products (row-major blocks) -----------------------------------------
 // C(p,q) row-major = X(n,p)^T Y(n,q)
-void gram(lb_ctx *c, int64_t n, int p, const double *x, int ldx, int q, const double *y, int ldy, double *cmat);
+// symmetric: the caller guarantees X^T Y is symmetric and p == q (S^T (A S), W^T (B W)): only the
+// upper 64x64 tiles are computed and mirrored
+void gram(lb_ctx *c, int64_t n, int p, const double *x, int ldx, int q, const double *y, int ldy, double *cmat,
+          bool symmetric = false);
 // Y(n,q) = alpha * X(n,p) C(p,q) + beta * Y;  X must not alias Y
 void update(lb_ctx *c, int64_t n, int p, const double *x, int ldx, int q, const double *cmat, int ldc, double alpha,
             double beta, double *y, int ldy);
 // W(n,q) <- W L^-T  with L (q,q) row-major lower Cholesky factor (in place)
 void trsm_right_lt(lb_ctx *c, int64_t n, int q, const double *l, double *w, int ldw);
+
+// hand-written DMMA kernels (dmma.cu); gram()/update() dispatch to them unless LAPY_B200_DENSE=cublas
+void gram_dmma(lb_ctx *c, int64_t n, int p, const double *x, int ldx, int q, const double *y, int ldy, double *cmat,
+               bool symmetric);
+void update_dmma(lb_ctx *c, int64_t n, int p, const double *x, int ldx, int q, const double *cmat, int ldc,
+                 double alpha, double beta, double *y, int ldy);
 
 // ---- small dense (device, cuSOLVER) ------------------------------------------------------------
 // in-place lower Cholesky of the row-major (q,q) SPD matrix g; returns LAPACK info (0 = ok)

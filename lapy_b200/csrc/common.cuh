@@ -8,6 +8,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -207,6 +208,9 @@ struct lb_mesh {
     lb::DBuf<int32_t> inc;      // (k*nt)
     int64_t n_ref = 0;          // max referenced vertex + 1 (matrix dimension)
     bool has_inc = false;
+    // locality ordering of the vertices (Morton order of a 128^3 cell grid): new -> old and
+    // old -> new; handed to the matrices assembled from this mesh (solver-internal renumbering)
+    std::shared_ptr<lb::DBuf<int32_t>> order, order_inv;
 };
 
 struct lb_mat {
@@ -217,4 +221,7 @@ struct lb_mat {
     lb::DBuf<int32_t> indices;  // (nnz) sorted, unique per row
     lb::DBuf<double> data;      // (nnz)
     bool diagonal = false;      // every stored entry is on the diagonal (lumped mass / identity)
+    // optional locality ordering hint (from the mesh the matrix was assembled on): new -> old,
+    // old -> new.  Solvers may renumber internally; results are always in the caller's order.
+    std::shared_ptr<lb::DBuf<int32_t>> order, order_inv;
 };

@@ -230,6 +230,34 @@ int lb_spmm(lb_ctx *c, lb_mat *mat, const double *x, int64_t m, double *y) {
     LB_API_END
 }
 
+int lb_block_gram(lb_ctx *c, int64_t n, int64_t p, const double *x, int64_t q, const double *y, double *cmat) {
+    LB_API_BEGIN
+    LB_REQUIRE(c && x && y && cmat && n > 0 && p > 0 && q > 0 && p <= 4096 && q <= 4096, "lb_block_gram: bad argument");
+    DeviceGuard g(c->device);
+    DBuf<double> dx(c, (size_t)n * p), dy(c, (size_t)n * q), dc(c, (size_t)p * q);
+    h2d(c, dx.p, x, (size_t)n * p * sizeof(double));
+    h2d(c, dy.p, y, (size_t)n * q * sizeof(double));
+    gram(c, n, (int)p, dx.p, (int)p, (int)q, dy.p, (int)q, dc.p, false);
+    d2h(c, cmat, dc.p, (size_t)p * q * sizeof(double));
+    sync(c);
+    LB_API_END
+}
+
+int lb_block_update(lb_ctx *c, int64_t n, int64_t p, const double *x, int64_t q, const double *cmat, double alpha,
+                    double beta, double *y) {
+    LB_API_BEGIN
+    LB_REQUIRE(c && x && y && cmat && n > 0 && p > 0 && q > 0 && p <= 384 && q <= 4096, "lb_block_update: bad argument");
+    DeviceGuard g(c->device);
+    DBuf<double> dx(c, (size_t)n * p), dy(c, (size_t)n * q), dc(c, (size_t)p * q);
+    h2d(c, dx.p, x, (size_t)n * p * sizeof(double));
+    h2d(c, dy.p, y, (size_t)n * q * sizeof(double));
+    h2d(c, dc.p, cmat, (size_t)p * q * sizeof(double));
+    update(c, n, (int)p, dx.p, (int)p, (int)q, dc.p, (int)q, alpha, beta, dy.p, (int)q);
+    d2h(c, y, dy.p, (size_t)n * q * sizeof(double));
+    sync(c);
+    LB_API_END
+}
+
 int lb_solve(lb_ctx *c, lb_mat *a, double alpha, lb_mat *b, double beta, const double *rhs, int64_t m,
              const int64_t *fix_idx, int64_t nfix, const double *fix_val, double tol, int maxit, int project_nullspace,
              double *x, lb_info *info) {

@@ -322,3 +322,23 @@ def test_user_assigned_mass_and_errors(golden):
         fem.poisson(h, dtup=(np.array([0, 0]), np.array([1.0, 1.0])))
     with pytest.raises(ValueError):
         fem.poisson(h, dtup=(np.array([0, 1]),))
+
+
+@pytest.mark.parametrize("n,p,q", [(1000, 8, 8), (4097, 64, 64), (10001, 192, 192), (5003, 83, 21), (20000, 128, 60), (777, 1, 5)])
+def test_dmma_block_products_match_numpy(n, p, q):
+    """Hand-written DMMA Gram / update kernels vs NumPy (fp64, different summation order)."""
+    from lapy_b200 import _lib
+
+    ctx = _lib.default_context()
+    rng = np.random.default_rng(n + p + q)
+    x, y = rng.standard_normal((n, p)), rng.standard_normal((n, q))
+    c = _lib.block_gram(ctx, x, y)
+    ref = x.T @ y
+    assert np.abs(c - ref).max() <= 1e-12 * np.sqrt(n) * 10
+    cm = rng.standard_normal((p, q))
+    y0 = rng.standard_normal((n, q))
+    out = _lib.block_update(ctx, x, cm, alpha=0.75, beta=-1.5, y=y0)
+    ref = 0.75 * x @ cm - 1.5 * y0
+    assert np.abs(out - ref).max() <= 1e-12 * p
+    out = _lib.block_update(ctx, x, cm)
+    assert np.abs(out - x @ cm).max() <= 1e-12 * p
