@@ -226,6 +226,11 @@ def main():
         ctx.timer_start()
         _lib.assemble(ctx, dmesh, kind, False)
         asm_ms.append(ctx.timer_stop())
+    # SpMV / SpMM kernel alone (x, y resident): the north star names SpMV >= 60 % of the HBM roofline
+    a_dev, _b = _lib.assemble(ctx, dmesh, kind, False)
+    spmv_ms = _lib.spmm_benchmark(ctx, a_dev, 1, 50)
+    spmm64_ms = _lib.spmm_benchmark(ctx, a_dev, 64, 20)
+    del _b
     t_ms = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
@@ -276,6 +281,10 @@ def main():
             "s_per_mesh": ms_step * 1e-3,
             "assembly": {"ms": asm, "gelem_per_s": nt / (asm * 1e-3) / 1e9 if asm else None,
                          "roofline_frac": (4 * mesh.t.shape[1] * nt + 24 * nv + 2 * (12 * nnz + 4 * (nv + 1))) / (asm * 1e-3) / 1e9 / peak if asm else None},
+            "spmv": {"ms": spmv_ms, "gb_per_s": (12 * nnz + 4 * (nv + 1) + 16 * nv) / (spmv_ms * 1e-3) / 1e9,
+                     "roofline_frac": (12 * nnz + 4 * (nv + 1) + 16 * nv) / (spmv_ms * 1e-3) / 1e9 / peak,
+                     "spmm64_ms": spmm64_ms, "spmm64_roofline_frac": (12 * nnz + 4 * (nv + 1) + 16 * nv * 64) / (spmm64_ms * 1e-3) / 1e9 / peak,
+                     "note": "caller's vertex order (no renumbering), x/y resident in HBM"},
             "eigs": {"iterations": info["iterations"], "amg_levels": info["amg_levels"], "residual": info["residual"],
                      "amg_setup_ms": info["setup_ms"], "lobpcg_ms": info["solve_ms"]},
             "gpu_launches": int(launches),

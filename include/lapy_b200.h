@@ -109,6 +109,9 @@ int lb_mat_free(lb_mat *m);
 /* y (n,m) row-major = M x (n,m) row-major; replaces csc_matvec(s) (lapy/solver.py:844-846) */
 int lb_spmm(lb_ctx *ctx, lb_mat *mat, const double *x, int64_t m, double *y);
 
+/* device-resident timing of the SpMM kernel (x, y stay in HBM): ms per launch, CUDA events */
+int lb_spmm_benchmark(lb_ctx *ctx, lb_mat *mat, int64_t m, int reps, double *ms_per_launch);
+
 /* dense tall-skinny block products on the fp64 tensor cores (hand-written DMMA kernels), the
  * contractions LAPACK performs inside ARPACK for the reference (lapy/solver.py:713); row-major:
  * C(p,q) = X(n,p)^T Y(n,q)   and   Y(n,q) = alpha X(n,p) C(p,q) + beta Y */

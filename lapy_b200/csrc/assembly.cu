@@ -335,12 +335,22 @@ __global__ void __launch_bounds__(kRowThreads) row_count_kernel(
     int off = base + incl - ub;
     int32_t *keys = (s_total <= cap) ? skeys + off : scratch + ((int64_t)beg * (K - 1) + r);
     int cnt = 0;
-    for (int p = beg; p < end; p++) {
-        int4 ti = __ldg(t4 + (inc[p] >> 2));
-        insert_key(keys, cnt, ti.x);
-        insert_key(keys, cnt, ti.y);
-        insert_key(keys, cnt, ti.z);
-        if (K == 4) insert_key(keys, cnt, ti.w);
+    for (int p0 = beg; p0 < end; p0 += 4) {  // 4 independent gathers in flight per thread
+        int code[4];
+        int4 tb[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) code[u] = p0 + u < end ? __ldg(inc + p0 + u) : -1;
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+            if (code[u] >= 0) tb[u] = __ldg(t4 + (code[u] >> 2));
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            if (code[u] < 0) continue;
+            insert_key(keys, cnt, tb[u].x);
+            insert_key(keys, cnt, tb[u].y);
+            insert_key(keys, cnt, tb[u].z);
+            if (K == 4) insert_key(keys, cnt, tb[u].w);
+        }
     }
     if (r < n) {
         row_nnz[r] = cnt;
@@ -395,12 +405,34 @@ __global__ void __launch_bounds__(kRowThreads) row_fill_kernel(
         int cnt = 0;
         double lump = 0.0;
         const int beg = inc_ptr[r], end = inc_ptr[r + 1];
+        constexpr int UB = K == 3 ? 4 : 1;  // triangles: 4 independent gathers in flight per thread
+        int codeb[UB];
+        int4 tib[UB];
+        D4 qb[UB];
         for (int p = beg; p < end; p++) {
-            const int code = inc[p];
+            const int u = (p - beg) % UB;
+            if (u == 0) {
+#pragma unroll
+                for (int w = 0; w < UB; w++) codeb[w] = p + w < end ? __ldg(inc + p + w) : -1;
+#pragma unroll
+                for (int w = 0; w < UB; w++)
+                    if (codeb[w] >= 0) {
+                        tib[w] = __ldg(t4 + (codeb[w] >> 2));
+                        if (K == 3) qb[w] = ldg_d4(rec + (codeb[w] >> 2));
+                    }
+            }
+            int code = codeb[0];
+            int4 ti = tib[0];
+            D4 q = qb[0];
+#pragma unroll
+            for (int w = 1; w < UB; w++)
+                if (u == w) {
+                    code = codeb[w];
+                    ti = tib[w];
+                    q = qb[w];
+                }
             const int e = code >> 2, c = code & 3;
-            const int4 ti = __ldg(t4 + e);
             if (K == 3) {
-                D4 q = ldg_d4(rec + e);
                 double a12 = q.x, a23 = q.y, a31 = q.z, bii = q.w;
                 if (bii < 0.0) {  // clamped element (solver.py:159): divide by the global mean
                     const double vm = consts->vol_mean;

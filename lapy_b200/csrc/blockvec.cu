@@ -10,48 +10,71 @@ namespace lb {
 // ---- SpMM: a group of G lanes per row, lanes over columns -------------------------------------
 // Each nonzero (j, a) is broadcast to the group; the group streams row j of X as one contiguous
 // segment (8*m bytes), so X traffic is fully coalesced; matrix entries are read once per row.
-template <int G>
+// A CTA owns a contiguous strip of kSpmmStrip rows and its warps walk the strip interleaved, so the
+// X rows shared by neighbouring matrix rows (mesh neighbours after the locality renumbering) are
+// served by the SM's L1 instead of L2: the L2 -> SM traffic drops from ~nnz/row x to ~1-2x |X|.
+constexpr int kSpmmStrip = 128;
+
+template <int G, bool VEC>
 __global__ void __launch_bounds__(256) spmm_kernel(int64_t n, const int32_t *__restrict__ indptr,
                                                    const int32_t *__restrict__ indices,
                                                    const double *__restrict__ val, const double *__restrict__ x,
                                                    int ldx, double *y, int ldy, int m, int mode,
                                                    const double *b, int ldb) {
-    const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
-    const int lane = threadIdx.x % G;
-    if (row >= n) return;
-    const int beg = indptr[row], end = indptr[row + 1];
-    for (int c0 = 0; c0 < m; c0 += 2 * G) {
-        const int ca = c0 + lane, cb = ca + G;
-        const bool ha = ca < m, hb = cb < m;
-        double s0 = 0.0, s1 = 0.0;
-        int p = beg;
-        for (; p + 1 < end; p += 2) {
-            const int j0 = __ldg(indices + p), j1 = __ldg(indices + p + 1);
-            const double a0 = __ldg(val + p), a1 = __ldg(val + p + 1);
-            const double *x0 = x + (int64_t)j0 * ldx, *x1 = x + (int64_t)j1 * ldx;
-            double u0 = ha ? __ldg(x0 + ca) : 0.0, u1 = hb ? __ldg(x0 + cb) : 0.0;
-            double w0 = ha ? __ldg(x1 + ca) : 0.0, w1 = hb ? __ldg(x1 + cb) : 0.0;
-            s0 = fma(a0, u0, s0);
-            s1 = fma(a0, u1, s1);
-            s0 = fma(a1, w0, s0);
-            s1 = fma(a1, w1, s1);
+    constexpr int GROUPS = 256 / G;  // rows in flight per CTA
+    const int grp = threadIdx.x / G, lane = threadIdx.x % G;
+    const int64_t strip0 = (int64_t)blockIdx.x * kSpmmStrip;
+    const int64_t strip1 = min(n, strip0 + kSpmmStrip);
+    for (int64_t row = strip0 + grp; row < strip1; row += GROUPS) {
+        const int beg = __ldg(indptr + row), end = __ldg(indptr + row + 1);
+        for (int c0 = 0; c0 < m; c0 += 2 * G) {
+            // VEC: lane owns columns c0 + 2*lane, +1 (one 16-byte load); else c0 + lane, c0 + lane + G
+            const int ca = VEC ? c0 + 2 * lane : c0 + lane;
+            const int cb = VEC ? ca + 1 : ca + G;
+            const bool ha = ca < m, hb = cb < m;
+            double s0 = 0.0, s1 = 0.0;
+            int p = beg;
+            for (; p + 1 < end; p += 2) {
+                const int j0 = __ldg(indices + p), j1 = __ldg(indices + p + 1);
+                const double a0 = __ldg(val + p), a1 = __ldg(val + p + 1);
+                const double *x0 = x + (int64_t)j0 * ldx, *x1 = x + (int64_t)j1 * ldx;
+                double u0, u1, w0, w1;
+                if (VEC) {
+                    const double2 u = hb ? __ldg(reinterpret_cast<const double2 *>(x0 + ca)) : make_double2(0.0, 0.0);
+                    const double2 w = hb ? __ldg(reinterpret_cast<const double2 *>(x1 + ca)) : make_double2(0.0, 0.0);
+                    u0 = u.x; u1 = u.y; w0 = w.x; w1 = w.y;
+                    if (!hb && ha) {
+                        u0 = __ldg(x0 + ca);
+                        w0 = __ldg(x1 + ca);
+                    }
+                } else {
+                    u0 = ha ? __ldg(x0 + ca) : 0.0;
+                    u1 = hb ? __ldg(x0 + cb) : 0.0;
+                    w0 = ha ? __ldg(x1 + ca) : 0.0;
+                    w1 = hb ? __ldg(x1 + cb) : 0.0;
+                }
+                s0 = fma(a0, u0, s0);
+                s1 = fma(a0, u1, s1);
+                s0 = fma(a1, w0, s0);
+                s1 = fma(a1, w1, s1);
+            }
+            if (p < end) {
+                const int j0 = __ldg(indices + p);
+                const double a0 = __ldg(val + p);
+                const double *x0 = x + (int64_t)j0 * ldx;
+                if (ha) s0 = fma(a0, __ldg(x0 + ca), s0);
+                if (hb) s1 = fma(a0, __ldg(x0 + cb), s1);
+            }
+            if (mode == 1) {
+                if (ha) s0 = b[row * ldb + ca] - s0;
+                if (hb) s1 = b[row * ldb + cb] - s1;
+            } else if (mode == 2) {
+                if (ha) s0 = b[row * ldb + ca] + s0;
+                if (hb) s1 = b[row * ldb + cb] + s1;
+            }
+            if (ha) y[row * ldy + ca] = s0;
+            if (hb) y[row * ldy + cb] = s1;
         }
-        if (p < end) {
-            const int j0 = __ldg(indices + p);
-            const double a0 = __ldg(val + p);
-            const double *x0 = x + (int64_t)j0 * ldx;
-            if (ha) s0 = fma(a0, __ldg(x0 + ca), s0);
-            if (hb) s1 = fma(a0, __ldg(x0 + cb), s1);
-        }
-        if (mode == 1) {
-            if (ha) s0 = b[row * ldb + ca] - s0;
-            if (hb) s1 = b[row * ldb + cb] - s1;
-        } else if (mode == 2) {
-            if (ha) s0 = b[row * ldb + ca] + s0;
-            if (hb) s1 = b[row * ldb + cb] + s1;
-        }
-        if (ha) y[row * ldy + ca] = s0;
-        if (hb) y[row * ldy + cb] = s1;
     }
 }
 
@@ -123,15 +146,21 @@ void spmm(lb_ctx *c, const lb_mat *a, const double *x, int ldx, double *y, int l
     const double *v = a->data.p;
     if (m <= 2) {
         LB_LAUNCH(c, spmv_kernel, cdiv(n * 8, 256), 256, 0, n, ip, ix, v, x, ldx, y, ldy, m, mode, b, ldb);
-    } else if (m <= 8) {
-        LB_LAUNCH(c, spmm_kernel<4>, cdiv(n * 4, 256), 256, 0, n, ip, ix, v, x, ldx, y, ldy, m, mode, b, ldb);
-    } else if (m <= 16) {
-        LB_LAUNCH(c, spmm_kernel<8>, cdiv(n * 8, 256), 256, 0, n, ip, ix, v, x, ldx, y, ldy, m, mode, b, ldb);
-    } else if (m <= 32) {
-        LB_LAUNCH(c, spmm_kernel<16>, cdiv(n * 16, 256), 256, 0, n, ip, ix, v, x, ldx, y, ldy, m, mode, b, ldb);
-    } else {
-        LB_LAUNCH(c, spmm_kernel<32>, cdiv(n * 32, 256), 256, 0, n, ip, ix, v, x, ldx, y, ldy, m, mode, b, ldb);
+        return;
     }
+    // 16-byte vector loads of X need even leading dimension and a 16-byte aligned base
+    const bool vec = (ldx % 2 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+    const int grid = cdiv(n, kSpmmStrip);
+#define LB_SPMM(G)                                                                                       \
+    do {                                                                                                 \
+        if (vec) LB_LAUNCH(c, (spmm_kernel<G, true>), grid, 256, 0, n, ip, ix, v, x, ldx, y, ldy, m, mode, b, ldb); \
+        else LB_LAUNCH(c, (spmm_kernel<G, false>), grid, 256, 0, n, ip, ix, v, x, ldx, y, ldy, m, mode, b, ldb);    \
+    } while (0)
+    if (m <= 8) LB_SPMM(4);
+    else if (m <= 16) LB_SPMM(8);
+    else if (m <= 32) LB_SPMM(16);
+    else LB_SPMM(32);
+#undef LB_SPMM
 }
 
 // ---- column dots ------------------------------------------------------------------------------

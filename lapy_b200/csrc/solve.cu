@@ -230,6 +230,25 @@ int lb_spmm(lb_ctx *c, lb_mat *mat, const double *x, int64_t m, double *y) {
     LB_API_END
 }
 
+// device-resident timing of y = M x (m columns): ms per launch over `reps` launches (CUDA events)
+int lb_spmm_benchmark(lb_ctx *c, lb_mat *mat, int64_t m, int reps, double *ms_per_launch) {
+    LB_API_BEGIN
+    LB_REQUIRE(c && mat && ms_per_launch && m >= 1 && m <= 1024 && reps >= 1, "lb_spmm_benchmark: bad argument");
+    DeviceGuard g(c->device);
+    const int64_t n = mat->n;
+    DBuf<double> dx(c, (size_t)n * m), dy(c, (size_t)n * m);
+    fill_random(c, n, (int)m, dx.p, (int)m, 42);
+    for (int i = 0; i < 3; i++) spmm(c, mat, dx.p, (int)m, dy.p, (int)m, (int)m);
+    LB_CUDA(cudaEventRecord(c->ev0, c->stream));
+    for (int i = 0; i < reps; i++) spmm(c, mat, dx.p, (int)m, dy.p, (int)m, (int)m);
+    LB_CUDA(cudaEventRecord(c->ev1, c->stream));
+    LB_CUDA(cudaEventSynchronize(c->ev1));
+    float ms = 0;
+    LB_CUDA(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    *ms_per_launch = ms / reps;
+    LB_API_END
+}
+
 int lb_block_gram(lb_ctx *c, int64_t n, int64_t p, const double *x, int64_t q, const double *y, double *cmat) {
     LB_API_BEGIN
     LB_REQUIRE(c && x && y && cmat && n > 0 && p > 0 && q > 0 && p <= 4096 && q <= 4096, "lb_block_gram: bad argument");
