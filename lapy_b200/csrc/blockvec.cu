@@ -14,6 +14,7 @@ namespace lb {
 // X rows shared by neighbouring matrix rows (mesh neighbours after the locality renumbering) are
 // served by the SM's L1 instead of L2: the L2 -> SM traffic drops from ~nnz/row x to ~1-2x |X|.
 constexpr int kSpmmStrip = 128;
+constexpr int kSpmmCap = 2048;  // CSR entries of a strip staged in shared memory (24 KB)
 
 template <int G, bool VEC>
 __global__ void __launch_bounds__(256) spmm_kernel(int64_t n, const int32_t *__restrict__ indptr,
@@ -21,12 +22,30 @@ __global__ void __launch_bounds__(256) spmm_kernel(int64_t n, const int32_t *__r
                                                    const double *__restrict__ val, const double *__restrict__ x,
                                                    int ldx, double *y, int ldy, int m, int mode,
                                                    const double *b, int ldb) {
+    // The strip's CSR segment is contiguous: stage it in shared memory with coalesced loads, so
+    // the per-row loop has no dependent global load in front of the X gathers (idx -> address):
+    // all gathers of a row are issued back to back (memory-level parallelism = row length).
+    __shared__ int32_t s_idx[kSpmmCap];
+    __shared__ double s_val[kSpmmCap];
+    __shared__ int32_t s_ptr[kSpmmStrip + 1];
     constexpr int GROUPS = 256 / G;  // rows in flight per CTA
     const int grp = threadIdx.x / G, lane = threadIdx.x % G;
     const int64_t strip0 = (int64_t)blockIdx.x * kSpmmStrip;
-    const int64_t strip1 = min(n, strip0 + kSpmmStrip);
-    for (int64_t row = strip0 + grp; row < strip1; row += GROUPS) {
-        const int beg = __ldg(indptr + row), end = __ldg(indptr + row + 1);
+    const int nrows = (int)(min(n, strip0 + kSpmmStrip) - strip0);
+    for (int i = threadIdx.x; i <= nrows; i += 256) s_ptr[i] = __ldg(indptr + strip0 + i);
+    __syncthreads();
+    const int base = s_ptr[0], total = s_ptr[nrows] - base;
+    const bool staged = total <= kSpmmCap;
+    if (staged) {
+        for (int i = threadIdx.x; i < total; i += 256) {
+            s_idx[i] = __ldg(indices + base + i);
+            s_val[i] = __ldg(val + base + i);
+        }
+    }
+    __syncthreads();
+    for (int lr = grp; lr < nrows; lr += GROUPS) {
+        const int64_t row = strip0 + lr;
+        const int beg = s_ptr[lr] - base, end = s_ptr[lr + 1] - base;
         for (int c0 = 0; c0 < m; c0 += 2 * G) {
             // VEC: lane owns columns c0 + 2*lane, +1 (one 16-byte load); else c0 + lane, c0 + lane + G
             const int ca = VEC ? c0 + 2 * lane : c0 + lane;
@@ -34,36 +53,44 @@ __global__ void __launch_bounds__(256) spmm_kernel(int64_t n, const int32_t *__r
             const bool ha = ca < m, hb = cb < m;
             double s0 = 0.0, s1 = 0.0;
             int p = beg;
-            for (; p + 1 < end; p += 2) {
-                const int j0 = __ldg(indices + p), j1 = __ldg(indices + p + 1);
-                const double a0 = __ldg(val + p), a1 = __ldg(val + p + 1);
-                const double *x0 = x + (int64_t)j0 * ldx, *x1 = x + (int64_t)j1 * ldx;
-                double u0, u1, w0, w1;
-                if (VEC) {
-                    const double2 u = hb ? __ldg(reinterpret_cast<const double2 *>(x0 + ca)) : make_double2(0.0, 0.0);
-                    const double2 w = hb ? __ldg(reinterpret_cast<const double2 *>(x1 + ca)) : make_double2(0.0, 0.0);
-                    u0 = u.x; u1 = u.y; w0 = w.x; w1 = w.y;
-                    if (!hb && ha) {
-                        u0 = __ldg(x0 + ca);
-                        w0 = __ldg(x1 + ca);
-                    }
-                } else {
-                    u0 = ha ? __ldg(x0 + ca) : 0.0;
-                    u1 = hb ? __ldg(x0 + cb) : 0.0;
-                    w0 = ha ? __ldg(x1 + ca) : 0.0;
-                    w1 = hb ? __ldg(x1 + cb) : 0.0;
+            for (; p + 3 < end; p += 4) {
+                int j[4];
+                double a[4], u0[4], u1[4];
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    j[q] = staged ? s_idx[p + q] : __ldg(indices + base + p + q);
+                    a[q] = staged ? s_val[p + q] : __ldg(val + base + p + q);
                 }
-                s0 = fma(a0, u0, s0);
-                s1 = fma(a0, u1, s1);
-                s0 = fma(a1, w0, s0);
-                s1 = fma(a1, w1, s1);
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const double *xr = x + (int64_t)j[q] * ldx;
+                    if (VEC && hb) {
+                        const double2 v = __ldg(reinterpret_cast<const double2 *>(xr + ca));
+                        u0[q] = v.x;
+                        u1[q] = v.y;
+                    } else {
+                        u0[q] = ha ? __ldg(xr + ca) : 0.0;
+                        u1[q] = hb ? __ldg(xr + cb) : 0.0;
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    s0 = fma(a[q], u0[q], s0);
+                    s1 = fma(a[q], u1[q], s1);
+                }
             }
-            if (p < end) {
-                const int j0 = __ldg(indices + p);
-                const double a0 = __ldg(val + p);
-                const double *x0 = x + (int64_t)j0 * ldx;
-                if (ha) s0 = fma(a0, __ldg(x0 + ca), s0);
-                if (hb) s1 = fma(a0, __ldg(x0 + cb), s1);
+            for (; p < end; p++) {
+                const int j0 = staged ? s_idx[p] : __ldg(indices + base + p);
+                const double a0 = staged ? s_val[p] : __ldg(val + base + p);
+                const double *xr = x + (int64_t)j0 * ldx;
+                if (VEC && hb) {
+                    const double2 v = __ldg(reinterpret_cast<const double2 *>(xr + ca));
+                    s0 = fma(a0, v.x, s0);
+                    s1 = fma(a0, v.y, s1);
+                } else {
+                    if (ha) s0 = fma(a0, __ldg(xr + ca), s0);
+                    if (hb) s1 = fma(a0, __ldg(xr + cb), s1);
+                }
             }
             if (mode == 1) {
                 if (ha) s0 = b[row * ldb + ca] - s0;
@@ -115,6 +142,58 @@ __global__ void __launch_bounds__(256) spmv_kernel(int64_t n, const int32_t *__r
     }
 }
 
+// ---- SpMV, CSR-stream form: the CTA stages the products a_ij * x_j of a strip of 128 rows in
+// shared memory (one independent gather per thread and entry: maximal memory-level parallelism,
+// CSR arrays read fully coalesced), then one thread per row sums its segment left to right.
+constexpr int kSpmvRows = 128;  // ~900 (tri) / ~1900 (tet) entries per strip
+constexpr int kSpmvCap = 2944;  // 2 x 23 KB products + row pointers < 48 KB static
+
+__global__ void __launch_bounds__(256) spmv_stream_kernel(int64_t n, const int32_t *__restrict__ indptr,
+                                                          const int32_t *__restrict__ indices,
+                                                          const double *__restrict__ val,
+                                                          const double *__restrict__ x, int ldx, double *y, int ldy,
+                                                          int m, int mode, const double *b, int ldb) {
+    __shared__ double s_prod[2][kSpmvCap];
+    __shared__ int32_t s_ptr[kSpmvRows + 1];
+    const int64_t strip0 = (int64_t)blockIdx.x * kSpmvRows;
+    const int nrows = (int)(min(n, strip0 + kSpmvRows) - strip0);
+    for (int i = threadIdx.x; i <= nrows; i += 256) s_ptr[i] = __ldg(indptr + strip0 + i);
+    __syncthreads();
+    const int base = s_ptr[0], total = s_ptr[nrows] - base;
+    if (total <= kSpmvCap) {
+        for (int i = threadIdx.x; i < total; i += 256) {
+            const int j = __ldg(indices + base + i);
+            const double a = __ldg(val + base + i);
+            s_prod[0][i] = a * __ldg(x + (int64_t)j * ldx);
+            if (m > 1) s_prod[1][i] = a * __ldg(x + (int64_t)j * ldx + 1);
+        }
+        __syncthreads();
+        if (threadIdx.x < nrows) {
+            const int64_t row = strip0 + threadIdx.x;
+            const int beg = s_ptr[threadIdx.x] - base, end = s_ptr[threadIdx.x + 1] - base;
+            for (int col = 0; col < m; col++) {
+                double s = 0.0;
+                for (int p = beg; p < end; p++) s += s_prod[col][p];
+                if (mode == 1) s = b[row * ldb + col] - s;
+                else if (mode == 2) s = b[row * ldb + col] + s;
+                y[row * ldy + col] = s;
+            }
+        }
+    } else {  // very long rows: one thread per row straight from global memory
+        if (threadIdx.x < nrows) {
+            const int64_t row = strip0 + threadIdx.x;
+            for (int col = 0; col < m; col++) {
+                double s = 0.0;
+                for (int p = s_ptr[threadIdx.x]; p < s_ptr[threadIdx.x + 1]; p++)
+                    s += __ldg(val + p) * __ldg(x + (int64_t)__ldg(indices + p) * ldx + col);
+                if (mode == 1) s = b[row * ldb + col] - s;
+                else if (mode == 2) s = b[row * ldb + col] + s;
+                y[row * ldy + col] = s;
+            }
+        }
+    }
+}
+
 // diagonal matrix (lumped mass, identity): entries only on the diagonal, possibly missing rows
 __global__ void diag_spmm_kernel(int64_t n, const int32_t *__restrict__ indptr, const double *__restrict__ val,
                                  const double *__restrict__ x, int ldx, double *y, int ldy, int m,
@@ -145,7 +224,7 @@ void spmm(lb_ctx *c, const lb_mat *a, const double *x, int ldx, double *y, int l
     const int32_t *ip = a->indptr.p, *ix = a->indices.p;
     const double *v = a->data.p;
     if (m <= 2) {
-        LB_LAUNCH(c, spmv_kernel, cdiv(n * 8, 256), 256, 0, n, ip, ix, v, x, ldx, y, ldy, m, mode, b, ldb);
+        LB_LAUNCH(c, spmv_stream_kernel, cdiv(n, kSpmvRows), 256, 0, n, ip, ix, v, x, ldx, y, ldy, m, mode, b, ldb);
         return;
     }
     // 16-byte vector loads of X need even leading dimension and a 16-byte aligned base
