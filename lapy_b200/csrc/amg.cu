@@ -637,9 +637,9 @@ static void cycle(Amg &amg, int l, const double *b, int ldb, double *x, int ldx,
     smooth(amg, l, x, ldx, b, ldb, m, false);
 }
 
-void amg_apply(Amg &amg, const double *r, int ldr, double *z, int ldz, int m) {
+void amg_apply(Amg &amg, const double *r, int ldr, double *z, int ldz, int m, int level) {
     LB_REQUIRE(m <= amg.mcap, "AMG applied to %d columns but sized for %d", m, amg.mcap);
-    cycle(amg, 0, r, ldr, z, ldz, m, true);
+    cycle(amg, level, r, ldr, z, ldz, m, true);
 }
 
 }  // namespace lb

@@ -42,8 +42,8 @@ struct AmgOptions {
 
 // K is consumed (moved into level 0).  mcap: max number of simultaneous right-hand sides.
 std::unique_ptr<Amg> amg_setup(lb_ctx *c, std::unique_ptr<lb_mat> K, int mcap, const AmgOptions &opt);
-// z (n,m) = V-cycle(r (n,m)); r is not modified
-void amg_apply(Amg &amg, const double *r, int ldr, double *z, int ldz, int m);
+// z (n_level, m) = cycle(r) starting at `level` (0 = finest); r is not modified
+void amg_apply(Amg &amg, const double *r, int ldr, double *z, int ldz, int m, int level = 0);
 
 // C = alpha*A + beta*B for matrices with identical pattern or diagonal B (new matrix)
 std::unique_ptr<lb_mat> mat_axpby(lb_ctx *c, const lb_mat *a, double alpha, const lb_mat *b, double beta);

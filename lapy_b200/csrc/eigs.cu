@@ -161,35 +161,15 @@ struct EigStats {
     double residual = 0, setup_ms = 0, solve_ms = 0;
 };
 
-static EigStats lobpcg(lb_ctx *c, const lb_mat *A0, const lb_mat *B0, int k, double sigma, double tol, int maxit,
-                       double *h_evals, double *h_evecs) {
-    const int64_t n = A0->n;
+// One level of the (nested) iteration: LOBPCG on (A, B) with the multigrid cycle started at
+// `lvl` as preconditioner.  x0 (n, m): optional initial block; x_out (n, m, ld = m): result block.
+static EigStats lobpcg_core(lb_ctx *c, const lb_mat *A, const lb_mat *B, Amg *amg, int lvl, const double *x0, int ldx0,
+                            int k, int m, double tol, int maxit, std::vector<double> &lam, double *x_out) {
+    const int64_t n = A->n;
     EigStats st;
-    // solver-internal locality renumbering (Morton order of the mesh the matrices came from):
-    // neighbouring rows of X become neighbouring in memory, so the SpMM gathers hit L2 instead of
-    // DRAM (ncu: 4.0x -> ~1x of the algorithmic traffic).  Results are returned in the caller's order.
-    std::unique_ptr<lb_mat> Ap, Bp;
-    const lb_mat *A = A0, *B = B0;
-    const bool reorder = A0->order && A0->order == B0->order && (int64_t)A0->order->n == n && !getenv("LAPY_B200_NOREORDER");
-    if (reorder) {
-        Ap = permute_symmetric(c, A0, A0->order->p, A0->order_inv->p);
-        Bp = permute_symmetric(c, B0, A0->order->p, A0->order_inv->p);
-        A = Ap.get();
-        B = Bp.get();
-    }
-    int m = ((k + std::max(6, (k + 3) / 4) + 7) / 8) * 8;
-    if (const char *e = getenv("LAPY_B200_BLOCK")) m = std::max(k + 1, atoi(e));
     const int ld = 3 * m;
     st.block = m;
-
-    // preconditioner on K = A - sigma*B (SPD for sigma < 0)
-    const double shift = sigma < 0 ? -sigma : 1e-2;
-    AmgOptions opt;
-    if (const char *e = getenv("LAPY_B200_CHEB")) opt.cheb_deg = std::max(1, atoi(e));
-    if (const char *e = getenv("LAPY_B200_GAMMA")) opt.gamma = std::max(1, atoi(e));
-    auto amg = amg_setup(c, mat_axpby(c, A, 1.0, B, shift), m, opt);
     st.levels = (int)amg->levels.size();
-    st.setup_ms = amg->setup_ms;
 
     cudaEvent_t e0, e1;
     LB_CUDA(cudaEventCreate(&e0));
@@ -203,13 +183,18 @@ static EigStats lobpcg(lb_ctx *c, const lb_mat *A0, const lb_mat *B0, int k, dou
     DBuf<double> Rbuf(c, (size_t)n * m), tmp(c, (size_t)n * m);
     DBuf<double> G(c, (size_t)ld * ld), evd(c, ld), lam_d(c, m), coef(c, (size_t)ld * 2 * m), dots(c, 2 * m);
     DBuf<int> idx_d(c, m);
-    std::vector<double> lam(m), hG, hC, hQ, coefh, rr(2 * m);
+    std::vector<double> hG, hC, hQ, coefh, rr(2 * m);
+    lam.assign(m, 0.0);
     std::vector<int> act(m), idx(m);
     int cur = 0;
 
     // ---- initial block: constants + pseudo-random, B-orthonormalised, one Rayleigh-Ritz
-    fill_random(c, n, m, S[0].p, ld, 0x1234567ull);
-    LB_LAUNCH(c, set_column, cdiv(n, 256), 256, 0, n, S[0].p, ld, 0, 1.0);
+    if (x0) {
+        copy_cols(c, n, m, x0, ldx0, S[0].p, ld);  // prolonged coarse-level eigenvectors
+    } else {
+        fill_random(c, n, m, S[0].p, ld, 0x1234567ull);
+        LB_LAUNCH(c, set_column, cdiv(n, 256), 256, 0, n, S[0].p, ld, 0, 1.0);
+    }
     int kept = b_orthonormalize(c, B, n, m, S[0].p, ld, BS[0].p, ld, tmp.p);
     LB_REQUIRE(kept == m, "initial block is rank deficient");
     spmm(c, A, S[0].p, ld, AS[0].p, ld, m);
@@ -302,11 +287,11 @@ static EigStats lobpcg(lb_ctx *c, const lb_mat *A0, const lb_mat *B0, int k, dou
         residual_cols(c, n, ma, idx_d.p, lam_d.p, AS[cur].p, ld, BS[cur].p, ld, Rbuf.p, ma);
         const int w0 = m + mp;
         double *W = S[cur].p + w0, *AW = AS[cur].p + w0, *BW = BS[cur].p + w0;
-        amg_apply(*amg, Rbuf.p, ma, W, ld, ma);
+        amg_apply(*amg, Rbuf.p, ma, W, ld, ma, lvl);
         for (int vc = 1; vc < vcycles; vc++) {
             // second cycle on the residual of the first: W += V(R - K W)
-            spmm(c, amg->levels[0].K.get(), W, ld, tmp.p, ma, ma, 1, Rbuf.p, ma);
-            amg_apply(*amg, tmp.p, ma, Rbuf.p, ma, ma);  // Rbuf is free to overwrite only after use below
+            spmm(c, amg->levels[lvl].K.get(), W, ld, tmp.p, ma, ma, 1, Rbuf.p, ma);
+            amg_apply(*amg, tmp.p, ma, Rbuf.p, ma, ma, lvl);  // Rbuf is free to overwrite only after use below
             axpby_cols(c, n, ma, nullptr, 1.0, Rbuf.p, ma, nullptr, 1.0, W, ld);
             residual_cols(c, n, ma, idx_d.p, lam_d.p, AS[cur].p, ld, BS[cur].p, ld, Rbuf.p, ma);
         }
@@ -340,17 +325,84 @@ static EigStats lobpcg(lb_ctx *c, const lb_mat *A0, const lb_mat *B0, int k, dou
     cudaEventDestroy(e1);
     st.solve_ms = ms;
 
+    copy_cols(c, n, m, S[cur].p, ld, x_out, m);
+    return st;
+}
+
+// Driver: locality renumbering, AMG setup, nested iteration (coarse-level eigenvectors prolonged
+// as the initial block of the next finer level - the eigen-analogue of full multigrid), output.
+static EigStats lobpcg(lb_ctx *c, const lb_mat *A0, const lb_mat *B0, int k, double sigma, double tol, int maxit,
+                       double *h_evals, double *h_evecs) {
+    const int64_t n = A0->n;
+    // solver-internal locality renumbering (Morton order of the mesh the matrices came from):
+    // neighbouring rows of X become neighbouring in memory, so the SpMM gathers hit L1/L2 instead
+    // of DRAM (ncu: 4.0x -> 1.1x of the algorithmic traffic).  Results return in the caller's order.
+    std::unique_ptr<lb_mat> Ap, Bp;
+    const lb_mat *A = A0, *B = B0;
+    const bool reorder = A0->order && A0->order == B0->order && (int64_t)A0->order->n == n && !getenv("LAPY_B200_NOREORDER");
+    if (reorder) {
+        Ap = permute_symmetric(c, A0, A0->order->p, A0->order_inv->p);
+        Bp = permute_symmetric(c, B0, A0->order->p, A0->order_inv->p);
+        A = Ap.get();
+        B = Bp.get();
+    }
+    int m = ((k + std::max(6, (k + 3) / 4) + 7) / 8) * 8;
+    if (const char *e = getenv("LAPY_B200_BLOCK")) m = std::max(k + 1, atoi(e));
+
+    // preconditioner on K = A - sigma*B (SPD for sigma < 0)
+    const double shift = sigma < 0 ? -sigma : 1e-2;
+    AmgOptions opt;
+    if (const char *e = getenv("LAPY_B200_CHEB")) opt.cheb_deg = std::max(1, atoi(e));
+    if (const char *e = getenv("LAPY_B200_GAMMA")) opt.gamma = std::max(1, atoi(e));
+    auto amg = amg_setup(c, mat_axpby(c, A, 1.0, B, shift), m, opt);
+
+    // ---- nested iteration: coarse pencils (K_l, B_l), B_{l+1} = R_l B_l P_l (Galerkin, like K_l).
+    // K_l = A_l + shift*B_l has the eigenvectors of (A_l, B_l); only the vectors are carried up.
+    const int nlev = (int)amg->levels.size();
+    int depth = 0;  // number of coarse levels that get their own eigensolve
+    if (!getenv("LAPY_B200_NONESTED"))
+        while (depth + 1 < nlev - 1 && amg->levels[depth + 1].K->n >= std::max<int64_t>(8 * m, 4000)) depth++;
+    std::vector<std::unique_ptr<lb_mat>> Bl(depth + 1);
+    for (int l = 0; l < depth; l++) {
+        const lb_mat *bl = l == 0 ? B : Bl[l].get();
+        auto BP = spgemm(c, bl, amg->levels[l].P.get());
+        Bl[l + 1] = spgemm(c, amg->levels[l].R.get(), BP.get());
+        Bl[l + 1]->ncols = -1;
+    }
+    EigStats st, stc;
+    std::vector<double> lam;
+    DBuf<double> xc, xf;  // coarse result, prolonged initial block
+    double coarse_ms = 0;
+    for (int l = depth; l >= 1; l--) {
+        const lb_mat *Kl = amg->levels[l].K.get();
+        DBuf<double> xo(c, (size_t)Kl->n * m);
+        stc = lobpcg_core(c, Kl, Bl[l].get(), amg.get(), l, xf.p, m, k, m, std::max(tol, 1e-5), 80, lam, xo.p);
+        coarse_ms += stc.solve_ms;
+        if (c->trace)
+            fprintf(stderr, "[lb trace] nested level %d (n=%lld): %d iterations, residual %.2e, %.1f ms\n", l,
+                    (long long)Kl->n, stc.iterations, stc.residual, stc.solve_ms);
+        // prolong: X_{l-1} = P_{l-1} X_l
+        const lb_mat *P = amg->levels[l - 1].P.get();
+        xf.alloc(c, (size_t)P->n * m);
+        spmm(c, P, xo.p, m, xf.p, m, m);
+    }
+    DBuf<double> xout(c, (size_t)n * m);
+    st = lobpcg_core(c, A, B, amg.get(), 0, depth ? xf.p : nullptr, m, k, m, tol, maxit, lam, xout.p);
+    st.setup_ms = amg->setup_ms;
+    st.solve_ms += coarse_ms;
+
     for (int j = 0; j < k; j++) h_evals[j] = lam[j];
     if (reorder) {
         // row i of the caller's numbering = row inv[i] of the renumbered block
-        double *out = S[cur ^ 1].p;
-        gather_rows(c, n, k, A0->order_inv->p, S[cur].p, ld, out, k);
-        d2h(c, h_evecs, out, (size_t)n * k * sizeof(double));
+        DBuf<double> out(c, (size_t)n * k);
+        gather_rows(c, n, k, A0->order_inv->p, xout.p, m, out.p, k);
+        d2h(c, h_evecs, out.p, (size_t)n * k * sizeof(double));
+        sync(c);
     } else {
-        LB_CUDA(cudaMemcpy2DAsync(h_evecs, (size_t)k * 8, S[cur].p, (size_t)ld * 8, (size_t)k * 8, n,
+        LB_CUDA(cudaMemcpy2DAsync(h_evecs, (size_t)k * 8, xout.p, (size_t)m * 8, (size_t)k * 8, n,
                                   cudaMemcpyDeviceToHost, c->stream));
+        sync(c);
     }
-    sync(c);
     return st;
 }
 
