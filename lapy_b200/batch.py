@@ -1,0 +1,85 @@
+"""Mesh-parallel batches (BASELINE.json config 5: BrainPrint-style ShapeDNA over many surfaces).
+
+The path shards by mesh: every unit (one surface) is independent, so rank r of a
+``torch.distributed`` job (one process per GPU, torchrun) processes meshes ``r, r+W, r+2W, ...`` on
+its own device and context; there is no data-path collective - only the k eigenvalues per mesh
+are gathered at the end.  The reference has no equivalent (single process).
+"""
+
+from __future__ import annotations
+
+import os
+from typing import Callable, Sequence
+
+import numpy as np
+
+
+def shard_indices(n_items: int, rank: int, world: int) -> list[int]:
+    """Round-robin assignment mesh i -> rank i mod world."""
+    if not (0 <= rank < world):
+        raise ValueError("rank must be in [0, world)")
+    return list(range(rank, n_items, world))
+
+
+def _dist():
+    import torch.distributed as dist
+
+    return dist if dist.is_available() and dist.is_initialized() else None
+
+
+def batched_shapedna(
+    meshes: Sequence | Callable[[int], object],
+    n_meshes: int | None = None,
+    k: int = 50,
+    lump: bool = False,
+    compute: Callable | None = None,
+    gather: bool = True,
+):
+    """ShapeDNA eigenvalues of a batch of meshes, sharded over the ranks of the current process
+    group (or run serially without one).
+
+    ``meshes``: a sequence of geometries or a factory ``i -> geometry`` (with ``n_meshes``), so
+    that a rank only materialises its own shard.  ``compute(mesh, k, lump) -> (k,) eigenvalues``
+    defaults to :func:`lapy_b200.shapedna.compute_shapedna` on this rank's GPU.
+    Returns an ``(n_meshes, k)`` array on every rank (``gather=True``) or ``{index: (k,)}`` of
+    the local shard.
+    """
+    dist = _dist()
+    rank = dist.get_rank() if dist else 0
+    world = dist.get_world_size() if dist else 1
+    if callable(meshes):
+        if n_meshes is None:
+            raise ValueError("n_meshes is required with a mesh factory")
+        get = meshes
+    else:
+        n_meshes = len(meshes)
+        get = meshes.__getitem__
+    if compute is None:
+        from .shapedna import compute_shapedna
+
+        def compute(mesh, k, lump):
+            return compute_shapedna(mesh, k=k, lump=lump)["Eigenvalues"]
+
+    local = {}
+    for i in shard_indices(n_meshes, rank, world):
+        ev = np.asarray(compute(get(i), k, lump), dtype=np.float64)
+        if ev.shape != (k,):
+            raise ValueError(f"compute returned shape {ev.shape}, expected ({k},)")
+        local[i] = ev
+    if not gather:
+        return local
+    out = np.zeros((n_meshes, k), np.float64)
+    if dist is None:
+        for i, ev in local.items():
+            out[i] = ev
+        return out
+    import torch
+
+    dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+    if dev == "cuda":
+        dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    buf = torch.zeros((n_meshes, k), dtype=torch.float64, device=dev)
+    for i, ev in local.items():
+        buf[i] = torch.from_numpy(ev).to(dev)
+    dist.all_reduce(buf, op=dist.ReduceOp.SUM)  # disjoint rows: a sum is a gather
+    return buf.cpu().numpy()
