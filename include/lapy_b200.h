@@ -145,6 +145,9 @@ int lb_gradient(lb_ctx *ctx, lb_mesh *mesh, const double *f, int64_t nf, double 
 /* x (nt,nf,3) -> d (nv,nf): tria_compute_divergence lapy/diffgeo.py:303-387,
  * tet_compute_divergence :925-1006 */
 int lb_divergence(lb_ctx *ctx, lb_mesh *mesh, const double *x, int64_t nf, double *d);
+/* mean length of the unique edges of the mesh `pattern` (a stiffness matrix) was assembled on:
+ * TriaMesh.avg_edge_length lapy/tria_mesh.py:735-748, TetMesh lapy/tet_mesh.py:182-195 (fp64) */
+int lb_avg_edge_length(lb_ctx *ctx, lb_mesh *mesh, lb_mat *pattern, double *out);
 #ifdef __cplusplus
 }
 #endif

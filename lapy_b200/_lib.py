@@ -66,6 +66,7 @@ SIGNATURES = {
     "lb_block_update": [_vp, _i64, _i64, _vp, _i64, _vp, _dbl, _dbl, _vp],
     "lb_eigs": [_vp, _vp, _vp, _int, _dbl, _dbl, _int, _vp, _vp, C.POINTER(Info)],
     "lb_solve": [_vp, _vp, _dbl, _vp, _dbl, _vp, _i64, _vp, _i64, _vp, _dbl, _int, _int, _vp, C.POINTER(Info)],
+    "lb_avg_edge_length": [_vp, _vp, _vp, C.POINTER(_dbl)],
     "lb_gradient": [_vp, _vp, _vp, _i64, _vp],
     "lb_divergence": [_vp, _vp, _vp, _i64, _vp],
 }
@@ -377,3 +378,10 @@ def spmm_benchmark(ctx: Context, mat: DeviceMatrix, m: int = 1, reps: int = 20) 
     ms = C.c_double()
     check(lib().lb_spmm_benchmark(ctx.handle, mat.handle, int(m), int(reps), C.byref(ms)))
     return ms.value
+
+
+def avg_edge_length(ctx: Context, mesh: DeviceMesh, pattern: DeviceMatrix) -> float:
+    """Mean unique-edge length on the device (fp64 meshes; lb_avg_edge_length)."""
+    out = C.c_double()
+    check(lib().lb_avg_edge_length(ctx.handle, mesh.handle, pattern.handle, C.byref(out)))
+    return out.value

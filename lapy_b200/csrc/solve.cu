@@ -93,6 +93,62 @@ __global__ void pcg_beta(int m, double *__restrict__ rz, const double *__restric
     rz[j] = rz_new[j];
 }
 
+// ---- componentwise-accurate Jacobi for strongly diagonally dominant M-matrices (heat) ----------
+// x_new_i = (b_i - sum_{j != i} K_ij x_j) / K_ii.  For K = B_lumped + t A with non-positive
+// off-diagonals every term is non-negative: no cancellation, the iterates increase monotonically
+// from 0 and converge with COMPONENTWISE relative accuracy - which the heat method needs
+// (compute_geodesic_f normalises grad u, and u spans hundreds of orders of magnitude; a Krylov
+// method only controls the global energy norm and leaves the far field as noise).  A sparse LU
+// (the reference, lapy/heat.py:226) has the same componentwise accuracy.
+constexpr int kJacRows = 128;
+constexpr int kJacCap = 2944;
+
+__global__ void __launch_bounds__(256) jacobi_stream_kernel(int64_t n, const int32_t *__restrict__ indptr,
+                                                            const int32_t *__restrict__ indices,
+                                                            const double *__restrict__ val,
+                                                            const double *__restrict__ x, const double *__restrict__ b,
+                                                            double *__restrict__ y, int ld, int m,
+                                                            unsigned long long *__restrict__ max_rel) {
+    __shared__ double s_prod[2][kJacCap];
+    __shared__ int32_t s_ptr[kJacRows + 1];
+    const int64_t strip0 = (int64_t)blockIdx.x * kJacRows;
+    const int nrows = (int)(min(n, strip0 + kJacRows) - strip0);
+    for (int i = threadIdx.x; i <= nrows; i += 256) s_ptr[i] = __ldg(indptr + strip0 + i);
+    __syncthreads();
+    const int base = s_ptr[0], total = s_ptr[nrows] - base;
+    const bool staged = total <= kJacCap;
+    if (staged) {
+        for (int i = threadIdx.x; i < total; i += 256) {
+            const int j = __ldg(indices + base + i);
+            const double a = __ldg(val + base + i);
+            s_prod[0][i] = a * __ldg(x + (int64_t)j * ld);
+            if (m > 1) s_prod[1][i] = a * __ldg(x + (int64_t)j * ld + 1);
+        }
+    }
+    __syncthreads();
+    double rel = 0.0;
+    if (threadIdx.x < nrows) {
+        const int64_t row = strip0 + threadIdx.x;
+        const int beg = s_ptr[threadIdx.x], end = s_ptr[threadIdx.x + 1];
+        for (int col = 0; col < m; col++) {
+            double off = 0.0, diag = 0.0;
+            for (int p = beg; p < end; p++) {
+                const int j = __ldg(indices + p);
+                const double a = __ldg(val + p);
+                if (j == row) diag = a;
+                else off += staged ? s_prod[col][p - base] : a * __ldg(x + (int64_t)j * ld + col);
+            }
+            const double xo = x[row * ld + col];
+            const double xn = diag > 0.0 ? (b[row * ld + col] - off) / diag : 0.0;
+            y[row * ld + col] = xn;
+            if (xn != 0.0) rel = fmax(rel, fabs(xn - xo) / fabs(xn));
+        }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) rel = fmax(rel, __shfl_xor_sync(0xffffffffu, rel, o));
+    if ((threadIdx.x & 31) == 0 && rel > 0.0) atomicMax(max_rel, (unsigned long long)__double_as_longlong(rel));
+}
+
 struct SolveStats {
     int iterations = 0, converged = 0, levels = 0;
     double residual = 0, setup_ms = 0, solve_ms = 0;
@@ -115,6 +171,70 @@ static SolveStats block_pcg(lb_ctx *c, lb_mat *K, const double *rhs, double *x, 
     bool use_amg = !(off_ratio < 0.95);  // kappa(D^-1 K) <= (1+r)/(1-r) < 39
     if (force_prec == 1) use_amg = false;
     if (force_prec == 2) use_amg = true;
+    if (!use_amg && force_prec == 0 && !project && off_ratio < 0.9) {
+        // componentwise Jacobi (see jacobi_stream_kernel), two columns at a time; checks the max
+        // relative increment every 64 sweeps; falls through to PCG if it does not contract
+        // (input that is not an M-matrix)
+        cudaEvent_t j0, j1;
+        LB_CUDA(cudaEventCreate(&j0));
+        LB_CUDA(cudaEventCreate(&j1));
+        LB_CUDA(cudaEventRecord(j0, c->stream));
+        DBuf<double> xa(c, (size_t)n * m), xb(c, (size_t)n * m);
+        DBuf<unsigned long long> mr(c, 1);
+        const int grid = cdiv(n, kJacRows);
+        const double jtol = std::max(tol, 1e-13) * (1.0 - off_ratio);
+        bool ok = true;
+        int sweeps_max = 0;
+        double rel_max = 0.0;
+        for (int c0 = 0; c0 < m && ok; c0 += 2) {
+            const int mc = std::min(2, m - c0);
+            xa.zero();
+            double *cur = xa.p + c0, *nxt = xb.p + c0;
+            const double *bb = rhs + c0;
+            double rel = 1.0, prev = 2.0;
+            int sweeps = 0, stalls = 0;
+            ok = false;
+            while (sweeps < 400000) {
+                for (int i = 0; i < 63; i++) {
+                    LB_LAUNCH(c, jacobi_stream_kernel, grid, 256, 0, n, K->indptr.p, K->indices.p, K->data.p, cur, bb,
+                              nxt, m, mc, mr.p);
+                    std::swap(cur, nxt);
+                }
+                mr.zero();
+                LB_LAUNCH(c, jacobi_stream_kernel, grid, 256, 0, n, K->indptr.p, K->indices.p, K->data.p, cur, bb, nxt, m,
+                          mc, mr.p);
+                std::swap(cur, nxt);
+                sweeps += 64;
+                unsigned long long bits2 = 0;
+                read_back(c, &bits2, mr.p, 1);
+                std::memcpy(&rel, &bits2, 8);
+                if (rel <= jtol) {
+                    ok = true;
+                    break;
+                }
+                // rel stays 1 while the front still reaches new vertices; afterwards it must contract
+                if (rel < 1.0 && rel >= prev && ++stalls > 8) break;
+                prev = rel;
+            }
+            if (ok) copy_cols(c, n, mc, cur, m, x + c0, m);
+            sweeps_max = std::max(sweeps_max, sweeps);
+            rel_max = std::max(rel_max, rel);
+        }
+        LB_CUDA(cudaEventRecord(j1, c->stream));
+        LB_CUDA(cudaEventSynchronize(j1));
+        float jms = 0;
+        cudaEventElapsedTime(&jms, j0, j1);
+        cudaEventDestroy(j0);
+        cudaEventDestroy(j1);
+        if (ok) {
+            st.iterations = sweeps_max;
+            st.converged = m;
+            st.residual = rel_max;
+            st.solve_ms = jms;
+            st.levels = -1;  // marks the componentwise Jacobi path
+            return st;
+        }
+    }
     std::unique_ptr<Amg> amg;
     DBuf<double> dinv;
     if (use_amg) {
@@ -210,6 +330,62 @@ static SolveStats block_pcg(lb_ctx *c, lb_mat *K, const double *rhs, double *x, 
     return st;
 }
 
+// mean length of the unique edges = strict upper triangle of the stiffness pattern
+// (TriaMesh.avg_edge_length lapy/tria_mesh.py:735-748: triu(adj_sym, 1)); edge vectors and lengths
+// in fp64, fixed-tree reduction
+__global__ void edge_length_partial(int64_t n, const int32_t *__restrict__ ptr, const int32_t *__restrict__ idx,
+                                    const D4 *__restrict__ v4, double *__restrict__ psum,
+                                    unsigned long long *__restrict__ pcnt) {
+    double s = 0.0;
+    unsigned long long cnt = 0;
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x) {
+        const D4 a = ldg_d4(v4 + r);
+        for (int p = ptr[r]; p < ptr[r + 1]; p++) {
+            const int j = idx[p];
+            if (j <= r) continue;
+            const D4 q = ldg_d4(v4 + j);
+            const double dx = a.x - q.x, dy = a.y - q.y, dz = a.z - q.z;
+            s += sqrt((dx * dx + dy * dy) + dz * dz);
+            cnt++;
+        }
+    }
+    __shared__ double ss[256];
+    __shared__ unsigned long long sc[256];
+    ss[threadIdx.x] = s;
+    sc[threadIdx.x] = cnt;
+    __syncthreads();
+    for (int o = 128; o; o >>= 1) {
+        if (threadIdx.x < o) {
+            ss[threadIdx.x] += ss[threadIdx.x + o];
+            sc[threadIdx.x] += sc[threadIdx.x + o];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        psum[blockIdx.x] = ss[0];
+        pcnt[blockIdx.x] = sc[0];
+    }
+}
+
+static double avg_edge_length_device(lb_ctx *c, lb_mesh *mesh, lb_mat *pattern) {
+    const int nb = 1024;
+    DBuf<double> psum(c, nb);
+    DBuf<unsigned long long> pcnt(c, nb);
+    LB_LAUNCH(c, edge_length_partial, nb, 256, 0, pattern->n, pattern->indptr.p, pattern->indices.p, mesh->v4.p, psum.p,
+              pcnt.p);
+    std::vector<double> hs(nb);
+    std::vector<unsigned long long> hc(nb);
+    read_back(c, hs.data(), psum.p, nb);
+    read_back(c, hc.data(), pcnt.p, nb);
+    double s = 0;
+    unsigned long long cnt = 0;
+    for (int i = 0; i < nb; i++) {
+        s += hs[i];
+        cnt += hc[i];
+    }
+    return cnt ? s / (double)cnt : 0.0;
+}
+
 }  // namespace lb
 
 using namespace lb;
@@ -246,6 +422,15 @@ int lb_spmm_benchmark(lb_ctx *c, lb_mat *mat, int64_t m, int reps, double *ms_pe
     float ms = 0;
     LB_CUDA(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
     *ms_per_launch = ms / reps;
+    LB_API_END
+}
+
+int lb_avg_edge_length(lb_ctx *c, lb_mesh *mesh, lb_mat *pattern, double *out) {
+    LB_API_BEGIN
+    LB_REQUIRE(c && mesh && pattern && out, "lb_avg_edge_length: NULL argument");
+    LB_REQUIRE(pattern->n <= mesh->nv, "matrix does not belong to this mesh");
+    DeviceGuard g(c->device);
+    *out = avg_edge_length_device(c, mesh, pattern);
     LB_API_END
 }
 

@@ -168,8 +168,15 @@ def test_heat_geodesic_grad_div_vs_golden(golden, name):
     mesh = golden_mesh(g)
     seeds = g["heat_seeds"]
     u = heat.diffusion(mesh, seeds, m=1.0)
-    assert u.shape == g["heat_u"].shape
-    assert np.abs(u - g["heat_u"]).max() <= 1e-8 * np.abs(g["heat_u"]).max()
+    ref_u = g["heat_u"]
+    assert u.shape == ref_u.shape
+    assert np.abs(u - ref_u).max() <= 1e-8 * np.abs(ref_u).max()
+    # the heat method needs COMPONENTWISE relative accuracy (u spans 30-150 orders of magnitude and
+    # compute_geodesic_f normalises its gradient): the sparse LU of the reference has it, so must we
+    nz = np.abs(ref_u) > 1e-280
+    assert np.all(np.abs(u - ref_u)[nz] <= 1e-7 * np.abs(ref_u)[nz]), (np.abs(u - ref_u)[nz] / np.abs(ref_u)[nz]).max()
+    geo_own = diffgeo.compute_geodesic_f(mesh, u)  # geodesics from OUR heat solution
+    assert np.abs(geo_own - g["geodesic"]).max() <= (1e-6 if mesh.v.dtype == np.float64 else 5e-6) * g["geodesic"].max()
     # gradient: same operation order as the reference -> bit-identical
     np.testing.assert_array_equal(diffgeo.compute_gradient(mesh, g["f"][:, 0]), g["grad_1d"])
     np.testing.assert_array_equal(diffgeo.compute_gradient(mesh, g["f"]), g["grad_2d"])
