@@ -169,9 +169,10 @@ static SolveStats block_pcg(lb_ctx *c, lb_mat *K, const double *rhs, double *x, 
     double off_ratio;
     std::memcpy(&off_ratio, &bits, 8);
     bool use_amg = !(off_ratio < 0.95);  // kappa(D^-1 K) <= (1+r)/(1-r) < 39
+    if (c->trace) fprintf(stderr, "[lb trace] solve: n=%lld m=%d off-diagonal ratio %.4f project=%d\n", (long long)n, m, off_ratio, (int)project);
     if (force_prec == 1) use_amg = false;
     if (force_prec == 2) use_amg = true;
-    if (!use_amg && force_prec == 0 && !project && off_ratio < 0.9) {
+    if (force_prec == 0 && !project && off_ratio < 0.99) {
         // componentwise Jacobi (see jacobi_stream_kernel), two columns at a time; checks the max
         // relative increment every 64 sweeps; falls through to PCG if it does not contract
         // (input that is not an M-matrix)
@@ -208,6 +209,9 @@ static SolveStats block_pcg(lb_ctx *c, lb_mat *K, const double *rhs, double *x, 
                 unsigned long long bits2 = 0;
                 read_back(c, &bits2, mr.p, 1);
                 std::memcpy(&rel, &bits2, 8);
+                if (c->trace && (sweeps % 512 == 0 || rel <= jtol))
+                    fprintf(stderr, "[lb trace] jacobi cols %d..: %d sweeps, max relative increment %.3e (target %.1e)\n", c0,
+                            sweeps, rel, jtol);
                 if (rel <= jtol) {
                     ok = true;
                     break;

@@ -33,10 +33,18 @@ mesh = M.icosphere(9)
 (u), t_heat = timed(lambda: heat.diffusion(mesh, [0], m=1.0))
 (u), t_heat2 = timed(lambda: heat.diffusion(mesh, [0], m=1.0))
 hinfo = heat.diffusion.last_info
-(g), t_geo = timed(lambda: diffgeo.compute_geodesic_f(mesh, u))
-(g), t_geo2 = timed(lambda: diffgeo.compute_geodesic_f(mesh, u))
+# m=1 (t = h^2 = 5.6e-6): u underflows beyond ~1.7 rad and (grad u)^2 beyond ~0.8 rad, for the
+# reference as well (np.sqrt((gradf**2).sum(1)) -> 0 -> inf -> nan_to_num): the heat method needs a
+# larger t at this resolution.  m=16 gives sqrt(t) = 4h, the diffusion length of level 7 with m=1.
+(u16), t_heat16 = timed(lambda: heat.diffusion(mesh, [0], m=16.0))
+hinfo16 = heat.diffusion.last_info
+(g), t_geo = timed(lambda: diffgeo.compute_geodesic_f(mesh, u16))
+(g), t_geo2 = timed(lambda: diffgeo.compute_geodesic_f(mesh, u16))
 far = int(np.argmin(mesh.v @ mesh.v[0]))
-out["heat_geodesic_L9"] = dict(heat_s=t_heat2, heat_info=hinfo, geodesic_s=t_geo2, geodesic_max=float(g.max()), pi=float(np.pi),
-                               geodesic_at_antipode=float(g[far]), u0=float(u[0]), usum=float(u.sum()))
+exact = np.arccos(np.clip(mesh.v @ mesh.v[0], -1, 1))
+out["heat_geodesic_L9"] = dict(heat_m1_s=t_heat2, heat_m1_info=hinfo, u0=float(u[0]), usum=float(u.sum()), u_min=float(u.min()),
+                               heat_m16_s=t_heat16, heat_m16_info=hinfo16, geodesic_s=t_geo2, geodesic_max=float(g.max()),
+                               pi=float(np.pi), geodesic_at_antipode=float(g[far]),
+                               max_abs_err_vs_great_circle=float(np.abs(g - exact).max()))
 print(json.dumps(out["heat_geodesic_L9"]), flush=True)
 json.dump(out, open("gpurun_out/configs_fullsize_r1.json", "w"), indent=1)
