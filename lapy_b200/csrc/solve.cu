@@ -212,11 +212,13 @@ static SolveStats block_pcg(lb_ctx *c, lb_mat *K, const double *rhs, double *x, 
                 if (c->trace && (sweeps % 512 == 0 || rel <= jtol))
                     fprintf(stderr, "[lb trace] jacobi cols %d..: %d sweeps, max relative increment %.3e (target %.1e)\n", c0,
                             sweeps, rel, jtol);
-                if (rel <= jtol) {
+                // converged: increment below the target, or stagnating at the rounding floor (operators
+                // with positive off-diagonals - obtuse elements - have cancellation in b - N x)
+                if (rel <= jtol || (rel < 1e-9 && rel >= 0.5 * prev)) {
                     ok = true;
                     break;
                 }
-                // rel stays 1 while the front still reaches new vertices; afterwards it must contract
+                // rel stays >= 1 while the front still reaches new vertices; afterwards it must contract
                 if (rel < 1.0 && rel >= prev && ++stalls > 8) break;
                 prev = rel;
             }
