@@ -109,8 +109,10 @@ int lb_mat_free(lb_mat *m);
 /* y (n,m) row-major = M x (n,m) row-major; replaces csc_matvec(s) (lapy/solver.py:844-846) */
 int lb_spmm(lb_ctx *ctx, lb_mat *mat, const double *x, int64_t m, double *y);
 
-/* device-resident timing of the SpMM kernel (x, y stay in HBM): ms per launch, CUDA events */
-int lb_spmm_benchmark(lb_ctx *ctx, lb_mat *mat, int64_t m, int reps, double *ms_per_launch);
+/* device-resident timing of the SpMM kernel (x, y stay in HBM): ms per launch, CUDA events;
+ * renumber != 0: on the locality-renumbered copy the solvers iterate with */
+int lb_spmm_benchmark(lb_ctx *ctx, lb_mat *mat, int64_t m, int reps, int renumber,
+                      double *ms_per_launch);
 
 /* dense tall-skinny block products on the fp64 tensor cores (hand-written DMMA kernels), the
  * contractions LAPACK performs inside ARPACK for the reference (lapy/solver.py:713); row-major:

@@ -61,7 +61,7 @@ SIGNATURES = {
     "lb_mat_upload": [_vp, _i64, _i64, _vp, _vp, _vp, _pp],
     "lb_mat_free": [_vp],
     "lb_spmm": [_vp, _vp, _vp, _i64, _vp],
-    "lb_spmm_benchmark": [_vp, _vp, _i64, _int, C.POINTER(_dbl)],
+    "lb_spmm_benchmark": [_vp, _vp, _i64, _int, _int, C.POINTER(_dbl)],
     "lb_block_gram": [_vp, _i64, _i64, _vp, _i64, _vp, _vp],
     "lb_block_update": [_vp, _i64, _i64, _vp, _i64, _vp, _dbl, _dbl, _vp],
     "lb_eigs": [_vp, _vp, _vp, _int, _dbl, _dbl, _int, _vp, _vp, C.POINTER(Info)],
@@ -373,10 +373,10 @@ def block_update(ctx: Context, x: np.ndarray, cmat: np.ndarray, alpha=1.0, beta=
     return out
 
 
-def spmm_benchmark(ctx: Context, mat: DeviceMatrix, m: int = 1, reps: int = 20) -> float:
+def spmm_benchmark(ctx: Context, mat: DeviceMatrix, m: int = 1, reps: int = 20, renumber: bool = False) -> float:
     """Device time (ms) of one y = M x launch with m columns, x / y resident in HBM."""
     ms = C.c_double()
-    check(lib().lb_spmm_benchmark(ctx.handle, mat.handle, int(m), int(reps), C.byref(ms)))
+    check(lib().lb_spmm_benchmark(ctx.handle, mat.handle, int(m), int(reps), int(renumber), C.byref(ms)))
     return ms.value
 
 

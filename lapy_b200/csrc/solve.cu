@@ -413,11 +413,17 @@ int lb_spmm(lb_ctx *c, lb_mat *mat, const double *x, int64_t m, double *y) {
 }
 
 // device-resident timing of y = M x (m columns): ms per launch over `reps` launches (CUDA events)
-int lb_spmm_benchmark(lb_ctx *c, lb_mat *mat, int64_t m, int reps, double *ms_per_launch) {
+int lb_spmm_benchmark(lb_ctx *c, lb_mat *mat0, int64_t m, int reps, int renumber, double *ms_per_launch) {
     LB_API_BEGIN
-    LB_REQUIRE(c && mat && ms_per_launch && m >= 1 && m <= 1024 && reps >= 1, "lb_spmm_benchmark: bad argument");
+    LB_REQUIRE(c && mat0 && ms_per_launch && m >= 1 && m <= 1024 && reps >= 1, "lb_spmm_benchmark: bad argument");
     DeviceGuard g(c->device);
-    const int64_t n = mat->n;
+    const int64_t n = mat0->n;
+    std::unique_ptr<lb_mat> perm;
+    lb_mat *mat = mat0;
+    if (renumber && mat0->order && (int64_t)mat0->order->n == n) {  // the numbering the solvers work in
+        perm = permute_symmetric(c, mat0, mat0->order->p, mat0->order_inv->p);
+        mat = perm.get();
+    }
     DBuf<double> dx(c, (size_t)n * m), dy(c, (size_t)n * m);
     fill_random(c, n, (int)m, dx.p, (int)m, 42);
     for (int i = 0; i < 3; i++) spmm(c, mat, dx.p, (int)m, dy.p, (int)m, (int)m);
