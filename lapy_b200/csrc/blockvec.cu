@@ -21,64 +21,72 @@ __global__ void __launch_bounds__(256) spmm_kernel(int64_t n, const int32_t *__r
                                                    const double *__restrict__ val, const double *__restrict__ x,
                                                    int ldx, double *y, int ldy, int m, int mode,
                                                    const double *b, int ldb) {
-    // (staging the strip's CSR segment in shared memory was measured slower: -14 %; the index
-    // loads below are warp-uniform broadcasts and four rows of X are gathered per step)
+    // ncu (round 1): this kernel is L1/TEX-throughput bound (73 %), not DRAM bound (44 %): every
+    // nonzero cost one 512-byte X request plus two broadcast requests for (index, value).  The
+    // group now fetches a row's (index, value) pairs with ONE coalesced load each (lane q holds
+    // entry q) and broadcasts them by warp shuffle, leaving only the X gathers on the L1 pipe.
+    // (Staging the strip's CSR segment in shared memory instead was measured 14 % slower.)
     constexpr int GROUPS = 256 / G;  // rows in flight per CTA
-    constexpr bool staged = false;
-    const int32_t *s_idx = nullptr;
-    const double *s_val = nullptr;
     const int grp = threadIdx.x / G, lane = threadIdx.x % G;
+    const unsigned gmask = G == 32 ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31) / G * G));
     const int64_t strip0 = (int64_t)blockIdx.x * kSpmmStrip;
     const int nrows = (int)(min(n, strip0 + kSpmmStrip) - strip0);
-    const int32_t *s_ptr = indptr + strip0;
-    const int base = 0;
     for (int lr = grp; lr < nrows; lr += GROUPS) {
         const int64_t row = strip0 + lr;
-        const int beg = __ldg(s_ptr + lr), end = __ldg(s_ptr + lr + 1);
+        const int beg = __ldg(indptr + row), end = __ldg(indptr + row + 1);
+        // VEC: lane owns columns c0 + 2*lane, +1 (one 16-byte load); else c0 + lane, c0 + lane + G
         for (int c0 = 0; c0 < m; c0 += 2 * G) {
-            // VEC: lane owns columns c0 + 2*lane, +1 (one 16-byte load); else c0 + lane, c0 + lane + G
             const int ca = VEC ? c0 + 2 * lane : c0 + lane;
             const int cb = VEC ? ca + 1 : ca + G;
             const bool ha = ca < m, hb = cb < m;
             double s0 = 0.0, s1 = 0.0;
-            int p = beg;
-            for (; p + 3 < end; p += 4) {
-                int j[4];
-                double a[4], u0[4], u1[4];
-#pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    j[q] = staged ? s_idx[p + q] : __ldg(indices + base + p + q);
-                    a[q] = staged ? s_val[p + q] : __ldg(val + base + p + q);
+            for (int p0 = beg; p0 < end; p0 += G) {
+                const int cnt = min(G, end - p0);
+                int jl = 0;
+                double al = 0.0;
+                if (lane < cnt) {
+                    jl = __ldg(indices + p0 + lane);
+                    al = __ldg(val + p0 + lane);
                 }
+                int q = 0;
+                for (; q + 3 < cnt; q += 4) {
+                    int j[4];
+                    double a[4], u0[4], u1[4];
 #pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    const double *xr = x + (int64_t)j[q] * ldx;
-                    if (VEC && hb) {
-                        const double2 v = __ldg(reinterpret_cast<const double2 *>(xr + ca));
-                        u0[q] = v.x;
-                        u1[q] = v.y;
-                    } else {
-                        u0[q] = ha ? __ldg(xr + ca) : 0.0;
-                        u1[q] = hb ? __ldg(xr + cb) : 0.0;
+                    for (int w = 0; w < 4; w++) {
+                        j[w] = __shfl_sync(gmask, jl, q + w, G);
+                        a[w] = __shfl_sync(gmask, al, q + w, G);
+                    }
+#pragma unroll
+                    for (int w = 0; w < 4; w++) {
+                        const double *xr = x + (int64_t)j[w] * ldx;
+                        if (VEC && hb) {
+                            const double2 v = __ldg(reinterpret_cast<const double2 *>(xr + ca));
+                            u0[w] = v.x;
+                            u1[w] = v.y;
+                        } else {
+                            u0[w] = ha ? __ldg(xr + ca) : 0.0;
+                            u1[w] = hb ? __ldg(xr + cb) : 0.0;
+                        }
+                    }
+#pragma unroll
+                    for (int w = 0; w < 4; w++) {
+                        s0 = fma(a[w], u0[w], s0);
+                        s1 = fma(a[w], u1[w], s1);
                     }
                 }
-#pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    s0 = fma(a[q], u0[q], s0);
-                    s1 = fma(a[q], u1[q], s1);
-                }
-            }
-            for (; p < end; p++) {
-                const int j0 = staged ? s_idx[p] : __ldg(indices + base + p);
-                const double a0 = staged ? s_val[p] : __ldg(val + base + p);
-                const double *xr = x + (int64_t)j0 * ldx;
-                if (VEC && hb) {
-                    const double2 v = __ldg(reinterpret_cast<const double2 *>(xr + ca));
-                    s0 = fma(a0, v.x, s0);
-                    s1 = fma(a0, v.y, s1);
-                } else {
-                    if (ha) s0 = fma(a0, __ldg(xr + ca), s0);
-                    if (hb) s1 = fma(a0, __ldg(xr + cb), s1);
+                for (; q < cnt; q++) {
+                    const int j0 = __shfl_sync(gmask, jl, q, G);
+                    const double a0 = __shfl_sync(gmask, al, q, G);
+                    const double *xr = x + (int64_t)j0 * ldx;
+                    if (VEC && hb) {
+                        const double2 v = __ldg(reinterpret_cast<const double2 *>(xr + ca));
+                        s0 = fma(a0, v.x, s0);
+                        s1 = fma(a0, v.y, s1);
+                    } else {
+                        if (ha) s0 = fma(a0, __ldg(xr + ca), s0);
+                        if (hb) s1 = fma(a0, __ldg(xr + cb), s1);
+                    }
                 }
             }
             if (mode == 1) {
@@ -137,12 +145,13 @@ __global__ void __launch_bounds__(256) spmv_kernel(int64_t n, const int32_t *__r
 constexpr int kSpmvRows = 128;  // ~900 (tri) / ~1900 (tet) entries per strip
 constexpr int kSpmvCap = 2944;  // 2 x 23 KB products + row pointers < 48 KB static
 
+template <int MC>
 __global__ void __launch_bounds__(256) spmv_stream_kernel(int64_t n, const int32_t *__restrict__ indptr,
                                                           const int32_t *__restrict__ indices,
                                                           const double *__restrict__ val,
                                                           const double *__restrict__ x, int ldx, double *y, int ldy,
                                                           int m, int mode, const double *b, int ldb) {
-    __shared__ double s_prod[2][kSpmvCap];
+    __shared__ double s_prod[MC][kSpmvCap];
     __shared__ int32_t s_ptr[kSpmvRows + 1];
     const int64_t strip0 = (int64_t)blockIdx.x * kSpmvRows;
     const int nrows = (int)(min(n, strip0 + kSpmvRows) - strip0);
@@ -154,7 +163,7 @@ __global__ void __launch_bounds__(256) spmv_stream_kernel(int64_t n, const int32
             const int j = __ldg(indices + base + i);
             const double a = __ldg(val + base + i);
             s_prod[0][i] = a * __ldg(x + (int64_t)j * ldx);
-            if (m > 1) s_prod[1][i] = a * __ldg(x + (int64_t)j * ldx + 1);
+            if (MC > 1) s_prod[MC - 1][i] = a * __ldg(x + (int64_t)j * ldx + 1);
         }
         __syncthreads();
         if (threadIdx.x < nrows) {
@@ -213,7 +222,8 @@ void spmm(lb_ctx *c, const lb_mat *a, const double *x, int ldx, double *y, int l
     const int32_t *ip = a->indptr.p, *ix = a->indices.p;
     const double *v = a->data.p;
     if (m <= 2) {
-        LB_LAUNCH(c, spmv_stream_kernel, cdiv(n, kSpmvRows), 256, 0, n, ip, ix, v, x, ldx, y, ldy, m, mode, b, ldb);
+        if (m == 1) LB_LAUNCH(c, spmv_stream_kernel<1>, cdiv(n, kSpmvRows), 256, 0, n, ip, ix, v, x, ldx, y, ldy, m, mode, b, ldb);
+        else LB_LAUNCH(c, spmv_stream_kernel<2>, cdiv(n, kSpmvRows), 256, 0, n, ip, ix, v, x, ldx, y, ldy, m, mode, b, ldb);
         return;
     }
     // 16-byte vector loads of X need even leading dimension and a 16-byte aligned base
