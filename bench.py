@@ -290,7 +290,7 @@ def main():
         classes = {
             k: {"launches": v["launches"], "ms_per_step": v["ms"] / args.steps,
                 "rate": v["work"] / (v["ms"] * 1e-3) / 1e9 if v["ms"] else None,
-                "rate_unit": "GB/s" if k in ("spmm", "col_dots") else "GFLOP/s"}
+                "rate_unit": "GB/s" if k in ("spmm", "col_dots", "elementwise") else "GFLOP/s"}
             for k, v in prof.items()
         }  # fmt: skip
         asm = float(np.median(asm_ms)) if asm_ms else None

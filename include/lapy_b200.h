@@ -75,9 +75,10 @@ const char *lb_version(void);
 int lb_timer_start(lb_ctx *ctx);
 int lb_timer_stop(lb_ctx *ctx, double *ms);
 /* per-kernel-class device timing (CUDA events around the hot launches): classes are
- * 0 SpMM, 1 Gram (X^T Y), 2 block update (X C), 3 triangular solve, 4 column dots, 5 reserved.
+ * 0 SpMM, 1 Gram (X^T Y), 2 block update (X C), 3 small dense (syevd, coarse solves), 4 column
+ * dots, 5 elementwise block kernels.
  * enable clears the records; report fills arrays of 6: launches, device ms, work (algorithmic
- * bytes for classes 0/4, flops for 1-3). */
+ * bytes for classes 0/4/5, flops for 1-3). */
 int lb_profile_enable(lb_ctx *ctx, int on);
 int lb_profile_report(lb_ctx *ctx, int64_t *count, double *ms, double *work);
 /* number of kernels this library has launched on ctx since creation */

@@ -149,7 +149,7 @@ class Context:
         check(lib().lb_timer_stop(self.handle, C.byref(ms)))
         return ms.value
 
-    PROFILE_CLASSES = ("spmm", "gram", "update", "trsm", "col_dots", "reserved")
+    PROFILE_CLASSES = ("spmm", "gram", "update", "small_dense", "col_dots", "elementwise")
 
     def profile_enable(self, on: bool = True):
         check(lib().lb_profile_enable(self.handle, int(on)))

@@ -20,7 +20,7 @@ __global__ void __launch_bounds__(256) spmm_kernel(int64_t n, const int32_t *__r
                                                    const int32_t *__restrict__ indices,
                                                    const double *__restrict__ val, const double *__restrict__ x,
                                                    int ldx, double *y, int ldy, int m, int mode,
-                                                   const double *b, int ldb) {
+                                                   const double *b, int ldb, SpmmEpilogue epi) {
     // ncu (round 1): this kernel is L1/TEX-throughput bound (73 %), not DRAM bound (44 %): every
     // nonzero cost one 512-byte X request plus two broadcast requests for (index, value).  The
     // group now fetches a row's (index, value) pairs with ONE coalesced load each (lane q holds
@@ -95,6 +95,34 @@ __global__ void __launch_bounds__(256) spmm_kernel(int64_t n, const int32_t *__r
             } else if (mode == 2) {
                 if (ha) s0 = b[row * ldb + ca] + s0;
                 if (hb) s1 = b[row * ldb + cb] + s1;
+            } else if (mode == 3) {
+                // fused first Chebyshev step: r = b - K x (written to y), d = c2 * dinv o r (out2)
+                const double di = epi.c2 * __ldg(epi.dinv + row);
+                if (ha) {
+                    s0 = b[row * ldb + ca] - s0;
+                    epi.out2[row * epi.ldout2 + ca] = di * s0;
+                }
+                if (hb) {
+                    s1 = b[row * ldb + cb] - s1;
+                    epi.out2[row * epi.ldout2 + cb] = di * s1;
+                }
+            } else if (mode == 4) {
+                // fused last Chebyshev step (x gathers d): rr = b - K d; dn = c1 d + c2 dinv o rr;
+                // sol (+)= d + dn; neither the residual nor dn is written
+                const double di = epi.c2 * __ldg(epi.dinv + row);
+                if (ha) {
+                    const double dold = x[row * ldx + ca];
+                    const double dn = fma(epi.c1, dold, di * (b[row * ldb + ca] - s0));
+                    double *sp = epi.out2 + row * epi.ldout2 + ca;
+                    *sp = (epi.overwrite ? 0.0 : *sp) + dold + dn;
+                }
+                if (hb) {
+                    const double dold = x[row * ldx + cb];
+                    const double dn = fma(epi.c1, dold, di * (b[row * ldb + cb] - s1));
+                    double *sp = epi.out2 + row * epi.ldout2 + cb;
+                    *sp = (epi.overwrite ? 0.0 : *sp) + dold + dn;
+                }
+                continue;
             }
             if (ha) y[row * ldy + ca] = s0;
             if (hb) y[row * ldy + cb] = s1;
@@ -208,7 +236,10 @@ __global__ void diag_spmm_kernel(int64_t n, const int32_t *__restrict__ indptr, 
 }
 
 void spmm(lb_ctx *c, const lb_mat *a, const double *x, int ldx, double *y, int ldy, int m, int mode, const double *b,
-          int ldb) {
+          int ldb, const SpmmEpilogue *epi_in) {
+    SpmmEpilogue epi{};
+    if (epi_in) epi = *epi_in;
+    LB_REQUIRE(mode <= 2 || (epi_in && !a->diagonal && m > 2), "fused SpMM epilogues need a general matrix and m > 2");
     const int64_t n = a->n;
     if (n == 0 || m == 0) return;
     const int64_t xrows = a->ncols < 0 ? a->n : a->ncols;
@@ -231,8 +262,8 @@ void spmm(lb_ctx *c, const lb_mat *a, const double *x, int ldx, double *y, int l
     const int grid = cdiv(n, kSpmmStrip);
 #define LB_SPMM(G)                                                                                       \
     do {                                                                                                 \
-        if (vec) LB_LAUNCH(c, (spmm_kernel<G, true>), grid, 256, 0, n, ip, ix, v, x, ldx, y, ldy, m, mode, b, ldb); \
-        else LB_LAUNCH(c, (spmm_kernel<G, false>), grid, 256, 0, n, ip, ix, v, x, ldx, y, ldy, m, mode, b, ldb);    \
+        if (vec) LB_LAUNCH(c, (spmm_kernel<G, true>), grid, 256, 0, n, ip, ix, v, x, ldx, y, ldy, m, mode, b, ldb, epi); \
+        else LB_LAUNCH(c, (spmm_kernel<G, false>), grid, 256, 0, n, ip, ix, v, x, ldx, y, ldy, m, mode, b, ldb, epi);    \
     } while (0)
     if (m <= 8) LB_SPMM(4);
     else if (m <= 16) LB_SPMM(8);
@@ -304,6 +335,7 @@ __global__ void axpby_cols_kernel(int64_t n, int cols, const double *__restrict_
 void axpby_cols(lb_ctx *c, int64_t n, int cols, const double *a, double a_const, const double *x, int ldx,
                 const double *b, double b_const, double *y, int ldy) {
     if (n * cols == 0) return;
+    ProfScope prof(c, PROF_ELEMENTWISE, 24.0 * n * cols);
     LB_LAUNCH(c, axpby_cols_kernel, cdiv(n * cols, 256), 256, 0, n, cols, a, a_const, x, ldx, b, b_const, y, ldy);
 }
 
@@ -321,11 +353,13 @@ __global__ void residual_cols_kernel(int64_t n, int ncols, const int *__restrict
 void residual_cols(lb_ctx *c, int64_t n, int ncols, const int *idx, const double *lam, const double *ax, int ldax,
                    const double *mx, int ldmx, double *out, int ldout) {
     if (n * ncols == 0) return;
+    ProfScope prof(c, PROF_ELEMENTWISE, 24.0 * n * ncols);
     LB_LAUNCH(c, residual_cols_kernel, cdiv(n * ncols, 256), 256, 0, n, ncols, idx, lam, ax, ldax, mx, ldmx, out, ldout);
 }
 
 void copy_cols(lb_ctx *c, int64_t n, int cols, const double *x, int ldx, double *y, int ldy) {
     if (n * cols == 0) return;
+    ProfScope prof(c, PROF_ELEMENTWISE, 16.0 * n * cols);
     LB_CUDA(cudaMemcpy2DAsync(y, (size_t)ldy * 8, x, (size_t)ldx * 8, (size_t)cols * 8, n, cudaMemcpyDeviceToDevice,
                               c->stream));
 }
@@ -341,6 +375,7 @@ __global__ void scale_rows_kernel(int64_t n, int cols, const double *__restrict_
 
 void scale_rows(lb_ctx *c, int64_t n, int cols, const double *d, const double *x, int ldx, double *y, int ldy) {
     if (n * cols == 0) return;
+    ProfScope prof(c, PROF_ELEMENTWISE, 16.0 * n * cols);
     LB_LAUNCH(c, scale_rows_kernel, cdiv(n * cols, 256), 256, 0, n, cols, d, x, ldx, y, ldy);
 }
 

@@ -11,8 +11,17 @@ namespace lb {
 // Y(n,m) = A X                       (mode 0)
 // Y(n,m) = B - A X                   (mode 1, residual; B may alias Y)
 // Y(n,m) = B + A X                   (mode 2; B may alias Y)
+// Y(n,m) = B - A X and D = c2 * dinv o Y               (mode 3, fused first Chebyshev step)
+// SOL (+)= X + c1 X + c2 * dinv o (B - A X)              (mode 4, fused last Chebyshev step; Y unused)
+struct SpmmEpilogue {
+    const double *dinv = nullptr;
+    double *out2 = nullptr;  // D (mode 3) / SOL (mode 4)
+    int ldout2 = 0;
+    double c1 = 0.0, c2 = 0.0;
+    int overwrite = 0;  // mode 4: SOL = ... instead of SOL += ...
+};
 void spmm(lb_ctx *c, const lb_mat *a, const double *x, int ldx, double *y, int ldy, int m, int mode = 0,
-          const double *b = nullptr, int ldb = 0);
+          const double *b = nullptr, int ldb = 0, const SpmmEpilogue *epi = nullptr);
 
 // out[j] = sum_i X[i,j] * Y[i,j], j < cols  (deterministic two-stage reduction), device output
 void col_dots(lb_ctx *c, int64_t n, int cols, const double *x, int ldx, const double *y, int ldy, double *out);

@@ -119,6 +119,7 @@ int chol_lower(lb_ctx *c, int q, double *g) {
 }
 
 int sym_eig(lb_ctx *c, int s, double *g, double *evals) {
+    ProfScope prof(c, PROF_TRSM, 9.0 * s * s * s);  // reported as class "small_dense" (syevd / coarse solves)
     int lwork = 0;
     LB_CUSOLVER(cusolverDnDsyevd_bufferSize(solver(c), CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_UPPER, s, g, s, evals,
                                             &lwork));
@@ -142,6 +143,7 @@ void dense_chol_solve_prepare(lb_ctx *c, int q, double *g) {
 
 // X_rm(q,m) <- G^-1 X given the factor from dense_chol_solve_prepare (row-major lower L)
 void dense_chol_solve(lb_ctx *c, int q, const double *l, int m, double *x, int ldx) {
+    ProfScope prof(c, PROF_TRSM, 2.0 * q * q * m);
     // row-major X(q,m) is column-major X^T (m,q): solve X^T <- X^T G^-1 = X^T (U^T U)^-1 from the right
     const double one = 1.0;
     LB_CUBLAS(cublasDtrsm(blas(c), CUBLAS_SIDE_RIGHT, CUBLAS_FILL_MODE_UPPER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, m, q,
