@@ -231,9 +231,13 @@ def main():
     ctx.profile_enable(True)
     with ClockSampler(local_rank) as clk:
         ctx.timer_start()  # CUDA events on the library's stream (the stream every kernel runs on)
+        step_wall = []
         for _ in range(args.steps):
+            t_s = time.perf_counter()
             ev, evec, info, nnz = step()
+            step_wall.append((time.perf_counter() - t_s) * 1e3)
         dev_ms = ctx.timer_stop()
+    print(f"[bench] rank {rank}: per-step wall ms {[round(x, 1) for x in step_wall]}", file=sys.stderr)
     prof = ctx.profile_report()
     ctx.profile_enable(False)
     launches = ctx.launch_count() - l0

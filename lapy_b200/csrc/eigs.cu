@@ -137,6 +137,86 @@ static int host_orth(int s, int m, const std::vector<double> &C, int q, std::vec
     return kept;
 }
 
+// Rayleigh-Ritz coefficient matrix on the device (one CTA, everything in shared memory):
+//   Cx  = the m lowest eigenvectors of S^T A S (rows of evT),
+//   Cp  = the [P W] part of the active columns of Cx, orthogonalised against Cx and among
+//         themselves by classical Gram-Schmidt with re-orthogonalisation; dependent columns dropped
+//   coef (s, m + kept) row-major = [Cx | Cp].
+// Replaces a host loop that cost ~7 ms per Rayleigh-Ritz step (plus two PCIe round trips).
+__global__ void __launch_bounds__(1024) rr_coef_kernel(const double *__restrict__ evT, int s, int m,
+                                                       const int *__restrict__ act, int q, double *__restrict__ coef,
+                                                       int *__restrict__ kept_out) {
+    extern __shared__ double sm[];
+    double *cx = sm;                     // [m][s]
+    double *qq = cx + (size_t)m * s;     // [q][s]
+    double *dots = qq + (size_t)q * s;   // [m + q]
+    __shared__ int s_kept;
+    __shared__ double s_n0, s_n1;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarp = blockDim.x >> 5;
+    for (int i = tid; i < m * s; i += blockDim.x) cx[i] = evT[i];
+    __syncthreads();
+    for (int i = tid; i < q * s; i += blockDim.x) {
+        const int j = i / s, r = i - j * s;
+        qq[i] = r >= m ? cx[(size_t)act[j] * s + r] : 0.0;
+    }
+    if (tid == 0) s_kept = 0;
+    __syncthreads();
+    for (int j = 0; j < q; j++) {
+        double *col = qq + (size_t)j * s;
+        const int kept = s_kept;
+        if (warp == 0) {
+            double a = 0.0;
+            for (int i = lane; i < s; i += 32) a += col[i] * col[i];
+#pragma unroll
+            for (int o = 16; o; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+            if (lane == 0) s_n0 = sqrt(a);
+        }
+        __syncthreads();
+        const int nb = m + kept;
+        for (int rep = 0; rep < 2; rep++) {
+            for (int b = warp; b < nb; b += nwarp) {
+                const double *bv = b < m ? cx + (size_t)b * s : qq + (size_t)(b - m) * s;
+                double a = 0.0;
+                for (int i = lane; i < s; i += 32) a += bv[i] * col[i];
+#pragma unroll
+                for (int o = 16; o; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+                if (lane == 0) dots[b] = a;
+            }
+            __syncthreads();
+            if (tid < s) {
+                double v = col[tid];
+                for (int b = 0; b < m; b++) v -= dots[b] * cx[(size_t)b * s + tid];
+                for (int b = 0; b < kept; b++) v -= dots[m + b] * qq[(size_t)b * s + tid];
+                col[tid] = v;
+            }
+            __syncthreads();
+        }
+        if (warp == 0) {
+            double a = 0.0;
+            for (int i = lane; i < s; i += 32) a += col[i] * col[i];
+#pragma unroll
+            for (int o = 16; o; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+            if (lane == 0) s_n1 = sqrt(a);
+        }
+        __syncthreads();
+        const double n0 = s_n0, n1 = s_n1;
+        const bool keep = n0 > 0.0 && !(n1 < 1e-8 * n0) && !(n1 < 1e-14);
+        if (keep) {
+            double *dst = qq + (size_t)kept * s;
+            if (tid < s) dst[tid] = col[tid] / n1;  // kept <= j: never overwrites a column still to be processed
+        }
+        __syncthreads();
+        if (tid == 0 && keep) s_kept = kept + 1;
+        __syncthreads();
+    }
+    const int kept = s_kept, w = m + kept;
+    for (int i = tid; i < s * w; i += blockDim.x) {
+        const int r = i / w, cidx = i - r * w;
+        coef[i] = cidx < m ? cx[(size_t)cidx * s + r] : qq[(size_t)(cidx - m) * s + r];
+    }
+    if (tid == 0) *kept_out = kept;
+}
+
 struct PhaseTimer {
     lb_ctx *c;
     double t0 = 0;
@@ -182,7 +262,7 @@ static EigStats lobpcg_core(lb_ctx *c, const lb_mat *A, const lb_mat *B, Amg *am
     DBuf<double> BS[2] = {DBuf<double>(c, blk), DBuf<double>(c, blk)};
     DBuf<double> Rbuf(c, (size_t)n * m), tmp(c, (size_t)n * m);
     DBuf<double> G(c, (size_t)ld * ld), evd(c, ld), lam_d(c, m), coef(c, (size_t)ld * 2 * m), dots(c, 2 * m);
-    DBuf<int> idx_d(c, m);
+    DBuf<int> idx_d(c, m), kept_d(c, 1);
     std::vector<double> hG, hC, hQ, coefh, rr(2 * m);
     lam.assign(m, 0.0);
     std::vector<int> act(m), idx(m);
@@ -203,28 +283,47 @@ static EigStats lobpcg_core(lb_ctx *c, const lb_mat *A, const lb_mat *B, Amg *am
         gram(c, n, s, S[cur].p, ld, s, AS[cur].p, ld, G.p, true);
         int info = sym_eig(c, s, G.p, evd.p);
         LB_REQUIRE(info == 0, "Rayleigh-Ritz eigen-decomposition failed (info=%d)", info);
-        hG.resize((size_t)m * s);
-        d2h(c, hG.data(), G.p, hG.size() * sizeof(double));  // rows 0..m-1 = the m smallest eigenvectors
-        d2h(c, lam.data(), evd.p, m * sizeof(double));
-        sync(c);
-        hC.assign((size_t)s * m, 0.0);  // Cx (s x m) row-major
-        for (int j = 0; j < m; j++)
-            for (int i = 0; i < s; i++) hC[(size_t)i * m + j] = hG[(size_t)j * s + i];
         const int q = (int)active_cols.size();
-        mp_new = 0;
-        if (s > m && q > 0) {
-            hQ.assign((size_t)s * q, 0.0);
-            for (int a = 0; a < q; a++)
-                for (int i = m; i < s; i++) hQ[(size_t)i * q + a] = hC[(size_t)i * m + active_cols[a]];
-            mp_new = host_orth(s, m, hC, q, hQ);
+        const bool want_p = s > m && q > 0;
+        const size_t smem = ((size_t)(m + (want_p ? q : 0)) * s + m + q) * sizeof(double);
+        int w;
+        if (smem <= 200 * 1024) {
+            // coefficient matrix built on the device; the host only needs lambda and the count
+            if (want_p) h2d(c, idx_d.p, active_cols.data(), q * sizeof(int));
+            static bool attr = false;
+            if (!attr) {
+                LB_CUDA(cudaFuncSetAttribute(rr_coef_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+                attr = true;
+            }
+            LB_LAUNCH(c, rr_coef_kernel, 1, 1024, smem, G.p, s, m, idx_d.p, want_p ? q : 0, coef.p, kept_d.p);
+            d2h(c, lam.data(), evd.p, m * sizeof(double));
+            int hk = 0;
+            read_back(c, &hk, kept_d.p, 1);
+            mp_new = hk;
+            w = m + mp_new;
+        } else {
+            hG.resize((size_t)m * s);
+            d2h(c, hG.data(), G.p, hG.size() * sizeof(double));  // rows 0..m-1 = the m smallest eigenvectors
+            d2h(c, lam.data(), evd.p, m * sizeof(double));
+            sync(c);
+            hC.assign((size_t)s * m, 0.0);  // Cx (s x m) row-major
+            for (int j = 0; j < m; j++)
+                for (int i = 0; i < s; i++) hC[(size_t)i * m + j] = hG[(size_t)j * s + i];
+            mp_new = 0;
+            if (want_p) {
+                hQ.assign((size_t)s * q, 0.0);
+                for (int a = 0; a < q; a++)
+                    for (int i = m; i < s; i++) hQ[(size_t)i * q + a] = hC[(size_t)i * m + active_cols[a]];
+                mp_new = host_orth(s, m, hC, q, hQ);
+            }
+            w = m + mp_new;
+            coefh.assign((size_t)s * w, 0.0);
+            for (int i = 0; i < s; i++) {
+                for (int j = 0; j < m; j++) coefh[(size_t)i * w + j] = hC[(size_t)i * m + j];
+                for (int j = 0; j < mp_new; j++) coefh[(size_t)i * w + m + j] = hQ[(size_t)i * q + j];
+            }
+            h2d(c, coef.p, coefh.data(), coefh.size() * sizeof(double));
         }
-        const int w = m + mp_new;
-        coefh.assign((size_t)s * w, 0.0);
-        for (int i = 0; i < s; i++) {
-            for (int j = 0; j < m; j++) coefh[(size_t)i * w + j] = hC[(size_t)i * m + j];
-            for (int j = 0; j < mp_new; j++) coefh[(size_t)i * w + m + j] = hQ[(size_t)i * q + j];
-        }
-        h2d(c, coef.p, coefh.data(), coefh.size() * sizeof(double));
         const int nxt = cur ^ 1;
         update(c, n, s, S[cur].p, ld, w, coef.p, w, 1.0, 0.0, S[nxt].p, ld);
         // A [X P] and B [X P] are recomputed by SpMM (HBM-bound, ~2 ms at level 9) instead of
