@@ -82,6 +82,9 @@ struct lb_ctx {
     };
     std::vector<ProfRec> prof;
     std::vector<cudaEvent_t> prof_pool;
+    // two pinned staging buffers for large device -> pageable-host results (eigenvectors)
+    void *stage[2] = {nullptr, nullptr};
+    cudaEvent_t stage_ev[2] = {nullptr, nullptr};
 };
 
 namespace lb {
@@ -147,6 +150,9 @@ inline void d2d(lb_ctx *c, void *dst, const void *src, size_t bytes) {
     if (bytes) LB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, c->stream));
 }
 inline void sync(lb_ctx *c) { LB_CUDA(cudaStreamSynchronize(c->stream)); }
+// large result download into pageable host memory: chunked through pinned staging buffers, the
+// host-side copy of chunk i (4 threads) overlaps the DMA of chunk i+1.  Synchronous.
+void d2h_large(lb_ctx *c, void *dst, const void *src, size_t bytes);
 
 // read back a few scalars (stream-ordered, then wait)
 template <class T>

@@ -1,6 +1,7 @@
 // ctx.cu - context life cycle, error reporting, prefix sums, matrix upload / download.
 #include <chrono>
 #include <cstdlib>
+#include <thread>
 
 #include "common.cuh"
 
@@ -18,6 +19,52 @@ void set_error(const char *fmt, ...) {
     va_start(ap, fmt);
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
+}
+
+// ---- large downloads -----------------------------------------------------------------------------
+constexpr size_t kStageBytes = 64ull << 20;
+
+static void parallel_memcpy(char *dst, const char *src, size_t bytes) {
+    const int nt = 4;
+    if (bytes < (8u << 20)) {
+        std::memcpy(dst, src, bytes);
+        return;
+    }
+    std::thread th[nt - 1];
+    const size_t part = (bytes / nt + 4095) & ~size_t(4095);
+    for (int t = 1; t < nt; t++) {
+        const size_t off = std::min(bytes, part * t), len = std::min(part, bytes - off);
+        th[t - 1] = std::thread([=] { if (len) std::memcpy(dst + off, src + off, len); });
+    }
+    std::memcpy(dst, src, std::min(part, bytes));
+    for (int t = 1; t < nt; t++) th[t - 1].join();
+}
+
+void d2h_large(lb_ctx *c, void *dst, const void *src, size_t bytes) {
+    if (bytes < (32u << 20)) {
+        d2h(c, dst, src, bytes);
+        sync(c);
+        return;
+    }
+    for (int i = 0; i < 2; i++) {
+        if (!c->stage[i]) {
+            LB_CUDA(cudaMallocHost(&c->stage[i], kStageBytes));
+            LB_CUDA(cudaEventCreateWithFlags(&c->stage_ev[i], cudaEventDisableTiming));
+        }
+    }
+    const size_t nchunks = (bytes + kStageBytes - 1) / kStageBytes;
+    auto issue = [&](size_t k) {
+        const size_t off = k * kStageBytes, len = std::min(kStageBytes, bytes - off);
+        LB_CUDA(cudaMemcpyAsync(c->stage[k & 1], (const char *)src + off, len, cudaMemcpyDeviceToHost, c->stream));
+        LB_CUDA(cudaEventRecord(c->stage_ev[k & 1], c->stream));
+    };
+    issue(0);
+    for (size_t k = 0; k < nchunks; k++) {
+        LB_CUDA(cudaEventSynchronize(c->stage_ev[k & 1]));
+        if (k + 1 < nchunks) issue(k + 1);  // uses the other buffer, already drained
+        const size_t off = k * kStageBytes, len = std::min(kStageBytes, bytes - off);
+        parallel_memcpy((char *)dst + off, (const char *)c->stage[k & 1], len);
+    }
 }
 
 // ---- per-class device timing ------------------------------------------------------------------
@@ -217,6 +264,10 @@ int lb_ctx_destroy(lb_ctx *c) {
         cudaEventDestroy(r.e1);
     }
     for (auto e : c->prof_pool) cudaEventDestroy(e);
+    for (int i = 0; i < 2; i++) {
+        if (c->stage[i]) cudaFreeHost(c->stage[i]);
+        if (c->stage_ev[i]) cudaEventDestroy(c->stage_ev[i]);
+    }
     cudaEventDestroy(c->ev0);
     cudaEventDestroy(c->ev1);
     cudaFreeHost(c->pinned);
@@ -305,9 +356,9 @@ int lb_mat_download(lb_mat *m, int32_t *indptr, int32_t *indices, double *data) 
     LB_REQUIRE(m, "matrix is NULL");
     lb_ctx *c = m->ctx;
     DeviceGuard g(c->device);
-    if (indptr) d2h(c, indptr, m->indptr.p, (m->n + 1) * sizeof(int32_t));
-    if (indices) d2h(c, indices, m->indices.p, m->nnz * sizeof(int32_t));
-    if (data) d2h(c, data, m->data.p, m->nnz * sizeof(double));
+    if (indptr) d2h_large(c, indptr, m->indptr.p, (m->n + 1) * sizeof(int32_t));
+    if (indices) d2h_large(c, indices, m->indices.p, m->nnz * sizeof(int32_t));
+    if (data) d2h_large(c, data, m->data.p, m->nnz * sizeof(double));
     sync(c);
     LB_API_END
 }

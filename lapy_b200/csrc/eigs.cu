@@ -437,6 +437,7 @@ static EigStats lobpcg_core(lb_ctx *c, const lb_mat *A, const lb_mat *B, Amg *am
 static EigStats lobpcg(lb_ctx *c, const lb_mat *A0, const lb_mat *B0, int k, double sigma, double tol, int maxit,
                        double *h_evals, double *h_evecs) {
     const int64_t n = A0->n;
+    phase(c, "(enter eigs)");
     // solver-internal locality renumbering (Morton order of the mesh the matrices came from):
     // neighbouring rows of X become neighbouring in memory, so the SpMM gathers hit L1/L2 instead
     // of DRAM (ncu: 4.0x -> 1.1x of the algorithmic traffic).  Results return in the caller's order.
@@ -457,7 +458,9 @@ static EigStats lobpcg(lb_ctx *c, const lb_mat *A0, const lb_mat *B0, int k, dou
     AmgOptions opt;
     if (const char *e = getenv("LAPY_B200_CHEB")) opt.cheb_deg = std::max(1, atoi(e));
     if (const char *e = getenv("LAPY_B200_GAMMA")) opt.gamma = std::max(1, atoi(e));
+    phase(c, "eigs: renumber A, B");
     auto amg = amg_setup(c, mat_axpby(c, A, 1.0, B, shift), m, opt);
+    phase(c, "eigs: AMG setup");
 
     // ---- nested iteration: coarse pencils (K_l, B_l), B_{l+1} = R_l B_l P_l (Galerkin, like K_l).
     // K_l = A_l + shift*B_l has the eigenvectors of (A_l, B_l); only the vectors are carried up.
@@ -473,6 +476,7 @@ static EigStats lobpcg(lb_ctx *c, const lb_mat *A0, const lb_mat *B0, int k, dou
         Bl[l + 1] = spgemm(c, amg->levels[l].R.get(), BP.get());
         Bl[l + 1]->ncols = -1;
     }
+    phase(c, "eigs: coarse mass (Galerkin)");
     EigStats st, stc;
     std::vector<double> lam;
     DBuf<double> xc, xf;  // coarse result, prolonged initial block
@@ -490,8 +494,10 @@ static EigStats lobpcg(lb_ctx *c, const lb_mat *A0, const lb_mat *B0, int k, dou
         xf.alloc(c, (size_t)P->n * m);
         spmm(c, P, xo.p, m, xf.p, m, m);
     }
+    phase(c, "eigs: nested coarse solves");
     DBuf<double> xout(c, (size_t)n * m);
     st = lobpcg_core(c, A, B, amg.get(), 0, depth ? xf.p : nullptr, m, k, m, tol, maxit, lam, xout.p);
+    phase(c, "eigs: fine-level LOBPCG");
     st.setup_ms = amg->setup_ms;
     st.solve_ms += coarse_ms;
 
@@ -500,13 +506,13 @@ static EigStats lobpcg(lb_ctx *c, const lb_mat *A0, const lb_mat *B0, int k, dou
         // row i of the caller's numbering = row inv[i] of the renumbered block
         DBuf<double> out(c, (size_t)n * k);
         gather_rows(c, n, k, A0->order_inv->p, xout.p, m, out.p, k);
-        d2h(c, h_evecs, out.p, (size_t)n * k * sizeof(double));
-        sync(c);
+        d2h_large(c, h_evecs, out.p, (size_t)n * k * sizeof(double));
     } else {
-        LB_CUDA(cudaMemcpy2DAsync(h_evecs, (size_t)k * 8, xout.p, (size_t)m * 8, (size_t)k * 8, n,
-                                  cudaMemcpyDeviceToHost, c->stream));
-        sync(c);
+        DBuf<double> out(c, (size_t)n * k);
+        copy_cols(c, n, k, xout.p, m, out.p, k);
+        d2h_large(c, h_evecs, out.p, (size_t)n * k * sizeof(double));
     }
+    phase(c, "eigs: un-renumber + D2H");
     return st;
 }
 
