@@ -249,6 +249,30 @@ __global__ void incidence_fill(const int4 *__restrict__ t4, int64_t nt, int k,
     if (k == 4) inc[inc_ptr[ti.w] + atomicAdd(cursor + ti.w, 1)] = code + 3;
 }
 
+// assembly form of the incidence: one 16-byte record per (vertex, incident element) that already
+// carries the other vertices of the element in the reference's triplet order for that column, so
+// the row kernels never gather the element array:  {element*4 + corner, k0, k1, k2}
+//   triangle corner 0: (t2, t3)   1: (t1, t3)   2: (t2, t1)          (solver.py:171-175)
+//   tet      corner 0: (t2,t3,t4) 1: (t1,t3,t4) 2: (t2,t1,t4) 3: (t1,t2,t3)   (solver.py:472-497)
+__global__ void incidence_fill4(const int4 *__restrict__ t4, int64_t nt, int k,
+                                const int32_t *__restrict__ inc_ptr, int32_t *__restrict__ cursor,
+                                int4 *__restrict__ inc4) {
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= nt) return;
+    const int4 ti = __ldg(t4 + e);
+    const int code = (int)e * 4;
+    if (k == 3) {
+        inc4[inc_ptr[ti.x] + atomicAdd(cursor + ti.x, 1)] = make_int4(code, ti.y, ti.z, -1);
+        inc4[inc_ptr[ti.y] + atomicAdd(cursor + ti.y, 1)] = make_int4(code + 1, ti.x, ti.z, -1);
+        inc4[inc_ptr[ti.z] + atomicAdd(cursor + ti.z, 1)] = make_int4(code + 2, ti.y, ti.x, -1);
+    } else {
+        inc4[inc_ptr[ti.x] + atomicAdd(cursor + ti.x, 1)] = make_int4(code, ti.y, ti.z, ti.w);
+        inc4[inc_ptr[ti.y] + atomicAdd(cursor + ti.y, 1)] = make_int4(code + 1, ti.x, ti.z, ti.w);
+        inc4[inc_ptr[ti.z] + atomicAdd(cursor + ti.z, 1)] = make_int4(code + 2, ti.y, ti.x, ti.w);
+        inc4[inc_ptr[ti.w] + atomicAdd(cursor + ti.w, 1)] = make_int4(code + 3, ti.x, ti.y, ti.z);
+    }
+}
+
 // per-vertex insertion sort of the (atomically ordered) incidence codes -> deterministic
 __global__ void incidence_sort(const int32_t *__restrict__ inc_ptr, int32_t *__restrict__ inc, int64_t n) {
     int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -304,9 +328,8 @@ __device__ __forceinline__ void accumulate(int32_t *keys, double *av, double *bv
 // dynamic smem: cap int32 keys.  Blocks whose upper bound exceeds cap use the global scratch.
 template <int K>
 __global__ void __launch_bounds__(kRowThreads) row_count_kernel(
-    const int4 *__restrict__ t4, const int32_t *__restrict__ inc_ptr, const int32_t *__restrict__ inc,
-    int64_t n, int cap, int32_t *__restrict__ scratch, int32_t *__restrict__ row_nnz,
-    int32_t *__restrict__ row_has) {
+    const int32_t *__restrict__ inc_ptr, const int4 *__restrict__ inc4, int64_t n, int cap,
+    int32_t *__restrict__ scratch, int32_t *__restrict__ row_nnz, int32_t *__restrict__ row_has) {
     extern __shared__ int32_t skeys[];
     __shared__ int s_total;
     int64_t r = (int64_t)blockIdx.x * kRowThreads + threadIdx.x;
@@ -335,22 +358,12 @@ __global__ void __launch_bounds__(kRowThreads) row_count_kernel(
     int off = base + incl - ub;
     int32_t *keys = (s_total <= cap) ? skeys + off : scratch + ((int64_t)beg * (K - 1) + r);
     int cnt = 0;
-    for (int p0 = beg; p0 < end; p0 += 4) {  // 4 independent gathers in flight per thread
-        int code[4];
-        int4 tb[4];
-#pragma unroll
-        for (int u = 0; u < 4; u++) code[u] = p0 + u < end ? __ldg(inc + p0 + u) : -1;
-#pragma unroll
-        for (int u = 0; u < 4; u++)
-            if (code[u] >= 0) tb[u] = __ldg(t4 + (code[u] >> 2));
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-            if (code[u] < 0) continue;
-            insert_key(keys, cnt, tb[u].x);
-            insert_key(keys, cnt, tb[u].y);
-            insert_key(keys, cnt, tb[u].z);
-            if (K == 4) insert_key(keys, cnt, tb[u].w);
-        }
+    if (ninc) insert_key(keys, cnt, (int)r);
+    for (int p = beg; p < end; p++) {  // streaming: the records of a row are contiguous
+        const int4 q = __ldg(inc4 + p);
+        insert_key(keys, cnt, q.y);
+        insert_key(keys, cnt, q.z);
+        if (K == 4) insert_key(keys, cnt, q.w);
     }
     if (r < n) {
         row_nnz[r] = cnt;
@@ -372,9 +385,8 @@ struct RowOut {
 
 template <int K>
 __global__ void __launch_bounds__(kRowThreads) row_fill_kernel(
-    const int4 *__restrict__ t4, const D4 *__restrict__ rec, const int32_t *__restrict__ inc_ptr,
-    const int32_t *__restrict__ inc, int64_t n, int cap, const ElemConsts *__restrict__ consts,
-    int degen_div_f32, RowOut out) {
+    const D4 *__restrict__ rec, const int32_t *__restrict__ inc_ptr, int4 *inc4, int64_t n, int cap,
+    const ElemConsts *__restrict__ consts, int degen_div_f32, RowOut out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *s_a = reinterpret_cast<double *>(smem_raw);
     double *s_b = s_a + cap;
@@ -405,32 +417,59 @@ __global__ void __launch_bounds__(kRowThreads) row_fill_kernel(
         int cnt = 0;
         double lump = 0.0;
         const int beg = inc_ptr[r], end = inc_ptr[r + 1];
-        constexpr int UB = K == 3 ? 4 : 1;  // triangles: 4 independent gathers in flight per thread
-        int codeb[UB];
-        int4 tib[UB];
-        D4 qb[UB];
-        for (int p = beg; p < end; p++) {
-            const int u = (p - beg) % UB;
-            if (u == 0) {
+        const int ninc = end - beg;
+        // The incidence records were placed by atomics: restore the reference's triplet order
+        // (element ascending).  Triangles with valence <= 8 are sorted in registers by a 19-comparator
+        // network and their element records gathered together (8 independent loads in flight);
+        // longer rows / tets sort their own segment in place and stream it.
+        constexpr int RS = 8;
+        int4 qi[RS];
+        D4 qr[RS];
+        const bool in_regs = K == 3 && ninc <= RS;
+        if (in_regs) {
 #pragma unroll
-                for (int w = 0; w < UB; w++) codeb[w] = p + w < end ? __ldg(inc + p + w) : -1;
+            for (int u = 0; u < RS; u++) qi[u] = u < ninc ? inc4[beg + u] : make_int4(INT_MAX, 0, 0, 0);
+#define LB_CSWAP(i, j)                  \
+    if (qi[i].x > qi[j].x) {            \
+        const int4 tmp_ = qi[i];        \
+        qi[i] = qi[j];                  \
+        qi[j] = tmp_;                   \
+    }
+            LB_CSWAP(0, 1) LB_CSWAP(2, 3) LB_CSWAP(4, 5) LB_CSWAP(6, 7) LB_CSWAP(0, 2) LB_CSWAP(1, 3) LB_CSWAP(4, 6)
+            LB_CSWAP(5, 7) LB_CSWAP(1, 2) LB_CSWAP(5, 6) LB_CSWAP(0, 4) LB_CSWAP(3, 7) LB_CSWAP(1, 5) LB_CSWAP(2, 6)
+            LB_CSWAP(1, 4) LB_CSWAP(3, 6) LB_CSWAP(2, 4) LB_CSWAP(3, 5) LB_CSWAP(3, 4)
+#undef LB_CSWAP
 #pragma unroll
-                for (int w = 0; w < UB; w++)
-                    if (codeb[w] >= 0) {
-                        tib[w] = __ldg(t4 + (codeb[w] >> 2));
-                        if (K == 3) qb[w] = ldg_d4(rec + (codeb[w] >> 2));
-                    }
-            }
-            int code = codeb[0];
-            int4 ti = tib[0];
-            D4 q = qb[0];
-#pragma unroll
-            for (int w = 1; w < UB; w++)
-                if (u == w) {
-                    code = codeb[w];
-                    ti = tib[w];
-                    q = qb[w];
+            for (int u = 0; u < RS; u++)
+                if (u < ninc) qr[u] = ldg_d4(rec + (qi[u].x >> 2));
+        } else {
+            for (int i = beg + 1; i < end; i++) {
+                const int4 key = inc4[i];
+                int j = i - 1;
+                while (j >= beg && inc4[j].x > key.x) {
+                    inc4[j + 1] = inc4[j];
+                    j--;
                 }
+                inc4[j + 1] = key;
+            }
+        }
+        for (int p = beg; p < end; p++) {
+            int4 r4;
+            D4 q;
+            if (in_regs) {
+                r4 = qi[0];
+                q = qr[0];
+#pragma unroll
+                for (int w = 1; w < RS; w++)
+                    if (p - beg == w) {
+                        r4 = qi[w];
+                        q = qr[w];
+                    }
+            } else {
+                r4 = inc4[p];
+                if (K == 3) q = ldg_d4(rec + (r4.x >> 2));
+            }
+            const int code = r4.x;
             const int e = code >> 2, c = code & 3;
             if (K == 3) {
                 double a12 = q.x, a23 = q.y, a31 = q.z, bii = q.w;
@@ -454,12 +493,14 @@ __global__ void __launch_bounds__(kRowThreads) row_fill_kernel(
                 // column = corner c; rows in the reference's triplet order (solver.py:171-175)
                 // the diagonal (row sum = 0, solver.py:167-169) is formed in the element dtype
                 double m0, m1;
+                k0 = r4.y;  // neighbours already in the triplet order of this column
+                k1 = r4.z;
                 if (c == 0) {
-                    k0 = ti.y; x0 = a12; k1 = ti.z; x1 = a31; m0 = a12; m1 = a31;
+                    x0 = a12; x1 = a31; m0 = a12; m1 = a31;
                 } else if (c == 1) {
-                    k0 = ti.x; x0 = a12; k1 = ti.z; x1 = a23; m0 = a12; m1 = a23;
+                    x0 = a12; x1 = a23; m0 = a12; m1 = a23;
                 } else {
-                    k0 = ti.y; x0 = a23; k1 = ti.x; x1 = a31; m0 = a31; m1 = a23;
+                    x0 = a23; x1 = a31; m0 = a31; m1 = a23;
                 }
                 xd = degen_div_f32 ? (double)__fsub_rn(-(float)m0, (float)m1) : __dsub_rn(-m0, m1);
                 if (want_pat) {
@@ -504,14 +545,17 @@ __global__ void __launch_bounds__(kRowThreads) row_fill_kernel(
                 int k0, k1, k2;
                 double x0, x1, x2, xd;
                 // column = corner c; rows in the reference's triplet order (solver.py:472-497)
+                k0 = r4.y;
+                k1 = r4.z;
+                k2 = r4.w;
                 if (c == 0) {
-                    k0 = ti.y; x0 = a12; k1 = ti.z; x1 = a13; k2 = ti.w; x2 = a14; xd = a11;
+                    x0 = a12; x1 = a13; x2 = a14; xd = a11;
                 } else if (c == 1) {
-                    k0 = ti.x; x0 = a12; k1 = ti.z; x1 = a23; k2 = ti.w; x2 = a24; xd = a22;
+                    x0 = a12; x1 = a23; x2 = a24; xd = a22;
                 } else if (c == 2) {
-                    k0 = ti.y; x0 = a23; k1 = ti.x; x1 = a13; k2 = ti.w; x2 = a34; xd = a33;
+                    x0 = a23; x1 = a13; x2 = a34; xd = a33;
                 } else {
-                    k0 = ti.x; x0 = a14; k1 = ti.y; x1 = a24; k2 = ti.z; x2 = a34; xd = a44;
+                    x0 = a14; x1 = a24; x2 = a34; xd = a44;
                 }
                 if (want_pat) {
                     accumulate(keys, av, bv, cnt, k0, x0, bij, want_a, want_b);
@@ -644,14 +688,15 @@ __global__ void invert_order_kernel(int64_t n, const int32_t *__restrict__ order
     if (i < n) inv[order[i]] = (int)i;
 }
 
-void ensure_order(lb_mesh *mesh) {
-    if (mesh->order) return;
-    lb_ctx *c = mesh->ctx;
-    const int64_t n = mesh->n_ref;
+void ensure_order(lb_order &o) {
+    if (o.ready) return;
+    lb_ctx *c = o.ctx;
+    const int64_t n = o.n;
+    const D4 *v4 = o.v4->p;
     constexpr int kCells = 128 * 128 * 128;
     const int nb = 256;
     DBuf<double> box(c, 6 * nb);
-    LB_LAUNCH(c, bbox_kernel, nb, 256, 0, mesh->v4.p, n, box.p);
+    LB_LAUNCH(c, bbox_kernel, nb, 256, 0, v4, n, box.p);
     std::vector<double> h(6 * nb);
     read_back(c, h.data(), box.p, h.size());
     double lo[3], hi[3];
@@ -667,17 +712,16 @@ void ensure_order(lb_mesh *mesh) {
     for (int k = 0; k < 3; k++) sc[k] = hi[k] > lo[k] ? 127.999 / (hi[k] - lo[k]) : 0.0;
     DBuf<int32_t> cell(c, n), hist(c, kCells), cptr(c, kCells + 1);
     hist.zero();
-    LB_LAUNCH(c, morton_cell_kernel, cdiv(n, 256), 256, 0, mesh->v4.p, n, lo[0], lo[1], lo[2], sc[0], sc[1], sc[2],
-              cell.p, hist.p);
+    LB_LAUNCH(c, morton_cell_kernel, cdiv(n, 256), 256, 0, v4, n, lo[0], lo[1], lo[2], sc[0], sc[1], sc[2], cell.p,
+              hist.p);
     exclusive_scan_i32(c, hist.p, cptr.p, kCells);
     hist.zero();
-    auto order = std::make_shared<DBuf<int32_t>>(c, (size_t)n);
-    auto inv = std::make_shared<DBuf<int32_t>>(c, (size_t)n);
-    LB_LAUNCH(c, order_fill_kernel, cdiv(n, 256), 256, 0, n, cell.p, cptr.p, hist.p, order->p);
-    LB_LAUNCH(c, incidence_sort, cdiv(kCells, 128), 128, 0, cptr.p, order->p, (int64_t)kCells);
-    LB_LAUNCH(c, invert_order_kernel, cdiv(n, 256), 256, 0, n, order->p, inv->p);
-    mesh->order = order;
-    mesh->order_inv = inv;
+    o.order.alloc(c, (size_t)n);
+    o.inv.alloc(c, (size_t)n);
+    LB_LAUNCH(c, order_fill_kernel, cdiv(n, 256), 256, 0, n, cell.p, cptr.p, hist.p, o.order.p);
+    LB_LAUNCH(c, incidence_sort, cdiv(kCells, 128), 128, 0, cptr.p, o.order.p, (int64_t)kCells);
+    LB_LAUNCH(c, invert_order_kernel, cdiv(n, 256), 256, 0, n, o.order.p, o.inv.p);
+    o.ready = true;
 }
 
 template <class T>
@@ -689,7 +733,7 @@ static void run_element_pass(lb_mesh *mesh, int kind, const double *u1, const do
     DBuf<double> partial(c, nblocks);
     const typename Ex<T>::V4 *v4;
     if constexpr (sizeof(T) == 4) v4 = mesh->v4f.p;
-    else v4 = mesh->v4.p;
+    else v4 = mesh->v4s->p;
     switch (kind) {
         case LB_FEM_TRIA: {
             auto kern = tria_element_kernel<T, MODE_FEM>;
@@ -727,8 +771,8 @@ static lb_mat *new_mat(lb_ctx *c, int64_t n, int64_t nnz) {
 }
 
 template <int K>
-static void run_rows(lb_mesh *mesh, const D4 *rec, const ElemConsts *consts, bool want_a, bool lump,
-                     bool degen_f32, lb_mat **a_out, lb_mat **b_out) {
+static void run_rows(lb_mesh *mesh, const D4 *rec, const ElemConsts *consts, const int32_t *aptr, int4 *inc4,
+                     bool want_a, bool lump, bool degen_f32, lb_mat **a_out, lb_mat **b_out) {
     lb_ctx *c = mesh->ctx;
     const int64_t n = mesh->n_ref;
     const int nblocks = cdiv(n, kRowThreads);
@@ -738,8 +782,8 @@ static void run_rows(lb_mesh *mesh, const D4 *rec, const ElemConsts *consts, boo
     DBuf<int32_t> scratch(c, (size_t)mesh->k * mesh->nt * (K - 1) + n);
     if (cap_keys * 4 > 40 * 1024)
         LB_CUDA(cudaFuncSetAttribute(row_count_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap_keys * 4));
-    LB_LAUNCH(c, row_count_kernel<K>, nblocks, kRowThreads, cap_keys * 4, mesh->t4.p, mesh->inc_ptr.p, mesh->inc.p,
-              n, cap_keys, scratch.p, row_nnz.p, row_has.p);
+    LB_LAUNCH(c, row_count_kernel<K>, nblocks, kRowThreads, cap_keys * 4, aptr, inc4, n, cap_keys, scratch.p,
+              row_nnz.p, row_has.p);
     phase(c, "row count");
     const bool full_b = !lump;
     lb_mat *A = nullptr, *B = nullptr;
@@ -782,13 +826,13 @@ static void run_rows(lb_mesh *mesh, const D4 *rec, const ElemConsts *consts, boo
             const int smem = cap * 20;
             if (smem > 40 * 1024)
                 LB_CUDA(cudaFuncSetAttribute(row_fill_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-            LB_LAUNCH(c, row_fill_kernel<K>, nblocks, kRowThreads, smem, mesh->t4.p, rec, mesh->inc_ptr.p,
-                      mesh->inc.p, n, cap, consts, (int)degen_f32, out);
+            LB_LAUNCH(c, row_fill_kernel<K>, nblocks, kRowThreads, smem, rec, aptr, inc4, n, cap, consts,
+                      (int)degen_f32, out);
         } else {
             // mass only + lumped: no CSR pattern needed, but the same kernel does the sums
             const int cap = 0;
-            LB_LAUNCH(c, row_fill_kernel<K>, nblocks, kRowThreads, 16, mesh->t4.p, rec, mesh->inc_ptr.p,
-                      mesh->inc.p, n, cap, consts, (int)degen_f32, out);
+            LB_LAUNCH(c, row_fill_kernel<K>, nblocks, kRowThreads, 16, rec, aptr, inc4, n, cap, consts, (int)degen_f32,
+                      out);
         }
     } catch (...) {
         delete A;
@@ -823,7 +867,7 @@ int lb_mesh_create(lb_ctx *c, const void *v, int v_dtype, int64_t nv, const void
         m->nt = nt;
         m->k = k;
         m->v_dtype = v_dtype;
-        m->v4.alloc(c, nv);
+        m->v4s = std::make_shared<DBuf<D4>>(c, (size_t)nv);
         m->t4.alloc(c, nt);
         if (v_dtype == LB_F32) m->v4f.alloc(c, nv);
         const size_t vbytes = (size_t)nv * 3 * (v_dtype == LB_F32 ? 4 : 8);
@@ -836,9 +880,9 @@ int lb_mesh_create(lb_ctx *c, const void *v, int v_dtype, int64_t nv, const void
         h2d(c, raw_v.p, v, vbytes);
         h2d(c, raw_t.p, t, tbytes);
         if (v_dtype == LB_F32)
-            LB_LAUNCH(c, convert_vertices<float>, cdiv(nv, 256), 256, 0, (const float *)raw_v.p, nv, m->v4.p, m->v4f.p);
+            LB_LAUNCH(c, convert_vertices<float>, cdiv(nv, 256), 256, 0, (const float *)raw_v.p, nv, m->v4s->p, m->v4f.p);
         else
-            LB_LAUNCH(c, convert_vertices<double>, cdiv(nv, 256), 256, 0, (const double *)raw_v.p, nv, m->v4.p,
+            LB_LAUNCH(c, convert_vertices<double>, cdiv(nv, 256), 256, 0, (const double *)raw_v.p, nv, m->v4s->p,
                       (float4 *)nullptr);
         if (t_itemsize == 4)
             LB_LAUNCH(c, convert_elements<int32_t>, cdiv(nt, 256), 256, 0, (const int32_t *)raw_t.p, nt, k, m->t4.p,
@@ -871,10 +915,10 @@ int lb_mesh_update_vertices(lb_mesh *m, const void *v, int v_dtype) {
     m->v_dtype = v_dtype;
     if (v_dtype == LB_F32) {
         if (!m->v4f.p) m->v4f.alloc(c, m->nv);
-        LB_LAUNCH(c, convert_vertices<float>, cdiv(m->nv, 256), 256, 0, (const float *)raw_v.p, m->nv, m->v4.p,
+        LB_LAUNCH(c, convert_vertices<float>, cdiv(m->nv, 256), 256, 0, (const float *)raw_v.p, m->nv, m->v4s->p,
                   m->v4f.p);
     } else {
-        LB_LAUNCH(c, convert_vertices<double>, cdiv(m->nv, 256), 256, 0, (const double *)raw_v.p, m->nv, m->v4.p,
+        LB_LAUNCH(c, convert_vertices<double>, cdiv(m->nv, 256), 256, 0, (const double *)raw_v.p, m->nv, m->v4s->p,
                   (float4 *)nullptr);
     }
     sync(c);  // raw_v is borrowed from the caller until here
@@ -888,8 +932,7 @@ int lb_mesh_drop_cache(lb_mesh *m) {
     m->inc_ptr.release();
     m->inc.release();
     m->has_inc = false;
-    m->order.reset();
-    m->order_inv.reset();
+    m->ord.reset();
     LB_API_END
 }
 
@@ -924,31 +967,32 @@ int lb_fem_assemble(lb_ctx *c, lb_mesh *mesh, int kind, int lump, const double *
         h2d(c, d_u2.p, u2, 3 * nt * sizeof(double));
         h2d(c, d_am.p, aniso_mat, 2 * nt * sizeof(double));
     }
-    DBuf<int32_t> deg;
-    if (!mesh->has_inc) {
-        deg.alloc(c, mesh->nv);
-        deg.zero();
-    }
+    DBuf<int32_t> deg(c, mesh->nv), aptr(c, mesh->nv + 1);
+    DBuf<int4> inc4(c, (size_t)mesh->k * nt);
+    deg.zero();
     if (mesh->v_dtype == LB_F32)
         run_element_pass<float>(mesh, kind, d_u1.p, d_u2.p, d_am.p, rec.p, deg.p, consts.p);
     else
         run_element_pass<double>(mesh, kind, d_u1.p, d_u2.p, d_am.p, rec.p, deg.p, consts.p);
     phase(c, "element pass");
-    if (!mesh->has_inc) build_incidence(mesh, deg);
+    exclusive_scan_i32(c, deg.p, aptr.p, mesh->nv);
+    deg.zero();
+    LB_LAUNCH(c, incidence_fill4, cdiv(nt, 256), 256, 0, mesh->t4.p, nt, mesh->k, aptr.p, deg.p, inc4.p);
     phase(c, "incidence");
     if (a_out) *a_out = nullptr;
     // clamped elements: the aniso numerators are fp64 even for fp32 meshes (solver.py:278-280)
     const bool degen_f32 = mesh->v_dtype == LB_F32 && kind != LB_FEM_TRIA_ANISO;
-    if (mesh->k == 3) run_rows<3>(mesh, rec.p, consts.p, want_a, lump != 0, degen_f32, a_out, b_out);
-    else run_rows<4>(mesh, rec.p, consts.p, want_a, lump != 0, degen_f32, a_out, b_out);
-    if (mesh->nv >= 20000) {  // locality hint for the solvers (internal renumbering)
-        ensure_order(mesh);
-        if (a_out && *a_out) {
-            (*a_out)->order = mesh->order;
-            (*a_out)->order_inv = mesh->order_inv;
+    if (mesh->k == 3) run_rows<3>(mesh, rec.p, consts.p, aptr.p, inc4.p, want_a, lump != 0, degen_f32, a_out, b_out);
+    else run_rows<4>(mesh, rec.p, consts.p, aptr.p, inc4.p, want_a, lump != 0, degen_f32, a_out, b_out);
+    if (mesh->nv >= 20000) {  // locality renumbering for the solvers: shared, computed on first use
+        if (!mesh->ord) {
+            mesh->ord = std::make_shared<lb_order>();
+            mesh->ord->ctx = c;
+            mesh->ord->v4 = mesh->v4s;
+            mesh->ord->n = mesh->n_ref;
         }
-        (*b_out)->order = mesh->order;
-        (*b_out)->order_inv = mesh->order_inv;
+        if (a_out && *a_out) (*a_out)->ord = mesh->ord;
+        (*b_out)->ord = mesh->ord;
     }
     sync(c);  // u1/u2/aniso_mat are borrowed host buffers
     phase(c, "rows");

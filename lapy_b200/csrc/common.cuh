@@ -200,12 +200,26 @@ void exclusive_scan_i32(lb_ctx *ctx, const int32_t *in, int32_t *out, int64_t n)
 }  // namespace lb
 
 // ---- device objects ---------------------------------------------------------------------
+// Locality renumbering of the vertices (Morton order of a 128^3 cell grid), shared by a mesh and
+// the matrices assembled on it and computed lazily by the first solver that wants it.
+struct lb_order {
+    lb_ctx *ctx = nullptr;
+    std::shared_ptr<lb::DBuf<lb::D4>> v4;  // vertex positions (kept alive for the lazy computation)
+    int64_t n = 0;                         // matrix dimension (max referenced vertex + 1)
+    lb::DBuf<int32_t> order, inv;          // new -> old, old -> new; empty until ensure()
+    bool ready = false;
+};
+namespace lb {
+void ensure_order(lb_order &o);  // assembly.cu
+}
+
 struct lb_mesh {
     lb_ctx *ctx = nullptr;
     int64_t nv = 0, nt = 0;
     int k = 3;              // vertices per element
     int v_dtype = LB_F64;   // dtype of the caller's vertices: element math runs in it
-    lb::DBuf<lb::D4> v4;    // (nv) fp64 xyz + pad: one 32-byte sector per gathered vertex
+    std::shared_ptr<lb::DBuf<lb::D4>> v4s;  // owner of v4 (shared with lb_order)
+    lb::DBuf<lb::D4> &v4ref() { return *v4s; }
     lb::DBuf<float4> v4f;   // (nv) fp32 xyz + pad, only when v_dtype == LB_F32
     lb::DBuf<int4> t4;      // (nt) int32 x4, triangles padded with -1: one 16-byte load
     // vertex -> (element, corner) incidence, built on first use: code = element*4 + corner,
@@ -214,9 +228,7 @@ struct lb_mesh {
     lb::DBuf<int32_t> inc;      // (k*nt)
     int64_t n_ref = 0;          // max referenced vertex + 1 (matrix dimension)
     bool has_inc = false;
-    // locality ordering of the vertices (Morton order of a 128^3 cell grid): new -> old and
-    // old -> new; handed to the matrices assembled from this mesh (solver-internal renumbering)
-    std::shared_ptr<lb::DBuf<int32_t>> order, order_inv;
+    std::shared_ptr<lb_order> ord;  // handed to the matrices assembled from this mesh
 };
 
 struct lb_mat {
@@ -227,7 +239,7 @@ struct lb_mat {
     lb::DBuf<int32_t> indices;  // (nnz) sorted, unique per row
     lb::DBuf<double> data;      // (nnz)
     bool diagonal = false;      // every stored entry is on the diagonal (lumped mass / identity)
-    // optional locality ordering hint (from the mesh the matrix was assembled on): new -> old,
-    // old -> new.  Solvers may renumber internally; results are always in the caller's order.
-    std::shared_ptr<lb::DBuf<int32_t>> order, order_inv;
+    // optional locality ordering (from the mesh the matrix was assembled on).  Solvers may
+    // renumber internally; results are always returned in the caller's order.
+    std::shared_ptr<lb_order> ord;
 };

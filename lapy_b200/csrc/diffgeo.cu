@@ -172,12 +172,12 @@ int lb_gradient(lb_ctx *c, lb_mesh *mesh, const double *f, int64_t nf, double *g
         if (mesh->v_dtype == LB_F32)
             LB_LAUNCH(c, tria_gradient_kernel<float>, grid, 256, 0, mesh->v4f.p, mesh->t4.p, nt, df.p, (int)nf, dg.p);
         else
-            LB_LAUNCH(c, tria_gradient_kernel<double>, grid, 256, 0, mesh->v4.p, mesh->t4.p, nt, df.p, (int)nf, dg.p);
+            LB_LAUNCH(c, tria_gradient_kernel<double>, grid, 256, 0, mesh->v4s->p, mesh->t4.p, nt, df.p, (int)nf, dg.p);
     } else {
         if (mesh->v_dtype == LB_F32)
             LB_LAUNCH(c, tet_gradient_kernel<float>, grid, 256, 0, mesh->v4f.p, mesh->t4.p, nt, df.p, (int)nf, dg.p);
         else
-            LB_LAUNCH(c, tet_gradient_kernel<double>, grid, 256, 0, mesh->v4.p, mesh->t4.p, nt, df.p, (int)nf, dg.p);
+            LB_LAUNCH(c, tet_gradient_kernel<double>, grid, 256, 0, mesh->v4s->p, mesh->t4.p, nt, df.p, (int)nf, dg.p);
     }
     d2h(c, g, dg.p, (size_t)nt * nf * 3 * sizeof(double));
     sync(c);
@@ -199,12 +199,12 @@ int lb_divergence(lb_ctx *c, lb_mesh *mesh, const double *x, int64_t nf, double 
         if (mesh->v_dtype == LB_F32)
             LB_LAUNCH(c, tria_div_corner_kernel<float>, grid, 256, 0, mesh->v4f.p, mesh->t4.p, nt, dx.p, (int)nf, cx.p);
         else
-            LB_LAUNCH(c, tria_div_corner_kernel<double>, grid, 256, 0, mesh->v4.p, mesh->t4.p, nt, dx.p, (int)nf, cx.p);
+            LB_LAUNCH(c, tria_div_corner_kernel<double>, grid, 256, 0, mesh->v4s->p, mesh->t4.p, nt, dx.p, (int)nf, cx.p);
     } else {
         if (mesh->v_dtype == LB_F32)
             LB_LAUNCH(c, tet_div_corner_kernel<float>, grid, 256, 0, mesh->v4f.p, mesh->t4.p, nt, dx.p, (int)nf, cx.p);
         else
-            LB_LAUNCH(c, tet_div_corner_kernel<double>, grid, 256, 0, mesh->v4.p, mesh->t4.p, nt, dx.p, (int)nf, cx.p);
+            LB_LAUNCH(c, tet_div_corner_kernel<double>, grid, 256, 0, mesh->v4s->p, mesh->t4.p, nt, dx.p, (int)nf, cx.p);
     }
     // 0.5 * sum (tria, diffgeo.py:365, :385);  -(1/6) * sum (tet, diffgeo.py:986, :1004)
     const double scale = k == 3 ? 0.5 : -(1.0 / 6.0);

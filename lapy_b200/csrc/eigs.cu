@@ -443,10 +443,11 @@ static EigStats lobpcg(lb_ctx *c, const lb_mat *A0, const lb_mat *B0, int k, dou
     // of DRAM (ncu: 4.0x -> 1.1x of the algorithmic traffic).  Results return in the caller's order.
     std::unique_ptr<lb_mat> Ap, Bp;
     const lb_mat *A = A0, *B = B0;
-    const bool reorder = A0->order && A0->order == B0->order && (int64_t)A0->order->n == n && !getenv("LAPY_B200_NOREORDER");
+    const bool reorder = A0->ord && A0->ord == B0->ord && A0->ord->n == n && !getenv("LAPY_B200_NOREORDER");
     if (reorder) {
-        Ap = permute_symmetric(c, A0, A0->order->p, A0->order_inv->p);
-        Bp = permute_symmetric(c, B0, A0->order->p, A0->order_inv->p);
+        ensure_order(*A0->ord);
+        Ap = permute_symmetric(c, A0, A0->ord->order.p, A0->ord->inv.p);
+        Bp = permute_symmetric(c, B0, A0->ord->order.p, A0->ord->inv.p);
         A = Ap.get();
         B = Bp.get();
     }
@@ -505,7 +506,7 @@ static EigStats lobpcg(lb_ctx *c, const lb_mat *A0, const lb_mat *B0, int k, dou
     if (reorder) {
         // row i of the caller's numbering = row inv[i] of the renumbered block
         DBuf<double> out(c, (size_t)n * k);
-        gather_rows(c, n, k, A0->order_inv->p, xout.p, m, out.p, k);
+        gather_rows(c, n, k, A0->ord->inv.p, xout.p, m, out.p, k);
         d2h_large(c, h_evecs, out.p, (size_t)n * k * sizeof(double));
     } else {
         DBuf<double> out(c, (size_t)n * k);

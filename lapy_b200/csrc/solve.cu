@@ -377,7 +377,7 @@ static double avg_edge_length_device(lb_ctx *c, lb_mesh *mesh, lb_mat *pattern) 
     const int nb = 1024;
     DBuf<double> psum(c, nb);
     DBuf<unsigned long long> pcnt(c, nb);
-    LB_LAUNCH(c, edge_length_partial, nb, 256, 0, pattern->n, pattern->indptr.p, pattern->indices.p, mesh->v4.p, psum.p,
+    LB_LAUNCH(c, edge_length_partial, nb, 256, 0, pattern->n, pattern->indptr.p, pattern->indices.p, mesh->v4s->p, psum.p,
               pcnt.p);
     std::vector<double> hs(nb);
     std::vector<unsigned long long> hc(nb);
@@ -420,8 +420,9 @@ int lb_spmm_benchmark(lb_ctx *c, lb_mat *mat0, int64_t m, int reps, int renumber
     const int64_t n = mat0->n;
     std::unique_ptr<lb_mat> perm;
     lb_mat *mat = mat0;
-    if (renumber && mat0->order && (int64_t)mat0->order->n == n) {  // the numbering the solvers work in
-        perm = permute_symmetric(c, mat0, mat0->order->p, mat0->order_inv->p);
+    if (renumber && mat0->ord && mat0->ord->n == n) {  // the numbering the solvers work in
+        ensure_order(*mat0->ord);
+        perm = permute_symmetric(c, mat0, mat0->ord->order.p, mat0->ord->inv.p);
         mat = perm.get();
     }
     DBuf<double> dx(c, (size_t)n * m), dy(c, (size_t)n * m);
