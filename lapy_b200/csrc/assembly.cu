@@ -424,7 +424,6 @@ __global__ void __launch_bounds__(kRowThreads) row_fill_kernel(
         // longer rows / tets sort their own segment in place and stream it.
         constexpr int RS = 8;
         int4 qi[RS];
-        D4 qr[RS];
         const bool in_regs = K == 3 && ninc <= RS;
         if (in_regs) {
 #pragma unroll
@@ -439,9 +438,6 @@ __global__ void __launch_bounds__(kRowThreads) row_fill_kernel(
             LB_CSWAP(5, 7) LB_CSWAP(1, 2) LB_CSWAP(5, 6) LB_CSWAP(0, 4) LB_CSWAP(3, 7) LB_CSWAP(1, 5) LB_CSWAP(2, 6)
             LB_CSWAP(1, 4) LB_CSWAP(3, 6) LB_CSWAP(2, 4) LB_CSWAP(3, 5) LB_CSWAP(3, 4)
 #undef LB_CSWAP
-#pragma unroll
-            for (int u = 0; u < RS; u++)
-                if (u < ninc) qr[u] = ldg_d4(rec + (qi[u].x >> 2));
         } else {
             for (int i = beg + 1; i < end; i++) {
                 const int4 key = inc4[i];
@@ -453,22 +449,7 @@ __global__ void __launch_bounds__(kRowThreads) row_fill_kernel(
                 inc4[j + 1] = key;
             }
         }
-        for (int p = beg; p < end; p++) {
-            int4 r4;
-            D4 q;
-            if (in_regs) {
-                r4 = qi[0];
-                q = qr[0];
-#pragma unroll
-                for (int w = 1; w < RS; w++)
-                    if (p - beg == w) {
-                        r4 = qi[w];
-                        q = qr[w];
-                    }
-            } else {
-                r4 = inc4[p];
-                if (K == 3) q = ldg_d4(rec + (r4.x >> 2));
-            }
+        auto body = [&](const int4 r4, const D4 q) {
             const int code = r4.x;
             const int e = code >> 2, c = code & 3;
             if (K == 3) {
@@ -563,6 +544,20 @@ __global__ void __launch_bounds__(kRowThreads) row_fill_kernel(
                     accumulate(keys, av, bv, cnt, k2, x2, bij, want_a, want_b);
                     accumulate(keys, av, bv, cnt, (int)r, xd, bii, want_a, want_b);
                 }
+            }
+                };
+        if (in_regs) {
+            // fully unrolled: the element-record loads have register-known addresses, so the
+            // compiler may hoist them above the shared-memory accumulation of earlier incidences
+#pragma unroll
+            for (int u = 0; u < RS; u++)
+                if (u < ninc) body(qi[u], ldg_d4(rec + (qi[u].x >> 2)));
+        } else {
+            for (int p = beg; p < end; p++) {
+                const int4 r4 = inc4[p];
+                D4 q = {0.0, 0.0, 0.0, 0.0};
+                if (K == 3) q = ldg_d4(rec + (r4.x >> 2));
+                body(r4, q);
             }
         }
         if (out.lump_ptr && end > beg) {
