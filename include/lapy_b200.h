@@ -84,6 +84,15 @@ int lb_profile_report(lb_ctx *ctx, int64_t *count, double *ms, double *work);
 /* number of kernels this library has launched on ctx since creation */
 int lb_launch_count(lb_ctx *ctx, int64_t *count);
 
+/* ---- row-partitioned multi-GPU mode (one process per GPU, NCCL) -------------------------------
+ * rank 0 creates an id (128 bytes), the host program broadcasts it (torch.distributed, MPI, ...),
+ * every rank calls lb_comm_init on its context.  Afterwards lb_eigs on that context runs
+ * row-partitioned over all ranks: every rank passes the same (full) matrices and receives the full
+ * result.  The reference has no distributed mode. */
+int lb_nccl_unique_id(unsigned char *out128);
+int lb_comm_init(lb_ctx *ctx, int world, int rank, const unsigned char *id128);
+int lb_comm_destroy(lb_ctx *ctx);
+
 /* ---- mesh upload: geometry.v / geometry.t as the reference's Solver reads them --------- */
 /* v: (nv,3) LB_F32|LB_F64; t: (nt,k) signed integers of t_itemsize 4|8 bytes, k = 3|4.
  * Replaces the fancy-index gathers at lapy/solver.py:145-150, :418-425. */

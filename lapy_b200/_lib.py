@@ -51,6 +51,9 @@ SIGNATURES = {
     "lb_launch_count": [_vp, C.POINTER(_i64)],
     "lb_profile_enable": [_vp, _int],
     "lb_profile_report": [_vp, _vp, _vp, _vp],
+    "lb_nccl_unique_id": [_vp],
+    "lb_comm_init": [_vp, _int, _int, _vp],
+    "lb_comm_destroy": [_vp],
     "lb_mesh_create": [_vp, _vp, _int, _i64, _vp, _int, _i64, _int, _pp],
     "lb_mesh_update_vertices": [_vp, _vp, _int],
     "lb_mesh_drop_cache": [_vp],
@@ -140,6 +143,28 @@ class Context:
 
     def sync(self):
         check(lib().lb_ctx_sync(self.handle))
+
+    def init_row_partition(self):
+        """Join the row-partitioned mode: all ranks of the current torch.distributed group create
+        one NCCL communicator inside the library (lb_comm_init); afterwards ``Solver.eigs`` on this
+        context runs one eigensolve cooperatively over all ranks."""
+        import torch
+        import torch.distributed as dist
+
+        rank, world = dist.get_rank(), dist.get_world_size()
+        buf = np.zeros(128, np.uint8)
+        if rank == 0:
+            check(lib().lb_nccl_unique_id(ptr(buf)))
+        t = torch.from_numpy(buf)
+        if dist.get_backend() == "nccl":
+            t = t.to(torch.device("cuda", self.device))
+        dist.broadcast(t, 0)
+        buf = np.ascontiguousarray(t.cpu().numpy())
+        check(lib().lb_comm_init(self.handle, world, rank, ptr(buf)))
+        self.world, self.rank = world, rank
+
+    def leave_row_partition(self):
+        check(lib().lb_comm_destroy(self.handle))
 
     def timer_start(self):
         check(lib().lb_timer_start(self.handle))

@@ -83,3 +83,13 @@ def batched_shapedna(
         buf[i] = torch.from_numpy(ev).to(dev)
     dist.all_reduce(buf, op=dist.ReduceOp.SUM)  # disjoint rows: a sum is a gather
     return buf.cpu().numpy()
+
+
+def row_partition(n: int, world: int) -> list[tuple[int, int]]:
+    """Contiguous row blocks of the row-partitioned single-mesh mode (csrc/eigs.cu lobpcg_dist):
+    ``rows_per_rank = ceil(n / world)``, rank r owns ``[r*rpr, min(n, (r+1)*rpr))`` of the
+    locality-renumbered operator."""
+    if world < 1:
+        raise ValueError("world must be >= 1")
+    rpr = (n + world - 1) // world
+    return [(min(n, r * rpr), min(n, (r + 1) * rpr)) for r in range(world)]

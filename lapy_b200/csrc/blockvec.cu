@@ -402,18 +402,18 @@ __device__ __forceinline__ uint64_t splitmix64(uint64_t z) {
     return z ^ (z >> 31);
 }
 
-__global__ void fill_random_kernel(int64_t n, int cols, double *__restrict__ x, int ldx, uint64_t seed) {
+__global__ void fill_random_kernel(int64_t n, int cols, double *__restrict__ x, int ldx, uint64_t seed, int64_t row0) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n * cols) return;
     const int64_t row = t / cols;
     const int col = (int)(t - row * cols);
-    const uint64_t h = splitmix64(splitmix64(seed + (uint64_t)col) ^ (uint64_t)row);
+    const uint64_t h = splitmix64(splitmix64(seed + (uint64_t)col) ^ (uint64_t)(row0 + row));
     x[row * ldx + col] = (double)(h >> 11) * (2.0 / 9007199254740992.0) - 1.0;  // uniform [-1,1)
 }
 
-void fill_random(lb_ctx *c, int64_t n, int cols, double *x, int ldx, uint64_t seed) {
+void fill_random(lb_ctx *c, int64_t n, int cols, double *x, int ldx, uint64_t seed, int64_t row0) {
     if (n * cols == 0) return;
-    LB_LAUNCH(c, fill_random_kernel, cdiv(n * cols, 256), 256, 0, n, cols, x, ldx, seed);
+    LB_LAUNCH(c, fill_random_kernel, cdiv(n * cols, 256), 256, 0, n, cols, x, ldx, seed, row0);
 }
 
 __global__ void extract_diag_kernel(int64_t n, const int32_t *__restrict__ indptr, const int32_t *__restrict__ indices,

@@ -38,7 +38,8 @@ void copy_cols(lb_ctx *c, int64_t n, int cols, const double *x, int ldx, double 
 void scale_rows(lb_ctx *c, int64_t n, int cols, const double *d, const double *x, int ldx, double *y, int ldy);
 // subtract from every column its mean (constant null-space projection, lapy/diffgeo.py:156 solve)
 void remove_col_means(lb_ctx *c, int64_t n, int cols, double *x, int ldx);
-void fill_random(lb_ctx *c, int64_t n, int cols, double *x, int ldx, uint64_t seed);
+// row0: global index of the first local row (row-partitioned mode: same values as one process)
+void fill_random(lb_ctx *c, int64_t n, int cols, double *x, int ldx, uint64_t seed, int64_t row0 = 0);
 void extract_diagonal(lb_ctx *c, const lb_mat *a, double *d);  // d[i] = A[i,i] (0 if not stored)
 
 // ---- dense tall-skinny products (row-major blocks) -----------------------------------------

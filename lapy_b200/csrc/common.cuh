@@ -61,6 +61,7 @@ struct Error {
 
 }  // namespace lb
 
+struct lb_dist;
 struct lb_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -82,6 +83,7 @@ struct lb_ctx {
     };
     std::vector<ProfRec> prof;
     std::vector<cudaEvent_t> prof_pool;
+    lb_dist *dist = nullptr;  // NCCL communicator of the row-partitioned mode (lb_comm_init)
     // two pinned staging buffers for large device -> pageable-host results (eigenvectors)
     void *stage[2] = {nullptr, nullptr};
     cudaEvent_t stage_ev[2] = {nullptr, nullptr};

@@ -20,8 +20,43 @@
 #include <cusolverDn.h>
 
 #include "amg.cuh"
+#include "dist.cuh"
 
 namespace lb {
+
+// ---- row-partitioned mode: the three operations that communicate --------------------------------
+// Every rank owns the rows [rank*rpr, min(n, (rank+1)*rpr)) of the renumbered operator and the
+// matching rows of all block vectors.  SpMM all-gathers the block vector first (the operator's
+// columns are global); Gram matrices and column dots are summed over the ranks.  With D == NULL
+// these are the single-GPU operations.
+struct DistOps {
+    const DistCtx *d = nullptr;
+    int64_t rpr = 0;        // rows per rank (last rank may own fewer)
+    int64_t n_local = 0;
+    DBuf<double> pack, gath;  // (rpr, wcap), (world*rpr, wcap)
+};
+
+static void d_spmm(lb_ctx *c, DistOps *D, const lb_mat *a, const double *x, int ldx, double *y, int ldy, int w) {
+    if (!D) {
+        spmm(c, a, x, ldx, y, ldy, w);
+        return;
+    }
+    copy_cols(c, D->n_local, w, x, ldx, D->pack.p, w);
+    dist_allgather(c, D->d, D->pack.p, D->gath.p, (size_t)D->rpr * w);
+    spmm(c, a, D->gath.p, w, y, ldy, w);
+}
+
+static void d_gram(lb_ctx *c, DistOps *D, int64_t n, int p, const double *x, int ldx, int q, const double *y, int ldy,
+                   double *cmat, bool symmetric = false) {
+    gram(c, n, p, x, ldx, q, y, ldy, cmat, symmetric);
+    if (D) dist_allreduce_sum(c, D->d, cmat, (size_t)p * q);
+}
+
+static void d_dots(lb_ctx *c, DistOps *D, int64_t n, int cols, const double *x, int ldx, const double *y, int ldy,
+                   double *out) {
+    col_dots(c, n, cols, x, ldx, y, ldy, out);
+    if (D) dist_allreduce_sum(c, D->d, out, cols);
+}
 
 __global__ void set_column(int64_t n, double *x, int ld, int col, double v) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -31,13 +66,13 @@ __global__ void set_column(int64_t n, double *x, int ld, int col, double v) {
 // Cholesky-QR of W (n, q) in the B inner product, repeated twice; falls back to an eigen-based
 // whitening (SVQB) when the Gram matrix is numerically singular.  On return bw = B w.
 // Returns the number of columns kept (columns with negligible norm are dropped by SVQB).
-static int b_orthonormalize(lb_ctx *c, const lb_mat *B, int64_t n, int q, double *w, int ldw, double *bw, int ldbw,
-                            double *tmp /* n x q scratch, ld = q */, bool need_bw = true) {
+static int b_orthonormalize(lb_ctx *c, DistOps *D, const lb_mat *B, int64_t n, int q, double *w, int ldw, double *bw,
+                            int ldbw, double *tmp /* n x q scratch, ld = q */, bool need_bw = true) {
     DBuf<double> G(c, (size_t)q * q), ev(c, q);
     int kept = q;
     for (int rep = 0; rep < 2; rep++) {
-        spmm(c, B, w, ldw, bw, ldbw, kept);
-        gram(c, n, kept, w, ldw, kept, bw, ldbw, G.p, true);
+        d_spmm(c, D, B, w, ldw, bw, ldbw, kept);
+        d_gram(c, D, n, kept, w, ldw, kept, bw, ldbw, G.p, true);
         DBuf<double> Gc(c, (size_t)kept * kept);
         d2d(c, Gc.p, G.p, (size_t)kept * kept * sizeof(double));
         int info = chol_lower(c, kept, Gc.p);
@@ -99,7 +134,7 @@ static int b_orthonormalize(lb_ctx *c, const lb_mat *B, int64_t n, int q, double
         sync(c);
         kept = newq;
     }
-    if (need_bw) spmm(c, B, w, ldw, bw, ldbw, kept);
+    if (need_bw) d_spmm(c, D, B, w, ldw, bw, ldbw, kept);
     return kept;
 }
 
@@ -244,7 +279,8 @@ struct EigStats {
 // One level of the (nested) iteration: LOBPCG on (A, B) with the multigrid cycle started at
 // `lvl` as preconditioner.  x0 (n, m): optional initial block; x_out (n, m, ld = m): result block.
 static EigStats lobpcg_core(lb_ctx *c, const lb_mat *A, const lb_mat *B, Amg *amg, int lvl, const double *x0, int ldx0,
-                            int k, int m, double tol, int maxit, std::vector<double> &lam, double *x_out) {
+                            int k, int m, double tol, int maxit, std::vector<double> &lam, double *x_out,
+                            DistOps *D = nullptr, int64_t row0 = 0) {
     const int64_t n = A->n;
     EigStats st;
     const int ld = 3 * m;
@@ -272,15 +308,15 @@ static EigStats lobpcg_core(lb_ctx *c, const lb_mat *A, const lb_mat *B, Amg *am
     if (x0) {
         copy_cols(c, n, m, x0, ldx0, S[0].p, ld);  // prolonged coarse-level eigenvectors
     } else {
-        fill_random(c, n, m, S[0].p, ld, 0x1234567ull);
+        fill_random(c, n, m, S[0].p, ld, 0x1234567ull, row0);
         LB_LAUNCH(c, set_column, cdiv(n, 256), 256, 0, n, S[0].p, ld, 0, 1.0);
     }
-    int kept = b_orthonormalize(c, B, n, m, S[0].p, ld, BS[0].p, ld, tmp.p);
+    int kept = b_orthonormalize(c, D, B, n, m, S[0].p, ld, BS[0].p, ld, tmp.p);
     LB_REQUIRE(kept == m, "initial block is rank deficient");
-    spmm(c, A, S[0].p, ld, AS[0].p, ld, m);
+    d_spmm(c, D, A, S[0].p, ld, AS[0].p, ld, m);
     auto rayleigh_ritz = [&](int s, int mp_hint, const std::vector<int> &active_cols, int &mp_new) {
         // G = S^T A S (s x s); eigenvectors -> Cx; Cp from the active columns
-        gram(c, n, s, S[cur].p, ld, s, AS[cur].p, ld, G.p, true);
+        d_gram(c, D, n, s, S[cur].p, ld, s, AS[cur].p, ld, G.p, true);
         int info = sym_eig(c, s, G.p, evd.p);
         LB_REQUIRE(info == 0, "Rayleigh-Ritz eigen-decomposition failed (info=%d)", info);
         const int q = (int)active_cols.size();
@@ -328,8 +364,8 @@ static EigStats lobpcg_core(lb_ctx *c, const lb_mat *A, const lb_mat *B, Amg *am
         update(c, n, s, S[cur].p, ld, w, coef.p, w, 1.0, 0.0, S[nxt].p, ld);
         // A [X P] and B [X P] are recomputed by SpMM (HBM-bound, ~2 ms at level 9) instead of
         // being carried through two more (n, s) x (s, w) products (~13 ms): cheaper and drift-free
-        spmm(c, A, S[nxt].p, ld, AS[nxt].p, ld, w);
-        spmm(c, B, S[nxt].p, ld, BS[nxt].p, ld, w);
+        d_spmm(c, D, A, S[nxt].p, ld, AS[nxt].p, ld, w);
+        d_spmm(c, D, B, S[nxt].p, ld, BS[nxt].p, ld, w);
         h2d(c, lam_d.p, lam.data(), m * sizeof(double));
         sync(c);  // coefh / lam are host buffers
         cur = nxt;
@@ -354,8 +390,8 @@ static EigStats lobpcg_core(lb_ctx *c, const lb_mat *A, const lb_mat *B, Amg *am
         std::iota(idx.begin(), idx.end(), 0);
         h2d(c, idx_d.p, idx.data(), m * sizeof(int));
         residual_cols(c, n, m, idx_d.p, lam_d.p, AS[cur].p, ld, BS[cur].p, ld, Rbuf.p, m);
-        col_dots(c, n, m, Rbuf.p, m, Rbuf.p, m, dots.p);
-        col_dots(c, n, m, BS[cur].p, ld, BS[cur].p, ld, dots.p + m);
+        d_dots(c, D, n, m, Rbuf.p, m, Rbuf.p, m, dots.p);
+        d_dots(c, D, n, m, BS[cur].p, ld, BS[cur].p, ld, dots.p + m);
         read_back(c, rr.data(), dots.p, 2 * m);
         double lam_mean = 0;
         for (int j = 0; j < k; j++) lam_mean += std::fabs(lam[j]);
@@ -400,14 +436,14 @@ static EigStats lobpcg_core(lb_ctx *c, const lb_mat *A, const lb_mat *B, Amg *am
         // (T r is not nearly parallel to span[X P], so one pass leaves O(10 eps) - checked by the
         // B-orthonormality assertion of the GPU tests)
         for (int rep = 0; rep < (it < 2 ? 2 : ortho_passes); rep++) {
-            gram(c, n, w0, BS[cur].p, ld, ma, W, ld, G.p);                        // (w0 x ma)
+            d_gram(c, D, n, w0, BS[cur].p, ld, ma, W, ld, G.p);                   // (w0 x ma)
             update(c, n, w0, S[cur].p, ld, ma, G.p, ma, -1.0, 1.0, W, ld);        // W -= [X P] G
         }
         pt.stop(2);
-        const int mw = b_orthonormalize(c, B, n, ma, W, ld, BW, ld, tmp.p, false);
+        const int mw = b_orthonormalize(c, D, B, n, ma, W, ld, BW, ld, tmp.p, false);
         if (mw == 0) break;  // nothing left to add: stagnation
         pt.stop(3);
-        spmm(c, A, W, ld, AW, ld, mw);
+        d_spmm(c, D, A, W, ld, AW, ld, mw);
         pt.stop(4);
         // ---- Rayleigh-Ritz on [X P W]
         rayleigh_ritz(w0 + mw, mp, active_cols, mp);
@@ -517,6 +553,65 @@ static EigStats lobpcg(lb_ctx *c, const lb_mat *A0, const lb_mat *B0, int k, dou
     return st;
 }
 
+// ---- row-partitioned driver ------------------------------------------------------------------------
+// Every rank holds the full (identical) A and B - assembled redundantly, 1-30 ms - renumbers them,
+// keeps its contiguous row block, preconditions with an AMG hierarchy of its own diagonal block
+// (block-Jacobi / non-overlapping additive Schwarz: no communication inside the cycle) and runs the
+// same LOBPCG: identical small dense problems on every rank (all-reduced Gram matrices are bitwise
+// equal), so no rank needs to be told what the others decided.
+static EigStats lobpcg_dist(lb_ctx *c, const DistCtx *dist, const lb_mat *A0, const lb_mat *B0, int k, double sigma,
+                            double tol, int maxit, double *h_evals, double *h_evecs) {
+    const int64_t n = A0->n;
+    std::unique_ptr<lb_mat> Ap, Bp;
+    const lb_mat *A = A0, *B = B0;
+    const bool reorder = A0->ord && A0->ord == B0->ord && A0->ord->n == n;
+    if (reorder) {
+        ensure_order(*A0->ord);
+        Ap = permute_symmetric(c, A0, A0->ord->order.p, A0->ord->inv.p);
+        Bp = permute_symmetric(c, B0, A0->ord->order.p, A0->ord->inv.p);
+        A = Ap.get();
+        B = Bp.get();
+    }
+    const int m = ((k + std::max(6, (k + 3) / 4) + 7) / 8) * 8;
+    const int world = dist->world, rank = dist->rank;
+    const int64_t rpr = (n + world - 1) / world;
+    const int64_t r0 = std::min(n, rank * rpr), r1 = std::min(n, r0 + rpr);
+    LB_REQUIRE(r1 - r0 >= 4 * m, "row block of rank %d too small (%lld rows) for a block of %d", rank, (long long)(r1 - r0), m);
+    const double shift = sigma < 0 ? -sigma : 1e-2;
+    auto Kfull = mat_axpby(c, A, 1.0, B, shift);  // on the full matrices: handles a diagonal (lumped) B
+    auto Ar = row_block(c, A, r0, r1, world * rpr);
+    auto Br = row_block(c, B, r0, r1, world * rpr);  // general CSR with global columns (also when B is diagonal)
+    auto Kr = row_block(c, Kfull.get(), r0, r1, world * rpr);
+    Kfull.reset();
+    auto Kll = diag_block(c, Kr.get(), r0, r1);
+    Kr.reset();
+    Ap.reset();  // the full renumbered copies are no longer needed
+    Bp.reset();
+    AmgOptions opt;
+    auto amg = amg_setup(c, std::move(Kll), m, opt);
+    DistOps D;
+    D.d = dist;
+    D.rpr = rpr;
+    D.n_local = r1 - r0;
+    D.pack.alloc(c, (size_t)rpr * 2 * m);
+    D.pack.zero();
+    D.gath.alloc(c, (size_t)world * rpr * 2 * m);
+    std::vector<double> lam;
+    DBuf<double> xloc(c, (size_t)(r1 - r0) * m);
+    EigStats st = lobpcg_core(c, Ar.get(), Br.get(), amg.get(), 0, nullptr, 0, k, m, tol, maxit, lam, xloc.p, &D, r0);
+    st.setup_ms = amg->setup_ms;
+    for (int j = 0; j < k; j++) h_evals[j] = lam[j];
+    // all-gather the k eigenvector columns, undo the renumbering, return the full array on every rank
+    DBuf<double> pk(c, (size_t)rpr * k), full(c, (size_t)world * rpr * k), out(c, (size_t)n * k);
+    pk.zero();
+    copy_cols(c, r1 - r0, k, xloc.p, m, pk.p, k);
+    dist_allgather(c, dist, pk.p, full.p, (size_t)rpr * k);
+    if (reorder) gather_rows(c, n, k, A0->ord->inv.p, full.p, k, out.p, k);
+    else d2d(c, out.p, full.p, (size_t)n * k * sizeof(double));
+    d2h_large(c, h_evecs, out.p, (size_t)n * k * sizeof(double));
+    return st;
+}
+
 // ---- dense path for tiny problems (n too small for a 3m-wide basis) -----------------------------
 __global__ void densify_sym(int64_t n, const int32_t *__restrict__ ptr, const int32_t *__restrict__ idx,
                             const double *__restrict__ val, double *__restrict__ dense) {
@@ -586,6 +681,8 @@ extern "C" int lb_eigs(lb_ctx *c, lb_mat *a, lb_mat *b, int k, double sigma, dou
     if (a->n <= std::max<int64_t>(4 * m, 600)) {
         dense_eigs(c, a, b, k, evals, evecs);
         st.converged = k;
+    } else if (c->dist && c->dist->world > 1) {
+        st = lobpcg_dist(c, c->dist, a, b, k, sigma, tol, maxit, evals, evecs);
     } else {
         st = lobpcg(c, a, b, k, sigma, tol, maxit, evals, evecs);
     }

@@ -10,7 +10,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from lapy_b200.batch import batched_shapedna, shard_indices
+from lapy_b200.batch import batched_shapedna, row_partition, shard_indices
 
 
 def test_shard_indices_partition():
@@ -70,3 +70,13 @@ def test_world_size_2_gloo_gather():
     for rank, out, seen in res:
         np.testing.assert_array_equal(out, ref)  # every rank holds the full table
         assert seen == list(range(rank, 7, 2))  # and computed only its own shard
+
+
+def test_row_partition_covers_all_rows():
+    for n in (1, 7, 40962, 2621442, 1771561):
+        for world in (1, 2, 4, 8):
+            parts = row_partition(n, world)
+            assert parts[0][0] == 0 and parts[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(parts, parts[1:]))
+            sizes = [b - a for a, b in parts]
+            assert max(sizes) == -(-n // world) and all(s >= 0 for s in sizes)
