@@ -29,12 +29,35 @@ namespace lb {
 // matching rows of all block vectors.  SpMM all-gathers the block vector first (the operator's
 // columns are global); Gram matrices and column dots are summed over the ranks.  With D == NULL
 // these are the single-GPU operations.
+// plain cudaMalloc buffer: NCCL transports (P2P / IPC) must not be handed stream-ordered pool memory
+struct RawBuf {
+    double *p = nullptr;
+    size_t n = 0;
+    void alloc(size_t count) {
+        release();
+        n = count;
+        if (count) LB_CUDA(cudaMalloc((void **)&p, count * sizeof(double)));
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+    }
+    ~RawBuf() { release(); }
+};
+
 struct DistOps {
     const DistCtx *d = nullptr;
     int64_t rpr = 0;        // rows per rank (last rank may own fewer)
     int64_t n_local = 0;
-    DBuf<double> pack, gath;  // (rpr, wcap), (world*rpr, wcap)
+    RawBuf pack, gath, red;  // (rpr, wcap), (world*rpr, wcap), all-reduce staging
 };
+
+static void d_allreduce(lb_ctx *c, DistOps *D, double *buf, size_t count) {
+    LB_REQUIRE(count <= D->red.n, "all-reduce staging buffer too small");
+    d2d(c, D->red.p, buf, count * sizeof(double));
+    dist_allreduce_sum(c, D->d, D->red.p, count);
+    d2d(c, buf, D->red.p, count * sizeof(double));
+}
 
 static void d_spmm(lb_ctx *c, DistOps *D, const lb_mat *a, const double *x, int ldx, double *y, int ldy, int w) {
     if (!D) {
@@ -49,13 +72,13 @@ static void d_spmm(lb_ctx *c, DistOps *D, const lb_mat *a, const double *x, int 
 static void d_gram(lb_ctx *c, DistOps *D, int64_t n, int p, const double *x, int ldx, int q, const double *y, int ldy,
                    double *cmat, bool symmetric = false) {
     gram(c, n, p, x, ldx, q, y, ldy, cmat, symmetric);
-    if (D) dist_allreduce_sum(c, D->d, cmat, (size_t)p * q);
+    if (D) d_allreduce(c, D, cmat, (size_t)p * q);
 }
 
 static void d_dots(lb_ctx *c, DistOps *D, int64_t n, int cols, const double *x, int ldx, const double *y, int ldy,
                    double *out) {
     col_dots(c, n, cols, x, ldx, y, ldy, out);
-    if (D) dist_allreduce_sum(c, D->d, out, cols);
+    if (D) d_allreduce(c, D, out, cols);
 }
 
 __global__ void set_column(int64_t n, double *x, int ld, int col, double v) {
@@ -593,21 +616,23 @@ static EigStats lobpcg_dist(lb_ctx *c, const DistCtx *dist, const lb_mat *A0, co
     D.d = dist;
     D.rpr = rpr;
     D.n_local = r1 - r0;
-    D.pack.alloc(c, (size_t)rpr * 2 * m);
-    D.pack.zero();
-    D.gath.alloc(c, (size_t)world * rpr * 2 * m);
+    D.pack.alloc((size_t)rpr * 2 * m);
+    LB_CUDA(cudaMemsetAsync(D.pack.p, 0, D.pack.n * sizeof(double), c->stream));
+    D.gath.alloc((size_t)world * rpr * 2 * m);
+    D.red.alloc((size_t)9 * m * m + 4 * m);
+    if (c->trace) fprintf(stderr, "[lb trace] rank %d: rows [%lld, %lld) of %lld, AMG levels %zu\n", rank, (long long)r0,
+                          (long long)r1, (long long)n, amg->levels.size());
     std::vector<double> lam;
     DBuf<double> xloc(c, (size_t)(r1 - r0) * m);
     EigStats st = lobpcg_core(c, Ar.get(), Br.get(), amg.get(), 0, nullptr, 0, k, m, tol, maxit, lam, xloc.p, &D, r0);
     st.setup_ms = amg->setup_ms;
     for (int j = 0; j < k; j++) h_evals[j] = lam[j];
     // all-gather the k eigenvector columns, undo the renumbering, return the full array on every rank
-    DBuf<double> pk(c, (size_t)rpr * k), full(c, (size_t)world * rpr * k), out(c, (size_t)n * k);
-    pk.zero();
-    copy_cols(c, r1 - r0, k, xloc.p, m, pk.p, k);
-    dist_allgather(c, dist, pk.p, full.p, (size_t)rpr * k);
-    if (reorder) gather_rows(c, n, k, A0->ord->inv.p, full.p, k, out.p, k);
-    else d2d(c, out.p, full.p, (size_t)n * k * sizeof(double));
+    DBuf<double> out(c, (size_t)n * k);
+    copy_cols(c, r1 - r0, k, xloc.p, m, D.pack.p, k);
+    dist_allgather(c, dist, D.pack.p, D.gath.p, (size_t)rpr * k);
+    if (reorder) gather_rows(c, n, k, A0->ord->inv.p, D.gath.p, k, out.p, k);
+    else d2d(c, out.p, D.gath.p, (size_t)n * k * sizeof(double));
     d2h_large(c, h_evecs, out.p, (size_t)n * k * sizeof(double));
     return st;
 }

@@ -53,9 +53,9 @@ def test_two_rank_row_partitioned_eigs():
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    res = [q.get(timeout=600) for _ in procs]
+    res = [q.get(timeout=150) for _ in procs]
     for p in procs:
-        p.join(timeout=120)
+        p.join(timeout=60)
         assert p.exitcode == 0
     ref = load_golden("spectra")["ico6_k50"]
     for rank, ev, orth, resid, info in res:
