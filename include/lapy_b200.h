@@ -92,6 +92,9 @@ int lb_launch_count(lb_ctx *ctx, int64_t *count);
 int lb_nccl_unique_id(unsigned char *out128);
 int lb_comm_init(lb_ctx *ctx, int world, int rank, const unsigned char *id128);
 int lb_comm_destroy(lb_ctx *ctx);
+/* self-check of the communicating primitives (row-partitioned SpMM, all-reduced Gram) against
+ * redundant full computations on this rank: errs[0], errs[1] = max abs differences */
+int lb_dist_selftest(lb_ctx *ctx, lb_mat *a, double *errs);
 
 /* ---- mesh upload: geometry.v / geometry.t as the reference's Solver reads them --------- */
 /* v: (nv,3) LB_F32|LB_F64; t: (nt,k) signed integers of t_itemsize 4|8 bytes, k = 3|4.

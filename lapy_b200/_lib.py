@@ -54,6 +54,7 @@ SIGNATURES = {
     "lb_nccl_unique_id": [_vp],
     "lb_comm_init": [_vp, _int, _int, _vp],
     "lb_comm_destroy": [_vp],
+    "lb_dist_selftest": [_vp, _vp, _vp],
     "lb_mesh_create": [_vp, _vp, _int, _i64, _vp, _int, _i64, _int, _pp],
     "lb_mesh_update_vertices": [_vp, _vp, _int],
     "lb_mesh_drop_cache": [_vp],
@@ -162,6 +163,14 @@ class Context:
         buf = np.ascontiguousarray(t.cpu().numpy())
         check(lib().lb_comm_init(self.handle, world, rank, ptr(buf)))
         self.world, self.rank = world, rank
+
+    def init_row_partition_single(self):
+        """One-rank communicator (testing aid: exercises the row-partitioned code path on one GPU
+        together with LAPY_B200_FORCE_DIST=1)."""
+        buf = np.zeros(128, np.uint8)
+        check(lib().lb_nccl_unique_id(ptr(buf)))
+        check(lib().lb_comm_init(self.handle, 1, 0, ptr(buf)))
+        self.world, self.rank = 1, 0
 
     def leave_row_partition(self):
         check(lib().lb_comm_destroy(self.handle))
