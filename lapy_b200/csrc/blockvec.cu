@@ -130,43 +130,6 @@ __global__ void __launch_bounds__(256) spmm_kernel(int64_t n, const int32_t *__r
     }
 }
 
-// ---- SpMV for 1-2 columns: 8 lanes per row, lanes over nonzeros, fixed shuffle tree -------------
-__global__ void __launch_bounds__(256) spmv_kernel(int64_t n, const int32_t *__restrict__ indptr,
-                                                   const int32_t *__restrict__ indices,
-                                                   const double *__restrict__ val, const double *__restrict__ x,
-                                                   int ldx, double *y, int ldy, int m, int mode,
-                                                   const double *b, int ldb) {
-    constexpr int G = 8;
-    const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
-    const int lane = threadIdx.x % G;
-    double s0 = 0.0, s1 = 0.0;
-    if (row < n) {
-        const int beg = indptr[row], end = indptr[row + 1];
-        for (int p = beg + lane; p < end; p += G) {
-            const int j = __ldg(indices + p);
-            const double a = __ldg(val + p);
-            s0 = fma(a, __ldg(x + (int64_t)j * ldx), s0);
-            if (m > 1) s1 = fma(a, __ldg(x + (int64_t)j * ldx + 1), s1);
-        }
-    }
-#pragma unroll
-    for (int o = G / 2; o; o >>= 1) {
-        s0 += __shfl_xor_sync(0xffffffffu, s0, o);
-        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-    }
-    if (row < n && lane == 0) {
-        if (mode == 1) {
-            s0 = b[row * ldb] - s0;
-            if (m > 1) s1 = b[row * ldb + 1] - s1;
-        } else if (mode == 2) {
-            s0 = b[row * ldb] + s0;
-            if (m > 1) s1 = b[row * ldb + 1] + s1;
-        }
-        y[row * ldy] = s0;
-        if (m > 1) y[row * ldy + 1] = s1;
-    }
-}
-
 // ---- SpMV, CSR-stream form: the CTA stages the products a_ij * x_j of a strip of 128 rows in
 // shared memory (one independent gather per thread and entry: maximal memory-level parallelism,
 // CSR arrays read fully coalesced), then one thread per row sums its segment left to right.

@@ -51,8 +51,6 @@ void gram(lb_ctx *c, int64_t n, int p, const double *x, int ldx, int q, const do
 // Y(n,q) = alpha * X(n,p) C(p,q) + beta * Y;  X must not alias Y
 void update(lb_ctx *c, int64_t n, int p, const double *x, int ldx, int q, const double *cmat, int ldc, double alpha,
             double beta, double *y, int ldy);
-// W(n,q) <- W L^-T  with L (q,q) row-major lower Cholesky factor (in place)
-void trsm_right_lt(lb_ctx *c, int64_t n, int q, const double *l, double *w, int ldw);
 
 // hand-written DMMA kernels (dmma.cu); gram()/update() dispatch to them unless LAPY_B200_DENSE=cublas
 void gram_dmma(lb_ctx *c, int64_t n, int p, const double *x, int ldx, int q, const double *y, int ldy, double *cmat,

@@ -95,16 +95,6 @@ void update(lb_ctx *c, int64_t n, int p, const double *x, int ldx, int q, const 
     c->launches++;
 }
 
-void trsm_right_lt(lb_ctx *c, int64_t n, int q, const double *l, double *w, int ldw) {
-    if (q == 0 || n == 0) return;
-    ProfScope prof(c, PROF_TRSM, 1.0 * n * q * q);
-    const double one = 1.0;
-    // W_rm <- W_rm L^-T  <=>  W_cm <- L^-1 W_cm; row-major lower L is column-major upper U = L^T
-    LB_CUBLAS(cublasDtrsm(blas(c), CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_UPPER, CUBLAS_OP_T, CUBLAS_DIAG_NON_UNIT, q,
-                          (int)n, &one, l, q, w, ldw));
-    c->launches++;
-}
-
 int chol_lower(lb_ctx *c, int q, double *g) {
     int lwork = 0;
     LB_CUSOLVER(cusolverDnDpotrf_bufferSize(solver(c), CUBLAS_FILL_MODE_UPPER, q, g, q, &lwork));
