@@ -133,19 +133,19 @@ __global__ void __launch_bounds__(256) spmm_kernel(int64_t n, const int32_t *__r
 // ---- SpMV, CSR-stream form: the CTA stages the products a_ij * x_j of a strip of 128 rows in
 // shared memory (one independent gather per thread and entry: maximal memory-level parallelism,
 // CSR arrays read fully coalesced), then one thread per row sums its segment left to right.
-constexpr int kSpmvRows = 128;  // ~900 (tri) / ~1900 (tet) entries per strip
+constexpr int kSpmvRowsMax = 256;  // rows per CTA: 256 (short rows, ~7 entries) or 128 (tets, ~15)
 constexpr int kSpmvCap = 2944;  // 2 x 23 KB products + row pointers < 48 KB static
 
-template <int MC>
+template <int MC, int ROWS>
 __global__ void __launch_bounds__(256) spmv_stream_kernel(int64_t n, const int32_t *__restrict__ indptr,
                                                           const int32_t *__restrict__ indices,
                                                           const double *__restrict__ val,
                                                           const double *__restrict__ x, int ldx, double *y, int ldy,
                                                           int m, int mode, const double *b, int ldb) {
     __shared__ double s_prod[MC][kSpmvCap];
-    __shared__ int32_t s_ptr[kSpmvRows + 1];
-    const int64_t strip0 = (int64_t)blockIdx.x * kSpmvRows;
-    const int nrows = (int)(min(n, strip0 + kSpmvRows) - strip0);
+    __shared__ int32_t s_ptr[ROWS + 1];
+    const int64_t strip0 = (int64_t)blockIdx.x * ROWS;
+    const int nrows = (int)(min(n, strip0 + ROWS) - strip0);
     for (int i = threadIdx.x; i <= nrows; i += 256) s_ptr[i] = __ldg(indptr + strip0 + i);
     __syncthreads();
     const int base = s_ptr[0], total = s_ptr[nrows] - base;
@@ -216,8 +216,14 @@ void spmm(lb_ctx *c, const lb_mat *a, const double *x, int ldx, double *y, int l
     const int32_t *ip = a->indptr.p, *ix = a->indices.p;
     const double *v = a->data.p;
     if (m <= 2) {
-        if (m == 1) LB_LAUNCH(c, spmv_stream_kernel<1>, cdiv(n, kSpmvRows), 256, 0, n, ip, ix, v, x, ldx, y, ldy, m, mode, b, ldb);
-        else LB_LAUNCH(c, spmv_stream_kernel<2>, cdiv(n, kSpmvRows), 256, 0, n, ip, ix, v, x, ldx, y, ldy, m, mode, b, ldb);
+        // 256 rows per CTA when the strip's entries fit the staging buffer on average (<= 10 per row)
+        const bool wide = a->nnz <= 10 * n;
+#define LB_SPMV(MC, ROWS) LB_LAUNCH(c, (spmv_stream_kernel<MC, ROWS>), cdiv(n, ROWS), 256, 0, n, ip, ix, v, x, ldx, y, ldy, m, mode, b, ldb)
+        if (m == 1 && wide) LB_SPMV(1, 256);
+        else if (m == 1) LB_SPMV(1, 128);
+        else if (wide) LB_SPMV(2, 256);
+        else LB_SPMV(2, 128);
+#undef LB_SPMV
         return;
     }
     // 16-byte vector loads of X need even leading dimension and a 16-byte aligned base

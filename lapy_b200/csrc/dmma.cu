@@ -11,6 +11,8 @@
 // The k index inside an 8-chunk is permuted (lane t owns k = 2t and 2t+1, used by two successive
 // MMAs) so that the A operand of `update` is one 16-byte load per lane; a sum over k is
 // order-independent up to rounding and the order is fixed -> bit-reproducible.
+#include <cstdlib>
+
 #include "blockvec.cuh"
 
 namespace lb {
@@ -101,8 +103,154 @@ __global__ void __launch_bounds__(256, 2)
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// update, pipelined form: the same 128 x 64 CTA tile, but X (128 rows x 8 k) and C (8 k x 64 cols)
+// chunks stream through a 4-stage cp.async ring in shared memory, so the tensor pipe is not
+// stalled on global-load latency (v1: 61 % tensor-active).  Needs 16-byte aligned rows of X and C;
+// the dispatcher falls back to the direct-load kernel otherwise.
+//   Xs[stage][row][8]      stride 8 doubles: quarter-warps read 8 x 16 B conflict-free
+//   Cs[stage][k][kUpdStride]
+// ---------------------------------------------------------------------------------------------
+constexpr int kUpdStages = 4;
+
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src, bool valid) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    const int sz = valid ? 16 : 0;  // src-size 0: the 16 destination bytes are zero-filled
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gmem_src), "r"(sz));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N));
+}
+
+__global__ void __launch_bounds__(256, 2)
+    update_dmma_pipe_kernel(int64_t n, int p, const double *__restrict__ x, int ldx, int q,
+                            const double *__restrict__ cmat, int ldc, double alpha, double beta, double *y, int ldy) {
+    extern __shared__ __align__(16) double smem_pipe[];
+    double *xs = smem_pipe;                                 // [stages][128][8]
+    double *cs = smem_pipe + kUpdStages * 128 * 8;          // [stages][8][kUpdStride]
+    const int p8 = (p + 7) & ~7, nchunk = p8 / 8;
+    const int col_tile = blockIdx.y * 64;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const int wr = (warp & 3) * 32, wc = (warp >> 2) * 32;
+    const int64_t ntiles = (n + 127) / 128;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t row_base = tile * 128;
+        auto issue = [&](int chunk, int stage) {
+            const int k8 = chunk * 8;
+            // X chunk: 128 rows x 64 B = 512 pieces of 16 B, two per thread
+#pragma unroll
+            for (int it = 0; it < 2; it++) {
+                const int piece = threadIdx.x + it * 256;
+                const int r = piece >> 2, part = piece & 3;
+                const int64_t row = row_base + r;
+                const int k = k8 + 2 * part;
+                const bool ok = row < n && k < p;
+                const double *src = x + (ok ? row : 0) * ldx + (ok ? k : 0);
+                double *dst = xs + ((size_t)stage * 128 + r) * 8 + 2 * part;
+                if (ok && k + 1 >= p) {  // last odd column: plain stores of the single valid value
+                    dst[0] = __ldg(src);
+                    dst[1] = 0.0;
+                } else {
+                    cp_async16(dst, src, ok);
+                }
+            }
+            // C chunk: 8 rows x 64 cols = 256 pieces of 16 B, one per thread
+            {
+                const int r = threadIdx.x >> 5, part = threadIdx.x & 31;
+                const int k = k8 + r, col = col_tile + 2 * part;
+                const bool ok = k < p && col + 1 < q;
+                const double *src = cmat + (int64_t)(k < p ? k : 0) * ldc + (col + 1 < q ? col : 0);
+                double *dst = cs + ((size_t)stage * 8 + r) * kUpdStride + 2 * part;
+                if (!ok && k < p && col < q) {  // ragged last column
+                    dst[0] = __ldg(cmat + (int64_t)k * ldc + col);
+                    dst[1] = 0.0;
+                } else {
+                    cp_async16(dst, src, ok);
+                }
+            }
+        };
+        double acc[4][4][2];
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+        __syncthreads();  // the previous tile's readers are done with the ring
+#pragma unroll
+        for (int s0 = 0; s0 < kUpdStages - 1; s0++) {
+            if (s0 < nchunk) issue(s0, s0);
+            cp_async_commit();
+        }
+        for (int ch = 0; ch < nchunk; ch++) {
+            cp_async_wait<kUpdStages - 2>();
+            __syncthreads();  // chunk ch has landed for every thread; stage (ch-1) is free again
+            const int nx = ch + kUpdStages - 1;
+            if (nx < nchunk) issue(nx, nx % kUpdStages);
+            cp_async_commit();
+            const int stage = ch % kUpdStages;
+            const double *xst = xs + (size_t)stage * 128 * 8;
+            const double *cst = cs + (size_t)stage * 8 * kUpdStride;
+            double a0[4], a1[4], b0[4], b1[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const double2 v = *reinterpret_cast<const double2 *>(xst + (wr + 8 * i + g) * 8 + 2 * t);
+                a0[i] = v.x;
+                a1[i] = v.y;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                b0[j] = cst[(2 * t) * kUpdStride + wc + 8 * j + g];
+                b1[j] = cst[(2 * t + 1) * kUpdStride + wc + 8 * j + g];
+            }
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    dmma884(acc[i][j][0], acc[i][j][1], a0[i], b0[j]);
+                    dmma884(acc[i][j][0], acc[i][j][1], a1[i], b1[j]);
+                }
+        }
+        cp_async_wait<0>();
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int64_t r = row_base + wr + 8 * i + g;
+            if (r >= n) continue;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int col = col_tile + wc + 8 * j + 2 * t;
+                double *yp = y + r * ldy + col;
+                if (col < q) yp[0] = beta == 0.0 ? alpha * acc[i][j][0] : alpha * acc[i][j][0] + beta * yp[0];
+                if (col + 1 < q) yp[1] = beta == 0.0 ? alpha * acc[i][j][1] : alpha * acc[i][j][1] + beta * yp[1];
+            }
+        }
+    }
+}
+
 void update_dmma(lb_ctx *c, int64_t n, int p, const double *x, int ldx, int q, const double *cmat, int ldc,
                  double alpha, double beta, double *y, int ldy) {
+    static int use_pipe = -1;
+    if (use_pipe < 0) {
+        const char *e = getenv("LAPY_B200_UPDATE");
+        use_pipe = (e && !strcmp(e, "direct")) ? 0 : 1;
+    }
+    const bool aligned = (ldx % 2 == 0) && (ldc % 2 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) &&
+                         ((reinterpret_cast<uintptr_t>(cmat) & 15) == 0);
+    if (use_pipe && aligned) {
+        const size_t smem = (size_t)kUpdStages * (128 * 8 + 8 * kUpdStride) * sizeof(double);
+        static bool attr_pipe = false;
+        if (!attr_pipe) {
+            LB_CUDA(cudaFuncSetAttribute(update_dmma_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr_pipe = true;
+        }
+        const int ytiles = cdiv(q, 64);
+        const int64_t ntiles = (n + 127) / 128;
+        const int gx = (int)std::min<int64_t>(ntiles, std::max(1, (kSMs * 2) / ytiles));
+        dim3 grid(gx, ytiles);
+        LB_LAUNCH(c, update_dmma_pipe_kernel, grid, 256, smem, n, p, x, ldx, q, cmat, ldc, alpha, beta, y, ldy);
+        return;
+    }
     const int p8 = (p + 7) & ~7;
     const size_t smem = (size_t)p8 * kUpdStride * sizeof(double);
     static bool attr_set = false;
