@@ -195,6 +195,44 @@ def test_heat_geodesic_grad_div_vs_golden(golden, name):
     assert np.abs(geo2 - g["geodesic_2d"]).max() <= gtol * g["geodesic_2d"].max()
 
 
+def test_heat_geodesic_poisson_renumbered_path_vs_oracle():
+    """Meshes >= 20000 vertices are solved in the Morton-cell numbering (lb_solve); the answers must
+    still come back in the caller's order and match the SuperLU oracle: heat componentwise, geodesics,
+    Poisson with Dirichlet data and pure Neumann."""
+    import lapy_b200
+    from lapy_b200 import diffgeo, heat, mesh as M
+    from oracle import fem as ofem, solve as osolve
+
+    mesh = M.icosphere(6)  # 40962 vertices, hierarchical (poor-locality) vertex order
+    seeds = [0, 17, 40000]
+    u = heat.diffusion(mesh, seeds, m=1.0)
+    ref_u = osolve.diffusion(mesh, seeds, m=1.0)
+    nz = np.abs(ref_u) > 1e-280
+    assert np.all(np.abs(u - ref_u)[nz] <= 1e-7 * np.abs(ref_u)[nz]), (np.abs(u - ref_u)[nz] / np.abs(ref_u)[nz]).max()
+    um = heat.diffusion(mesh, [[0], [5, 6, 7]], m=4.0)  # two seed sets -> two columns
+    ref_um = osolve.diffusion(mesh, [[0], [5, 6, 7]], m=4.0)
+    nz = np.abs(ref_um) > 1e-280
+    assert um.shape == ref_um.shape
+    assert np.all(np.abs(um - ref_um)[nz] <= 1e-7 * np.abs(ref_um)[nz])
+    geo = diffgeo.compute_geodesic_f(mesh, u)
+    ref_geo = osolve.geodesic_f(mesh, ref_u)
+    assert np.abs(geo - ref_geo).max() <= 1e-6 * ref_geo.max()
+    fem = lapy_b200.Solver(mesh, lump=True)
+    a, b = ofem.fem(mesh, lump=True)
+    rng = np.random.default_rng(3)
+    h = rng.standard_normal((len(mesh.v), 2))
+    didx = np.array([3, 1000, 20000, 40961])
+    dval = np.array([0.5, -1.0, 2.0, 0.0])
+    x = fem.poisson(h, dtup=(didx, dval))
+    ref = osolve.poisson(a, b, h, dtup=(didx, dval))
+    assert np.abs(x - ref).max() <= 1e-8 * np.abs(ref).max()
+    np.testing.assert_array_equal(x[didx], np.column_stack((dval, dval)))
+    h0 = h[:, 0] - (b @ h[:, 0]).sum() / b.sum()  # compatible right-hand side for the singular system
+    x0 = fem.poisson(h0)
+    ref0 = osolve.poisson(a, b, h0)
+    assert np.abs((x0 - x0.mean()) - (ref0 - ref0.mean())).max() <= 1e-7 * np.abs(ref0 - ref0.mean()).max()
+
+
 def test_reference_geodesic_expected_outcomes(golden):
     """test_TriaMesh_Geodesics.py:185 / expected_outcomes.json: max geodesic 0.60497826 (rtol 1e-5)."""
     from lapy_b200 import Solver, diffgeo, heat
