@@ -239,11 +239,8 @@ void update_dmma(lb_ctx *c, int64_t n, int p, const double *x, int ldx, int q, c
                          ((reinterpret_cast<uintptr_t>(cmat) & 15) == 0);
     if (use_pipe && aligned) {
         const size_t smem = (size_t)kUpdStages * (128 * 8 + 8 * kUpdStride) * sizeof(double);
-        static bool attr_pipe = false;
-        if (!attr_pipe) {
-            LB_CUDA(cudaFuncSetAttribute(update_dmma_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            attr_pipe = true;
-        }
+        // per device (a process may drive several contexts): set every time, it is a cheap host call
+        LB_CUDA(cudaFuncSetAttribute(update_dmma_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const int ytiles = cdiv(q, 64);
         const int64_t ntiles = (n + 127) / 128;
         const int gx = (int)std::min<int64_t>(ntiles, std::max(1, (kSMs * 2) / ytiles));
@@ -253,11 +250,7 @@ void update_dmma(lb_ctx *c, int64_t n, int p, const double *x, int ldx, int q, c
     }
     const int p8 = (p + 7) & ~7;
     const size_t smem = (size_t)p8 * kUpdStride * sizeof(double);
-    static bool attr_set = false;
-    if (!attr_set) {
-        LB_CUDA(cudaFuncSetAttribute(update_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_set = true;
-    }
+    LB_CUDA(cudaFuncSetAttribute(update_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     LB_REQUIRE(smem <= 200 * 1024, "block update: inner dimension %d too large", p);
     const int ytiles = cdiv(q, 64);
     const int64_t ntiles = (n + 127) / 128;

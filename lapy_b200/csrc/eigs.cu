@@ -349,11 +349,7 @@ static EigStats lobpcg_core(lb_ctx *c, const lb_mat *A, const lb_mat *B, Amg *am
         if (smem <= 200 * 1024) {
             // coefficient matrix built on the device; the host only needs lambda and the count
             if (want_p) h2d(c, idx_d.p, active_cols.data(), q * sizeof(int));
-            static bool attr = false;
-            if (!attr) {
-                LB_CUDA(cudaFuncSetAttribute(rr_coef_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-                attr = true;
-            }
+            LB_CUDA(cudaFuncSetAttribute(rr_coef_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
             LB_LAUNCH(c, rr_coef_kernel, 1, 1024, smem, G.p, s, m, idx_d.p, want_p ? q : 0, coef.p, kept_d.p);
             d2h(c, lam.data(), evd.p, m * sizeof(double));
             int hk = 0;
