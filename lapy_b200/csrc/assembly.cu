@@ -19,6 +19,8 @@
 //                        exactly once; no atomics on values -> bit-reproducible.
 // No sort of the 9T / 16T triplets is ever materialised (SURVEY.md §7 "Hard parts").
 #include <climits>
+#include <cstdlib>
+#include <cstring>
 
 #include "common.cuh"
 
@@ -329,12 +331,15 @@ __device__ __forceinline__ void accumulate(int32_t *keys, double *av, double *bv
 template <int K>
 __global__ void __launch_bounds__(kRowThreads) row_count_kernel(
     const int32_t *__restrict__ inc_ptr, const int4 *__restrict__ inc4, int64_t n, int cap,
-    int32_t *__restrict__ scratch, int32_t *__restrict__ row_nnz, int32_t *__restrict__ row_has) {
+    int32_t *__restrict__ scratch, int32_t *__restrict__ row_nnz, int32_t *__restrict__ row_has,
+    const int32_t *__restrict__ only_rows) {
     extern __shared__ int32_t skeys[];
     __shared__ int s_total;
     int64_t r = (int64_t)blockIdx.x * kRowThreads + threadIdx.x;
     int beg = 0, end = 0;
-    if (r < n) {
+    // only_rows != NULL: second pass behind the fused kernel, only the rows it flagged (global scratch)
+    const bool skip = r >= n || (only_rows && !only_rows[r]);
+    if (!skip) {
         beg = inc_ptr[r];
         end = inc_ptr[r + 1];
     }
@@ -356,7 +361,7 @@ __global__ void __launch_bounds__(kRowThreads) row_count_kernel(
     if (threadIdx.x == kRowThreads - 1) s_total = base + incl;
     __syncthreads();
     int off = base + incl - ub;
-    int32_t *keys = (s_total <= cap) ? skeys + off : scratch + ((int64_t)beg * (K - 1) + r);
+    int32_t *keys = (s_total <= cap && !only_rows) ? skeys + off : scratch + ((int64_t)beg * (K - 1) + r);
     int cnt = 0;
     if (ninc) insert_key(keys, cnt, (int)r);
     for (int p = beg; p < end; p++) {  // streaming: the records of a row are contiguous
@@ -365,7 +370,7 @@ __global__ void __launch_bounds__(kRowThreads) row_count_kernel(
         insert_key(keys, cnt, q.z);
         if (K == 4) insert_key(keys, cnt, q.w);
     }
-    if (r < n) {
+    if (!skip) {
         row_nnz[r] = cnt;
         row_has[r] = ninc > 0;
     }
@@ -386,7 +391,7 @@ struct RowOut {
 template <int K>
 __global__ void __launch_bounds__(kRowThreads) row_fill_kernel(
     const D4 *__restrict__ rec, const int32_t *__restrict__ inc_ptr, int4 *inc4, int64_t n, int cap,
-    const ElemConsts *__restrict__ consts, int degen_div_f32, RowOut out) {
+    const ElemConsts *__restrict__ consts, int degen_div_f32, RowOut out, const int32_t *__restrict__ only_rows) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *s_a = reinterpret_cast<double *>(smem_raw);
     double *s_b = s_a + cap;
@@ -399,9 +404,10 @@ __global__ void __launch_bounds__(kRowThreads) row_fill_kernel(
     const int blk_nnz = blk_end - blk_beg;
     const bool want_a = out.a_val != nullptr, want_b = out.b_val != nullptr;
     const bool want_pat = want_a || want_b;
-    const bool use_smem = want_pat && blk_nnz <= cap;
+    // only_rows != NULL: second pass behind the fused kernels, only the flagged rows, straight to global
+    const bool use_smem = want_pat && blk_nnz <= cap && !only_rows;
 
-    if (r < n) {
+    if (r < n && (!only_rows || only_rows[r])) {
         const int rbeg = out.indptr[r];
         int32_t *keys;
         double *av, *bv;
@@ -572,6 +578,246 @@ __global__ void __launch_bounds__(kRowThreads) row_fill_kernel(
     if (use_smem) {
         __syncthreads();
         for (int q = threadIdx.x; q < blk_nnz; q += kRowThreads) {
+            const int key = s_k[q];
+            if (want_a) {
+                out.a_idx[blk_beg + q] = key;
+                out.a_val[blk_beg + q] = s_a[q];
+            }
+            if (want_b) {
+                out.b_idx[blk_beg + q] = key;
+                out.b_val[blk_beg + q] = s_b[q];
+            }
+        }
+    }
+}
+
+// ---- fused tet rows (LAPY_B200_TET_ROWS=fused; experimental until validated on the GPU) -------------
+// ncu (round 1) on the per-thread tet kernels: count 1.5 ms + fill 6.9 ms at cube121, 9 % issue
+// utilisation, 12 warps per SM, long-scoreboard bound - the fill sorts the row's ~24 incidence
+// records in place in GLOBAL memory and then walks record -> element -> accumulate one dependent
+// load at a time; the key set is discovered twice (count, fill).  Fused form, still one thread per
+// row (SIMD across rows; a lane-cooperative variant was instruction bound):
+//   A  row_accumulate_tet: sort (code, index) pairs in shared memory, gather 4 incidences = 4 + 12
+//      independent loads at a time, accumulate (key, A, B) ONCE into a fixed-capacity slice of
+//      shared memory ([slot][thread]: conflict free), write the block's image to a scratch of the
+//      same layout fully coalesced, row_nnz = number of keys;
+//   -  scan -> indptr (as before);
+//   B  row_compact: scratch -> shared-memory image of the block's CSR segment -> coalesced stores.
+// Rows with more than kFusedSI incidences or kFusedCap entries are flagged and done by the
+// per-thread kernels restricted to those rows (only_rows).
+constexpr int kFusedSI = 32;   // sortable incidences per row
+constexpr int kFusedCap = 16;  // entries per row
+constexpr int kFusedBatch = 4;
+
+struct TetCorner {
+    double x0, x1, x2, xd, bii, lmp;
+};
+// the four triplet values of corner c of a tet (column = corner, rows in the reference's triplet
+// order solver.py:472-497), its mass entries and lumped share
+__device__ __forceinline__ TetCorner tet_corner_values(int code, const D4 *__restrict__ rec,
+                                                       const ElemConsts *__restrict__ consts, int degen_div_f32) {
+    const int e = code >> 2, c = code & 3;
+    const D4 *rp = rec + 3 * (int64_t)e;
+    const D4 q0 = ldg_d4(rp), q1 = ldg_d4(rp + 1), q2 = ldg_d4(rp + 2);
+    double a12 = q0.x, a13 = q0.y, a14 = q0.z, a23 = q0.w, a24 = q1.x, a34 = q1.y;
+    double a11 = q1.z, a22 = q1.w, a33 = q2.x, a44 = q2.y, bii = q2.z, lmp = q2.w;
+    if (bii < 0.0) {  // clamped element: divide the numerators by the global mean (solver.py:436-437)
+        const double vm = consts->vol_mean;
+        if (degen_div_f32) {
+            const float vf = (float)vm;
+            float f12 = __fdiv_rn((float)a12, vf), f13 = __fdiv_rn((float)a13, vf);
+            float f14 = __fdiv_rn((float)a14, vf), f23 = __fdiv_rn((float)a23, vf);
+            float f24 = __fdiv_rn((float)a24, vf), f34 = __fdiv_rn((float)a34, vf);
+            a11 = (double)__fdiv_rn(__fsub_rn(__fsub_rn(-f12, f13), f14), 6.f);
+            a22 = (double)__fdiv_rn(__fsub_rn(__fsub_rn(-f12, f23), f24), 6.f);
+            a33 = (double)__fdiv_rn(__fsub_rn(__fsub_rn(-f13, f23), f34), 6.f);
+            a44 = (double)__fdiv_rn(__fsub_rn(__fsub_rn(-f14, f24), f34), 6.f);
+            a12 = (double)__fdiv_rn(f12, 6.f); a13 = (double)__fdiv_rn(f13, 6.f);
+            a14 = (double)__fdiv_rn(f14, 6.f); a23 = (double)__fdiv_rn(f23, 6.f);
+            a24 = (double)__fdiv_rn(f24, 6.f); a34 = (double)__fdiv_rn(f34, 6.f);
+        } else {
+            double f12 = __ddiv_rn(a12, vm), f13 = __ddiv_rn(a13, vm), f14 = __ddiv_rn(a14, vm);
+            double f23 = __ddiv_rn(a23, vm), f24 = __ddiv_rn(a24, vm), f34 = __ddiv_rn(a34, vm);
+            a11 = __ddiv_rn(__dsub_rn(__dsub_rn(-f12, f13), f14), 6.0);
+            a22 = __ddiv_rn(__dsub_rn(__dsub_rn(-f12, f23), f24), 6.0);
+            a33 = __ddiv_rn(__dsub_rn(__dsub_rn(-f13, f23), f34), 6.0);
+            a44 = __ddiv_rn(__dsub_rn(__dsub_rn(-f14, f24), f34), 6.0);
+            a12 = __ddiv_rn(f12, 6.0); a13 = __ddiv_rn(f13, 6.0); a14 = __ddiv_rn(f14, 6.0);
+            a23 = __ddiv_rn(f23, 6.0); a24 = __ddiv_rn(f24, 6.0); a34 = __ddiv_rn(f34, 6.0);
+        }
+        bii = consts->bii_deg;
+        lmp = consts->lump_deg;
+    }
+    TetCorner t;
+    t.bii = bii;
+    t.lmp = lmp;
+    if (c == 0) {
+        t.x0 = a12; t.x1 = a13; t.x2 = a14; t.xd = a11;
+    } else if (c == 1) {
+        t.x0 = a12; t.x1 = a23; t.x2 = a24; t.xd = a22;
+    } else if (c == 2) {
+        t.x0 = a23; t.x1 = a13; t.x2 = a34; t.xd = a33;
+    } else {
+        t.x0 = a14; t.x1 = a24; t.x2 = a34; t.xd = a44;
+    }
+    return t;
+}
+
+constexpr size_t kFusedSmemA = (size_t)kRowThreads * (kFusedSI * 8 + kFusedCap * 20);
+
+__global__ void __launch_bounds__(kRowThreads) row_accumulate_tet(
+    const D4 *__restrict__ rec, const int32_t *__restrict__ inc_ptr, const int4 *__restrict__ inc4, int64_t n,
+    const ElemConsts *__restrict__ consts, int degen_div_f32, int32_t *__restrict__ row_nnz,
+    int32_t *__restrict__ row_has, int32_t *__restrict__ row_big, int32_t *__restrict__ sc_key,
+    double *__restrict__ sc_a, double *__restrict__ sc_b, double *__restrict__ sc_lump) {
+    constexpr int T = kRowThreads, SI = kFusedSI, CAP = kFusedCap, NB = kFusedBatch;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    unsigned long long *s_ord = reinterpret_cast<unsigned long long *>(smem_raw);  // [SI][T]
+    double *s_a = reinterpret_cast<double *>(s_ord + SI * T);                      // [CAP][T]
+    double *s_b = s_a + CAP * T;                                                   // [CAP][T]
+    int32_t *s_k = reinterpret_cast<int32_t *>(s_b + CAP * T);                     // [CAP][T]
+    __shared__ int s_maxcnt;
+    const int t = threadIdx.x;
+    const int64_t r = (int64_t)blockIdx.x * T + t;
+    if (t == 0) s_maxcnt = 0;
+    __syncthreads();
+    int cnt = 0;
+    bool big = false;
+    if (r < n) {
+        const int beg = inc_ptr[r], ninc = inc_ptr[r + 1] - beg;
+        double lump = 0.0;
+        if (ninc > SI) {
+            big = true;
+        } else if (ninc > 0) {
+            // 1. (code << 8 | index) pairs, insertion-sorted in shared memory; codes fetched 8 at a time
+            for (int i0 = 0; i0 < ninc; i0 += 8) {
+                int c8[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) c8[u] = i0 + u < ninc ? __ldg(&inc4[beg + i0 + u].x) : 0;
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    const int i = i0 + u;
+                    if (i < ninc) {
+                        const unsigned long long key = ((unsigned long long)(unsigned)c8[u] << 8) | (unsigned)i;
+                        int j = i - 1;
+                        while (j >= 0 && s_ord[j * T + t] > key) {
+                            s_ord[(j + 1) * T + t] = s_ord[j * T + t];
+                            j--;
+                        }
+                        s_ord[(j + 1) * T + t] = key;
+                    }
+                }
+            }
+            // 2. replay in triplet order, NB incidences (NB + 3 NB independent loads) at a time
+            auto acc = [&](int key, double va, double vb) {
+                int pos = cnt;
+                while (pos > 0 && s_k[(pos - 1) * T + t] >= key) pos--;
+                if (pos < cnt && s_k[pos * T + t] == key) {
+                    s_a[pos * T + t] = __dadd_rn(s_a[pos * T + t], va);
+                    s_b[pos * T + t] = __dadd_rn(s_b[pos * T + t], vb);
+                    return;
+                }
+                if (cnt == CAP) {
+                    big = true;
+                    return;
+                }
+                for (int q = cnt; q > pos; q--) {
+                    s_k[q * T + t] = s_k[(q - 1) * T + t];
+                    s_a[q * T + t] = s_a[(q - 1) * T + t];
+                    s_b[q * T + t] = s_b[(q - 1) * T + t];
+                }
+                s_k[pos * T + t] = key;
+                s_a[pos * T + t] = va;  // first addend itself, like csr_sum_duplicates (keeps -0.0)
+                s_b[pos * T + t] = vb;
+                cnt++;
+            };
+            for (int j0 = 0; j0 < ninc && !big; j0 += NB) {
+                int4 q[NB];
+                TetCorner tc[NB];
+#pragma unroll
+                for (int u = 0; u < NB; u++)
+                    q[u] = j0 + u < ninc ? __ldg(inc4 + beg + (int)(s_ord[(j0 + u) * T + t] & 255ull)) : make_int4(0, 0, 0, 0);
+#pragma unroll
+                for (int u = 0; u < NB; u++)
+                    if (j0 + u < ninc) tc[u] = tet_corner_values(q[u].x, rec, consts, degen_div_f32);
+#pragma unroll
+                for (int u = 0; u < NB; u++)
+                    if (j0 + u < ninc) {
+                        const double bij = 0.5 * tc[u].bii;
+                        lump += tc[u].lmp;
+                        acc(q[u].y, tc[u].x0, bij);
+                        acc(q[u].z, tc[u].x1, bij);
+                        acc(q[u].w, tc[u].x2, bij);
+                        acc((int)r, tc[u].xd, tc[u].bii);
+                    }
+            }
+        }
+        row_has[r] = ninc > 0;
+        row_big[r] = big;
+        row_nnz[r] = big ? -1 : cnt;  // -1: the per-thread count kernel (only_rows) fills it in
+        sc_lump[r] = lump;
+        if (!big && cnt > 0) atomicMax(&s_maxcnt, cnt);
+    }
+    __syncthreads();
+    // 3. the block's [slot][thread] image, slots below the block maximum, fully coalesced
+    const int total = s_maxcnt * T;
+    const size_t base = (size_t)blockIdx.x * CAP * T;
+    for (int i = t; i < total; i += T) {
+        sc_key[base + i] = s_k[i];
+        sc_a[base + i] = s_a[i];
+        sc_b[base + i] = s_b[i];
+    }
+}
+
+// scratch ([block][slot][thread]) -> CSR.  Flagged rows are left to row_fill_kernel(only_rows).
+__global__ void __launch_bounds__(kRowThreads) row_compact_kernel(int64_t n, const int32_t *__restrict__ row_big,
+                                                                  const int32_t *__restrict__ sc_key,
+                                                                  const double *__restrict__ sc_a,
+                                                                  const double *__restrict__ sc_b,
+                                                                  const double *__restrict__ sc_lump, RowOut out) {
+    constexpr int T = kRowThreads, CAP = kFusedCap;
+    __shared__ double s_a[CAP * T];
+    __shared__ double s_b[CAP * T];
+    __shared__ int32_t s_k[CAP * T];
+    const int t = threadIdx.x;
+    const int64_t r0 = (int64_t)blockIdx.x * T, r = r0 + t;
+    const int64_t rlast = min(r0 + (int64_t)T, n);
+    const int blk_beg = out.indptr[r0], blk_nnz = out.indptr[rlast] - blk_beg;
+    const bool want_a = out.a_val != nullptr, want_b = out.b_val != nullptr;
+    const bool use_smem = blk_nnz <= CAP * T;  // false only when flagged rows make the block long
+    const size_t base = (size_t)blockIdx.x * CAP * T;
+    if (r < n && !row_big[r]) {
+        const int rbeg = out.indptr[r], cnt = out.indptr[r + 1] - rbeg;
+        for (int q = 0; q < cnt; q++) {
+            const int key = sc_key[base + q * T + t];
+            const double a = sc_a[base + q * T + t], b = sc_b[base + q * T + t];
+            if (use_smem) {
+                const int o = rbeg - blk_beg + q;
+                s_k[o] = key;
+                s_a[o] = a;
+                s_b[o] = b;
+            } else {
+                if (want_a) {
+                    out.a_idx[rbeg + q] = key;
+                    out.a_val[rbeg + q] = a;
+                }
+                if (want_b) {
+                    out.b_idx[rbeg + q] = key;
+                    out.b_val[rbeg + q] = b;
+                }
+            }
+        }
+        if (out.lump_ptr && out.lump_ptr[r + 1] > out.lump_ptr[r]) {
+            const int lp = out.lump_ptr[r];
+            out.lump_idx[lp] = (int)r;
+            out.lump_val[lp] = sc_lump[r];
+        }
+    }
+    if (use_smem) {
+        __syncthreads();
+        // segments of flagged rows hold stale shared memory here; row_fill_kernel(only_rows) runs
+        // after this kernel and rewrites them
+        for (int q = t; q < blk_nnz; q += T) {
             const int key = s_k[q];
             if (want_a) {
                 out.a_idx[blk_beg + q] = key;
@@ -777,8 +1023,27 @@ static void run_rows(lb_mesh *mesh, const D4 *rec, const ElemConsts *consts, con
     DBuf<int32_t> scratch(c, (size_t)mesh->k * mesh->nt * (K - 1) + n);
     if (cap_keys * 4 > 40 * 1024)
         LB_CUDA(cudaFuncSetAttribute(row_count_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap_keys * 4));
+    // tets, LAPY_B200_TET_ROWS=fused: accumulate once into a per-row scratch, compact after the scan
+    bool fused = false;
+    if (K == 4 && (want_a || !lump)) {
+        const char *e = getenv("LAPY_B200_TET_ROWS");
+        fused = e && !strcmp(e, "fused");
+    }
+    DBuf<int32_t> row_big, sc_key;
+    DBuf<double> sc_a, sc_b, sc_lump;
+    if (fused) {
+        const size_t slots = (size_t)nblocks * kFusedCap * kRowThreads;
+        row_big.alloc(c, n);
+        sc_key.alloc(c, slots);
+        sc_a.alloc(c, slots);
+        sc_b.alloc(c, slots);
+        sc_lump.alloc(c, n);
+        LB_CUDA(cudaFuncSetAttribute(row_accumulate_tet, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFusedSmemA));
+        LB_LAUNCH(c, row_accumulate_tet, nblocks, kRowThreads, kFusedSmemA, rec, aptr, inc4, n, consts, (int)degen_f32,
+                  row_nnz.p, row_has.p, row_big.p, sc_key.p, sc_a.p, sc_b.p, sc_lump.p);
+    }
     LB_LAUNCH(c, row_count_kernel<K>, nblocks, kRowThreads, cap_keys * 4, aptr, inc4, n, cap_keys, scratch.p,
-              row_nnz.p, row_has.p);
+              row_nnz.p, row_has.p, fused ? row_big.p : (const int32_t *)nullptr);
     phase(c, "row count");
     const bool full_b = !lump;
     lb_mat *A = nullptr, *B = nullptr;
@@ -821,13 +1086,20 @@ static void run_rows(lb_mesh *mesh, const D4 *rec, const ElemConsts *consts, con
             const int smem = cap * 20;
             if (smem > 40 * 1024)
                 LB_CUDA(cudaFuncSetAttribute(row_fill_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-            LB_LAUNCH(c, row_fill_kernel<K>, nblocks, kRowThreads, smem, rec, aptr, inc4, n, cap, consts,
-                      (int)degen_f32, out);
+            if (fused) {
+                LB_LAUNCH(c, row_compact_kernel, nblocks, kRowThreads, 0, n, row_big.p, sc_key.p, sc_a.p, sc_b.p, sc_lump.p,
+                          out);
+                LB_LAUNCH(c, row_fill_kernel<K>, nblocks, kRowThreads, 16, rec, aptr, inc4, n, cap, consts,
+                          (int)degen_f32, out, (const int32_t *)row_big.p);
+            } else {
+                LB_LAUNCH(c, row_fill_kernel<K>, nblocks, kRowThreads, smem, rec, aptr, inc4, n, cap, consts,
+                          (int)degen_f32, out, (const int32_t *)nullptr);
+            }
         } else {
             // mass only + lumped: no CSR pattern needed, but the same kernel does the sums
             const int cap = 0;
             LB_LAUNCH(c, row_fill_kernel<K>, nblocks, kRowThreads, 16, rec, aptr, inc4, n, cap, consts, (int)degen_f32,
-                      out);
+                      out, (const int32_t *)nullptr);
         }
     } catch (...) {
         delete A;

@@ -181,6 +181,47 @@ def test_tet_cube_vs_oracle():
     _check(lapy_b200.Solver(mesh, lump=True).mass, tl, bl_ref, "Blump")
 
 
+def _tet_fan():
+    """All 320 surface triangles of a level-2 icosphere joined to the centre: a vertex with 320
+    incident tets and 162 neighbours (oversized row), surface vertices with 5-6."""
+    from lapy_b200 import mesh as M
+
+    ico = M.icosphere(2)
+    v = np.vstack([ico.v, [[0.01, -0.02, 0.03]]])
+    t = np.column_stack([ico.t, np.full(len(ico.t), len(ico.v))])
+    return M.TetMesh(v, t)
+
+
+@pytest.mark.parametrize("mode", ["fused"])
+def test_tet_row_kernel_variants_match_default(monkeypatch, mode):
+    """LAPY_B200_TET_ROWS selects an alternative implementation of the tet row kernels: it must
+    reproduce the default kernels (and therefore the sequential model) bit for bit, including
+    flagged oversized rows, float32 meshes and the lumped mass."""
+    import lapy_b200
+    from lapy_b200 import mesh as M
+
+    cube = M.cube_tets(13)
+    cube32 = M.TetMesh(cube.v.astype(np.float32), cube.t)
+    for mesh in (cube, cube32, _tet_fan()):
+        for lump in (False, True):
+            monkeypatch.delenv("LAPY_B200_TET_ROWS", raising=False)
+            ref = lapy_b200.Solver(mesh, lump=lump)
+            ra, rb = ref.stiffness, ref.mass
+            monkeypatch.setenv("LAPY_B200_TET_ROWS", mode)
+            alt = lapy_b200.Solver(mesh, lump=lump)
+            for x, y in ((alt.stiffness, ra), (alt.mass, rb)):
+                np.testing.assert_array_equal(x.indptr, y.indptr)
+                np.testing.assert_array_equal(x.indices, y.indices)
+                np.testing.assert_array_equal(x.data, y.data)
+    monkeypatch.delenv("LAPY_B200_TET_ROWS", raising=False)
+    fan = _tet_fan()
+    ta, tb, tl = _triplets(fan.v, fan.t, "tet")
+    a_ref, b_ref = ofem.fem(fan)
+    fem = lapy_b200.Solver(fan)
+    _check(fem.stiffness, ta, a_ref, "fan A")
+    _check(fem.mass, tb, b_ref, "fan B")
+
+
 def test_high_valence_fan():
     """A vertex with 3000 incident triangles: exercises the oversized-block paths."""
     import lapy_b200
