@@ -19,6 +19,10 @@ struct NcclApi {
     decltype(&ncclCommDestroy) CommDestroy = nullptr;
     decltype(&ncclAllReduce) AllReduce = nullptr;
     decltype(&ncclAllGather) AllGather = nullptr;
+    decltype(&ncclSend) Send = nullptr;
+    decltype(&ncclRecv) Recv = nullptr;
+    decltype(&ncclGroupStart) GroupStart = nullptr;
+    decltype(&ncclGroupEnd) GroupEnd = nullptr;
     decltype(&ncclGetErrorString) GetErrorString = nullptr;
 };
 constexpr ncclResult_t ncclSuccessV = ncclSuccess;
@@ -40,6 +44,10 @@ static NcclApi &nccl() {
         api.AllReduce = (decltype(api.AllReduce))dlsym(h, "ncclAllReduce");
         api.AllGather = (decltype(api.AllGather))dlsym(h, "ncclAllGather");
         api.GetErrorString = (decltype(api.GetErrorString))dlsym(h, "ncclGetErrorString");
+        api.Send = (decltype(api.Send))dlsym(h, "ncclSend");
+        api.Recv = (decltype(api.Recv))dlsym(h, "ncclRecv");
+        api.GroupStart = (decltype(api.GroupStart))dlsym(h, "ncclGroupStart");
+        api.GroupEnd = (decltype(api.GroupEnd))dlsym(h, "ncclGroupEnd");
         if (!api.GetUniqueId || !api.CommInitRank || !api.AllReduce || !api.AllGather) {
             set_error("libnccl.so.2 lacks the expected symbols");
             throw Error{LB_ERR_UNSUPPORTED};
@@ -66,6 +74,31 @@ void dist_allreduce_sum(lb_ctx *c, const DistCtx *d, double *buf, size_t count) 
 
 void dist_allgather(lb_ctx *c, const DistCtx *d, const double *send, double *recv, size_t count_per_rank) {
     LB_NCCL(nccl().AllGather(send, recv, count_per_rank, ncclFloat64V, (ncclComm_t)d->comm, c->stream));
+}
+
+void dist_allgather_i32(lb_ctx *c, const DistCtx *d, const int32_t *send, int32_t *recv, size_t count_per_rank) {
+    LB_NCCL(nccl().AllGather(send, recv, count_per_rank, ncclInt32, (ncclComm_t)d->comm, c->stream));
+}
+
+void dist_exchange(lb_ctx *c, const DistCtx *d, const void *send, const int64_t *off_s, const int64_t *cnt_s,
+                   void *recv, const int64_t *off_r, const int64_t *cnt_r, int elem_size) {
+    NcclApi &api = nccl();
+    if (!api.Send || !api.Recv || !api.GroupStart || !api.GroupEnd) {
+        set_error("libnccl.so.2 lacks ncclSend/ncclRecv (needs NCCL >= 2.7)");
+        throw Error{LB_ERR_UNSUPPORTED};
+    }
+    const ncclDataType_t dt = elem_size == 8 ? ncclDouble : ncclInt32;
+    const char *sp = static_cast<const char *>(send);
+    char *rp = static_cast<char *>(recv);
+    LB_NCCL(api.GroupStart());
+    for (int p = 0; p < d->world; p++) {
+        if (p == d->rank) continue;
+        if (cnt_s[p] > 0)
+            LB_NCCL(api.Send(sp + (size_t)off_s[p] * elem_size, (size_t)cnt_s[p], dt, p, (ncclComm_t)d->comm, c->stream));
+        if (cnt_r[p] > 0)
+            LB_NCCL(api.Recv(rp + (size_t)off_r[p] * elem_size, (size_t)cnt_r[p], dt, p, (ncclComm_t)d->comm, c->stream));
+    }
+    LB_NCCL(api.GroupEnd());
 }
 
 }  // namespace lb

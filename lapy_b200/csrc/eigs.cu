@@ -19,6 +19,8 @@
 
 #include <cusolverDn.h>
 
+#include <map>
+
 #include "amg.cuh"
 #include "dist.cuh"
 
@@ -29,28 +31,131 @@ namespace lb {
 // matching rows of all block vectors.  SpMM all-gathers the block vector first (the operator's
 // columns are global); Gram matrices and column dots are summed over the ranks.  With D == NULL
 // these are the single-GPU operations.
-// plain cudaMalloc buffer: NCCL transports (P2P / IPC) must not be handed stream-ordered pool memory
-struct RawBuf {
-    double *p = nullptr;
-    size_t n = 0;
-    void alloc(size_t count) {
-        release();
-        n = count;
-        if (count) LB_CUDA(cudaMalloc((void **)&p, count * sizeof(double)));
-    }
-    void release() {
-        if (p) cudaFree(p);
-        p = nullptr;
-    }
-    ~RawBuf() { release(); }
+using RawBuf = RawBufT<double>;  // plain cudaMalloc (dist.cuh): NCCL must not be handed pool memory
+
+// Halo-exchange form of the row-partitioned SpMM (LAPY_B200_HALO=1; the default is still the
+// whole-block all-gather).  Per operator: the ghost columns of this rank's row block (sorted
+// global ids, grouped by owner), the rows every peer needs from this rank, and the row block
+// with its columns renumbered to [own rows | ghost rows], so that the ordinary SpMM kernel runs
+// on one contiguous (n_loc + n_ghost, w) input whose ghost part is filled by grouped
+// ncclSend / ncclRecv.  For a Morton-ordered surface the ghosts are O(sqrt(n)) rows per
+// neighbour instead of the n rows the all-gather moves.
+struct HaloPlan {
+    int64_t n_loc = 0, n_ghost = 0, n_send = 0;
+    int wcap = 0;
+    std::vector<int64_t> send_off, send_cnt, recv_off, recv_cnt;  // rows, per peer
+    RawBufT<int32_t> send_rows;     // local index of every row to send, grouped by destination
+    std::unique_ptr<lb_mat> local;  // row block, columns renumbered [own | ghosts] (unsorted rows)
+    RawBuf sendbuf, xg;             // (n_send, wcap) packed rows; (n_loc + n_ghost, wcap) SpMM input
 };
 
 struct DistOps {
     const DistCtx *d = nullptr;
     int64_t rpr = 0;        // rows per rank (last rank may own fewer)
     int64_t n_local = 0;
+    int64_t r0 = 0, r1 = 0;  // this rank's rows
     RawBuf pack, gath, red;  // (rpr, wcap), (world*rpr, wcap), all-reduce staging
+    bool halo = false;
+    int wcap = 0;
+    std::map<const lb_mat *, std::unique_ptr<HaloPlan>> plans;  // built on first use (collectively)
 };
+
+__global__ void halo_remap_kernel(int64_t nnz, const int32_t *__restrict__ idx, int r0, int r1, int nloc,
+                                  const int32_t *__restrict__ ghost, int ng, int32_t *__restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nnz) return;
+    const int col = idx[i];
+    if (col >= r0 && col < r1) {
+        out[i] = col - r0;
+        return;
+    }
+    int lo = 0, hi = ng;  // first position with ghost[pos] >= col (col is in the list)
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (ghost[mid] < col) lo = mid + 1;
+        else hi = mid;
+    }
+    out[i] = nloc + lo;
+}
+
+__global__ void halo_shift_kernel(int64_t cnt, int32_t *rows, int r0) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < cnt) rows[i] -= r0;
+}
+
+// collective over the communicator: every rank calls it for its own row block of the same operator
+static std::unique_ptr<HaloPlan> build_halo(lb_ctx *c, const DistCtx *d, const lb_mat *rows, int64_t r0, int64_t r1,
+                                            int64_t rpr, int wcap) {
+    const int W = d->world, me = d->rank;
+    auto h = std::make_unique<HaloPlan>();
+    h->n_loc = r1 - r0;
+    h->wcap = wcap;
+    const int64_t nnz = rows->nnz;
+    std::vector<int32_t> hidx((size_t)nnz);
+    d2h(c, hidx.data(), rows->indices.p, (size_t)nnz * sizeof(int32_t));
+    sync(c);
+    std::vector<uint8_t> mark((size_t)W * rpr, 0);
+    for (int32_t col : hidx)
+        if (col < r0 || col >= r1) mark[(size_t)col] = 1;
+    std::vector<int32_t> ghosts;
+    for (size_t i = 0; i < mark.size(); i++)
+        if (mark[i]) ghosts.push_back((int32_t)i);
+    h->n_ghost = (int64_t)ghosts.size();
+    h->recv_cnt.assign(W, 0);
+    h->recv_off.assign(W, 0);
+    h->send_cnt.assign(W, 0);
+    h->send_off.assign(W, 0);
+    for (int32_t g : ghosts) h->recv_cnt[g / rpr]++;
+    for (int p = 1; p < W; p++) h->recv_off[p] = h->recv_off[p - 1] + h->recv_cnt[p - 1];
+    // who needs how many of my rows: all-gather the request counts
+    RawBufT<int32_t> cnt_loc, cnt_all, d_ghost;
+    cnt_loc.alloc(W);
+    cnt_all.alloc((size_t)W * W);
+    std::vector<int32_t> hc(W), hall((size_t)W * W);
+    for (int p = 0; p < W; p++) hc[p] = (int32_t)h->recv_cnt[p];
+    h2d(c, cnt_loc.p, hc.data(), W * sizeof(int32_t));
+    dist_allgather_i32(c, d, cnt_loc.p, cnt_all.p, W);
+    d2h(c, hall.data(), cnt_all.p, hall.size() * sizeof(int32_t));
+    sync(c);
+    for (int p = 0; p < W; p++) h->send_cnt[p] = p == me ? 0 : hall[(size_t)p * W + me];
+    for (int p = 1; p < W; p++) h->send_off[p] = h->send_off[p - 1] + h->send_cnt[p - 1];
+    h->n_send = h->send_off[W - 1] + h->send_cnt[W - 1];
+    // request lists: my ghost ids go to their owners, the owners' requests come back as global row ids
+    d_ghost.alloc(std::max<size_t>(1, ghosts.size()));
+    if (!ghosts.empty()) h2d(c, d_ghost.p, ghosts.data(), ghosts.size() * sizeof(int32_t));
+    h->send_rows.alloc(std::max<size_t>(1, (size_t)h->n_send));
+    dist_exchange(c, d, d_ghost.p, h->recv_off.data(), h->recv_cnt.data(), h->send_rows.p, h->send_off.data(),
+                  h->send_cnt.data(), 4);
+    if (h->n_send) {
+        LB_LAUNCH(c, halo_shift_kernel, cdiv(h->n_send, 256), 256, 0, h->n_send, h->send_rows.p, (int)r0);
+        std::vector<int32_t> chk((size_t)h->n_send);
+        d2h(c, chk.data(), h->send_rows.p, chk.size() * sizeof(int32_t));
+        sync(c);
+        for (int32_t v : chk) LB_REQUIRE(v >= 0 && v < h->n_loc, "halo plan: peer requested row %d outside this rank's block", v);
+    }
+    // the row block with columns renumbered [own | ghosts]
+    auto m = std::make_unique<lb_mat>();
+    m->ctx = c;
+    m->n = h->n_loc;
+    m->ncols = h->n_loc + h->n_ghost;
+    m->nnz = nnz;
+    m->indptr.alloc(c, h->n_loc + 1);
+    m->indices.alloc(c, nnz);
+    m->data.alloc(c, nnz);
+    d2d(c, m->indptr.p, rows->indptr.p, (size_t)(h->n_loc + 1) * sizeof(int32_t));
+    d2d(c, m->data.p, rows->data.p, (size_t)nnz * sizeof(double));
+    if (nnz)
+        LB_LAUNCH(c, halo_remap_kernel, cdiv(nnz, 256), 256, 0, nnz, rows->indices.p, (int)r0, (int)r1, (int)h->n_loc,
+                  d_ghost.p, (int)h->n_ghost, m->indices.p);
+    h->local = std::move(m);
+    h->sendbuf.alloc(std::max<size_t>(1, (size_t)h->n_send * wcap));
+    h->xg.alloc((size_t)(h->n_loc + h->n_ghost) * wcap);
+    sync(c);  // d_ghost and the host vectors go out of scope
+    if (c->trace)
+        fprintf(stderr, "[lb trace] rank %d: halo plan: %lld own rows, %lld ghost rows, %lld rows to send\n", me,
+                (long long)h->n_loc, (long long)h->n_ghost, (long long)h->n_send);
+    return h;
+}
 
 static void d_allreduce(lb_ctx *c, DistOps *D, double *buf, size_t count) {
     LB_REQUIRE(count <= D->red.n, "all-reduce staging buffer too small");
@@ -62,6 +167,25 @@ static void d_allreduce(lb_ctx *c, DistOps *D, double *buf, size_t count) {
 static void d_spmm(lb_ctx *c, DistOps *D, const lb_mat *a, const double *x, int ldx, double *y, int ldy, int w) {
     if (!D) {
         spmm(c, a, x, ldx, y, ldy, w);
+        return;
+    }
+    if (D->halo) {
+        auto &slot = D->plans[a];
+        if (!slot) slot = build_halo(c, D->d, a, D->r0, D->r1, D->rpr, D->wcap);
+        HaloPlan &h = *slot;
+        LB_REQUIRE(w <= h.wcap, "halo exchange: block of %d columns exceeds the plan's capacity %d", w, h.wcap);
+        const int W = D->d->world;
+        copy_cols(c, h.n_loc, w, x, ldx, h.xg.p, w);
+        if (h.n_send) gather_rows(c, h.n_send, w, h.send_rows.p, x, ldx, h.sendbuf.p, w);
+        std::vector<int64_t> so(W), sc(W), ro(W), rc(W);
+        for (int p = 0; p < W; p++) {
+            so[p] = h.send_off[p] * w;
+            sc[p] = h.send_cnt[p] * w;
+            ro[p] = (h.n_loc + h.recv_off[p]) * w;
+            rc[p] = h.recv_cnt[p] * w;
+        }
+        dist_exchange(c, D->d, h.sendbuf.p, so.data(), sc.data(), h.xg.p, ro.data(), rc.data(), 8);
+        spmm(c, h.local.get(), h.xg.p, w, y, ldy, w);
         return;
     }
     copy_cols(c, D->n_local, w, x, ldx, D->pack.p, w);
@@ -612,6 +736,10 @@ static EigStats lobpcg_dist(lb_ctx *c, const DistCtx *dist, const lb_mat *A0, co
     D.d = dist;
     D.rpr = rpr;
     D.n_local = r1 - r0;
+    D.r0 = r0;
+    D.r1 = r1;
+    D.wcap = 2 * m;
+    if (const char *e = getenv("LAPY_B200_HALO")) D.halo = atoi(e) != 0;
     D.pack.alloc((size_t)rpr * 2 * m);
     LB_CUDA(cudaMemsetAsync(D.pack.p, 0, D.pack.n * sizeof(double), c->stream));
     D.gath.alloc((size_t)world * rpr * 2 * m);
@@ -707,6 +835,10 @@ extern "C" int lb_dist_selftest(lb_ctx *c, lb_mat *a, double *errs) {
     D.d = c->dist;
     D.rpr = rpr;
     D.n_local = r1 - r0;
+    D.r0 = r0;
+    D.r1 = r1;
+    D.wcap = w;
+    if (const char *e = getenv("LAPY_B200_HALO")) D.halo = atoi(e) != 0;
     D.pack.alloc((size_t)rpr * w);
     LB_CUDA(cudaMemsetAsync(D.pack.p, 0, D.pack.n * sizeof(double), c->stream));
     D.gath.alloc((size_t)world * rpr * w);

@@ -10,12 +10,13 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, halo):
     import torch
     import torch.distributed as dist
 
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
                       LOCAL_RANK=str(rank))  # fmt: skip
+    os.environ["LAPY_B200_HALO"] = str(int(halo))  # 1: boundary-only halo exchange, 0: whole-block all-gather
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     try:
@@ -37,7 +38,8 @@ def _worker(rank, world, port, q):
         dist.destroy_process_group()
 
 
-def test_two_rank_row_partitioned_eigs():
+@pytest.mark.parametrize("halo", [0, 1])
+def test_two_rank_row_partitioned_eigs(halo):
     import torch
     import torch.multiprocessing as mp
     from conftest import load_golden
@@ -50,7 +52,7 @@ def test_two_rank_row_partitioned_eigs():
     s.close()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, halo)) for r in range(2)]
     for p in procs:
         p.start()
     res = [q.get(timeout=150) for _ in procs]
