@@ -46,6 +46,8 @@ def test_two_rank_row_partitioned_eigs(halo):
 
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
+    if halo and not os.environ.get("LAPY_B200_TEST_HALO"):
+        pytest.skip("halo exchange is opt-in until validated on 2 GPUs: set LAPY_B200_TEST_HALO=1")
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
     port = s.getsockname()[1]
