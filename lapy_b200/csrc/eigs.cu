@@ -58,6 +58,11 @@ struct DistOps {
     bool halo = false;
     int wcap = 0;
     std::map<const lb_mat *, std::unique_ptr<HaloPlan>> plans;  // built on first use (collectively)
+    // replicated preconditioner (LAPY_B200_DIST_AMG=full): every rank holds the AMG hierarchy of the
+    // FULL operator and applies it to its share of the COLUMNS; see dist_precond
+    Amg *full_amg = nullptr;
+    int64_t n_full = 0;
+    RawBuf tpack, tfull_r, tfull_z;  // (n_local, mcap) packed slices; (n, ceil(mcap/world)) in / out
 };
 
 __global__ void halo_remap_kernel(int64_t nnz, const int32_t *__restrict__ idx, int r0, int r1, int nloc,
@@ -203,6 +208,45 @@ static void d_dots(lb_ctx *c, DistOps *D, int64_t n, int cols, const double *x, 
                    double *out) {
     col_dots(c, n, cols, x, ldx, y, ldy, out);
     if (D) d_allreduce(c, D, out, cols);
+}
+
+// Preconditioner of the row-partitioned mode with a replicated hierarchy: the W-cycle of the full
+// operator is applied column-wise in parallel.  Rank p takes the columns [p*mc, (p+1)*mc) of the
+// residual block: an all-to-all (grouped send/recv) turns the row-partitioned (n_local, ma) block
+// into a column-partitioned (n, mc) one, every rank runs the same cycle the single-GPU solver runs
+// (so the iteration count does not grow with the number of ranks, unlike the block-Jacobi
+// hierarchy), and the reverse all-to-all brings the rows back.  Traffic per application and rank:
+// 2 * n_local * ma * (world-1)/world doubles over NVLink, no communication inside the cycle.
+static void dist_precond(lb_ctx *c, DistOps *D, const double *r, int ldr, double *z, int ldz, int ma) {
+    const int W = D->d->world, me = D->d->rank;
+    const int mc = (ma + W - 1) / W;
+    auto c0 = [&](int p) { return std::min(ma, p * mc); };
+    auto cw = [&](int p) { return std::min(ma, (p + 1) * mc) - c0(p); };
+    auto row0 = [&](int p) { return std::min(D->n_full, (int64_t)p * D->rpr); };
+    auto rows = [&](int p) { return std::min(D->n_full, (int64_t)(p + 1) * D->rpr) - row0(p); };
+    const int64_t nl = D->n_local;
+    const int mine = cw(me);
+    LB_REQUIRE((size_t)nl * ma <= D->tpack.n && (size_t)D->n_full * mc <= D->tfull_r.n, "dist_precond: staging buffers too small");
+    std::vector<int64_t> so(W), sc(W), ro(W), rc(W);
+    // forward: my rows of column slice p -> rank p; rank p's rows of MY slice -> rows [row0(p), ...) of tfull_r
+    for (int p = 0; p < W; p++) {
+        so[p] = nl * c0(p);
+        sc[p] = nl * cw(p);
+        ro[p] = row0(p) * mine;
+        rc[p] = rows(p) * mine;
+        if (cw(p) == 0) continue;
+        if (p == me) copy_cols(c, nl, mine, r + c0(p), ldr, D->tfull_r.p + ro[p], mine);
+        else copy_cols(c, nl, cw(p), r + c0(p), ldr, D->tpack.p + so[p], cw(p));
+    }
+    dist_exchange(c, D->d, D->tpack.p, so.data(), sc.data(), D->tfull_r.p, ro.data(), rc.data(), 8);
+    if (mine) amg_apply(*D->full_amg, D->tfull_r.p, mine, D->tfull_z.p, mine, mine, 0);
+    // reverse: rows [row0(p), ...) of my result slice -> rank p; rank p's slice of MY rows -> tpack -> z
+    dist_exchange(c, D->d, D->tfull_z.p, ro.data(), rc.data(), D->tpack.p, so.data(), sc.data(), 8);
+    for (int p = 0; p < W; p++) {
+        if (cw(p) == 0) continue;
+        if (p == me) copy_cols(c, nl, mine, D->tfull_z.p + ro[p], mine, z + c0(p), ldz);
+        else copy_cols(c, nl, cw(p), D->tpack.p + so[p], cw(p), z + c0(p), ldz);
+    }
 }
 
 __global__ void set_column(int64_t n, double *x, int ld, int col, double v) {
@@ -566,8 +610,9 @@ static EigStats lobpcg_core(lb_ctx *c, const lb_mat *A, const lb_mat *B, Amg *am
         residual_cols(c, n, ma, idx_d.p, lam_d.p, AS[cur].p, ld, BS[cur].p, ld, Rbuf.p, ma);
         const int w0 = m + mp;
         double *W = S[cur].p + w0, *AW = AS[cur].p + w0, *BW = BS[cur].p + w0;
-        amg_apply(*amg, Rbuf.p, ma, W, ld, ma, lvl);
-        for (int vc = 1; vc < vcycles; vc++) {
+        if (D && D->full_amg) dist_precond(c, D, Rbuf.p, ma, W, ld, ma);
+        else amg_apply(*amg, Rbuf.p, ma, W, ld, ma, lvl);
+        for (int vc = 1; vc < vcycles && !(D && D->full_amg); vc++) {
             // second cycle on the residual of the first: W += V(R - K W)
             spmm(c, amg->levels[lvl].K.get(), W, ld, tmp.p, ma, ma, 1, Rbuf.p, ma);
             amg_apply(*amg, tmp.p, ma, Rbuf.p, ma, ma, lvl);  // Rbuf is free to overwrite only after use below
@@ -725,12 +770,46 @@ static EigStats lobpcg_dist(lb_ctx *c, const DistCtx *dist, const lb_mat *A0, co
     auto Ar = row_block(c, A, r0, r1, world * rpr);
     auto Br = row_block(c, B, r0, r1, world * rpr);  // general CSR with global columns (also when B is diagonal)
     auto Kr = row_block(c, Kfull.get(), r0, r1, world * rpr);
-    Kfull.reset();
     auto Kll = diag_block(c, Kr.get(), r0, r1);
     Kr.reset();
+    AmgOptions opt;
+    // opt-in (LAPY_B200_DIST_AMG=full): the hierarchy of the FULL operator on every rank (setup is
+    // 10-20 ms), applied column-parallel (dist_precond), and the nested-iteration start of the
+    // single-GPU driver computed redundantly on the small coarse levels
+    std::unique_ptr<Amg> amg_full;
+    DBuf<double> x_start;  // (n, m) prolonged coarse eigenvectors, identical on all ranks
+    bool have_start = false;
+    if (const char *e = getenv("LAPY_B200_DIST_AMG")) {
+        if (!strcmp(e, "full")) {
+            amg_full = amg_setup(c, std::move(Kfull), m, opt);
+            const int nlev = (int)amg_full->levels.size();
+            int depth = 0;
+            while (n >= 1000000 && depth + 1 < nlev - 1 &&
+                   amg_full->levels[depth + 1].K->n >= std::max<int64_t>(8 * m, 4000))
+                depth++;
+            std::vector<std::unique_ptr<lb_mat>> Bl(depth + 1);
+            for (int l = 0; l < depth; l++) {
+                const lb_mat *bl = l == 0 ? B : Bl[l].get();
+                auto BP = spgemm(c, bl, amg_full->levels[l].P.get());
+                Bl[l + 1] = spgemm(c, amg_full->levels[l].R.get(), BP.get());
+                Bl[l + 1]->ncols = -1;
+            }
+            std::vector<double> lamc;
+            for (int l = depth; l >= 1; l--) {
+                const lb_mat *Kl = amg_full->levels[l].K.get();
+                DBuf<double> xo(c, (size_t)Kl->n * m);
+                lobpcg_core(c, Kl, Bl[l].get(), amg_full.get(), l, have_start ? x_start.p : nullptr, m, k, m,
+                            std::max(tol, 1e-3), 60, lamc, xo.p);
+                const lb_mat *P = amg_full->levels[l - 1].P.get();
+                x_start.alloc(c, (size_t)P->n * m);
+                spmm(c, P, xo.p, m, x_start.p, m, m);
+                have_start = true;
+            }
+        }
+    }
+    Kfull.reset();
     Ap.reset();  // the full renumbered copies are no longer needed
     Bp.reset();
-    AmgOptions opt;
     auto amg = amg_setup(c, std::move(Kll), m, opt);
     DistOps D;
     D.d = dist;
@@ -744,11 +823,19 @@ static EigStats lobpcg_dist(lb_ctx *c, const DistCtx *dist, const lb_mat *A0, co
     LB_CUDA(cudaMemsetAsync(D.pack.p, 0, D.pack.n * sizeof(double), c->stream));
     D.gath.alloc((size_t)world * rpr * 2 * m);
     D.red.alloc((size_t)9 * m * m + 4 * m);
-    if (c->trace) fprintf(stderr, "[lb trace] rank %d: rows [%lld, %lld) of %lld, AMG levels %zu\n", rank, (long long)r0,
-                          (long long)r1, (long long)n, amg->levels.size());
+    if (amg_full) {
+        D.full_amg = amg_full.get();
+        D.n_full = n;
+        D.tpack.alloc((size_t)(r1 - r0) * m);
+        D.tfull_r.alloc((size_t)n * ((m + world - 1) / world));
+        D.tfull_z.alloc((size_t)n * ((m + world - 1) / world));
+    }
+    if (c->trace) fprintf(stderr, "[lb trace] rank %d: rows [%lld, %lld) of %lld, AMG levels %zu%s\n", rank, (long long)r0,
+                          (long long)r1, (long long)n, amg->levels.size(), amg_full ? " (replicated full hierarchy)" : "");
     std::vector<double> lam;
     DBuf<double> xloc(c, (size_t)(r1 - r0) * m);
-    EigStats st = lobpcg_core(c, Ar.get(), Br.get(), amg.get(), 0, nullptr, 0, k, m, tol, maxit, lam, xloc.p, &D, r0);
+    EigStats st = lobpcg_core(c, Ar.get(), Br.get(), amg.get(), 0, have_start ? x_start.p + (size_t)r0 * m : nullptr, m, k,
+                              m, tol, maxit, lam, xloc.p, &D, r0);
     st.setup_ms = amg->setup_ms;
     for (int j = 0; j < k; j++) h_evals[j] = lam[j];
     // all-gather the k eigenvector columns, undo the renumbering, return the full array on every rank

@@ -10,13 +10,13 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-def _worker(rank, world, port, q, halo):
+def _worker(rank, world, port, q, env):
     import torch
     import torch.distributed as dist
 
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
                       LOCAL_RANK=str(rank))  # fmt: skip
-    os.environ["LAPY_B200_HALO"] = str(int(halo))  # 1: boundary-only halo exchange, 0: whole-block all-gather
+    os.environ.update(env)
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     try:
@@ -38,23 +38,30 @@ def _worker(rank, world, port, q, halo):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("halo", [0, 1])
-def test_two_rank_row_partitioned_eigs(halo):
+VARIANTS = {
+    "allgather": {},  # default: whole-block all-gather SpMM, block-Jacobi AMG per rank
+    "halo": {"LAPY_B200_HALO": "1"},  # boundary-only halo exchange (grouped send/recv)
+    "halo+full-amg": {"LAPY_B200_HALO": "1", "LAPY_B200_DIST_AMG": "full"},  # + replicated hierarchy, column-parallel
+}
+
+
+@pytest.mark.parametrize("variant", list(VARIANTS))
+def test_two_rank_row_partitioned_eigs(variant):
     import torch
     import torch.multiprocessing as mp
     from conftest import load_golden
 
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
-    if halo and not os.environ.get("LAPY_B200_TEST_HALO"):
-        pytest.skip("halo exchange is opt-in until validated on 2 GPUs: set LAPY_B200_TEST_HALO=1")
+    if VARIANTS[variant] and not os.environ.get("LAPY_B200_TEST_HALO"):
+        pytest.skip("opt-in communication variants, not yet validated on 2 GPUs: set LAPY_B200_TEST_HALO=1")
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
     port = s.getsockname()[1]
     s.close()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, halo)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, VARIANTS[variant])) for r in range(2)]
     for p in procs:
         p.start()
     res = [q.get(timeout=150) for _ in procs]

@@ -1,4 +1,7 @@
-"""Debug driver for the row-partitioned mode: torchrun --nproc-per-node 2 tools/rowpart_dbg.py [level]"""
+"""Debug driver for the row-partitioned mode: torchrun --nproc-per-node 2 tools/rowpart_dbg.py [level]
+
+Variants by environment: LAPY_B200_HALO=1 (boundary-only halo exchange), LAPY_B200_DIST_AMG=full (replicated
+hierarchy applied column-parallel + nested start)."""
 import os, sys, time, faulthandler
 faulthandler.dump_traceback_later(100, exit=True)
 os.environ.setdefault("LAPY_B200_TRACE", "1")
