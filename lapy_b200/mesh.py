@@ -72,6 +72,18 @@ class TriaMesh(_Mesh):
     def __init__(self, v, t):
         super().__init__(v, t, 3)
 
+    def tria_areas(self) -> np.ndarray:
+        """Triangle areas by Heron's formula from the three edge lengths, like the reference
+        (lapy/tria_mesh.py:636-658), so ``area()`` agrees with ``lapy.TriaMesh.area()``."""
+        p0, p1, p2 = (self.v[self.t[:, c], :] for c in range(3))
+        a, b, c = (np.sqrt(np.sum(e * e, axis=1)) for e in (p1 - p0, p2 - p1, p0 - p2))
+        half = 0.5 * (a + b + c)
+        return np.sqrt(half * (half - a) * (half - b) * (half - c))
+
+    def area(self) -> float:
+        """Total surface area (lapy/tria_mesh.py:660-669)."""
+        return np.sum(self.tria_areas())
+
     def boundary_vertices(self) -> np.ndarray:
         """Sorted indices of vertices on edges that belong to exactly one triangle."""
         nv = self.v.shape[0]
