@@ -1,4 +1,6 @@
-"""Drop-in for the hot-path part of ``lapy.heat`` (reference lapy/heat.py:114-232)."""
+"""Drop-in for ``lapy.heat``: ``diffusion`` (reference lapy/heat.py:114-232) runs on the device;
+``diagonal`` / ``kernel`` (:19-111) are the reference's small dense products on the
+eigenpairs ``Solver.eigs`` returned, evaluated on the host arrays the caller holds."""
 
 from __future__ import annotations
 
@@ -10,6 +12,31 @@ from . import _lib
 from .solver import Solver
 
 logger = logging.getLogger(__name__)
+
+
+def diagonal(t, x, evecs: np.ndarray, evals: np.ndarray, n: int) -> np.ndarray:
+    """Heat kernel diagonal ``K(t, x, x) = sum_j exp(-lambda_j t) phi_j(x)^2`` over the first ``n``
+    eigenpairs (heat.py:19-59): rows = vertices ``x``, columns = times ``t``."""
+    if n > evecs.shape[1] or n > evals.shape[0]:
+        raise ValueError("n exceeds the number of available eigenpairs")
+    sq = evecs[x, 0:n] * evecs[x, 0:n]
+    return np.matmul(sq, np.exp(-np.matmul(evals[0:n], t)))
+
+
+def kernel(t, vfix: int, evecs: np.ndarray, evals: np.ndarray, n: int) -> np.ndarray:
+    """Heat kernel ``K_t(p, vfix) = sum_j exp(-lambda_j t) phi_j(p) phi_j(vfix)`` from all vertices to
+    one fixed vertex over the first ``n`` eigenpairs (heat.py:62-111): rows = vertices, columns = times.
+
+    The reference's expression multiplies the (n, n_times) exponentials by the (n,) row
+    ``evecs[vfix]`` without a trailing axis and only broadcasts for n_times == n; this is the formula
+    of its docstring.  ``evals`` may be (k,) or the (k, 1) column the reference documents, ``t`` a
+    scalar or any array of times."""
+    if n > evecs.shape[1] or n > evals.shape[0]:
+        raise ValueError("n exceeds the number of available eigenpairs")
+    lam = np.asarray(evals).reshape(-1)[0:n]
+    times = np.asarray(t, dtype=float).reshape(-1)
+    weights = np.exp(-lam[:, None] * times[None, :]) * evecs[vfix, 0:n][:, None]
+    return np.matmul(evecs[:, 0:n], weights)
 
 
 def diffusion(geometry, vids, m: float = 1.0, aniso=None, use_cholmod: bool = False, *, tol: float = 0.0):

@@ -86,3 +86,28 @@ def test_shapedna_post_processing_matches_the_reference():
     flat = TriaMesh(np.zeros((3, 3)), np.array([[0, 1, 2]]))
     with pytest.raises(ValueError, match="positive"):
         shapedna.normalize_ev(flat, ev, method="surface")
+
+
+def test_heat_kernel_and_diagonal():
+    """heat.diagonal equals the reference's expression (lapy/heat.py:58) on its documented shapes
+    (column of eigenvalues, row of times); heat.kernel follows the docstring formula."""
+    from lapy_b200 import heat
+
+    rng = np.random.default_rng(1)
+    evecs = rng.standard_normal((30, 6))
+    evals = np.abs(rng.standard_normal((6, 1))).cumsum(0)
+    t = np.array([[0.1, 0.5, 2.0]])
+    x = np.array([0, 3, 7])
+    d = heat.diagonal(t, x, evecs, evals, 4)
+    ref = np.matmul(evecs[x, 0:4] * evecs[x, 0:4], np.exp(-np.matmul(evals[0:4], t)))
+    np.testing.assert_array_equal(d, ref)
+    k = heat.kernel(t, 5, evecs, evals, 4)
+    assert k.shape == (30, 3)
+    want = sum(np.exp(-evals[j, 0] * t[0])[None, :] * evecs[:, j : j + 1] * evecs[5, j] for j in range(4))
+    np.testing.assert_allclose(k, want, rtol=1e-13, atol=1e-15)
+    np.testing.assert_allclose(heat.kernel(0.5, 5, evecs, evals[:, 0], 4)[:, 0], k[:, 1], rtol=1e-13)
+    np.testing.assert_allclose(np.diag(np.column_stack([heat.kernel(0.5, v, evecs, evals, 4)[:, 0] for v in range(30)])),
+                               heat.diagonal(np.array([[0.5]]), np.arange(30), evecs, evals, 4)[:, 0], rtol=1e-13)  # fmt: skip
+    for f in (heat.diagonal, heat.kernel):
+        with pytest.raises(ValueError, match="exceeds"):
+            f(t, 0 if f is heat.kernel else x, evecs, evals, 7)
