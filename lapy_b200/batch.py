@@ -34,6 +34,7 @@ def batched_shapedna(
     lump: bool = False,
     compute: Callable | None = None,
     gather: bool = True,
+    workers: int = 1,
 ):
     """ShapeDNA eigenvalues of a batch of meshes, sharded over the ranks of the current process
     group (or run serially without one).
@@ -43,6 +44,12 @@ def batched_shapedna(
     defaults to :func:`lapy_b200.shapedna.compute_shapedna` on this rank's GPU.
     Returns an ``(n_meshes, k)`` array on every rank (``gather=True``) or ``{index: (k,)}`` of
     the local shard.
+
+    ``workers`` > 1 processes that many meshes of the shard concurrently on this rank's GPU, one
+    host thread and one library context (= one CUDA stream, one cuSOLVER handle) each: at ~150k
+    vertices a mesh is launch- and latency-bound (small kernels, the dense Rayleigh-Ritz solve, host
+    synchronisations), so several streams fill the device.  The default ``compute`` then receives its
+    worker's context; a custom ``compute`` may take it as a fourth argument.
     """
     dist = _dist()
     rank = dist.get_rank() if dist else 0
@@ -54,18 +61,78 @@ def batched_shapedna(
     else:
         n_meshes = len(meshes)
         get = meshes.__getitem__
+    if workers < 1:
+        raise ValueError("workers must be >= 1")
+    takes_ctx = False
     if compute is None:
-        from .shapedna import compute_shapedna
+        from .solver import Solver
 
-        def compute(mesh, k, lump):
-            return compute_shapedna(mesh, k=k, lump=lump)["Eigenvalues"]
+        def compute(mesh, k, lump, ctx=None):
+            return Solver(mesh, lump=lump, ctx=ctx).eigs(k=k)[0]
 
-    local = {}
-    for i in shard_indices(n_meshes, rank, world):
-        ev = np.asarray(compute(get(i), k, lump), dtype=np.float64)
+        takes_ctx = True
+    else:
+        import inspect
+
+        try:
+            takes_ctx = len(inspect.signature(compute).parameters) >= 4
+        except (TypeError, ValueError):
+            takes_ctx = False
+
+    def one(i, ctx):
+        ev = compute(get(i), k, lump, ctx) if takes_ctx else compute(get(i), k, lump)
+        ev = np.asarray(ev, dtype=np.float64)
         if ev.shape != (k,):
             raise ValueError(f"compute returned shape {ev.shape}, expected ({k},)")
-        local[i] = ev
+        return ev
+
+    mine = shard_indices(n_meshes, rank, world)
+    local = {}
+    if workers == 1 or len(mine) <= 1:
+        for i in mine:
+            local[i] = one(i, None)
+    else:
+        import queue
+        import threading
+
+        todo: queue.SimpleQueue = queue.SimpleQueue()
+        for i in mine:
+            todo.put(i)
+        errors: list[BaseException] = []
+        lock = threading.Lock()
+
+        def run():
+            ctx = None
+            if takes_ctx:
+                try:
+                    from . import _lib
+
+                    ctx = _lib.Context(int(os.environ.get("LAPY_B200_DEVICE", os.environ.get("LOCAL_RANK", "0"))))
+                except BaseException as e:  # noqa: BLE001 - no device, library missing: re-raised by the caller
+                    with lock:
+                        errors.append(e)
+                    return
+            while not errors:
+                try:
+                    i = todo.get_nowait()
+                except queue.Empty:
+                    return
+                try:
+                    ev = one(i, ctx)
+                except BaseException as e:  # noqa: BLE001 - re-raised on the calling thread
+                    with lock:
+                        errors.append(e)
+                    return
+                with lock:
+                    local[i] = ev
+
+        threads = [threading.Thread(target=run, name=f"lapy-b200-batch-{w}") for w in range(min(workers, len(mine)))]
+        for th in threads:
+            th.start()
+        for th in threads:
+            th.join()
+        if errors:
+            raise errors[0]
     if not gather:
         return local
     out = np.zeros((n_meshes, k), np.float64)

@@ -80,3 +80,43 @@ def test_row_partition_covers_all_rows():
             assert all(a[1] == b[0] for a, b in zip(parts, parts[1:]))
             sizes = [b - a for a, b in parts]
             assert max(sizes) == -(-n // world) and all(s >= 0 for s in sizes)
+
+
+def test_worker_threads_process_every_mesh_once():
+    import threading
+    import time
+
+    seen, names = [], set()
+    lock = threading.Lock()
+
+    def compute(mesh, k, lump):
+        time.sleep(0.01)
+        with lock:
+            seen.append(mesh)
+            names.add(threading.current_thread().name)
+        return _fake_compute(mesh, k, lump)
+
+    out = batched_shapedna(lambda i: i, n_meshes=23, k=4, compute=compute, workers=4)
+    assert sorted(seen) == list(range(23))
+    assert len(names) == 4 and all(n.startswith("lapy-b200-batch-") for n in names)
+    for i in range(23):
+        np.testing.assert_array_equal(out[i], _fake_compute(i, 4, False))
+
+    got_ctx = []
+
+    def compute4(mesh, k, lump, ctx):  # a custom compute may take the worker's context ...
+        got_ctx.append(ctx)
+        return _fake_compute(mesh, k, lump)
+
+    batched_shapedna([0, 1, 2], k=3, compute=compute4)  # ... which is None on the serial path
+    assert got_ctx == [None, None, None]
+
+    def boom(mesh, k, lump):
+        if mesh == 5:
+            raise RuntimeError("mesh 5 is broken")
+        return _fake_compute(mesh, k, lump)
+
+    with pytest.raises(RuntimeError, match="mesh 5"):
+        batched_shapedna(lambda i: i, n_meshes=12, k=4, compute=boom, workers=3)
+    with pytest.raises(ValueError, match="workers"):
+        batched_shapedna([0], k=2, compute=_fake_compute, workers=0)
