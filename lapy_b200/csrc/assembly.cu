@@ -924,6 +924,59 @@ __global__ void order_fill_kernel(int64_t n, const int32_t *__restrict__ cell, c
     order[cptr[cid] + atomicAdd(cursor + cid, 1)] = (int)i;
 }
 
+// ---- vertex-granular variant (LAPY_B200_ORDER=fine, opt-in) -------------------------------------
+// Same 128^3 bins, but inside a bin the vertices follow the Morton curve of an 18-bit grid (11 more
+// bits per axis) instead of their index: consecutive rows of the renumbered operator are then mesh
+// neighbours, which is what a row-grouped SpMM needs (tools/study_row_groups.py: 4.2 instead of 5-6
+// distinct X rows per matrix row for groups of 4).  key = sub-code (33 bits) << 31 | vertex.
+__global__ void morton_fine_kernel(const D4 *__restrict__ v4, int64_t n, double ox, double oy, double oz, double sx,
+                                   double sy, double sz, int32_t *__restrict__ cell, int32_t *__restrict__ hist,
+                                   unsigned long long *__restrict__ key) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    D4 p = ldg_d4(v4 + i);
+    const unsigned q[3] = {(unsigned)min(262143, max(0, (int)((p.x - ox) * sx))),
+                           (unsigned)min(262143, max(0, (int)((p.y - oy) * sy))),
+                           (unsigned)min(262143, max(0, (int)((p.z - oz) * sz)))};
+    const int cid = (int)(spread3(q[0] >> 11) | (spread3(q[1] >> 11) << 1) | (spread3(q[2] >> 11) << 2));
+    unsigned long long sub = 0;
+    for (int b = 0; b < 11; b++)
+        for (int a = 0; a < 3; a++) sub |= (unsigned long long)((q[a] >> b) & 1u) << (3 * b + a);
+    cell[i] = cid;
+    key[i] = (sub << 31) | (unsigned long long)i;
+    atomicAdd(hist + cid, 1);
+}
+
+__global__ void order_fill_fine_kernel(int64_t n, const int32_t *__restrict__ cell, const int32_t *__restrict__ cptr,
+                                       int32_t *__restrict__ cursor, const unsigned long long *__restrict__ key,
+                                       unsigned long long *__restrict__ sorted) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int cid = cell[i];
+    sorted[cptr[cid] + atomicAdd(cursor + cid, 1)] = key[i];
+}
+
+// per-bin insertion sort of the 64-bit keys (bins hold tens of vertices), then the vertex ids
+__global__ void bin_sort_u64_kernel(const int32_t *__restrict__ cptr, unsigned long long *__restrict__ keys, int64_t nbins) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nbins) return;
+    const int beg = cptr[r], end = cptr[r + 1];
+    for (int i = beg + 1; i < end; i++) {
+        const unsigned long long k = keys[i];
+        int j = i - 1;
+        while (j >= beg && keys[j] > k) {
+            keys[j + 1] = keys[j];
+            j--;
+        }
+        keys[j + 1] = k;
+    }
+}
+
+__global__ void key_to_order_kernel(int64_t n, const unsigned long long *__restrict__ keys, int32_t *__restrict__ order) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) order[i] = (int)(keys[i] & 0x7fffffffull);
+}
+
 __global__ void invert_order_kernel(int64_t n, const int32_t *__restrict__ order, int32_t *__restrict__ inv) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) inv[order[i]] = (int)i;
@@ -953,6 +1006,24 @@ void ensure_order(lb_order &o) {
     for (int k = 0; k < 3; k++) sc[k] = hi[k] > lo[k] ? 127.999 / (hi[k] - lo[k]) : 0.0;
     DBuf<int32_t> cell(c, n), hist(c, kCells), cptr(c, kCells + 1);
     hist.zero();
+    const char *mode = getenv("LAPY_B200_ORDER");
+    if (mode && !strcmp(mode, "fine")) {
+        double sf[3];
+        for (int k = 0; k < 3; k++) sf[k] = hi[k] > lo[k] ? 262143.999 / (hi[k] - lo[k]) : 0.0;
+        DBuf<unsigned long long> key(c, n), sorted(c, n);
+        LB_LAUNCH(c, morton_fine_kernel, cdiv(n, 256), 256, 0, v4, n, lo[0], lo[1], lo[2], sf[0], sf[1], sf[2], cell.p,
+                  hist.p, key.p);
+        exclusive_scan_i32(c, hist.p, cptr.p, kCells);
+        hist.zero();
+        o.order.alloc(c, (size_t)n);
+        o.inv.alloc(c, (size_t)n);
+        LB_LAUNCH(c, order_fill_fine_kernel, cdiv(n, 256), 256, 0, n, cell.p, cptr.p, hist.p, key.p, sorted.p);
+        LB_LAUNCH(c, bin_sort_u64_kernel, cdiv(kCells, 128), 128, 0, cptr.p, sorted.p, (int64_t)kCells);
+        LB_LAUNCH(c, key_to_order_kernel, cdiv(n, 256), 256, 0, n, sorted.p, o.order.p);
+        LB_LAUNCH(c, invert_order_kernel, cdiv(n, 256), 256, 0, n, o.order.p, o.inv.p);
+        o.ready = true;
+        return;
+    }
     LB_LAUNCH(c, morton_cell_kernel, cdiv(n, 256), 256, 0, v4, n, lo[0], lo[1], lo[2], sc[0], sc[1], sc[2], cell.p,
               hist.p);
     exclusive_scan_i32(c, hist.p, cptr.p, kCells);

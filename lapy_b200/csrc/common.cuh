@@ -233,6 +233,16 @@ struct lb_mesh {
     std::shared_ptr<lb_order> ord;  // handed to the matrices assembled from this mesh
 };
 
+// row-grouped copy of a CSR matrix for the wide SpMM (blockvec.cu, LAPY_B200_SPMM=grouped): groups of
+// kGroupRows consecutive rows share the sorted union of their columns; entry e of a group holds one
+// column and kGroupRows values (0 where a row has no entry in that column)
+struct lb_grouped {
+    int64_t ngroups = 0, nent = 0;
+    lb::DBuf<int32_t> gptr;  // (ngroups + 1)
+    lb::DBuf<int32_t> gcol;  // (nent)
+    lb::DBuf<double> gval;   // (nent * kGroupRows), entry-major
+};
+
 struct lb_mat {
     lb_ctx *ctx = nullptr;
     int64_t n = 0, nnz = 0;     // n = number of rows
@@ -244,4 +254,5 @@ struct lb_mat {
     // optional locality ordering (from the mesh the matrix was assembled on).  Solvers may
     // renumber internally; results are always returned in the caller's order.
     std::shared_ptr<lb_order> ord;
+    mutable std::shared_ptr<lb_grouped> grp;  // built on first use by the grouped SpMM (values are snapshotted)
 };

@@ -567,6 +567,7 @@ int lb_solve(lb_ctx *c, lb_mat *a, double alpha, lb_mat *b, double beta, const d
         LB_LAUNCH(c, broadcast_cols, cdiv(n * mm, 256), 256, 0, n, mm, dval.p, dblock.p);
         spmm(c, K.get(), dblock.p, mm, d_rhs.p, mm, mm, 1, d_rhs.p, mm);
         LB_LAUNCH(c, mask_matrix, cdiv(n, 256), 256, 0, n, K->indptr.p, K->indices.p, K->data.p, is_fixed.p);
+        K->grp.reset();  // values changed in place: drop the row-grouped snapshot of the wide SpMM
         LB_LAUNCH(c, set_fixed_rows, cdiv(n * mm, 256), 256, 0, n, mm, is_fixed.p, dval.p, d_rhs.p);
     }
     int force = 0;
