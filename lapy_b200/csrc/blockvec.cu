@@ -459,12 +459,16 @@ void spmm(lb_ctx *c, const lb_mat *a, const double *x, int ldx, double *y, int l
     // 16-byte vector loads of X need even leading dimension and a 16-byte aligned base
     const bool vec = (ldx % 2 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
     const int grid = cdiv(n, kSpmmStrip);
-    if (vec && m > 32 && m <= 64) {
+    if (vec && m > 32) {
         const char *e = getenv("LAPY_B200_SPMM");
         if (e && !strcmp(e, "grouped")) {
             const lb_grouped *gr = grouped_of(c, a);
-            LB_LAUNCH(c, spmm_grouped_kernel, grid, 256, 0, n, gr->gptr.p, gr->gcol.p, gr->gval.p, x, ldx, y, ldy, m, mode, b,
-                      ldb, epi);
+            for (int c0 = 0; c0 < m; c0 += 64) {  // 64 columns per launch (the 2m-wide products take two)
+                SpmmEpilogue ep = epi;
+                if (ep.out2) ep.out2 += c0;
+                LB_LAUNCH(c, spmm_grouped_kernel, grid, 256, 0, n, gr->gptr.p, gr->gcol.p, gr->gval.p, x + c0, ldx, y + c0, ldy,
+                          std::min(64, m - c0), mode, b ? b + c0 : b, ldb, ep);
+            }
             return;
         }
     }
