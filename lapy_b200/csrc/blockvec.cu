@@ -141,9 +141,10 @@ __global__ void __launch_bounds__(256) spmm_kernel(int64_t n, const int32_t *__r
 // up to kGroupRows accumulators from it: 4.2 instead of 7 row loads per matrix row on a triangle
 // mesh in a vertex-granular Morton order (tools/study_row_groups.py).  Every row still sums its own
 // entries in ascending column order with the same fma chain, so the result equals spmm_kernel's
-// (a stored zero is skipped instead of added: identical for finite X).
-constexpr int kGroupRows = 4;
+// (a stored zero is skipped instead of added: identical for finite X).  Group size R = 2, 4 or 8
+// (LAPY_B200_SPMM=grouped2 | grouped | grouped8): 5.5 / 4.2 / 3.3 X rows per matrix row.
 
+template <int kGroupRows>
 __global__ void group_count_kernel(int64_t n, int64_t ngroups, const int32_t *__restrict__ indptr,
                                    const int32_t *__restrict__ indices, int32_t *__restrict__ gcount) {
     const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -170,6 +171,7 @@ __global__ void group_count_kernel(int64_t n, int64_t ngroups, const int32_t *__
     gcount[g] = cnt;
 }
 
+template <int kGroupRows>
 __global__ void group_fill_kernel(int64_t n, int64_t ngroups, const int32_t *__restrict__ indptr,
                                   const int32_t *__restrict__ indices, const double *__restrict__ val,
                                   const int32_t *__restrict__ gptr, int32_t *__restrict__ gcol,
@@ -204,13 +206,15 @@ __global__ void group_fill_kernel(int64_t n, int64_t ngroups, const int32_t *__r
     }
 }
 
+template <int kGroupRows>
 static const lb_grouped *grouped_of(lb_ctx *c, const lb_mat *a) {
-    if (a->grp) return a->grp.get();
+    if (a->grp && a->grp->rows == kGroupRows) return a->grp.get();
     auto gr = std::make_shared<lb_grouped>();
+    gr->rows = kGroupRows;
     const int64_t n = a->n, ng = (n + kGroupRows - 1) / kGroupRows;
     gr->ngroups = ng;
     DBuf<int32_t> gcount(c, ng);
-    LB_LAUNCH(c, group_count_kernel, cdiv(ng, 128), 128, 0, n, ng, a->indptr.p, a->indices.p, gcount.p);
+    LB_LAUNCH(c, group_count_kernel<kGroupRows>, cdiv(ng, 128), 128, 0, n, ng, a->indptr.p, a->indices.p, gcount.p);
     gr->gptr.alloc(c, ng + 1);
     exclusive_scan_i32(c, gcount.p, gr->gptr.p, ng);
     int32_t total = 0;
@@ -218,7 +222,7 @@ static const lb_grouped *grouped_of(lb_ctx *c, const lb_mat *a) {
     gr->nent = total;
     gr->gcol.alloc(c, (size_t)std::max(1, total));
     gr->gval.alloc(c, (size_t)std::max(1, total) * kGroupRows);
-    LB_LAUNCH(c, group_fill_kernel, cdiv(ng, 128), 128, 0, n, ng, a->indptr.p, a->indices.p, a->data.p, gr->gptr.p,
+    LB_LAUNCH(c, group_fill_kernel<kGroupRows>, cdiv(ng, 128), 128, 0, n, ng, a->indptr.p, a->indices.p, a->data.p, gr->gptr.p,
               gr->gcol.p, gr->gval.p);
     if (c->trace)
         fprintf(stderr, "[lb trace] grouped SpMM format: n=%lld nnz=%lld -> %lld group entries (%.2f X rows per matrix row)\n",
@@ -229,7 +233,8 @@ static const lb_grouped *grouped_of(lb_ctx *c, const lb_mat *a) {
 
 // m <= 64 columns: lane owns columns 2*lane, 2*lane + 1 (one 16-byte load per X row); a warp owns a
 // group, the 8 warps of a CTA walk the 32 groups of a 128-row strip interleaved
-__global__ void __launch_bounds__(256, 3) spmm_grouped_kernel(int64_t n, const int32_t *__restrict__ gptr,
+template <int kGroupRows>
+__global__ void __launch_bounds__(256, kGroupRows == 8 ? 2 : 3) spmm_grouped_kernel(int64_t n, const int32_t *__restrict__ gptr,
                                                               const int32_t *__restrict__ gcol,
                                                               const double *__restrict__ gval,
                                                               const double *__restrict__ x, int ldx, double *y, int ldy,
@@ -461,13 +466,21 @@ void spmm(lb_ctx *c, const lb_mat *a, const double *x, int ldx, double *y, int l
     const int grid = cdiv(n, kSpmmStrip);
     if (vec && m > 32) {
         const char *e = getenv("LAPY_B200_SPMM");
-        if (e && !strcmp(e, "grouped")) {
-            const lb_grouped *gr = grouped_of(c, a);
+        const int rows = !e ? 0 : !strcmp(e, "grouped") ? 4 : !strcmp(e, "grouped2") ? 2 : !strcmp(e, "grouped8") ? 8 : 0;
+        if (rows) {
+            const lb_grouped *gr = rows == 2 ? grouped_of<2>(c, a) : rows == 8 ? grouped_of<8>(c, a) : grouped_of<4>(c, a);
             for (int c0 = 0; c0 < m; c0 += 64) {  // 64 columns per launch (the 2m-wide products take two)
                 SpmmEpilogue ep = epi;
                 if (ep.out2) ep.out2 += c0;
-                LB_LAUNCH(c, spmm_grouped_kernel, grid, 256, 0, n, gr->gptr.p, gr->gcol.p, gr->gval.p, x + c0, ldx, y + c0, ldy,
-                          std::min(64, m - c0), mode, b ? b + c0 : b, ldb, ep);
+                const int mc = std::min(64, m - c0);
+                const double *bc = b ? b + c0 : b;
+#define LB_GROUPED(R)                                                                                                    \
+    LB_LAUNCH(c, spmm_grouped_kernel<R>, grid, 256, 0, n, gr->gptr.p, gr->gcol.p, gr->gval.p, x + c0, ldx, y + c0, ldy, mc, \
+              mode, bc, ldb, ep)
+                if (rows == 2) LB_GROUPED(2);
+                else if (rows == 8) LB_GROUPED(8);
+                else LB_GROUPED(4);
+#undef LB_GROUPED
             }
             return;
         }

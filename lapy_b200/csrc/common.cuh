@@ -234,13 +234,14 @@ struct lb_mesh {
 };
 
 // row-grouped copy of a CSR matrix for the wide SpMM (blockvec.cu, LAPY_B200_SPMM=grouped): groups of
-// kGroupRows consecutive rows share the sorted union of their columns; entry e of a group holds one
-// column and kGroupRows values (0 where a row has no entry in that column)
+// `rows` consecutive rows share the sorted union of their columns; entry e of a group holds one
+// column and `rows` values (0 where a row has no entry in that column)
 struct lb_grouped {
+    int rows = 0;
     int64_t ngroups = 0, nent = 0;
     lb::DBuf<int32_t> gptr;  // (ngroups + 1)
     lb::DBuf<int32_t> gcol;  // (nent)
-    lb::DBuf<double> gval;   // (nent * kGroupRows), entry-major
+    lb::DBuf<double> gval;   // (nent * rows), entry-major
 };
 
 struct lb_mat {
