@@ -769,6 +769,137 @@ __global__ void __launch_bounds__(kRowThreads) row_accumulate_tet(
     }
 }
 
+// triangle version of row_accumulate_tet (LAPY_B200_TRIA_ROWS=fused; written after the tet kernel was
+// validated, not yet run on a GPU): up to kFusedSItria incidences and kFusedCap entries per row,
+// one 32-byte element record per incidence, three triplets per incidence (solver.py:171-175).
+constexpr int kFusedSItria = 16;
+constexpr size_t kFusedSmemTria = (size_t)kRowThreads * (kFusedSItria * 8 + kFusedCap * 20);
+
+__global__ void __launch_bounds__(kRowThreads) row_accumulate_tria(
+    const D4 *__restrict__ rec, const int32_t *__restrict__ inc_ptr, const int4 *__restrict__ inc4, int64_t n,
+    const ElemConsts *__restrict__ consts, int degen_div_f32, int32_t *__restrict__ row_nnz,
+    int32_t *__restrict__ row_has, int32_t *__restrict__ row_big, int32_t *__restrict__ sc_key,
+    double *__restrict__ sc_a, double *__restrict__ sc_b, double *__restrict__ sc_lump) {
+    constexpr int T = kRowThreads, SI = kFusedSItria, CAP = kFusedCap, NB = kFusedBatch;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    unsigned long long *s_ord = reinterpret_cast<unsigned long long *>(smem_raw);  // [SI][T]
+    double *s_a = reinterpret_cast<double *>(s_ord + SI * T);                      // [CAP][T]
+    double *s_b = s_a + CAP * T;                                                   // [CAP][T]
+    int32_t *s_k = reinterpret_cast<int32_t *>(s_b + CAP * T);                     // [CAP][T]
+    __shared__ int s_maxcnt;
+    const int t = threadIdx.x;
+    const int64_t r = (int64_t)blockIdx.x * T + t;
+    if (t == 0) s_maxcnt = 0;
+    __syncthreads();
+    int cnt = 0;
+    bool big = false;
+    if (r < n) {
+        const int beg = inc_ptr[r], ninc = inc_ptr[r + 1] - beg;
+        double lump = 0.0;
+        if (ninc > SI) {
+            big = true;
+        } else if (ninc > 0) {
+            for (int i0 = 0; i0 < ninc; i0 += 8) {
+                int c8[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) c8[u] = i0 + u < ninc ? __ldg(&inc4[beg + i0 + u].x) : 0;
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    const int i = i0 + u;
+                    if (i < ninc) {
+                        const unsigned long long key = ((unsigned long long)(unsigned)c8[u] << 8) | (unsigned)i;
+                        int j = i - 1;
+                        while (j >= 0 && s_ord[j * T + t] > key) {
+                            s_ord[(j + 1) * T + t] = s_ord[j * T + t];
+                            j--;
+                        }
+                        s_ord[(j + 1) * T + t] = key;
+                    }
+                }
+            }
+            auto acc = [&](int key, double va, double vb) {
+                int pos = cnt;
+                while (pos > 0 && s_k[(pos - 1) * T + t] >= key) pos--;
+                if (pos < cnt && s_k[pos * T + t] == key) {
+                    s_a[pos * T + t] = __dadd_rn(s_a[pos * T + t], va);
+                    s_b[pos * T + t] = __dadd_rn(s_b[pos * T + t], vb);
+                    return;
+                }
+                if (cnt == CAP) {
+                    big = true;
+                    return;
+                }
+                for (int q = cnt; q > pos; q--) {
+                    s_k[q * T + t] = s_k[(q - 1) * T + t];
+                    s_a[q * T + t] = s_a[(q - 1) * T + t];
+                    s_b[q * T + t] = s_b[(q - 1) * T + t];
+                }
+                s_k[pos * T + t] = key;
+                s_a[pos * T + t] = va;  // first addend itself, like csr_sum_duplicates (keeps -0.0)
+                s_b[pos * T + t] = vb;
+                cnt++;
+            };
+            for (int j0 = 0; j0 < ninc && !big; j0 += NB) {
+                int4 q[NB];
+                D4 e[NB];
+#pragma unroll
+                for (int u = 0; u < NB; u++)
+                    q[u] = j0 + u < ninc ? __ldg(inc4 + beg + (int)(s_ord[(j0 + u) * T + t] & 255ull)) : make_int4(0, 0, 0, 0);
+#pragma unroll
+                for (int u = 0; u < NB; u++)
+                    if (j0 + u < ninc) e[u] = ldg_d4(rec + (q[u].x >> 2));
+#pragma unroll
+                for (int u = 0; u < NB; u++)
+                    if (j0 + u < ninc) {
+                        const int c = q[u].x & 3;
+                        double a12 = e[u].x, a23 = e[u].y, a31 = e[u].z, bii = e[u].w;
+                        if (bii < 0.0) {  // clamped element (solver.py:159): divide by the global mean
+                            const double vm = consts->vol_mean;
+                            if (degen_div_f32) {
+                                a12 = (double)__fdiv_rn((float)a12, (float)vm);
+                                a23 = (double)__fdiv_rn((float)a23, (float)vm);
+                                a31 = (double)__fdiv_rn((float)a31, (float)vm);
+                            } else {
+                                a12 = __ddiv_rn(a12, vm);
+                                a23 = __ddiv_rn(a23, vm);
+                                a31 = __ddiv_rn(a31, vm);
+                            }
+                            bii = consts->bii_deg;
+                        }
+                        const double bij = 0.5 * bii;
+                        lump += 2.0 * bii;  // vol/12 (vol/3 for fem_tria_mass) == 2*bii exactly
+                        double x0, x1, m0, m1;
+                        if (c == 0) {
+                            x0 = a12; x1 = a31; m0 = a12; m1 = a31;
+                        } else if (c == 1) {
+                            x0 = a12; x1 = a23; m0 = a12; m1 = a23;
+                        } else {
+                            x0 = a23; x1 = a31; m0 = a31; m1 = a23;
+                        }
+                        // the diagonal (row sum = 0, solver.py:167-169) is formed in the element dtype
+                        const double xd = degen_div_f32 ? (double)__fsub_rn(-(float)m0, (float)m1) : __dsub_rn(-m0, m1);
+                        acc(q[u].y, x0, bij);
+                        acc(q[u].z, x1, bij);
+                        acc((int)r, xd, bii);
+                    }
+            }
+        }
+        row_has[r] = ninc > 0;
+        row_big[r] = big;
+        row_nnz[r] = big ? -1 : cnt;
+        sc_lump[r] = lump;
+        if (!big && cnt > 0) atomicMax(&s_maxcnt, cnt);
+    }
+    __syncthreads();
+    const int total = s_maxcnt * T;
+    const size_t base = (size_t)blockIdx.x * CAP * T;
+    for (int i = t; i < total; i += T) {
+        sc_key[base + i] = s_k[i];
+        sc_a[base + i] = s_a[i];
+        sc_b[base + i] = s_b[i];
+    }
+}
+
 // scratch ([block][slot][thread]) -> CSR.  Flagged rows are left to row_fill_kernel(only_rows).
 __global__ void __launch_bounds__(kRowThreads) row_compact_kernel(int64_t n, const int32_t *__restrict__ row_big,
                                                                   const int32_t *__restrict__ sc_key,
@@ -1096,8 +1227,8 @@ static void run_rows(lb_mesh *mesh, const D4 *rec, const ElemConsts *consts, con
         LB_CUDA(cudaFuncSetAttribute(row_count_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap_keys * 4));
     // tets, LAPY_B200_TET_ROWS=fused: accumulate once into a per-row scratch, compact after the scan
     bool fused = false;
-    if (K == 4 && (want_a || !lump)) {
-        const char *e = getenv("LAPY_B200_TET_ROWS");
+    if (want_a || !lump) {
+        const char *e = getenv(K == 4 ? "LAPY_B200_TET_ROWS" : "LAPY_B200_TRIA_ROWS");
         fused = e && !strcmp(e, "fused");
     }
     DBuf<int32_t> row_big, sc_key;
@@ -1109,9 +1240,16 @@ static void run_rows(lb_mesh *mesh, const D4 *rec, const ElemConsts *consts, con
         sc_a.alloc(c, slots);
         sc_b.alloc(c, slots);
         sc_lump.alloc(c, n);
-        LB_CUDA(cudaFuncSetAttribute(row_accumulate_tet, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFusedSmemA));
-        LB_LAUNCH(c, row_accumulate_tet, nblocks, kRowThreads, kFusedSmemA, rec, aptr, inc4, n, consts, (int)degen_f32,
-                  row_nnz.p, row_has.p, row_big.p, sc_key.p, sc_a.p, sc_b.p, sc_lump.p);
+        if (K == 4) {
+            LB_CUDA(cudaFuncSetAttribute(row_accumulate_tet, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFusedSmemA));
+            LB_LAUNCH(c, row_accumulate_tet, nblocks, kRowThreads, kFusedSmemA, rec, aptr, inc4, n, consts, (int)degen_f32,
+                      row_nnz.p, row_has.p, row_big.p, sc_key.p, sc_a.p, sc_b.p, sc_lump.p);
+        } else {
+            LB_CUDA(cudaFuncSetAttribute(row_accumulate_tria, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)kFusedSmemTria));
+            LB_LAUNCH(c, row_accumulate_tria, nblocks, kRowThreads, kFusedSmemTria, rec, aptr, inc4, n, consts,
+                      (int)degen_f32, row_nnz.p, row_has.p, row_big.p, sc_key.p, sc_a.p, sc_b.p, sc_lump.p);
+        }
     }
     LB_LAUNCH(c, row_count_kernel<K>, nblocks, kRowThreads, cap_keys * 4, aptr, inc4, n, cap_keys, scratch.p,
               row_nnz.p, row_has.p, fused ? row_big.p : (const int32_t *)nullptr);

@@ -6,6 +6,8 @@ the kernel's summation order (oracle.sparse_build.coo_to_csc_sequential), and wi
 1e-12 * (sum of |addends|) of SciPy's own result (equal entries where SciPy's order coincides).
 """
 
+import os
+
 import numpy as np
 import pytest
 from conftest import golden_csc, golden_mesh
@@ -220,6 +222,38 @@ def test_tet_row_kernel_variants_match_default(monkeypatch, mode):
     fem = lapy_b200.Solver(fan)
     _check(fem.stiffness, ta, a_ref, "fan A")
     _check(fem.mass, tb, b_ref, "fan B")
+
+
+def test_tria_row_kernel_variant_matches_default(monkeypatch):
+    """LAPY_B200_TRIA_ROWS=fused (written after round 1's GPU budget was spent): must reproduce the
+    default kernels bit for bit - closed and open meshes, float32, lumped mass, a 3000-triangle fan."""
+    import lapy_b200
+    from lapy_b200 import mesh as M
+    from lapy_b200.mesh import TriaMesh
+
+    if not os.environ.get("LAPY_B200_TEST_EXPERIMENTAL"):
+        pytest.skip("opt-in kernel variant not yet validated on a GPU: set LAPY_B200_TEST_EXPERIMENTAL=1")
+    ico = M.icosphere(4)
+    ico32 = TriaMesh(ico.v.astype(np.float32), ico.t)
+    gx, gy = np.meshgrid(np.arange(40), np.arange(30), indexing="ij")
+    gid = (gx * 30 + gy)[:-1, :-1].reshape(-1)
+    square = TriaMesh(np.column_stack([gx.reshape(-1) * 0.1, gy.reshape(-1) * 0.13, np.zeros(gx.size)]),
+                      np.vstack([np.column_stack([gid, gid + 30, gid + 31]), np.column_stack([gid, gid + 31, gid + 1])]))  # fmt: skip
+    n = 3000
+    ang = np.linspace(0, 2 * np.pi, n, endpoint=False)
+    fan = TriaMesh(np.vstack([[0, 0, 0.3], np.column_stack([np.cos(ang), np.sin(ang), np.zeros(n)])]),
+                   np.column_stack([np.zeros(n, int), 1 + np.arange(n), 1 + (np.arange(n) + 1) % n]))  # fmt: skip
+    for mesh in (ico, ico32, square, fan):
+        for lump in (False, True):
+            monkeypatch.delenv("LAPY_B200_TRIA_ROWS", raising=False)
+            ref = lapy_b200.Solver(mesh, lump=lump)
+            ra, rb = ref.stiffness, ref.mass
+            monkeypatch.setenv("LAPY_B200_TRIA_ROWS", "fused")
+            alt = lapy_b200.Solver(mesh, lump=lump)
+            for x, y in ((alt.stiffness, ra), (alt.mass, rb)):
+                np.testing.assert_array_equal(x.indptr, y.indptr)
+                np.testing.assert_array_equal(x.indices, y.indices)
+                np.testing.assert_array_equal(x.data, y.data)
 
 
 def test_high_valence_fan():
