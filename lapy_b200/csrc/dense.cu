@@ -1,10 +1,10 @@
 // dense.cu - dense products on tall-skinny blocks and the small dense factorizations of the
 // Rayleigh-Ritz step.
 //
-// The tall-skinny products go to the hand-written fp64 DMMA kernels (dmma.cu; cuBLAS DGEMM only with
-// LAPY_B200_DENSE=cublas, the bring-up / A-B path); cuSOLVER does the <= 3m x 3m Cholesky and
-// symmetric eigenproblem (SURVEY.md §7 K8 allows a library here: it
-// replaces LAPACK inside ARPACK, is O(m^3) and independent of the mesh size).
+// The tall-skinny products go to the hand-written fp64 DMMA kernels (dmma.cu), always; cuSOLVER does
+// the <= 3m x 3m Cholesky and symmetric eigenproblem and cuBLAS the triangular solves of the coarsest
+// AMG level (SURVEY.md §7 K8 allows a library here: it replaces LAPACK inside ARPACK, is O(m^3) and
+// independent of the mesh size).
 #include <cublas_v2.h>
 #include <cusolverDn.h>
 
@@ -59,41 +59,18 @@ void destroy_dense_handles(lb_ctx *c) {
     c->cublas = c->cusolver = nullptr;
 }
 
-// Row-major (n,p) with leading dimension ld is column-major (p,n) with the same ld.
-static bool use_cublas() {
-    static int v = -1;
-    if (v < 0) {
-        const char *e = getenv("LAPY_B200_DENSE");
-        v = (e && !strcmp(e, "cublas")) ? 1 : 0;
-    }
-    return v == 1;
-}
-
 void gram(lb_ctx *c, int64_t n, int p, const double *x, int ldx, int q, const double *y, int ldy, double *cmat,
           bool symmetric) {
     if (p == 0 || q == 0) return;
     ProfScope prof(c, PROF_GRAM, 2.0 * n * p * q);
-    if (!use_cublas()) {
-        gram_dmma(c, n, p, x, ldx, q, y, ldy, cmat, symmetric && p == q);
-        return;
-    }
-    const double one = 1.0, zero = 0.0;
-    // C_rm(p,q) = X^T Y  <=>  C_cm(q,p) = Y_cm(q,n) * X_cm(p,n)^T
-    LB_CUBLAS(cublasDgemm(blas(c), CUBLAS_OP_N, CUBLAS_OP_T, q, p, (int)n, &one, y, ldy, x, ldx, &zero, cmat, q));
-    c->launches++;
+    gram_dmma(c, n, p, x, ldx, q, y, ldy, cmat, symmetric && p == q);
 }
 
 void update(lb_ctx *c, int64_t n, int p, const double *x, int ldx, int q, const double *cmat, int ldc, double alpha,
             double beta, double *y, int ldy) {
     if (q == 0 || n == 0) return;
     ProfScope prof(c, PROF_UPDATE, 2.0 * n * p * q);
-    if (!use_cublas()) {
-        update_dmma(c, n, p, x, ldx, q, cmat, ldc, alpha, beta, y, ldy);
-        return;
-    }
-    // Y_cm(q,n) = alpha * C_cm(q,p) * X_cm(p,n) + beta * Y_cm
-    LB_CUBLAS(cublasDgemm(blas(c), CUBLAS_OP_N, CUBLAS_OP_N, q, (int)n, p, &alpha, cmat, ldc, x, ldx, &beta, y, ldy));
-    c->launches++;
+    update_dmma(c, n, p, x, ldx, q, cmat, ldc, alpha, beta, y, ldy);
 }
 
 int chol_lower(lb_ctx *c, int q, double *g) {

@@ -958,7 +958,6 @@ extern "C" int lb_eigs(lb_ctx *c, lb_mat *a, lb_mat *b, int k, double sigma, dou
     }
     DeviceGuard g(c->device);
     if (tol <= 0) tol = 1e-9;
-    if (const char *e = getenv("LAPY_B200_TOL")) tol = atof(e);
     if (maxit <= 0) maxit = 200;
     EigStats st;
     const int m = ((k + std::max(6, (k + 3) / 4) + 7) / 8) * 8;

@@ -67,6 +67,31 @@ __global__ void dominance_margin(int64_t n, const int32_t *__restrict__ ptr, con
     if ((threadIdx.x & 31) == 0 && worst > 0.0) atomicMax(out_neg, (unsigned long long)__double_as_longlong(worst));
 }
 
+// max_i |sum_j K_ij| and max_i |K_ii|: is the constant vector (numerically) in the null space of K?
+__global__ void rowsum_diag_max(int64_t n, const int32_t *__restrict__ ptr, const int32_t *__restrict__ idx,
+                                const double *__restrict__ val, unsigned long long *__restrict__ out /* [2] */) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    double rs = 0.0, dg = 0.0;
+    if (i < n) {
+        double s = 0.0;
+        for (int p = ptr[i]; p < ptr[i + 1]; p++) {
+            s += val[p];
+            if (idx[p] == i) dg = fabs(val[p]);
+        }
+        rs = fabs(s);
+        if (!(rs == rs)) rs = 1e300;  // NaN entries: never treated as singular
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        rs = fmax(rs, __shfl_xor_sync(0xffffffffu, rs, o));
+        dg = fmax(dg, __shfl_xor_sync(0xffffffffu, dg, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (rs > 0.0) atomicMax(out, (unsigned long long)__double_as_longlong(rs));
+        if (dg > 0.0) atomicMax(out + 1, (unsigned long long)__double_as_longlong(dg));
+    }
+}
+
 __global__ void add_diag_shift(int64_t n, const int32_t *__restrict__ ptr, const int32_t *__restrict__ idx,
                                double *__restrict__ val, double eps) {
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -173,7 +198,10 @@ __global__ void __launch_bounds__(256) jacobi_stream_kernel(int64_t n, const int
             const double xo = x[row * ld + col];
             const double xn = diag > 0.0 ? (b[row * ld + col] - off) / diag : 0.0;
             y[row * ld + col] = xn;
-            if (xn != 0.0) rel = fmax(rel, fabs(xn - xo) / fabs(xn));
+            // a non-finite iterate (divergence, non-finite input) must read as "not converged":
+            // fmax() drops NaN, so it is mapped to +inf explicitly
+            if (!(fabs(xn) <= 1.79769313486231570e308)) rel = __longlong_as_double(0x7ff0000000000000ll);
+            else if (xn != 0.0) rel = fmax(rel, fabs(xn - xo) / fabs(xn));
         }
     }
 #pragma unroll
@@ -218,7 +246,8 @@ static SolveStats block_pcg(lb_ctx *c, lb_mat *K, const double *rhs, double *x, 
     if (c->trace) fprintf(stderr, "[lb trace] solve: n=%lld m=%d off-diagonal ratio %.4f project=%d\n", (long long)n, m, off_ratio, (int)project);
     if (force_prec == 1) use_amg = false;
     if (force_prec == 2) use_amg = true;
-    if (force_prec == 0 && !project && try_jacobi) {
+    // Jacobi needs strict diagonal dominance (off_ratio < 1) to contract
+    if (force_prec == 0 && !project && try_jacobi && off_ratio < 1.0) {
         // componentwise Jacobi (see jacobi_stream_kernel), two columns at a time; checks the max
         // relative increment every 64 sweeps; falls through to PCG if it does not contract
         // (input that is not an M-matrix)
@@ -241,7 +270,7 @@ static SolveStats block_pcg(lb_ctx *c, lb_mat *K, const double *rhs, double *x, 
             double *cur = xa.p + c0, *nxt = xb.p + c0;
             const double *bb = rhs + c0;
             double rel = 1.0, prev = 2.0;
-            int sweeps = 0, stalls = 0, since_best = 0;
+            int sweeps = 0, stalls = 0, since_best = 0, growing = 0;
             double best = INFINITY;
             ok = false;
             while (sweeps < 100000) {
@@ -267,6 +296,10 @@ static SolveStats block_pcg(lb_ctx *c, lb_mat *K, const double *rhs, double *x, 
                     ok = true;
                     break;
                 }
+                if (!std::isfinite(rel)) break;  // overflow / NaN: fall through to PCG
+                // rel >= 1 is normal while the front still reaches new vertices (at most ~diameter
+                // sweeps), but it must not keep GROWING: a divergent iteration is cut after 16 checks
+                if (rel >= 1.0 && rel > prev && ++growing > 16) break;
                 if (rel < 1e-9) {
                     if (rel < 0.9 * best) {
                         best = rel;
@@ -572,7 +605,22 @@ int lb_solve(lb_ctx *c, lb_mat *a, double alpha, lb_mat *b, double beta, const d
     }
     int force = 0;
     if (const char *e = getenv("LAPY_B200_PREC")) force = !strcmp(e, "jacobi") ? 1 : !strcmp(e, "amg") ? 2 : 0;
-    const bool project = project_nullspace != 0 && nfix == 0;
+    // project out the constants only if they ARE (numerically) in the null space: a user-assigned
+    // nonsingular operator (A + c*B, screened Poisson) must be solved as it is, like splu does.
+    // float32-assembled stiffness matrices have |A 1| ~ 1e-7 * diag: the threshold keeps them singular.
+    bool project = project_nullspace != 0 && nfix == 0;
+    if (project) {
+        DBuf<unsigned long long> rsd(c, 2);
+        rsd.zero();
+        LB_LAUNCH(c, rowsum_diag_max, cdiv(n, 256), 256, 0, n, K->indptr.p, K->indices.p, K->data.p, rsd.p);
+        unsigned long long hb[2];
+        read_back(c, hb, rsd.p, 2);
+        double rs, dg;
+        std::memcpy(&rs, &hb[0], 8);
+        std::memcpy(&dg, &hb[1], 8);
+        project = rs <= 1e-5 * dg;
+        if (c->trace) fprintf(stderr, "[lb trace] solve: max |K 1| = %.3e, max diag = %.3e -> project = %d\n", rs, dg, (int)project);
+    }
     // mass-dominated operators (backward Euler heat step: diagonal B, beta != 0): componentwise Jacobi
     const bool try_jacobi = beta != 0.0 && b != nullptr && b->diagonal && nfix == 0;
     // solver-internal locality renumbering (Morton order of the mesh the operator came from), as in

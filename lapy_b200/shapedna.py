@@ -78,11 +78,11 @@ def reweight_ev(evals: np.ndarray) -> np.ndarray:
 
 def compute_distance(ev1: np.ndarray, ev2: np.ndarray, dist: str = "euc"):
     """Euclidean distance of two ShapeDNA descriptors (shapedna.py:258-296); any other ``dist`` logs a
-    warning and returns None like the reference."""
+    warning and raises ``ValueError`` like the reference."""
     if dist == "euc":
         u, v = np.asarray(ev1, dtype=float), np.asarray(ev2, dtype=float)
         if u.ndim != 1 or v.ndim != 1:
             raise ValueError("Input vector should be 1-D.")
         return float(np.sqrt(np.dot(u - v, u - v)))
     logger.warning("Only Euclidean distance is currently implemented; received %s", dist)
-    return None
+    raise ValueError(f"Distance metric {dist} is not implemented.")

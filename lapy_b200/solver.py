@@ -23,21 +23,26 @@ _KIND = {"TriaMesh": _lib.FEM_TRIA, "TetMesh": _lib.FEM_TETRA}
 
 
 def _device_mesh(geometry, ctx):
-    """Upload (and cache on the geometry object) v / t."""
-    cached = getattr(geometry, "_lb_device_mesh", None)
-    if (
-        cached is not None
-        and cached[0] is geometry.v
-        and cached[1] is geometry.t
-        and cached[2].ctx is ctx
-        and cached[2].handle
-    ):
-        return cached[2]
-    dm = _lib.DeviceMesh(ctx, geometry.v, geometry.t)
-    try:
-        geometry._lb_device_mesh = (geometry.v, geometry.t, dm)
-    except AttributeError:  # geometry with __slots__
-        pass
+    """Upload ``geometry.v`` / ``geometry.t``.
+
+    The reference always reads the current host arrays, and an in-place edit (``mesh.v *= s``) does
+    not change array identity, so a device copy is only re-used when BOTH arrays are read-only
+    (``arr.flags.writeable = False``: callers that solve many problems on one mesh opt in that way);
+    otherwise every call uploads (19 ms at 2.6M vertices - cheaper than hashing the arrays)."""
+    v, t = geometry.v, geometry.t
+    frozen = not getattr(getattr(v, "flags", None), "writeable", True) and not getattr(
+        getattr(t, "flags", None), "writeable", True
+    )
+    if frozen:
+        cached = getattr(geometry, "_lb_device_mesh", None)
+        if cached is not None and cached[0] is v and cached[1] is t and cached[2].ctx is ctx and cached[2].handle:
+            return cached[2]
+    dm = _lib.DeviceMesh(ctx, v, t)
+    if frozen:
+        try:
+            geometry._lb_device_mesh = (v, t, dm)
+        except AttributeError:  # geometry with __slots__
+            pass
     return dm
 
 
@@ -60,6 +65,7 @@ class Solver:
         *,
         device: int | None = None,
         ctx: _lib.Context | None = None,
+        _mesh: _lib.DeviceMesh | None = None,
     ) -> None:
         self.sksparse = None
         self._dtype = np.dtype(dtype)
@@ -93,7 +99,7 @@ class Solver:
             kind, extra = _lib.FEM_TETRA, None
         else:
             raise ValueError('Geometry type "' + name + '" unknown')
-        self._mesh = _device_mesh(geometry, self._ctx)
+        self._mesh = _mesh if _mesh is not None and _mesh.ctx is self._ctx else _device_mesh(geometry, self._ctx)
         self._dev = dict(zip("ab", _lib.assemble(self._ctx, self._mesh, kind, lump, extra)))
         self._host = {"a": None, "b": None}
         self.geotype = type(geometry)

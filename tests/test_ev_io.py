@@ -75,7 +75,8 @@ def test_shapedna_post_processing_matches_the_reference():
     np.testing.assert_array_equal(shapedna.normalize_ev(ico, ev), g["norm_geometry"])
     np.testing.assert_array_equal(shapedna.reweight_ev(ev), g["reweighted"])
     assert shapedna.compute_distance(ev, ev[::-1].copy()) == pytest.approx(float(g["distance"]), rel=1e-15)
-    assert shapedna.compute_distance(ev, ev, dist="other") is None
+    with pytest.raises(ValueError, match="not implemented"):  # lapy/shapedna.py:292-296
+        shapedna.compute_distance(ev, ev, dist="other")
     with pytest.raises(ValueError, match="Unknown normalization"):
         shapedna.normalize_ev(ico, ev, method="nope")
     with pytest.raises(NotImplementedError):  # the minimal meshes carry no adjacency: volume needs a lapy mesh

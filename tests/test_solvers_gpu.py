@@ -123,14 +123,25 @@ def test_shapedna_ico5_k50(golden):
 
 
 @pytest.mark.parametrize("key,maker", [("ico6_k50", lambda M: M.icosphere(6)), ("ico7_k50", lambda M: M.icosphere(7)),
+                                       ("ico8_k50", lambda M: M.icosphere(8)), ("ico9_k50", lambda M: M.icosphere(9)),
                                        ("cube21_k50", lambda M: M.cube_tets(21)), ("cube31_k50", lambda M: M.cube_tets(31))])  # fmt: skip
 def test_k50_spectra_vs_reference(key, maker):
+    """k=50 spectra of the unmodified reference (tests/golden/spectra.npz; level 8 / 9 = BASELINE.md
+    §5.2, level 9 is the north-star configuration: 2,621,442 vertices, 1e-8 relative)."""
     import lapy_b200
     from lapy_b200 import mesh as M
 
     ref = load_golden("spectra")[key]
-    ev, _ = lapy_b200.Solver(maker(M)).eigs(k=50)
+    mesh = maker(M)
+    fem = lapy_b200.Solver(mesh)
+    ev, evec = fem.eigs(k=50)
     check_evals(ev, ref)
+    # size-independent properties of the eigenvectors, on the device-assembled matrices
+    b = fem.mass
+    assert evec.shape == (mesh.v.shape[0], 50)
+    np.testing.assert_allclose(evec.T @ (b @ evec), np.eye(50), atol=1e-9)
+    r = fem.stiffness @ evec - (b @ evec) * ev
+    assert np.abs(r).max() <= 1e-7 * np.abs(ev).max() * np.abs(b @ evec).max()
 
 
 def test_k50_lumped_and_small_k():
@@ -387,3 +398,65 @@ def test_dmma_block_products_match_numpy(n, p, q):
     assert np.abs(out - ref).max() <= 1e-12 * p
     out = _lib.block_update(ctx, x, cm)
     assert np.abs(out - x @ cm).max() <= 1e-12 * p
+
+
+def test_level7_heat_geodesic_reference_values():
+    """values the unmodified reference produced on the level-7 icosphere
+    (163,842 vertices): t, u[0], sum(u) of heat.diffusion(T,[0],m=1) and max / mean of
+    compute_geodesic_f(T,u).  The mesh is float64 with >= 100k vertices, so ``t`` comes from the
+    device edge-length kernel (lb_avg_edge_length), checked against the host formula as well."""
+    from lapy_b200 import _lib, diffgeo, heat
+    from lapy_b200 import mesh as M
+    from lapy_b200.solver import Solver
+
+    mesh = M.icosphere(7)
+    fem = Solver(mesh, lump=True)
+    h_dev = _lib.avg_edge_length(fem._ctx, fem._mesh, fem._device("a"))
+    assert abs(h_dev - mesh.avg_edge_length()) <= 1e-13 * h_dev
+    assert abs(h_dev**2 - 8.916850393006576e-05) <= 1e-12 * 8.916850393006576e-05
+    u = heat.diffusion(mesh, [0], m=1.0)
+    assert abs(u[0] - 3325.8603222719325) <= 1e-8 * 3325.8603222719325
+    assert abs(u.sum() - 14606.340887242888) <= 1e-8 * 14606.340887242888
+    g = diffgeo.compute_geodesic_f(mesh, u)
+    assert abs(g.max() - 3.1302828669840617) <= 1e-6 * np.pi
+    assert abs(g.mean() - 1.5653885315086715) <= 1e-6 * np.pi
+
+
+def test_assigned_nonsingular_stiffness_is_not_projected(golden):
+    """``fem.stiffness = A + c*B`` (screened Poisson) is nonsingular; without Dirichlet data
+    the solver must return K^-1 b like the reference's splu, not a zero-mean projection."""
+    import lapy_b200
+    from scipy.sparse.linalg import splu
+
+    g = golden("ico5")
+    fem = lapy_b200.Solver(golden_mesh(g), lump=True)
+    a, b = golden_csc(g, "A"), golden_csc(g, "B_lump")
+    k = (a + 0.5 * b).tocsc()
+    fem.stiffness = k
+    h = np.random.default_rng(1).standard_normal(a.shape[0]) + 3.0  # nonzero mean
+    x = fem.poisson(h)
+    ref = splu(k).solve(b @ h)
+    assert abs(ref.mean()) > 1.0  # the projected answer would have mean 0
+    assert np.abs(x - ref).max() <= 1e-8 * np.abs(ref).max()
+
+
+def test_in_place_mesh_edit_is_seen(golden):
+    """the reference reads the current host arrays on every call; an in-place edit of
+    ``mesh.v`` between two Solver constructions must not be served from a stale device copy."""
+    import lapy_b200
+
+    g = golden("ico3")
+    mesh = golden_mesh(g)
+    m0 = lapy_b200.Solver(mesh, lump=True).mass.sum()
+    mesh.v *= 2.0
+    m1 = lapy_b200.Solver(mesh, lump=True).mass.sum()
+    assert abs(m1 - 4.0 * m0) <= 1e-12 * m1
+    mesh.t[:, [1, 2]] = mesh.t[:, [2, 1]]  # flips the orientation: same matrices, different triplet order
+    a2 = lapy_b200.Solver(mesh, lump=True).stiffness
+    assert abs(a2 - 1.0 * golden_csc(g, "A")).max() < 1e-12
+    # read-only arrays opt in to the device-side cache
+    mesh.v.flags.writeable = False
+    mesh.t.flags.writeable = False
+    s1 = lapy_b200.Solver(mesh)
+    s2 = lapy_b200.Solver(mesh)
+    assert s1._mesh is s2._mesh
