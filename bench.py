@@ -11,9 +11,17 @@ With N>1 (torchrun, one rank per GPU) every rank processes its own mesh per step
 batch as in BrainPrint, no data-path collective) -> "scaling": "weak"; value = meshes all ranks
 processed / max-over-ranks device time.
 
-Prints ONE JSON line (rank 0).  `--impl reference` times the reference's CPU algorithm for the
-same path (the oracle: NumPy element math + SciPy COO->CSC + SuperLU + ARPACK, sequential) on a
-bounded sample.
+The eigenvalues of the LAST TIMED step are compared with the reference's (tests/golden/spectra.npz,
+produced by the unmodified reference); a relative error above 1e-8 makes the run fail (rc 3).
+
+Prints ONE JSON line (rank 0).  Sub-records (outside the timed region, N=1 unless noted):
+`configs` = BASELINE.json configs 3, 4, 5 at full size (tet cube 121^3, heat + geodesics on level 9,
+a batch of level-7 surfaces; the batch also at N>1), `rowpart` (N>1) = one mesh solved cooperatively
+by all ranks (row-partitioned, NCCL halo exchange).
+
+`--impl reference` times the reference's CPU algorithm for the same path (the oracle: NumPy element
+math + SciPy COO->CSC + SuperLU + ARPACK, sequential per mesh) for real on the largest icosphere
+level that fits a few minutes (level 8), one mesh per rank's worth of host processes.
 """
 
 from __future__ import annotations
@@ -32,6 +40,7 @@ sys.path.insert(0, ROOT)
 
 PEAK_FALLBACK_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
 METRIC = "shapedna_k50_meshes_per_s"
+PARITY_RTOL = 1e-8  # BASELINE.json north_star
 
 
 def measured_peak():
@@ -101,66 +110,243 @@ class ClockSampler:
 
 
 def make_workload(name, rank=0):
+    """-> (mesh, description, key of the reference spectrum in tests/golden/spectra.npz or None)"""
     from lapy_b200 import mesh as M
 
     if name == "icosphere9":
-        return M.icosphere(9), "level-9 icosphere, 2,621,442 v / 5,242,880 tris, ShapeDNA k=50 (BASELINE.json configs[1])"
+        return (M.icosphere(9), "level-9 icosphere, 2,621,442 v / 5,242,880 tris, ShapeDNA k=50 (BASELINE.json configs[1])",
+                "ico9_k50")  # fmt: skip
     if name.startswith("icosphere"):
         lvl = int(name[len("icosphere"):])
-        return M.icosphere(lvl), f"level-{lvl} icosphere (reduced size: NOT the headline config)"
+        return M.icosphere(lvl), f"level-{lvl} icosphere (reduced size: NOT the headline config)", f"ico{lvl}_k50"
     if name.startswith("brain"):  # BrainPrint-like batch surface (config 5)
-        return M.perturbed_sphere(7, seed=rank), "level-7 perturbed sphere, 163,842 v (BASELINE.json configs[4] unit)"
+        return M.perturbed_sphere(7, seed=rank), "level-7 perturbed sphere, 163,842 v (BASELINE.json configs[4] unit)", None
     if name.startswith("cube"):
         n = int(name[len("cube"):])
-        return M.cube_tets(n), f"structured tet cube n={n}"
+        return M.cube_tets(n), f"structured tet cube n={n}", f"cube{n}_k50"
     raise SystemExit(f"unknown workload {name}")
 
 
-def cpu_reference(args, full_mesh):
-    """The reference's algorithm on the host (oracle), bounded sample: ShapeDNA k of a level-7
-    icosphere (the full level-9 mesh costs ~26 min / 27 GB of SuperLU), scaled
-    linearly in the vertex count to one workload mesh (an under-estimate of the CPU time:
-    SuperLU fill grows ~n^1.4)."""
+def golden_spectrum(key, k):
+    if key is None or k != 50:
+        return None
+    p = os.path.join(ROOT, "tests", "golden", "spectra.npz")
+    if not os.path.exists(p):
+        return None
+    g = np.load(p)
+    return np.asarray(g[key]) if key in g else None
+
+
+def parity_record(ev, ref, key):
+    """Eigenvalues of the timed step against the unmodified reference's (relative, lambda_0 absolute)."""
+    if ref is None:
+        return {"checked": False, "why": "no reference spectrum for this workload / k in tests/golden/spectra.npz"}
+    ev, ref = np.asarray(ev), np.asarray(ref)
+    rel = float(np.max(np.abs(ev[1:] - ref[1:]) / np.abs(ref[1:])))
+    ok = bool(rel <= PARITY_RTOL and abs(ev[0]) <= 1e-8 and np.all(np.isfinite(ev)))
+    return {"checked": True, "ok": ok, "max_rel_err": rel, "rtol": PARITY_RTOL, "lam0": float(ev[0]), "lam0_ref": float(ref[0]),
+            "golden": f"tests/golden/spectra.npz[{key}] (unmodified reference, BASELINE.md §5.2)"}  # fmt: skip
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the oracle (= the reference's algorithm on SciPy SuperLU + ARPACK)
+# ------------------------------------------------------------------------------------------------
+def _cpu_shapedna_worker(level, k, q):
     from lapy_b200 import mesh as M
     from oracle import solve as osolve
 
-    nv_full = full_mesh.v.shape[0]
-    lvl = 7 if nv_full > 200000 else None
-    sample = M.icosphere(lvl) if lvl else full_mesh
+    mesh = M.icosphere(level)
     t0 = time.perf_counter()
-    osolve.shapedna(sample, k=args.k)
-    dt = time.perf_counter() - t0
-    scale = nv_full / sample.v.shape[0]
-    what = (
-        f"1 ShapeDNA k={args.k} of a level-7 icosphere (163,842 v) = {dt:.1f} s, scaled x{scale:.0f} (linear in vertices, "
-        "optimistic for the CPU) to one workload mesh; survey-measured full-size reference: 1557 s/mesh"
-        if lvl
-        else f"1 ShapeDNA k={args.k} of the workload mesh = {dt:.1f} s"
-    )
-    return 1.0 / (dt * scale), dt * scale, what
+    sd = osolve.shapedna(mesh, k=k)
+    q.put((time.perf_counter() - t0, float(sd["Eigenvalues"][1])))
+
+
+def cpu_shapedna_seconds(level, k, procs=1):
+    """Wall seconds for `procs` concurrent reference ShapeDNA runs (one sequential process each) of
+    the level-`level` icosphere; mesh generation is outside the timing."""
+    import multiprocessing as mp
+
+    if procs == 1:
+        from lapy_b200 import mesh as M
+        from oracle import solve as osolve
+
+        mesh = M.icosphere(level)
+        t0 = time.perf_counter()
+        osolve.shapedna(mesh, k=k)
+        return time.perf_counter() - t0, [time.perf_counter() - t0]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    # the BLAS inside SuperLU / ARPACK is threaded: split the host threads over the processes
+    # (oversubscription makes concurrent runs several times slower than sequential ones)
+    threads = str(max(1, (os.cpu_count() or 1) // procs))
+    saved = {v: os.environ.get(v) for v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS")}
+    for v in saved:
+        os.environ[v] = threads
+    try:
+        ps = [ctx.Process(target=_cpu_shapedna_worker, args=(level, k, q)) for _ in range(procs)]
+        for p in ps:
+            p.start()
+    finally:
+        for v, old in saved.items():
+            if old is None:
+                os.environ.pop(v, None)
+            else:
+                os.environ[v] = old
+    each = [q.get()[0] for _ in ps]
+    for p in ps:
+        p.join()
+    return max(each), each
+
+
+NV = {4: 2562, 5: 10242, 6: 40962, 7: 163842, 8: 655362, 9: 2621442}
 
 
 def run_reference(args, rank):
+    """Reference arm: a REAL measurement of the largest level that fits a few minutes (level 8,
+    ~2-4.5 min), labelled as executed.  The level-9 workload costs 13-26 min and 27 GB per mesh on
+    the CPU (1557 s measured offline), so it is only PROJECTED, in a separate field,
+    with the growth exponent measured in this run (level 7 -> 8)."""
     if rank != 0:
         return
-    mesh, desc = make_workload(args.workload)
-    # every step is the same bounded sample (~20-30 s of sequential SuperLU + ARPACK); the step and
-    # warm-up counts are capped so the whole run ends within a few minutes
-    warm, steps = min(args.warmup, 1), max(1, min(args.steps, 2))
-    for _ in range(warm):
-        cpu_reference(args, mesh)
-    runs = [cpu_reference(args, mesh) for _ in range(steps)]
-    sec = float(np.mean([r[1] for r in runs]))
-    val, what = 1.0 / sec, runs[-1][2] + f"; mean of {steps} timed run(s) after {warm} warm-up"
+    n_units = max(1, args.gpus)  # one mesh per GPU of the arm it is compared with
+    cores = os.cpu_count() or 1
+    procs = min(n_units, cores)
+    level = args.ref_level
+    try:
+        import psutil
+
+        if psutil.virtual_memory().available < procs * (9 << 30) and level >= 8:  # SuperLU at level 8: ~7 GB per process
+            level = 7
+    except Exception:
+        pass
+    t_small, _ = cpu_shapedna_seconds(level - 1, args.k, 1)  # also the warm-up (imports, page cache)
+    rounds = (n_units + procs - 1) // procs
+    wall = 0.0
+    each = []
+    for _ in range(rounds):
+        w, e = cpu_shapedna_seconds(level, args.k, procs)
+        wall += w
+        each += e
+    exponent = float(np.log(np.mean(each) / t_small) / np.log(NV[level] / NV[level - 1]))
+    proj9 = float(np.mean(each) * (NV[9] / NV[level]) ** exponent)
+    val = n_units / wall
+    what = (f"{n_units} x ShapeDNA k={args.k} of the level-{level} icosphere ({NV[level]:,} v) run for real by the oracle "
+            f"(SciPy SuperLU + ARPACK: sequential algorithms, threaded BLAS), {procs} concurrent process(es) on {cores} host threads: {wall:.1f} s wall; "
+            f"level {level - 1} took {t_small:.1f} s -> time ~ n^{exponent:.2f}")  # fmt: skip
     line = {
-        "impl": "reference", "metric": METRIC, "value": val, "unit": "meshes/s", "n_gpus": args.gpus, "steps": steps,
-        "warmup": warm, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "meshes/s", "n_gpus": args.gpus, "steps": 1,
+        "warmup": 0, "ms_per_step": wall * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": desc, "step": "Solver(mesh) + eigs(k): assembly + generalized eigensolve", "k": args.k},
-        "cpu_baseline": {"value": val, "unit": "meshes/s", "cores": 1, "kind": "port", "sample": what},
+        "config": {"workload": f"level-{level} icosphere, {NV[level]:,} v, ShapeDNA k={args.k}: the LARGEST level the CPU reference "
+                               "finishes within a few minutes - NOT the level-9 workload of the b200 arm (4x the vertices)",
+                   "step": "Solver(mesh) + eigs(k): assembly + splu + ARPACK shift-invert", "k": args.k,
+                   "meshes_per_step": n_units},
+        "cpu_baseline": {"value": val, "unit": "meshes/s", "cores": cores if procs == 1 else procs * max(1, cores // procs),
+                         "kind": "port", "sample": what},
         "e2e": {"value": val, "unit": "meshes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "level9_projection": {"s_per_mesh": proj9, "meshes_per_s": n_units / proj9 / rounds if rounds else None,
+                              "how": f"level-{level} time x 4^{exponent:.2f} (exponent measured in this run); "
+                                     "measured offline on the survey box: 1557 s/mesh (BASELINE.md §2)"},
+        "host": {"cpu_count": cores},
     }  # fmt: skip
     print(json.dumps(line), flush=True)
+
+
+def cpu_baseline_sample(args):
+    """cpu_baseline of the b200 arm: ~15-30 s of CPU work = the oracle's ShapeDNA on ONE level-7
+    icosphere (1/16 of the workload's vertices), reported as measured - not scaled."""
+    t, _ = cpu_shapedna_seconds(7, args.k, 1)
+    return {"value": 1.0 / t, "unit": "meshes/s", "cores": 1, "kind": "port",
+            "sample": f"1 ShapeDNA k={args.k} of a level-7 icosphere (163,842 v, 1/16 of the workload mesh) = {t:.1f} s on one host "
+                      "core; value is for THAT mesh size, not scaled. The level-9 mesh itself: 1557 s measured offline "
+                      "(BASELINE.md §2); `bench.py --impl reference` runs level 8 for real",
+            "sample_seconds": t, "sample_vertices": NV[7]}  # fmt: skip
+
+
+# ------------------------------------------------------------------------------------------------
+# sub-records: BASELINE.json configs 3, 4, 5 (outside the timed region)
+# ------------------------------------------------------------------------------------------------
+def extras_single_gpu(ctx, peak):
+    import lapy_b200
+    from lapy_b200 import _lib, diffgeo, heat
+    from lapy_b200 import mesh as M
+
+    out = {}
+
+    def timed(f):
+        ctx.sync()
+        t0 = time.perf_counter()
+        r = f()
+        ctx.sync()
+        return r, time.perf_counter() - t0
+
+    # config 3 on one GPU: 121^3 tet cube (1,771,561 v / 10,368,000 tets): assembly + eigs(k=50)
+    try:
+        mesh = M.cube_tets(121)
+        dm = _lib.DeviceMesh(ctx, mesh.v, mesh.t)
+        ms = []
+        for _ in range(4):
+            dm.drop_cache()
+            ctx.timer_start()
+            a, b = _lib.assemble(ctx, dm, _lib.FEM_TETRA, False)
+            ms.append(ctx.timer_stop())
+        nt, nv, nnz = mesh.t.shape[0], mesh.v.shape[0], a.nnz
+        algo = 16 * nt + 24 * nv + 2 * (12 * nnz + 4 * (nv + 1))
+        _lib.eigs(ctx, a, b, 50, -0.01)
+        (ev, _evec, info), t_eig = timed(lambda: _lib.eigs(ctx, a, b, 50, -0.01))
+        asm = float(np.median(ms[1:]))
+        out["cube121_tets"] = {"vertices": nv, "tets": nt, "nnz": int(nnz), "assembly_ms": asm, "assembly_gelem_per_s": nt / asm / 1e6,
+                               "assembly_roofline_frac": algo / (asm * 1e-3) / 1e9 / peak, "eigs_k50_s": t_eig,
+                               "iterations": info["iterations"], "residual": info["residual"],
+                               "lam1_over_pi2": float(ev[1] / np.pi**2), "lam0": float(ev[0])}  # fmt: skip
+        del a, b, dm, _evec
+    except Exception as e:  # a sub-record must not take the headline down
+        out["cube121_tets"] = {"error": repr(e)}
+    # config 4: heat diffusion + heat-method geodesics on the level-9 icosphere
+    try:
+        mesh = M.icosphere(9)
+        heat.diffusion(mesh, [0], m=1.0)
+        u, t_heat = timed(lambda: heat.diffusion(mesh, [0], m=1.0))
+        hinfo = dict(heat.diffusion.last_info)
+        # m=1 (t = h^2 = 5.6e-6) underflows beyond ~1.7 rad for the reference as well; m=16 gives the
+        # diffusion length of level 7 with m=1 and a usable geodesic field
+        u16, t_heat16 = timed(lambda: heat.diffusion(mesh, [0], m=16.0))
+        hinfo16 = dict(heat.diffusion.last_info)
+        diffgeo.compute_geodesic_f(mesh, u16)
+        g, t_geo = timed(lambda: diffgeo.compute_geodesic_f(mesh, u16))
+        exact = np.arccos(np.clip(mesh.v @ mesh.v[0], -1, 1))
+        out["heat_geodesic_L9"] = {"heat_m1_s": t_heat, "heat_m1_sweeps": hinfo["iterations"], "heat_m16_s": t_heat16,
+                                   "heat_m16_sweeps": hinfo16["iterations"], "u0_m1": float(u[0]), "geodesic_s": t_geo,
+                                   "geodesic_max": float(g.max()), "max_abs_err_vs_great_circle": float(np.abs(g - exact).max())}  # fmt: skip
+    except Exception as e:
+        out["heat_geodesic_L9"] = {"error": repr(e)}
+    return out
+
+
+def batch_record(world, workers=4, per_rank=12):
+    """config 5 (scaled down to `per_rank` surfaces per GPU): level-7 perturbed spheres, ShapeDNA k=50
+    each through lapy_b200.batch.batched_shapedna (round-robin over the ranks, `workers` concurrent
+    contexts per GPU)."""
+    import torch.distributed as dist
+
+    from lapy_b200 import mesh as M
+    from lapy_b200.batch import batched_shapedna
+
+    rank = dist.get_rank() if world > 1 else 0
+    total = per_rank * world
+    cache = {i: M.perturbed_sphere(7, seed=i) for i in range(rank, total, world)}
+    for m in cache.values():
+        m.v.flags.writeable = False
+        m.t.flags.writeable = False
+    batched_shapedna(cache.__getitem__, n_meshes=min(total, 2 * world), k=50, workers=workers)  # warm-up
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    ev = batched_shapedna(cache.__getitem__, n_meshes=total, k=50, workers=workers)
+    dt = time.perf_counter() - t0
+    return {"meshes": total, "vertices_per_mesh": 163842, "k": 50, "workers_per_gpu": workers, "seconds": dt,
+            "meshes_per_s": total / dt, "lam1_range": [float(ev[:, 1].min()), float(ev[:, 1].max())],
+            "note": "BASELINE.json configs[4] unit (512 surfaces) scaled to %d per GPU; wall clock incl. H2D / D2H" % per_rank}  # fmt: skip
 
 
 def main():
@@ -171,7 +357,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="icosphere9")
     ap.add_argument("--k", type=int, default=50)
+    ap.add_argument("--ref-level", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -186,7 +374,6 @@ def main():
     import torch
     import torch.distributed as dist
 
-    import lapy_b200
     from lapy_b200 import _lib
     from lapy_b200.shapedna import compute_shapedna
 
@@ -206,7 +393,7 @@ def main():
             os.close(saved)
     ctx = _lib.Context(local_rank)
 
-    mesh, desc = make_workload(args.workload, rank)
+    mesh, desc, gkey = make_workload(args.workload, rank)
     nt, nv = mesh.t.shape[0], mesh.v.shape[0]
     kind = _lib.FEM_TETRA if mesh.t.shape[1] == 4 else _lib.FEM_TRIA
     dmesh = _lib.DeviceMesh(ctx, mesh.v, mesh.t)  # inputs resident in HBM before the timed region
@@ -239,8 +426,10 @@ def main():
         dev_ms = ctx.timer_stop()
     print(f"[bench] rank {rank}: per-step wall ms {[round(x, 1) for x in step_wall]}", file=sys.stderr)
     prof = ctx.profile_report()
+    spmm_shapes = ctx.profile_shapes("spmm", 24)
     ctx.profile_enable(False)
     launches = ctx.launch_count() - l0
+    parity = parity_record(ev, golden_spectrum(gkey, args.k), gkey)  # the LAST TIMED step's eigenvalues
     barrier()
     # assembly alone (device time), outside the timed region
     for _ in range(5):
@@ -252,8 +441,11 @@ def main():
     a_dev, _b = _lib.assemble(ctx, dmesh, kind, False)
     spmv_ms = _lib.spmm_benchmark(ctx, a_dev, 1, 50)
     spmv_ren_ms = _lib.spmm_benchmark(ctx, a_dev, 1, 50, renumber=True)
-    spmm64_ms = _lib.spmm_benchmark(ctx, a_dev, 64, 20)
     spmm64_ren_ms = _lib.spmm_benchmark(ctx, a_dev, 64, 20, renumber=True)
+    # the instantiation that took the most device time inside the timed region (level-0 operators only)
+    lvl0 = [s for s in spmm_shapes if s["shape"][1] == nnz]
+    dom = max(lvl0, key=lambda s: s["ms"]) if lvl0 else None
+    dom_iso_ms = _lib.spmm_benchmark(ctx, a_dev, dom["shape"][0], 20, renumber=True) if dom else None
     del _b
     t_ms = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -267,8 +459,7 @@ def main():
     e2e_steps = max(1, min(args.steps, 3))
 
     def e2e_step():
-        hmesh.__dict__.pop("_lb_device_mesh", None)
-        return compute_shapedna(hmesh, k=args.k)
+        return compute_shapedna(hmesh, k=args.k)  # writable arrays: uploads v / t on every call
 
     e2e_step()
     barrier()
@@ -282,14 +473,22 @@ def main():
     e2e_s = float(e2e_s.item())
     h2d = vpin.nbytes + tpin.nbytes
     d2h = sd["Eigenvalues"].nbytes + sd["Eigenvectors"].nbytes
+    parity_e2e = parity_record(sd["Eigenvalues"], golden_spectrum(gkey, args.k), gkey)
+    del sd, evec, a_dev, dmesh
+
+    peak, peak_kind = measured_peak()
+    configs = {}
+    if not args.no_extras:
+        if world == 1 and rank == 0:
+            configs.update(extras_single_gpu(ctx, peak))
+        try:
+            configs["batch_L7"] = batch_record(world)
+        except Exception as e:
+            configs["batch_L7"] = {"error": repr(e)}
 
     if rank == 0:
-        peak, peak_kind = measured_peak()
         sp = prof.get("spmm", {"launches": 0, "ms": 0.0, "work": 0.0})
         class_rate = sp["work"] / (sp["ms"] * 1e-3) / 1e9 if sp["ms"] else 0.0
-        # dominant kernel: spmm_kernel<32> = K x (n, 64) block on the renumbered level-0 operator
-        spmm_bytes = 12 * nnz + 4 * (nv + 1) + 16 * nv * 64
-        achieved = spmm_bytes / (spmm64_ren_ms * 1e-3) / 1e9
         total_prof_ms = sum(v["ms"] for v in prof.values())
         classes = {
             k: {"launches": v["launches"], "ms_per_step": v["ms"] / args.steps,
@@ -297,7 +496,29 @@ def main():
                 "rate_unit": "GB/s" if k in ("spmm", "col_dots", "elementwise") else "GFLOP/s"}
             for k, v in prof.items()
         }  # fmt: skip
+        # roofline of the dominant kernel: algorithmic bytes of its launches in the timed region
+        # (12 nnz + 4 (V+1) + 8 m (rows of X + rows of Y [+ rows of B])) / their summed CUDA-event time
+        if dom:
+            m_dom = dom["shape"][0]
+            achieved = dom["work"] / (dom["ms"] * 1e-3) / 1e9
+            per_launch_bytes = dom["work"] / dom["launches"]
+            kernel = (f"spmm_kernel, level-0 operator (nnz {nnz:,}) x (n,{m_dom}) block: the SpMM instantiation with the largest "
+                      f"summed device time in the timed region ({dom['launches']} launches, {dom['ms'] / args.steps:.1f} ms/step)")
+        else:
+            m_dom, achieved, per_launch_bytes, kernel = 64, 0.0, 0.0, "spmm_kernel (no launches recorded)"
+        spmm64_bytes = 12 * nnz + 4 * (nv + 1) + 16 * nv * 64
+        traffic, traffic_src = None, None
+        tp = os.path.join(ROOT, "profiles", "ncu_dominant_kernel_r2.json")
+        if os.path.exists(tp):
+            try:
+                tj = json.load(open(tp))
+                if int(tj.get("columns", -1)) == int(m_dom):
+                    traffic, traffic_src = float(tj["dram_bytes_per_launch"]), tj.get("source")
+            except Exception:
+                pass
         asm = float(np.median(asm_ms)) if asm_ms else None
+        asm_bytes = 4 * mesh.t.shape[1] * nt + 24 * nv + 2 * (12 * nnz + 4 * (nv + 1))
+        spmv_bytes = 12 * nnz + 4 * (nv + 1) + 16 * nv
         line = {
             "metric": METRIC, "value": world / (ms_step * 1e-3), "unit": "meshes/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
@@ -306,35 +527,40 @@ def main():
                        "k": args.k, "sigma": -0.01, "tol": "1e-9 scaled residual", "parallelism": f"mesh-parallel x{world}",
                        "l2": "working set per step (S/AS/BS blocks 24 GB at level 9) exceeds the 126 MB L2"},
             "s_per_mesh": ms_step * 1e-3,
-            "assembly": {"ms": asm, "gelem_per_s": nt / (asm * 1e-3) / 1e9 if asm else None,
-                         "roofline_frac": (4 * mesh.t.shape[1] * nt + 24 * nv + 2 * (12 * nnz + 4 * (nv + 1))) / (asm * 1e-3) / 1e9 / peak if asm else None},
-            "spmv": {"ms": spmv_ms, "gb_per_s": (12 * nnz + 4 * (nv + 1) + 16 * nv) / (spmv_ms * 1e-3) / 1e9,
-                     "roofline_frac": (12 * nnz + 4 * (nv + 1) + 16 * nv) / (spmv_ms * 1e-3) / 1e9 / peak,
-                     "renumbered_ms": spmv_ren_ms,
-                     "renumbered_roofline_frac": (12 * nnz + 4 * (nv + 1) + 16 * nv) / (spmv_ren_ms * 1e-3) / 1e9 / peak,
-                     "spmm64_ms": spmm64_ms, "spmm64_roofline_frac": spmm_bytes / (spmm64_ms * 1e-3) / 1e9 / peak,
-                     "note": "ms / roofline_frac / spmm64: caller's vertex order; renumbered_*: Morton-cell order used inside the solvers; x, y resident in HBM"},
+            "parity": parity, "parity_e2e": parity_e2e,
+            "assembly": {"ms": asm, "gelem_per_s": nt / (asm * 1e-3) / 1e9 if asm else None, "algorithmic_bytes": int(asm_bytes),
+                         "roofline_frac": asm_bytes / (asm * 1e-3) / 1e9 / peak if asm else None},
+            "spmv": {"ms": spmv_ms, "gb_per_s": spmv_bytes / (spmv_ms * 1e-3) / 1e9, "roofline_frac": spmv_bytes / (spmv_ms * 1e-3) / 1e9 / peak,
+                     "renumbered_ms": spmv_ren_ms, "renumbered_roofline_frac": spmv_bytes / (spmv_ren_ms * 1e-3) / 1e9 / peak,
+                     "spmm64_renumbered_ms": spmm64_ren_ms, "spmm64_renumbered_roofline_frac": spmm64_bytes / (spmm64_ren_ms * 1e-3) / 1e9 / peak,
+                     "note": "ms / roofline_frac: caller's vertex order (what lb_spmm users get); renumbered_*: Morton-cell order used inside the solvers; x, y resident in HBM"},
             "eigs": {"iterations": info["iterations"], "amg_levels": info["amg_levels"], "residual": info["residual"],
                      "amg_setup_ms": info["setup_ms"], "lobpcg_ms": info["solve_ms"]},
             "gpu_launches": int(launches),
             "e2e": {"value": world / e2e_s, "unit": "meshes/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": e2e_s * 1e3},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": 3.235e9, "traffic_source": "ncu --set full, dram read+write of one m=64 launch (profiles/ncu_full_kernels_r1.csv)",
-                         "peak_kind": peak_kind,
-                         "kernel": "spmm_kernel<32,true>: level-0 operator (renumbered) x (n,64) block, CUDA events over 20 launches in this run",
-                         "algorithmic_bytes": int(spmm_bytes), "ms_per_launch": spmm64_ren_ms,
+                         "traffic": traffic, "traffic_source": traffic_src, "peak_kind": peak_kind, "kernel": kernel,
+                         "algorithmic_bytes": int(per_launch_bytes), "ms_per_launch": dom["ms"] / dom["launches"] if dom else None,
+                         "isolated_ms_per_launch": dom_iso_ms,
+                         "isolated_frac": (12 * nnz + 4 * (nv + 1) + 16 * nv * m_dom) / (dom_iso_ms * 1e-3) / 1e9 / peak if dom_iso_ms else None,
+                         "spmm_shapes_in_timed_region": [
+                             {"columns": s["shape"][0], "nnz": s["shape"][1], "launches": s["launches"], "ms_per_step": s["ms"] / args.steps,
+                              "gb_per_s": s["work"] / (s["ms"] * 1e-3) / 1e9 if s["ms"] else None} for s in spmm_shapes[:12]],
                          "class_in_timed_region": {"launches": sp["launches"], "ms_per_step": sp["ms"] / args.steps, "avg_gb_per_s": class_rate,
                                                    "share_of_profiled_device_time": sp["ms"] / total_prof_ms if total_prof_ms else None}},
             "kernel_classes": classes,
+            "configs": configs,
             "clocks": clk.summary(),
         }  # fmt: skip
-        if not args.no_cpu_baseline:
-            val, sec, what = cpu_reference(args, mesh)
-            line["cpu_baseline"] = {"value": val, "unit": "meshes/s", "cores": 1, "kind": "port", "sample": what}
+        if not args.no_cpu_baseline and world == 1:
+            line["cpu_baseline"] = cpu_baseline_sample(args)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+    if not (parity.get("ok", True) and parity_e2e.get("ok", True)):
+        print(f"[bench] PARITY FAILURE: {parity} / {parity_e2e}", file=sys.stderr)
+        sys.exit(3)
 
 
 if __name__ == "__main__":

@@ -81,6 +81,10 @@ int lb_timer_stop(lb_ctx *ctx, double *ms);
  * bytes for classes 0/4/5, flops for 1-3). */
 int lb_profile_enable(lb_ctx *ctx, int on);
 int lb_profile_report(lb_ctx *ctx, int64_t *count, double *ms, double *work);
+/* the records of one class aggregated by launch shape (SpMM: shape0 = columns, shape1 = nnz of the
+ * matrix; Gram / update: p, q; small dense: order), largest device time first; arrays of `cap` */
+int lb_profile_shapes(lb_ctx *ctx, int cls, int cap, int64_t *shape0, int64_t *shape1, int64_t *count,
+                      double *ms, double *work, int *nshapes);
 /* number of kernels this library has launched on ctx since creation */
 int lb_launch_count(lb_ctx *ctx, int64_t *count);
 

@@ -51,6 +51,7 @@ SIGNATURES = {
     "lb_launch_count": [_vp, C.POINTER(_i64)],
     "lb_profile_enable": [_vp, _int],
     "lb_profile_report": [_vp, _vp, _vp, _vp],
+    "lb_profile_shapes": [_vp, _int, _int, _vp, _vp, _vp, _vp, _vp, C.POINTER(_int)],
     "lb_nccl_unique_id": [_vp],
     "lb_comm_init": [_vp, _int, _int, _vp],
     "lb_comm_destroy": [_vp],
@@ -199,6 +200,18 @@ class Context:
             for i, name in enumerate(self.PROFILE_CLASSES)
             if cnt[i]
         }
+
+    def profile_shapes(self, cls: str, cap: int = 16) -> list[dict]:
+        """Records of one class aggregated by launch shape, largest device time first."""
+        s0, s1, cnt = (np.zeros(cap, np.int64) for _ in range(3))
+        ms, work = np.zeros(cap), np.zeros(cap)
+        n = C.c_int()
+        check(lib().lb_profile_shapes(self.handle, self.PROFILE_CLASSES.index(cls), cap, ptr(s0), ptr(s1), ptr(cnt),
+                                      ptr(ms), ptr(work), C.byref(n)))  # fmt: skip
+        return [
+            {"shape": (int(s0[i]), int(s1[i])), "launches": int(cnt[i]), "ms": float(ms[i]), "work": float(work[i])}
+            for i in range(n.value)
+        ]
 
     def launch_count(self) -> int:
         n = C.c_int64()

@@ -467,7 +467,7 @@ void spmm(lb_ctx *c, const lb_mat *a, const double *x, int ldx, double *y, int l
     if (n == 0 || m == 0) return;
     const int64_t xrows = a->ncols < 0 ? a->n : a->ncols;
     // algorithmic bytes: matrix once, X once, Y once (+ B once for the residual modes)
-    ProfScope prof(c, PROF_SPMM, 12.0 * a->nnz + 4.0 * (n + 1) + 8.0 * m * (xrows + n * (mode ? 2 : 1)));
+    ProfScope prof(c, PROF_SPMM, 12.0 * a->nnz + 4.0 * (n + 1) + 8.0 * m * (xrows + n * (mode ? 2 : 1)), m, a->nnz);
     if (a->diagonal) {
         LB_LAUNCH(c, diag_spmm_kernel, cdiv(n * m, 256), 256, 0, n, a->indptr.p, a->data.p, x, ldx, y, ldy, m, mode, b,
                   ldb);

@@ -80,6 +80,7 @@ struct lb_ctx {
         int cls;
         cudaEvent_t e0, e1;
         double work;  // algorithmic bytes (HBM-bound classes) or flops (dense classes)
+        int64_t shape[2];  // launch shape for the per-shape report: SpMM (columns, nnz), dense (p, q)
     };
     std::vector<ProfRec> prof;
     std::vector<cudaEvent_t> prof_pool;
@@ -192,7 +193,7 @@ enum ProfClass { PROF_SPMM = 0, PROF_GRAM, PROF_UPDATE, PROF_TRSM, PROF_DOTS, PR
 struct ProfScope {
     lb_ctx *c;
     int idx = -1;
-    ProfScope(lb_ctx *ctx, int cls, double work);
+    ProfScope(lb_ctx *ctx, int cls, double work, int64_t shape0 = 0, int64_t shape1 = 0);
     ~ProfScope();
 };
 

@@ -1,6 +1,7 @@
 // ctx.cu - context life cycle, error reporting, prefix sums, matrix upload / download.
 #include <sys/mman.h>
 
+#include <algorithm>
 #include <chrono>
 #include <cstdlib>
 #include <thread>
@@ -94,9 +95,9 @@ static cudaEvent_t prof_event(lb_ctx *c) {
     return e;
 }
 
-ProfScope::ProfScope(lb_ctx *ctx, int cls, double work) : c(ctx) {
+ProfScope::ProfScope(lb_ctx *ctx, int cls, double work, int64_t shape0, int64_t shape1) : c(ctx) {
     if (!c->profile) return;
-    lb_ctx::ProfRec r{cls, prof_event(c), prof_event(c), work};
+    lb_ctx::ProfRec r{cls, prof_event(c), prof_event(c), work, {shape0, shape1}};
     cudaEventRecord(r.e0, c->stream);
     idx = (int)c->prof.size();
     c->prof.push_back(r);
@@ -347,6 +348,47 @@ int lb_profile_report(lb_ctx *c, int64_t *count, double *ms, double *work) {
         ms[r.cls] += t;
         work[r.cls] += r.work;
     }
+    LB_API_END
+}
+
+// records of one class aggregated by launch shape, largest device time first; arrays of `cap`
+int lb_profile_shapes(lb_ctx *c, int cls, int cap, int64_t *shape0, int64_t *shape1, int64_t *count, double *ms,
+                      double *work, int *nshapes) {
+    LB_API_BEGIN
+    LB_REQUIRE(c && shape0 && shape1 && count && ms && work && nshapes && cap > 0, "NULL argument");
+    LB_REQUIRE(cls >= 0 && cls < PROF_NCLASS, "unknown profile class %d", cls);
+    DeviceGuard g(c->device);
+    sync(c);
+    struct Agg {
+        int64_t s0, s1, cnt;
+        double ms, work;
+    };
+    std::vector<Agg> agg;
+    for (auto &r : c->prof) {
+        if (r.cls != cls) continue;
+        float t = 0;
+        cudaEventElapsedTime(&t, r.e0, r.e1);
+        Agg *a = nullptr;
+        for (auto &x : agg)
+            if (x.s0 == r.shape[0] && x.s1 == r.shape[1]) a = &x;
+        if (!a) {
+            agg.push_back({r.shape[0], r.shape[1], 0, 0.0, 0.0});
+            a = &agg.back();
+        }
+        a->cnt++;
+        a->ms += t;
+        a->work += r.work;
+    }
+    std::sort(agg.begin(), agg.end(), [](const Agg &x, const Agg &y) { return x.ms > y.ms; });
+    const int k = (int)std::min<size_t>(agg.size(), (size_t)cap);
+    for (int i = 0; i < k; i++) {
+        shape0[i] = agg[i].s0;
+        shape1[i] = agg[i].s1;
+        count[i] = agg[i].cnt;
+        ms[i] = agg[i].ms;
+        work[i] = agg[i].work;
+    }
+    *nshapes = k;
     LB_API_END
 }
 

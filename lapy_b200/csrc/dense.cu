@@ -62,14 +62,14 @@ void destroy_dense_handles(lb_ctx *c) {
 void gram(lb_ctx *c, int64_t n, int p, const double *x, int ldx, int q, const double *y, int ldy, double *cmat,
           bool symmetric) {
     if (p == 0 || q == 0) return;
-    ProfScope prof(c, PROF_GRAM, 2.0 * n * p * q);
+    ProfScope prof(c, PROF_GRAM, 2.0 * n * p * q, p, q);
     gram_dmma(c, n, p, x, ldx, q, y, ldy, cmat, symmetric && p == q);
 }
 
 void update(lb_ctx *c, int64_t n, int p, const double *x, int ldx, int q, const double *cmat, int ldc, double alpha,
             double beta, double *y, int ldy) {
     if (q == 0 || n == 0) return;
-    ProfScope prof(c, PROF_UPDATE, 2.0 * n * p * q);
+    ProfScope prof(c, PROF_UPDATE, 2.0 * n * p * q, p, q);
     update_dmma(c, n, p, x, ldx, q, cmat, ldc, alpha, beta, y, ldy);
 }
 
@@ -87,7 +87,7 @@ int chol_lower(lb_ctx *c, int q, double *g) {
 }
 
 int sym_eig(lb_ctx *c, int s, double *g, double *evals) {
-    ProfScope prof(c, PROF_TRSM, 9.0 * s * s * s);  // reported as class "small_dense" (syevd / coarse solves)
+    ProfScope prof(c, PROF_TRSM, 9.0 * s * s * s, s, 0);  // reported as class "small_dense" (syevd / coarse solves)
     int lwork = 0;
     // opt-in A/B: cuSOLVER's Jacobi solver (LAPY_B200_EIG=syevj), usually quicker than the
     // divide-and-conquer one below a few hundred rows; same output convention (ascending, vectors in g)
@@ -135,7 +135,7 @@ void dense_chol_solve_prepare(lb_ctx *c, int q, double *g) {
 
 // X_rm(q,m) <- G^-1 X given the factor from dense_chol_solve_prepare (row-major lower L)
 void dense_chol_solve(lb_ctx *c, int q, const double *l, int m, double *x, int ldx) {
-    ProfScope prof(c, PROF_TRSM, 2.0 * q * q * m);
+    ProfScope prof(c, PROF_TRSM, 2.0 * q * q * m, q, m);
     // row-major X(q,m) is column-major X^T (m,q): solve X^T <- X^T G^-1 = X^T (U^T U)^-1 from the right
     const double one = 1.0;
     LB_CUBLAS(cublasDtrsm(blas(c), CUBLAS_SIDE_RIGHT, CUBLAS_FILL_MODE_UPPER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, m, q,

@@ -246,8 +246,10 @@ static SolveStats block_pcg(lb_ctx *c, lb_mat *K, const double *rhs, double *x, 
     if (c->trace) fprintf(stderr, "[lb trace] solve: n=%lld m=%d off-diagonal ratio %.4f project=%d\n", (long long)n, m, off_ratio, (int)project);
     if (force_prec == 1) use_amg = false;
     if (force_prec == 2) use_amg = true;
-    // Jacobi needs strict diagonal dominance (off_ratio < 1) to contract
-    if (force_prec == 0 && !project && try_jacobi && off_ratio < 1.0) {
+    // (not gated on off_ratio < 1: float32 tet meshes with obtuse elements have rows with
+    // off_ratio >= 1 and still contract - measured on data/cubeTetra.vtk; a non-contracting or
+    // non-finite iteration is detected below and falls through to PCG)
+    if (force_prec == 0 && !project && try_jacobi) {
         // componentwise Jacobi (see jacobi_stream_kernel), two columns at a time; checks the max
         // relative increment every 64 sweeps; falls through to PCG if it does not contract
         // (input that is not an M-matrix)
