@@ -334,6 +334,48 @@ std::unique_ptr<lb_mat> transpose(lb_ctx *c, const lb_mat *a) {
     return t;
 }
 
+// ---- numbering conversions ---------------------------------------------------------------------------
+std::unique_ptr<lb_mat> to_caller_order(lb_ctx *c, const lb_mat *a) {
+    LB_REQUIRE(a->permuted && a->ord && a->ord->ready, "matrix is not stored in a locality numbering");
+    // caller row i = stored row inv[i]; caller column = order[stored column]
+    auto out = permute_symmetric(c, a, a->ord->inv.p, a->ord->order.p);
+    LB_LAUNCH(c, sort_rows, cdiv(out->n, 128), 128, 0, out->n, out->indptr.p, out->indices.p, out->data.p);
+    return out;
+}
+
+static void into_numbering(lb_ctx *c, const lb_mat *x, const std::shared_ptr<lb_order> &ord, MatView &v) {
+    if (x->permuted && x->ord == ord) {
+        v.m = x;
+        return;
+    }
+    std::unique_ptr<lb_mat> plain;
+    const lb_mat *src = x;
+    if (x->permuted) {  // assembled on another mesh: through the caller's numbering
+        plain = to_caller_order(c, x);
+        src = plain.get();
+    }
+    LB_REQUIRE(src->n == ord->n, "matrix dimensions differ (%lld vs %lld)", (long long)src->n, (long long)ord->n);
+    v.owned = permute_symmetric(c, src, ord->order.p, ord->inv.p);
+    // sorted rows: a user-assigned matrix with the pattern of an assembled one must match it entry by entry
+    LB_LAUNCH(c, sort_rows, cdiv(v.owned->n, 128), 128, 0, v.owned->n, v.owned->indptr.p, v.owned->indices.p,
+              v.owned->data.p);
+    v.owned->permuted = true;
+    v.owned->ord = ord;
+    v.m = v.owned.get();
+}
+
+std::shared_ptr<lb_order> common_numbering(lb_ctx *c, const lb_mat *a, const lb_mat *b, MatView &va, MatView &vb) {
+    std::shared_ptr<lb_order> ord = a->permuted ? a->ord : (b && b->permuted ? b->ord : nullptr);
+    if (!ord) {
+        va.m = a;
+        vb.m = b;
+        return nullptr;
+    }
+    into_numbering(c, a, ord, va);
+    if (b) into_numbering(c, b, ord, vb);
+    return ord;
+}
+
 // =============================================================================================
 // aggregation
 // =============================================================================================

@@ -52,6 +52,17 @@ std::unique_ptr<lb_mat> spgemm(lb_ctx *c, const lb_mat *a, const lb_mat *b);
 std::unique_ptr<lb_mat> transpose(lb_ctx *c, const lb_mat *a);
 // P A P^T for the renumbering new -> old = order, old -> new = inv
 std::unique_ptr<lb_mat> permute_symmetric(lb_ctx *c, const lb_mat *a, const int32_t *order, const int32_t *inv);
+// a matrix stored in a mesh's locality numbering (lb_mat::permuted) as a new matrix in the caller's
+// numbering with sorted rows (= the canonical CSC the reference's callers see)
+std::unique_ptr<lb_mat> to_caller_order(lb_ctx *c, const lb_mat *a);
+// Operands of a solver call brought to ONE numbering: if any of them is stored in a locality
+// numbering, the others (uploaded by the user, in the caller's numbering) are permuted into it.
+struct MatView {
+    const lb_mat *m = nullptr;
+    std::unique_ptr<lb_mat> owned;
+};
+// returns the numbering the views are in (nullptr: the caller's); b may be NULL
+std::shared_ptr<lb_order> common_numbering(lb_ctx *c, const lb_mat *a, const lb_mat *b, MatView &va, MatView &vb);
 // rows [r0, r1) of a (CSR, global columns) and the square diagonal block of such a row block
 std::unique_ptr<lb_mat> row_block(lb_ctx *c, const lb_mat *a, int64_t r0, int64_t r1, int64_t ncols);
 std::unique_ptr<lb_mat> diag_block(lb_ctx *c, const lb_mat *rows, int64_t r0, int64_t r1);

@@ -3,6 +3,15 @@
 // Replaces lapy/solver.py:105-194 (_fem_tria), :196-308 (_fem_tria_aniso), :310-377
 // (fem_tria_mass), :379-533 (_fem_tetra) and the SciPy COO->CSC conversion they end in.
 //
+// Everything below runs on the mesh's SOLVER LAYOUT (lb_mesh::v4m / t4m, built once at upload):
+// vertices renumbered along the Morton curve, elements sorted by their smallest new vertex id.  Rows
+// that are neighbours in memory are neighbours on the mesh, so the gathers of the element and row
+// kernels (vertices, element records, incidence records) stay in L1 / L2 and the DRAM traffic is
+// close to the compulsory figure; the matrices come out in the numbering the solvers iterate in
+// (lb_mat::permuted) and are converted to the caller's canonical CSC only when downloaded.  The sum
+// of every entry still runs over its addends in the reference's triplet order (ascending CALLER
+// element id, then slot), so the values do not depend on the renumbering.
+//
 // Pipeline (all on the context's stream, one host read-back for nnz):
 //   1. element pass      one thread per element: gather 3|4 vertices (one 32 B sector each),
 //                        local cot / volume entries in the dtype of the caller's vertices with
@@ -125,9 +134,10 @@ __global__ void __launch_bounds__(256) tria_element_kernel(
         } else if (MODE == MODE_ANISO) {
             // projections and the weighted dot run in fp64 (u1, u2, aniso_mat are fp64 arrays)
             Vec3<double> a = vwiden(ea), b = vwiden(eb), c = vwiden(ec);
-            Vec3<double> w1 = {u1[3 * e], u1[3 * e + 1], u1[3 * e + 2]};
-            Vec3<double> w2 = {u2[3 * e], u2[3 * e + 1], u2[3 * e + 2]};
-            double m0 = am[2 * e], m1 = am[2 * e + 1];
+            const int64_t eo = ti.w;  // caller's element id (t4m is sorted): u1 / u2 / aniso_mat are the caller's arrays
+            Vec3<double> w1 = {u1[3 * eo], u1[3 * eo + 1], u1[3 * eo + 2]};
+            Vec3<double> w2 = {u2[3 * eo], u2[3 * eo + 1], u2[3 * eo + 2]};
+            double m0 = am[2 * eo], m1 = am[2 * eo + 1];
             double a0 = vdot(w1, a), a1 = vdot(w2, a), b0 = vdot(w1, b), b1 = vdot(w2, b);
             double c0 = vdot(w1, c), c1 = vdot(w2, c);
             auto adot = [&](double x0, double x1, double y0, double y1) {
@@ -256,6 +266,8 @@ __global__ void incidence_fill(const int4 *__restrict__ t4, int64_t nt, int k,
 // the row kernels never gather the element array:  {element*4 + corner, k0, k1, k2}
 //   triangle corner 0: (t2, t3)   1: (t1, t3)   2: (t2, t1)          (solver.py:171-175)
 //   tet      corner 0: (t2,t3,t4) 1: (t1,t3,t4) 2: (t2,t1,t4) 3: (t1,t2,t3)   (solver.py:472-497)
+// `element` is the position in the sorted element array t4m; the reference's triplet order is the
+// CALLER's element order: triangles carry that id in .w, tets look it up in eorig[] (inc_key)
 __global__ void incidence_fill4(const int4 *__restrict__ t4, int64_t nt, int k,
                                 const int32_t *__restrict__ inc_ptr, int32_t *__restrict__ cursor,
                                 int4 *__restrict__ inc4) {
@@ -264,15 +276,24 @@ __global__ void incidence_fill4(const int4 *__restrict__ t4, int64_t nt, int k,
     const int4 ti = __ldg(t4 + e);
     const int code = (int)e * 4;
     if (k == 3) {
-        inc4[inc_ptr[ti.x] + atomicAdd(cursor + ti.x, 1)] = make_int4(code, ti.y, ti.z, -1);
-        inc4[inc_ptr[ti.y] + atomicAdd(cursor + ti.y, 1)] = make_int4(code + 1, ti.x, ti.z, -1);
-        inc4[inc_ptr[ti.z] + atomicAdd(cursor + ti.z, 1)] = make_int4(code + 2, ti.y, ti.x, -1);
+        inc4[inc_ptr[ti.x] + atomicAdd(cursor + ti.x, 1)] = make_int4(code, ti.y, ti.z, ti.w);
+        inc4[inc_ptr[ti.y] + atomicAdd(cursor + ti.y, 1)] = make_int4(code + 1, ti.x, ti.z, ti.w);
+        inc4[inc_ptr[ti.z] + atomicAdd(cursor + ti.z, 1)] = make_int4(code + 2, ti.y, ti.x, ti.w);
     } else {
         inc4[inc_ptr[ti.x] + atomicAdd(cursor + ti.x, 1)] = make_int4(code, ti.y, ti.z, ti.w);
         inc4[inc_ptr[ti.y] + atomicAdd(cursor + ti.y, 1)] = make_int4(code + 1, ti.x, ti.z, ti.w);
         inc4[inc_ptr[ti.z] + atomicAdd(cursor + ti.z, 1)] = make_int4(code + 2, ti.y, ti.x, ti.w);
         inc4[inc_ptr[ti.w] + atomicAdd(cursor + ti.w, 1)] = make_int4(code + 3, ti.x, ti.y, ti.z);
     }
+}
+
+// position of an incidence record in the reference's triplet order of its column: caller's element
+// id, then corner.  Triangles: .w is the caller's element id (one corner per element and vertex
+// unless the element is degenerate: then the corner in .x breaks the tie - both fit 62 bits)
+template <int K>
+__device__ __forceinline__ long long inc_key(const int4 &q, const int32_t *__restrict__ eorig) {
+    if (K == 3) return ((long long)q.w << 2) | (q.x & 3);
+    return ((long long)__ldg(eorig + (q.x >> 2)) << 2) | (q.x & 3);
 }
 
 // per-vertex insertion sort of the (atomically ordered) incidence codes -> deterministic
@@ -390,8 +411,9 @@ struct RowOut {
 
 template <int K>
 __global__ void __launch_bounds__(kRowThreads) row_fill_kernel(
-    const D4 *__restrict__ rec, const int32_t *__restrict__ inc_ptr, int4 *inc4, int64_t n, int cap,
-    const ElemConsts *__restrict__ consts, int degen_div_f32, RowOut out, const int32_t *__restrict__ only_rows) {
+    const D4 *__restrict__ rec, const int32_t *__restrict__ inc_ptr, int4 *inc4, const int32_t *__restrict__ eorig,
+    int64_t n, int cap, const ElemConsts *__restrict__ consts, int degen_div_f32, RowOut out,
+    const int32_t *__restrict__ only_rows) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *s_a = reinterpret_cast<double *>(smem_raw);
     double *s_b = s_a + cap;
@@ -425,7 +447,7 @@ __global__ void __launch_bounds__(kRowThreads) row_fill_kernel(
         const int beg = inc_ptr[r], end = inc_ptr[r + 1];
         const int ninc = end - beg;
         // The incidence records were placed by atomics: restore the reference's triplet order
-        // (element ascending).  Triangles with valence <= 8 are sorted in registers by a 19-comparator
+        // (CALLER element id ascending, inc_key).  Triangles with valence <= 8 are sorted in registers by a 19-comparator
         // network and their element records gathered together (8 independent loads in flight);
         // longer rows / tets sort their own segment in place and stream it.
         constexpr int RS = 8;
@@ -433,12 +455,12 @@ __global__ void __launch_bounds__(kRowThreads) row_fill_kernel(
         const bool in_regs = K == 3 && ninc <= RS;
         if (in_regs) {
 #pragma unroll
-            for (int u = 0; u < RS; u++) qi[u] = u < ninc ? inc4[beg + u] : make_int4(INT_MAX, 0, 0, 0);
-#define LB_CSWAP(i, j)                  \
-    if (qi[i].x > qi[j].x) {            \
-        const int4 tmp_ = qi[i];        \
-        qi[i] = qi[j];                  \
-        qi[j] = tmp_;                   \
+            for (int u = 0; u < RS; u++) qi[u] = u < ninc ? inc4[beg + u] : make_int4(INT_MAX, 0, 0, INT_MAX);
+#define LB_CSWAP(i, j)                                                              \
+    if (qi[i].w > qi[j].w || (qi[i].w == qi[j].w && qi[i].x > qi[j].x)) {           \
+        const int4 tmp_ = qi[i];                                                    \
+        qi[i] = qi[j];                                                              \
+        qi[j] = tmp_;                                                               \
     }
             LB_CSWAP(0, 1) LB_CSWAP(2, 3) LB_CSWAP(4, 5) LB_CSWAP(6, 7) LB_CSWAP(0, 2) LB_CSWAP(1, 3) LB_CSWAP(4, 6)
             LB_CSWAP(5, 7) LB_CSWAP(1, 2) LB_CSWAP(5, 6) LB_CSWAP(0, 4) LB_CSWAP(3, 7) LB_CSWAP(1, 5) LB_CSWAP(2, 6)
@@ -447,8 +469,9 @@ __global__ void __launch_bounds__(kRowThreads) row_fill_kernel(
         } else {
             for (int i = beg + 1; i < end; i++) {
                 const int4 key = inc4[i];
+                const long long kk = inc_key<K>(key, eorig);
                 int j = i - 1;
-                while (j >= beg && inc4[j].x > key.x) {
+                while (j >= beg && inc_key<K>(inc4[j], eorig) > kk) {
                     inc4[j + 1] = inc4[j];
                     j--;
                 }
@@ -591,7 +614,7 @@ __global__ void __launch_bounds__(kRowThreads) row_fill_kernel(
     }
 }
 
-// ---- fused tet rows (LAPY_B200_TET_ROWS=fused; experimental until validated on the GPU) -------------
+// ---- fused tet rows (the default for tets: 9.4 -> 4.4 ms at 121^3 in the caller's numbering) --------
 // ncu (round 1) on the per-thread tet kernels: count 1.5 ms + fill 6.9 ms at cube121, 9 % issue
 // utilisation, 12 warps per SM, long-scoreboard bound - the fill sorts the row's ~24 incidence
 // records in place in GLOBAL memory and then walks record -> element -> accumulate one dependent
@@ -666,7 +689,8 @@ __device__ __forceinline__ TetCorner tet_corner_values(int code, const D4 *__res
 constexpr size_t kFusedSmemA = (size_t)kRowThreads * (kFusedSI * 8 + kFusedCap * 20);
 
 __global__ void __launch_bounds__(kRowThreads) row_accumulate_tet(
-    const D4 *__restrict__ rec, const int32_t *__restrict__ inc_ptr, const int4 *__restrict__ inc4, int64_t n,
+    const D4 *__restrict__ rec, const int32_t *__restrict__ inc_ptr, const int4 *__restrict__ inc4,
+    const int32_t *__restrict__ eorig, int64_t n,
     const ElemConsts *__restrict__ consts, int degen_div_f32, int32_t *__restrict__ row_nnz,
     int32_t *__restrict__ row_has, int32_t *__restrict__ row_big, int32_t *__restrict__ sc_key,
     double *__restrict__ sc_a, double *__restrict__ sc_b, double *__restrict__ sc_lump) {
@@ -691,14 +715,18 @@ __global__ void __launch_bounds__(kRowThreads) row_accumulate_tet(
         } else if (ninc > 0) {
             // 1. (code << 8 | index) pairs, insertion-sorted in shared memory; codes fetched 8 at a time
             for (int i0 = 0; i0 < ninc; i0 += 8) {
-                int c8[8];
+                int c8[8], o8[8];
 #pragma unroll
                 for (int u = 0; u < 8; u++) c8[u] = i0 + u < ninc ? __ldg(&inc4[beg + i0 + u].x) : 0;
+#pragma unroll
+                for (int u = 0; u < 8; u++) o8[u] = i0 + u < ninc ? __ldg(eorig + (c8[u] >> 2)) : 0;
 #pragma unroll
                 for (int u = 0; u < 8; u++) {
                     const int i = i0 + u;
                     if (i < ninc) {
-                        const unsigned long long key = ((unsigned long long)(unsigned)c8[u] << 8) | (unsigned)i;
+                        // (caller's element id, corner) = the reference's triplet order; low 8 bits: record index
+                        const unsigned long long key =
+                            ((((unsigned long long)(unsigned)o8[u] << 2) | (unsigned)(c8[u] & 3)) << 8) | (unsigned)i;
                         int j = i - 1;
                         while (j >= 0 && s_ord[j * T + t] > key) {
                             s_ord[(j + 1) * T + t] = s_ord[j * T + t];
@@ -760,137 +788,6 @@ __global__ void __launch_bounds__(kRowThreads) row_accumulate_tet(
     }
     __syncthreads();
     // 3. the block's [slot][thread] image, slots below the block maximum, fully coalesced
-    const int total = s_maxcnt * T;
-    const size_t base = (size_t)blockIdx.x * CAP * T;
-    for (int i = t; i < total; i += T) {
-        sc_key[base + i] = s_k[i];
-        sc_a[base + i] = s_a[i];
-        sc_b[base + i] = s_b[i];
-    }
-}
-
-// triangle version of row_accumulate_tet (LAPY_B200_TRIA_ROWS=fused; written after the tet kernel was
-// validated, not yet run on a GPU): up to kFusedSItria incidences and kFusedCap entries per row,
-// one 32-byte element record per incidence, three triplets per incidence (solver.py:171-175).
-constexpr int kFusedSItria = 16;
-constexpr size_t kFusedSmemTria = (size_t)kRowThreads * (kFusedSItria * 8 + kFusedCap * 20);
-
-__global__ void __launch_bounds__(kRowThreads) row_accumulate_tria(
-    const D4 *__restrict__ rec, const int32_t *__restrict__ inc_ptr, const int4 *__restrict__ inc4, int64_t n,
-    const ElemConsts *__restrict__ consts, int degen_div_f32, int32_t *__restrict__ row_nnz,
-    int32_t *__restrict__ row_has, int32_t *__restrict__ row_big, int32_t *__restrict__ sc_key,
-    double *__restrict__ sc_a, double *__restrict__ sc_b, double *__restrict__ sc_lump) {
-    constexpr int T = kRowThreads, SI = kFusedSItria, CAP = kFusedCap, NB = kFusedBatch;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    unsigned long long *s_ord = reinterpret_cast<unsigned long long *>(smem_raw);  // [SI][T]
-    double *s_a = reinterpret_cast<double *>(s_ord + SI * T);                      // [CAP][T]
-    double *s_b = s_a + CAP * T;                                                   // [CAP][T]
-    int32_t *s_k = reinterpret_cast<int32_t *>(s_b + CAP * T);                     // [CAP][T]
-    __shared__ int s_maxcnt;
-    const int t = threadIdx.x;
-    const int64_t r = (int64_t)blockIdx.x * T + t;
-    if (t == 0) s_maxcnt = 0;
-    __syncthreads();
-    int cnt = 0;
-    bool big = false;
-    if (r < n) {
-        const int beg = inc_ptr[r], ninc = inc_ptr[r + 1] - beg;
-        double lump = 0.0;
-        if (ninc > SI) {
-            big = true;
-        } else if (ninc > 0) {
-            for (int i0 = 0; i0 < ninc; i0 += 8) {
-                int c8[8];
-#pragma unroll
-                for (int u = 0; u < 8; u++) c8[u] = i0 + u < ninc ? __ldg(&inc4[beg + i0 + u].x) : 0;
-#pragma unroll
-                for (int u = 0; u < 8; u++) {
-                    const int i = i0 + u;
-                    if (i < ninc) {
-                        const unsigned long long key = ((unsigned long long)(unsigned)c8[u] << 8) | (unsigned)i;
-                        int j = i - 1;
-                        while (j >= 0 && s_ord[j * T + t] > key) {
-                            s_ord[(j + 1) * T + t] = s_ord[j * T + t];
-                            j--;
-                        }
-                        s_ord[(j + 1) * T + t] = key;
-                    }
-                }
-            }
-            auto acc = [&](int key, double va, double vb) {
-                int pos = cnt;
-                while (pos > 0 && s_k[(pos - 1) * T + t] >= key) pos--;
-                if (pos < cnt && s_k[pos * T + t] == key) {
-                    s_a[pos * T + t] = __dadd_rn(s_a[pos * T + t], va);
-                    s_b[pos * T + t] = __dadd_rn(s_b[pos * T + t], vb);
-                    return;
-                }
-                if (cnt == CAP) {
-                    big = true;
-                    return;
-                }
-                for (int q = cnt; q > pos; q--) {
-                    s_k[q * T + t] = s_k[(q - 1) * T + t];
-                    s_a[q * T + t] = s_a[(q - 1) * T + t];
-                    s_b[q * T + t] = s_b[(q - 1) * T + t];
-                }
-                s_k[pos * T + t] = key;
-                s_a[pos * T + t] = va;  // first addend itself, like csr_sum_duplicates (keeps -0.0)
-                s_b[pos * T + t] = vb;
-                cnt++;
-            };
-            for (int j0 = 0; j0 < ninc && !big; j0 += NB) {
-                int4 q[NB];
-                D4 e[NB];
-#pragma unroll
-                for (int u = 0; u < NB; u++)
-                    q[u] = j0 + u < ninc ? __ldg(inc4 + beg + (int)(s_ord[(j0 + u) * T + t] & 255ull)) : make_int4(0, 0, 0, 0);
-#pragma unroll
-                for (int u = 0; u < NB; u++)
-                    if (j0 + u < ninc) e[u] = ldg_d4(rec + (q[u].x >> 2));
-#pragma unroll
-                for (int u = 0; u < NB; u++)
-                    if (j0 + u < ninc) {
-                        const int c = q[u].x & 3;
-                        double a12 = e[u].x, a23 = e[u].y, a31 = e[u].z, bii = e[u].w;
-                        if (bii < 0.0) {  // clamped element (solver.py:159): divide by the global mean
-                            const double vm = consts->vol_mean;
-                            if (degen_div_f32) {
-                                a12 = (double)__fdiv_rn((float)a12, (float)vm);
-                                a23 = (double)__fdiv_rn((float)a23, (float)vm);
-                                a31 = (double)__fdiv_rn((float)a31, (float)vm);
-                            } else {
-                                a12 = __ddiv_rn(a12, vm);
-                                a23 = __ddiv_rn(a23, vm);
-                                a31 = __ddiv_rn(a31, vm);
-                            }
-                            bii = consts->bii_deg;
-                        }
-                        const double bij = 0.5 * bii;
-                        lump += 2.0 * bii;  // vol/12 (vol/3 for fem_tria_mass) == 2*bii exactly
-                        double x0, x1, m0, m1;
-                        if (c == 0) {
-                            x0 = a12; x1 = a31; m0 = a12; m1 = a31;
-                        } else if (c == 1) {
-                            x0 = a12; x1 = a23; m0 = a12; m1 = a23;
-                        } else {
-                            x0 = a23; x1 = a31; m0 = a31; m1 = a23;
-                        }
-                        // the diagonal (row sum = 0, solver.py:167-169) is formed in the element dtype
-                        const double xd = degen_div_f32 ? (double)__fsub_rn(-(float)m0, (float)m1) : __dsub_rn(-m0, m1);
-                        acc(q[u].y, x0, bij);
-                        acc(q[u].z, x1, bij);
-                        acc((int)r, xd, bii);
-                    }
-            }
-        }
-        row_has[r] = ninc > 0;
-        row_big[r] = big;
-        row_nnz[r] = big ? -1 : cnt;
-        sc_lump[r] = lump;
-        if (!big && cnt > 0) atomicMax(&s_maxcnt, cnt);
-    }
-    __syncthreads();
     const int total = s_maxcnt * T;
     const size_t base = (size_t)blockIdx.x * CAP * T;
     for (int i = t; i < total; i += T) {
@@ -1055,59 +952,6 @@ __global__ void order_fill_kernel(int64_t n, const int32_t *__restrict__ cell, c
     order[cptr[cid] + atomicAdd(cursor + cid, 1)] = (int)i;
 }
 
-// ---- vertex-granular variant (LAPY_B200_ORDER=fine, opt-in) -------------------------------------
-// Same 128^3 bins, but inside a bin the vertices follow the Morton curve of an 18-bit grid (11 more
-// bits per axis) instead of their index: consecutive rows of the renumbered operator are then mesh
-// neighbours, which is what a row-grouped SpMM needs (tools/study_row_groups.py: 4.2 instead of 5-6
-// distinct X rows per matrix row for groups of 4).  key = sub-code (33 bits) << 31 | vertex.
-__global__ void morton_fine_kernel(const D4 *__restrict__ v4, int64_t n, double ox, double oy, double oz, double sx,
-                                   double sy, double sz, int32_t *__restrict__ cell, int32_t *__restrict__ hist,
-                                   unsigned long long *__restrict__ key) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    D4 p = ldg_d4(v4 + i);
-    const unsigned q[3] = {(unsigned)min(262143, max(0, (int)((p.x - ox) * sx))),
-                           (unsigned)min(262143, max(0, (int)((p.y - oy) * sy))),
-                           (unsigned)min(262143, max(0, (int)((p.z - oz) * sz)))};
-    const int cid = (int)(spread3(q[0] >> 11) | (spread3(q[1] >> 11) << 1) | (spread3(q[2] >> 11) << 2));
-    unsigned long long sub = 0;
-    for (int b = 0; b < 11; b++)
-        for (int a = 0; a < 3; a++) sub |= (unsigned long long)((q[a] >> b) & 1u) << (3 * b + a);
-    cell[i] = cid;
-    key[i] = (sub << 31) | (unsigned long long)i;
-    atomicAdd(hist + cid, 1);
-}
-
-__global__ void order_fill_fine_kernel(int64_t n, const int32_t *__restrict__ cell, const int32_t *__restrict__ cptr,
-                                       int32_t *__restrict__ cursor, const unsigned long long *__restrict__ key,
-                                       unsigned long long *__restrict__ sorted) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const int cid = cell[i];
-    sorted[cptr[cid] + atomicAdd(cursor + cid, 1)] = key[i];
-}
-
-// per-bin insertion sort of the 64-bit keys (bins hold tens of vertices), then the vertex ids
-__global__ void bin_sort_u64_kernel(const int32_t *__restrict__ cptr, unsigned long long *__restrict__ keys, int64_t nbins) {
-    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= nbins) return;
-    const int beg = cptr[r], end = cptr[r + 1];
-    for (int i = beg + 1; i < end; i++) {
-        const unsigned long long k = keys[i];
-        int j = i - 1;
-        while (j >= beg && keys[j] > k) {
-            keys[j + 1] = keys[j];
-            j--;
-        }
-        keys[j + 1] = k;
-    }
-}
-
-__global__ void key_to_order_kernel(int64_t n, const unsigned long long *__restrict__ keys, int32_t *__restrict__ order) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) order[i] = (int)(keys[i] & 0x7fffffffull);
-}
-
 __global__ void invert_order_kernel(int64_t n, const int32_t *__restrict__ order, int32_t *__restrict__ inv) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) inv[order[i]] = (int)i;
@@ -1137,24 +981,6 @@ void ensure_order(lb_order &o) {
     for (int k = 0; k < 3; k++) sc[k] = hi[k] > lo[k] ? 127.999 / (hi[k] - lo[k]) : 0.0;
     DBuf<int32_t> cell(c, n), hist(c, kCells), cptr(c, kCells + 1);
     hist.zero();
-    const char *mode = getenv("LAPY_B200_ORDER");
-    if (mode && !strcmp(mode, "fine")) {
-        double sf[3];
-        for (int k = 0; k < 3; k++) sf[k] = hi[k] > lo[k] ? 262143.999 / (hi[k] - lo[k]) : 0.0;
-        DBuf<unsigned long long> key(c, n), sorted(c, n);
-        LB_LAUNCH(c, morton_fine_kernel, cdiv(n, 256), 256, 0, v4, n, lo[0], lo[1], lo[2], sf[0], sf[1], sf[2], cell.p,
-                  hist.p, key.p);
-        exclusive_scan_i32(c, hist.p, cptr.p, kCells);
-        hist.zero();
-        o.order.alloc(c, (size_t)n);
-        o.inv.alloc(c, (size_t)n);
-        LB_LAUNCH(c, order_fill_fine_kernel, cdiv(n, 256), 256, 0, n, cell.p, cptr.p, hist.p, key.p, sorted.p);
-        LB_LAUNCH(c, bin_sort_u64_kernel, cdiv(kCells, 128), 128, 0, cptr.p, sorted.p, (int64_t)kCells);
-        LB_LAUNCH(c, key_to_order_kernel, cdiv(n, 256), 256, 0, n, sorted.p, o.order.p);
-        LB_LAUNCH(c, invert_order_kernel, cdiv(n, 256), 256, 0, n, o.order.p, o.inv.p);
-        o.ready = true;
-        return;
-    }
     LB_LAUNCH(c, morton_cell_kernel, cdiv(n, 256), 256, 0, v4, n, lo[0], lo[1], lo[2], sc[0], sc[1], sc[2], cell.p,
               hist.p);
     exclusive_scan_i32(c, hist.p, cptr.p, kCells);
@@ -1167,6 +993,82 @@ void ensure_order(lb_order &o) {
     o.ready = true;
 }
 
+// ---- solver layout of a mesh ---------------------------------------------------------------------
+__global__ void gather_vertices_kernel(int64_t n, const int32_t *__restrict__ order, const D4 *__restrict__ v4,
+                                       const float4 *__restrict__ v4f, D4 *__restrict__ v4m,
+                                       float4 *__restrict__ v4fm) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    const int o = order[r];
+    const D4 p = ldg_d4(v4 + o);
+    st_d4(v4m + r, p.x, p.y, p.z, p.w);
+    if (v4fm) v4fm[r] = __ldg(v4f + o);
+}
+
+// sort key of an element = its smallest new vertex id; histogram for the counting sort
+__global__ void element_key_kernel(const int4 *__restrict__ t4, int64_t nt, int k, const int32_t *__restrict__ inv,
+                                   int32_t *__restrict__ key, int32_t *__restrict__ hist) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= nt) return;
+    const int4 ti = __ldg(t4 + e);
+    int m = min(inv[ti.x], min(inv[ti.y], inv[ti.z]));
+    if (k == 4) m = min(m, inv[ti.w]);
+    key[e] = m;
+    atomicAdd(hist + m, 1);
+}
+
+__global__ void element_fill_kernel(int64_t nt, const int32_t *__restrict__ key, const int32_t *__restrict__ kptr,
+                                    int32_t *__restrict__ cursor, int32_t *__restrict__ eperm) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= nt) return;
+    const int m = key[e];
+    eperm[kptr[m] + atomicAdd(cursor + m, 1)] = (int)e;
+}
+
+// t4m[pos] = element eperm[pos] with new vertex ids; triangles carry the caller's element id in .w
+__global__ void element_renumber_kernel(int64_t nt, int k, const int32_t *__restrict__ eperm,
+                                        const int4 *__restrict__ t4, const int32_t *__restrict__ inv,
+                                        int4 *__restrict__ t4m) {
+    const int64_t pos = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pos >= nt) return;
+    const int e = eperm[pos];
+    const int4 ti = __ldg(t4 + e);
+    t4m[pos] = make_int4(inv[ti.x], inv[ti.y], inv[ti.z], k == 4 ? inv[ti.w] : e);
+}
+
+static void refresh_layout_vertices(lb_mesh *m) {
+    lb_ctx *c = m->ctx;
+    const int64_t n = m->n_ref;
+    const bool f32 = m->v_dtype == LB_F32;
+    if (!m->v4m.p) m->v4m.alloc(c, n);
+    if (f32 && !m->v4fm.p) m->v4fm.alloc(c, n);
+    LB_LAUNCH(c, gather_vertices_kernel, cdiv(n, 256), 256, 0, n, m->ord->order.p, m->v4s->p,
+              f32 ? m->v4f.p : (const float4 *)nullptr, m->v4m.p, f32 ? m->v4fm.p : (float4 *)nullptr);
+}
+
+// Locality numbering + renumbered, sorted element array.  Deterministic: elements with the same key
+// are ordered by their id (per-key insertion sort behind the atomic fill).
+static void build_layout(lb_mesh *m) {
+    lb_ctx *c = m->ctx;
+    const int64_t n = m->n_ref, nt = m->nt;
+    m->ord = std::make_shared<lb_order>();
+    m->ord->ctx = c;
+    m->ord->v4 = m->v4s;
+    m->ord->n = n;
+    ensure_order(*m->ord);
+    refresh_layout_vertices(m);
+    DBuf<int32_t> key(c, nt), hist(c, n), kptr(c, n + 1);
+    hist.zero();
+    LB_LAUNCH(c, element_key_kernel, cdiv(nt, 256), 256, 0, m->t4.p, nt, m->k, m->ord->inv.p, key.p, hist.p);
+    exclusive_scan_i32(c, hist.p, kptr.p, n);
+    hist.zero();
+    m->eorig.alloc(c, nt);
+    LB_LAUNCH(c, element_fill_kernel, cdiv(nt, 256), 256, 0, nt, key.p, kptr.p, hist.p, m->eorig.p);
+    LB_LAUNCH(c, incidence_sort, cdiv(n, 128), 128, 0, kptr.p, m->eorig.p, n);
+    m->t4m.alloc(c, nt);
+    LB_LAUNCH(c, element_renumber_kernel, cdiv(nt, 256), 256, 0, nt, m->k, m->eorig.p, m->t4.p, m->ord->inv.p, m->t4m.p);
+}
+
 template <class T>
 static void run_element_pass(lb_mesh *mesh, int kind, const double *u1, const double *u2, const double *am,
                              D4 *rec, int32_t *deg, ElemConsts *consts) {
@@ -1175,27 +1077,27 @@ static void run_element_pass(lb_mesh *mesh, int kind, const double *u1, const do
     const int nblocks = cdiv(nt, 256);
     DBuf<double> partial(c, nblocks);
     const typename Ex<T>::V4 *v4;
-    if constexpr (sizeof(T) == 4) v4 = mesh->v4f.p;
-    else v4 = mesh->v4s->p;
+    if constexpr (sizeof(T) == 4) v4 = mesh->v4fm.p;
+    else v4 = mesh->v4m.p;
     switch (kind) {
         case LB_FEM_TRIA: {
             auto kern = tria_element_kernel<T, MODE_FEM>;
-            LB_LAUNCH(c, kern, nblocks, 256, 0, v4, mesh->t4.p, nt, u1, u2, am, rec, deg, partial.p);
+            LB_LAUNCH(c, kern, nblocks, 256, 0, v4, mesh->t4m.p, nt, u1, u2, am, rec, deg, partial.p);
             break;
         }
         case LB_FEM_TRIA_ANISO: {
             auto kern = tria_element_kernel<T, MODE_ANISO>;
-            LB_LAUNCH(c, kern, nblocks, 256, 0, v4, mesh->t4.p, nt, u1, u2, am, rec, deg, partial.p);
+            LB_LAUNCH(c, kern, nblocks, 256, 0, v4, mesh->t4m.p, nt, u1, u2, am, rec, deg, partial.p);
             break;
         }
         case LB_FEM_TRIA_MASS: {
             auto kern = tria_element_kernel<T, MODE_MASS>;
-            LB_LAUNCH(c, kern, nblocks, 256, 0, v4, mesh->t4.p, nt, u1, u2, am, rec, deg, partial.p);
+            LB_LAUNCH(c, kern, nblocks, 256, 0, v4, mesh->t4m.p, nt, u1, u2, am, rec, deg, partial.p);
             break;
         }
         default: {
             auto kern = tet_element_kernel<T>;
-            LB_LAUNCH(c, kern, nblocks, 256, 0, v4, mesh->t4.p, nt, rec, deg, partial.p);
+            LB_LAUNCH(c, kern, nblocks, 256, 0, v4, mesh->t4m.p, nt, rec, deg, partial.p);
         }
     }
     auto fin = finalize_consts<T>;
@@ -1219,18 +1121,16 @@ static void run_rows(lb_mesh *mesh, const D4 *rec, const ElemConsts *consts, con
     lb_ctx *c = mesh->ctx;
     const int64_t n = mesh->n_ref;
     const int nblocks = cdiv(n, kRowThreads);
+    const int32_t *eorig = mesh->eorig.p;
     // --- count
     const int cap_keys = K == 3 ? 4096 : 12288;  // int32 keys of shared memory per block
     DBuf<int32_t> row_nnz(c, n), row_has(c, n);
     DBuf<int32_t> scratch(c, (size_t)mesh->k * mesh->nt * (K - 1) + n);
     if (cap_keys * 4 > 40 * 1024)
         LB_CUDA(cudaFuncSetAttribute(row_count_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap_keys * 4));
-    // tets, LAPY_B200_TET_ROWS=fused: accumulate once into a per-row scratch, compact after the scan
-    bool fused = false;
-    if (want_a || !lump) {
-        const char *e = getenv(K == 4 ? "LAPY_B200_TET_ROWS" : "LAPY_B200_TRIA_ROWS");
-        fused = e && !strcmp(e, "fused");
-    }
+    // tets: accumulate once into a per-row scratch, compact after the scan (row_accumulate_tet); rows it
+    // flags (> 32 incidences or > 16 entries) go through the per-thread kernels restricted to them
+    const bool fused = K == 4 && (want_a || !lump);
     DBuf<int32_t> row_big, sc_key;
     DBuf<double> sc_a, sc_b, sc_lump;
     if (fused) {
@@ -1240,16 +1140,9 @@ static void run_rows(lb_mesh *mesh, const D4 *rec, const ElemConsts *consts, con
         sc_a.alloc(c, slots);
         sc_b.alloc(c, slots);
         sc_lump.alloc(c, n);
-        if (K == 4) {
-            LB_CUDA(cudaFuncSetAttribute(row_accumulate_tet, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFusedSmemA));
-            LB_LAUNCH(c, row_accumulate_tet, nblocks, kRowThreads, kFusedSmemA, rec, aptr, inc4, n, consts, (int)degen_f32,
-                      row_nnz.p, row_has.p, row_big.p, sc_key.p, sc_a.p, sc_b.p, sc_lump.p);
-        } else {
-            LB_CUDA(cudaFuncSetAttribute(row_accumulate_tria, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)kFusedSmemTria));
-            LB_LAUNCH(c, row_accumulate_tria, nblocks, kRowThreads, kFusedSmemTria, rec, aptr, inc4, n, consts,
-                      (int)degen_f32, row_nnz.p, row_has.p, row_big.p, sc_key.p, sc_a.p, sc_b.p, sc_lump.p);
-        }
+        LB_CUDA(cudaFuncSetAttribute(row_accumulate_tet, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFusedSmemA));
+        LB_LAUNCH(c, row_accumulate_tet, nblocks, kRowThreads, kFusedSmemA, rec, aptr, inc4, eorig, n, consts,
+                  (int)degen_f32, row_nnz.p, row_has.p, row_big.p, sc_key.p, sc_a.p, sc_b.p, sc_lump.p);
     }
     LB_LAUNCH(c, row_count_kernel<K>, nblocks, kRowThreads, cap_keys * 4, aptr, inc4, n, cap_keys, scratch.p,
               row_nnz.p, row_has.p, fused ? row_big.p : (const int32_t *)nullptr);
@@ -1298,17 +1191,17 @@ static void run_rows(lb_mesh *mesh, const D4 *rec, const ElemConsts *consts, con
             if (fused) {
                 LB_LAUNCH(c, row_compact_kernel, nblocks, kRowThreads, 0, n, row_big.p, sc_key.p, sc_a.p, sc_b.p, sc_lump.p,
                           out);
-                LB_LAUNCH(c, row_fill_kernel<K>, nblocks, kRowThreads, 16, rec, aptr, inc4, n, cap, consts,
+                LB_LAUNCH(c, row_fill_kernel<K>, nblocks, kRowThreads, 16, rec, aptr, inc4, eorig, n, cap, consts,
                           (int)degen_f32, out, (const int32_t *)row_big.p);
             } else {
-                LB_LAUNCH(c, row_fill_kernel<K>, nblocks, kRowThreads, smem, rec, aptr, inc4, n, cap, consts,
+                LB_LAUNCH(c, row_fill_kernel<K>, nblocks, kRowThreads, smem, rec, aptr, inc4, eorig, n, cap, consts,
                           (int)degen_f32, out, (const int32_t *)nullptr);
             }
         } else {
             // mass only + lumped: no CSR pattern needed, but the same kernel does the sums
             const int cap = 0;
-            LB_LAUNCH(c, row_fill_kernel<K>, nblocks, kRowThreads, 16, rec, aptr, inc4, n, cap, consts, (int)degen_f32,
-                      out, (const int32_t *)nullptr);
+            LB_LAUNCH(c, row_fill_kernel<K>, nblocks, kRowThreads, 16, rec, aptr, inc4, eorig, n, cap, consts,
+                      (int)degen_f32, out, (const int32_t *)nullptr);
         }
     } catch (...) {
         delete A;
@@ -1371,6 +1264,8 @@ int lb_mesh_create(lb_ctx *c, const void *v, int v_dtype, int64_t nv, const void
         LB_REQUIRE(mm[0] >= 0, "negative vertex index %lld in elements", mm[0]);
         LB_REQUIRE(mm[1] < nv, "Max index exceeds number of vertices");
         m->n_ref = mm[1] + 1;
+        build_layout(m);
+        sync(c);
     } catch (...) {
         delete m;
         throw;
@@ -1397,6 +1292,7 @@ int lb_mesh_update_vertices(lb_mesh *m, const void *v, int v_dtype) {
         LB_LAUNCH(c, convert_vertices<double>, cdiv(m->nv, 256), 256, 0, (const double *)raw_v.p, m->nv, m->v4s->p,
                   (float4 *)nullptr);
     }
+    refresh_layout_vertices(m);  // same numbering (a permutation stays valid when vertices move)
     sync(c);  // raw_v is borrowed from the caller until here
     LB_API_END
 }
@@ -1407,8 +1303,7 @@ int lb_mesh_drop_cache(lb_mesh *m) {
     DeviceGuard g(m->ctx->device);
     m->inc_ptr.release();
     m->inc.release();
-    m->has_inc = false;
-    m->ord.reset();
+    m->has_inc = false;  // the solver layout (numbering, sorted elements) is part of the upload and stays
     LB_API_END
 }
 
@@ -1443,7 +1338,7 @@ int lb_fem_assemble(lb_ctx *c, lb_mesh *mesh, int kind, int lump, const double *
         h2d(c, d_u2.p, u2, 3 * nt * sizeof(double));
         h2d(c, d_am.p, aniso_mat, 2 * nt * sizeof(double));
     }
-    DBuf<int32_t> deg(c, mesh->nv), aptr(c, mesh->nv + 1);
+    DBuf<int32_t> deg(c, mesh->n_ref), aptr(c, mesh->n_ref + 1);
     DBuf<int4> inc4(c, (size_t)mesh->k * nt);
     deg.zero();
     if (mesh->v_dtype == LB_F32)
@@ -1451,25 +1346,22 @@ int lb_fem_assemble(lb_ctx *c, lb_mesh *mesh, int kind, int lump, const double *
     else
         run_element_pass<double>(mesh, kind, d_u1.p, d_u2.p, d_am.p, rec.p, deg.p, consts.p);
     phase(c, "element pass");
-    exclusive_scan_i32(c, deg.p, aptr.p, mesh->nv);
+    exclusive_scan_i32(c, deg.p, aptr.p, mesh->n_ref);
     deg.zero();
-    LB_LAUNCH(c, incidence_fill4, cdiv(nt, 256), 256, 0, mesh->t4.p, nt, mesh->k, aptr.p, deg.p, inc4.p);
+    LB_LAUNCH(c, incidence_fill4, cdiv(nt, 256), 256, 0, mesh->t4m.p, nt, mesh->k, aptr.p, deg.p, inc4.p);
     phase(c, "incidence");
     if (a_out) *a_out = nullptr;
     // clamped elements: the aniso numerators are fp64 even for fp32 meshes (solver.py:278-280)
     const bool degen_f32 = mesh->v_dtype == LB_F32 && kind != LB_FEM_TRIA_ANISO;
     if (mesh->k == 3) run_rows<3>(mesh, rec.p, consts.p, aptr.p, inc4.p, want_a, lump != 0, degen_f32, a_out, b_out);
     else run_rows<4>(mesh, rec.p, consts.p, aptr.p, inc4.p, want_a, lump != 0, degen_f32, a_out, b_out);
-    if (mesh->nv >= 20000) {  // locality renumbering for the solvers: shared, computed on first use
-        if (!mesh->ord) {
-            mesh->ord = std::make_shared<lb_order>();
-            mesh->ord->ctx = c;
-            mesh->ord->v4 = mesh->v4s;
-            mesh->ord->n = mesh->n_ref;
-        }
-        if (a_out && *a_out) (*a_out)->ord = mesh->ord;
-        (*b_out)->ord = mesh->ord;
+    // the matrices are stored in the mesh's locality numbering (lb_mat::permuted)
+    if (a_out && *a_out) {
+        (*a_out)->ord = mesh->ord;
+        (*a_out)->permuted = true;
     }
+    (*b_out)->ord = mesh->ord;
+    (*b_out)->permuted = true;
     sync(c);  // u1/u2/aniso_mat are borrowed host buffers
     phase(c, "rows");
     LB_API_END

@@ -134,246 +134,6 @@ __global__ void __launch_bounds__(256) spmm_kernel(int64_t n, const int32_t *__r
     }
 }
 
-// ---- row-grouped SpMM (opt-in: LAPY_B200_SPMM=grouped) -------------------------------------------
-// The wide SpMM is bound by the L1TEX wavefront rate: every nonzero makes a warp load one 512-byte
-// row of X = 4 wavefronts.  Mesh-adjacent rows share most of their columns, so a
-// warp that owns kGroupRows consecutive rows loads every distinct X row of the group ONCE and feeds
-// up to kGroupRows accumulators from it: 4.2 instead of 7 row loads per matrix row on a triangle
-// mesh in a vertex-granular Morton order (tools/study_row_groups.py).  Every row still sums its own
-// entries in ascending column order with the same fma chain, so the result equals spmm_kernel's
-// (a stored zero is skipped instead of added: identical for finite X).  Group size R = 2, 4 or 8
-// (LAPY_B200_SPMM=grouped2 | grouped | grouped8): 5.5 / 4.2 / 3.3 X rows per matrix row.
-
-template <int kGroupRows>
-__global__ void group_count_kernel(int64_t n, int64_t ngroups, const int32_t *__restrict__ indptr,
-                                   const int32_t *__restrict__ indices, int32_t *__restrict__ gcount) {
-    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= ngroups) return;
-    int p[kGroupRows], e[kGroupRows];
-#pragma unroll
-    for (int r = 0; r < kGroupRows; r++) {
-        const int64_t row = g * kGroupRows + r;
-        p[r] = row < n ? indptr[row] : 0;
-        e[r] = row < n ? indptr[row + 1] : 0;
-    }
-    int cnt = 0;
-    while (true) {
-        int cmin = INT_MAX;
-#pragma unroll
-        for (int r = 0; r < kGroupRows; r++)
-            if (p[r] < e[r]) cmin = min(cmin, indices[p[r]]);
-        if (cmin == INT_MAX) break;
-#pragma unroll
-        for (int r = 0; r < kGroupRows; r++)
-            if (p[r] < e[r] && indices[p[r]] == cmin) p[r]++;
-        cnt++;
-    }
-    gcount[g] = cnt;
-}
-
-template <int kGroupRows>
-__global__ void group_fill_kernel(int64_t n, int64_t ngroups, const int32_t *__restrict__ indptr,
-                                  const int32_t *__restrict__ indices, const double *__restrict__ val,
-                                  const int32_t *__restrict__ gptr, int32_t *__restrict__ gcol,
-                                  double *__restrict__ gval) {
-    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= ngroups) return;
-    int p[kGroupRows], e[kGroupRows];
-#pragma unroll
-    for (int r = 0; r < kGroupRows; r++) {
-        const int64_t row = g * kGroupRows + r;
-        p[r] = row < n ? indptr[row] : 0;
-        e[r] = row < n ? indptr[row + 1] : 0;
-    }
-    int64_t o = gptr[g];
-    while (true) {
-        int cmin = INT_MAX;
-#pragma unroll
-        for (int r = 0; r < kGroupRows; r++)
-            if (p[r] < e[r]) cmin = min(cmin, indices[p[r]]);
-        if (cmin == INT_MAX) break;
-        gcol[o] = cmin;
-#pragma unroll
-        for (int r = 0; r < kGroupRows; r++) {
-            double a = 0.0;
-            if (p[r] < e[r] && indices[p[r]] == cmin) {
-                a = val[p[r]];
-                p[r]++;
-            }
-            gval[o * kGroupRows + r] = a;
-        }
-        o++;
-    }
-}
-
-template <int kGroupRows>
-static const lb_grouped *grouped_of(lb_ctx *c, const lb_mat *a) {
-    if (a->grp && a->grp->rows == kGroupRows) return a->grp.get();
-    auto gr = std::make_shared<lb_grouped>();
-    gr->rows = kGroupRows;
-    const int64_t n = a->n, ng = (n + kGroupRows - 1) / kGroupRows;
-    gr->ngroups = ng;
-    DBuf<int32_t> gcount(c, ng);
-    LB_LAUNCH(c, group_count_kernel<kGroupRows>, cdiv(ng, 128), 128, 0, n, ng, a->indptr.p, a->indices.p, gcount.p);
-    gr->gptr.alloc(c, ng + 1);
-    exclusive_scan_i32(c, gcount.p, gr->gptr.p, ng);
-    int32_t total = 0;
-    read_back(c, &total, gr->gptr.p + ng, 1);
-    gr->nent = total;
-    gr->gcol.alloc(c, (size_t)std::max(1, total));
-    gr->gval.alloc(c, (size_t)std::max(1, total) * kGroupRows);
-    LB_LAUNCH(c, group_fill_kernel<kGroupRows>, cdiv(ng, 128), 128, 0, n, ng, a->indptr.p, a->indices.p, a->data.p, gr->gptr.p,
-              gr->gcol.p, gr->gval.p);
-    if (c->trace)
-        fprintf(stderr, "[lb trace] grouped SpMM format: n=%lld nnz=%lld -> %lld group entries (%.2f X rows per matrix row)\n",
-                (long long)n, (long long)a->nnz, (long long)total, (double)total / (double)std::max<int64_t>(1, n));
-    a->grp = gr;
-    return gr.get();
-}
-
-// m <= 64 columns: lane owns columns 2*lane, 2*lane + 1 (one 16-byte load per X row); a warp owns a
-// group, the 8 warps of a CTA walk the 32 groups of a 128-row strip interleaved
-// STAGE: the CTA first copies the X rows of its own 128-row strip into shared memory (64 KB) and
-// serves the 83-85 % of the gathers that stay inside the strip from there (LDS.128: 4 wavefronts at
-// 1 cycle instead of ~2 through L1TEX); square operators only (X rows == matrix rows).
-template <int kGroupRows, bool STAGE>
-__global__ void __launch_bounds__(256, kGroupRows == 8 ? 2 : 3) spmm_grouped_kernel(int64_t n, const int32_t *__restrict__ gptr,
-                                                              const int32_t *__restrict__ gcol,
-                                                              const double *__restrict__ gval,
-                                                              const double *__restrict__ x, int ldx, double *y, int ldy,
-                                                              int m, int mode, const double *b, int ldb,
-                                                              SpmmEpilogue epi) {
-    constexpr int R = kGroupRows;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t group0 = (int64_t)blockIdx.x * (kSpmmStrip / R);
-    const int64_t ngroups = (n + R - 1) / R;
-    const int ca = 2 * lane, cb = ca + 1;
-    const bool ha = ca < m, hb = cb < m;
-    extern __shared__ __align__(16) double s_x[];  // STAGE: [kSpmmStrip][64]
-    const int64_t strip0 = (int64_t)blockIdx.x * kSpmmStrip;
-    if (STAGE) {
-        const int nrows = (int)(min(n, strip0 + kSpmmStrip) - strip0);
-        for (int lr = warp; lr < nrows; lr += 8) {
-            const double *xr = x + (strip0 + lr) * ldx;
-            if (hb) *reinterpret_cast<double2 *>(s_x + lr * 64 + ca) = __ldg(reinterpret_cast<const double2 *>(xr + ca));
-            else if (ha) s_x[lr * 64 + ca] = __ldg(xr + ca);
-        }
-        __syncthreads();
-    }
-    for (int lg = warp; lg < kSpmmStrip / R; lg += 8) {
-        const int64_t g = group0 + lg;
-        if (g >= ngroups) break;
-        const int beg = __ldg(gptr + g), end = __ldg(gptr + g + 1);
-        double s0[R], s1[R];
-#pragma unroll
-        for (int r = 0; r < R; r++) s0[r] = s1[r] = 0.0;
-        for (int p0 = beg; p0 < end; p0 += 32) {
-            const int cnt = min(32, end - p0);
-            int jl = 0;
-            double al[R];
-#pragma unroll
-            for (int r = 0; r < R; r++) al[r] = 0.0;
-            if (lane < cnt) {
-                jl = __ldg(gcol + p0 + lane);
-                const double2 *gv = reinterpret_cast<const double2 *>(gval + (size_t)(p0 + lane) * R);
-#pragma unroll
-                for (int r = 0; r < R; r += 2) {
-                    const double2 v = __ldg(gv + r / 2);
-                    al[r] = v.x;
-                    al[r + 1] = v.y;
-                }
-            }
-            for (int q0 = 0; q0 < cnt; q0 += 2) {
-                // two entries (two independent X-row loads) at a time
-                int j[2];
-                double a[2][R], u0[2], u1[2];
-#pragma unroll
-                for (int w = 0; w < 2; w++) {
-                    const int q = min(q0 + w, cnt - 1);
-                    j[w] = __shfl_sync(0xffffffffu, jl, q);
-#pragma unroll
-                    for (int r = 0; r < R; r++) a[w][r] = __shfl_sync(0xffffffffu, al[r], q);
-                }
-#pragma unroll
-                for (int w = 0; w < 2; w++) {
-                    u0[w] = u1[w] = 0.0;
-                    if (q0 + w < cnt) {
-                        const int64_t lj = (int64_t)j[w] - strip0;
-                        if (STAGE && lj >= 0 && lj < kSpmmStrip) {  // warp-uniform: j is a broadcast value
-                            if (hb) {
-                                const double2 v = *reinterpret_cast<const double2 *>(s_x + lj * 64 + ca);
-                                u0[w] = v.x;
-                                u1[w] = v.y;
-                            } else if (ha) {
-                                u0[w] = s_x[lj * 64 + ca];
-                            }
-                        } else {
-                            const double *xr = x + (int64_t)j[w] * ldx;
-                            if (hb) {
-                                const double2 v = __ldg(reinterpret_cast<const double2 *>(xr + ca));
-                                u0[w] = v.x;
-                                u1[w] = v.y;
-                            } else if (ha) {
-                                u0[w] = __ldg(xr + ca);
-                            }
-                        }
-                    }
-                }
-#pragma unroll
-                for (int w = 0; w < 2; w++)
-                    if (q0 + w < cnt) {
-#pragma unroll
-                        for (int r = 0; r < R; r++)
-                            if (a[w][r] != 0.0) {
-                                s0[r] = fma(a[w][r], u0[w], s0[r]);
-                                s1[r] = fma(a[w][r], u1[w], s1[r]);
-                            }
-                    }
-            }
-        }
-#pragma unroll
-        for (int r = 0; r < R; r++) {
-            const int64_t row = g * R + r;
-            if (row >= n) break;
-            double t0 = s0[r], t1 = s1[r];
-            if (mode == 1) {
-                if (ha) t0 = b[row * ldb + ca] - t0;
-                if (hb) t1 = b[row * ldb + cb] - t1;
-            } else if (mode == 2) {
-                if (ha) t0 = b[row * ldb + ca] + t0;
-                if (hb) t1 = b[row * ldb + cb] + t1;
-            } else if (mode == 3) {
-                const double di = epi.c2 * __ldg(epi.dinv + row);
-                if (ha) {
-                    t0 = b[row * ldb + ca] - t0;
-                    epi.out2[row * epi.ldout2 + ca] = di * t0;
-                }
-                if (hb) {
-                    t1 = b[row * ldb + cb] - t1;
-                    epi.out2[row * epi.ldout2 + cb] = di * t1;
-                }
-            } else if (mode == 4) {
-                const double di = epi.c2 * __ldg(epi.dinv + row);
-                if (ha) {
-                    const double dold = x[row * ldx + ca];
-                    const double dn = fma(epi.c1, dold, di * (b[row * ldb + ca] - t0));
-                    double *sp = epi.out2 + row * epi.ldout2 + ca;
-                    *sp = (epi.overwrite ? 0.0 : *sp) + dold + dn;
-                }
-                if (hb) {
-                    const double dold = x[row * ldx + cb];
-                    const double dn = fma(epi.c1, dold, di * (b[row * ldb + cb] - t1));
-                    double *sp = epi.out2 + row * epi.ldout2 + cb;
-                    *sp = (epi.overwrite ? 0.0 : *sp) + dold + dn;
-                }
-                continue;
-            }
-            if (ha) y[row * ldy + ca] = t0;
-            if (hb) y[row * ldy + cb] = t1;
-        }
-    }
-}
-
 // ---- SpMV, CSR-stream form: the CTA stages the products a_ij * x_j of a strip of rows in shared
 // memory (one independent gather per thread and entry: maximal memory-level parallelism, CSR
 // arrays read fully coalesced), then one thread per row sums its segment left to right.
@@ -489,41 +249,6 @@ void spmm(lb_ctx *c, const lb_mat *a, const double *x, int ldx, double *y, int l
     // 16-byte vector loads of X need even leading dimension and a 16-byte aligned base
     const bool vec = (ldx % 2 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
     const int grid = cdiv(n, kSpmmStrip);
-    if (vec && m > 32) {
-        const char *e = getenv("LAPY_B200_SPMM");
-        int rows = 0;
-        bool stage = false;
-        if (e && !strncmp(e, "grouped", 7)) {  // grouped | grouped2 | grouped8, optional suffix "s": staged strip
-            const char *t = e + 7;
-            rows = *t == '2' ? 2 : *t == '8' ? 8 : 4;
-            if (*t == '2' || *t == '8' || *t == '4') t++;
-            stage = *t == 's' && (a->ncols < 0 || a->ncols == n);
-        }
-        if (rows) {
-            const lb_grouped *gr = rows == 2 ? grouped_of<2>(c, a) : rows == 8 ? grouped_of<8>(c, a) : grouped_of<4>(c, a);
-            const size_t smem = stage ? (size_t)kSpmmStrip * 64 * sizeof(double) : 0;
-            for (int c0 = 0; c0 < m; c0 += 64) {  // 64 columns per launch (the 2m-wide products take two)
-                SpmmEpilogue ep = epi;
-                if (ep.out2) ep.out2 += c0;
-                const int mc = std::min(64, m - c0);
-                const double *bc = b ? b + c0 : b;
-#define LB_GROUPED(R, S)                                                                                                  \
-    do {                                                                                                                  \
-        if (S) LB_CUDA(cudaFuncSetAttribute(spmm_grouped_kernel<R, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        LB_LAUNCH(c, (spmm_grouped_kernel<R, S>), grid, 256, smem, n, gr->gptr.p, gr->gcol.p, gr->gval.p, x + c0, ldx, y + c0,  \
-                  ldy, mc, mode, bc, ldb, ep);                                                                            \
-    } while (0)
-                if (rows == 2 && stage) LB_GROUPED(2, true);
-                else if (rows == 2) LB_GROUPED(2, false);
-                else if (rows == 8 && stage) LB_GROUPED(8, true);
-                else if (rows == 8) LB_GROUPED(8, false);
-                else if (stage) LB_GROUPED(4, true);
-                else LB_GROUPED(4, false);
-#undef LB_GROUPED
-            }
-            return;
-        }
-    }
 #define LB_SPMM(G)                                                                                       \
     do {                                                                                                 \
         if (vec) LB_LAUNCH(c, (spmm_kernel<G, true>), grid, 256, 0, n, ip, ix, v, x, ldx, y, ldy, m, mode, b, ldb, epi); \

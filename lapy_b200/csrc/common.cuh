@@ -221,28 +221,28 @@ struct lb_mesh {
     int64_t nv = 0, nt = 0;
     int k = 3;              // vertices per element
     int v_dtype = LB_F64;   // dtype of the caller's vertices: element math runs in it
+    // ---- caller's numbering (gradient / divergence kernels, results returned per caller element)
     std::shared_ptr<lb::DBuf<lb::D4>> v4s;  // owner of v4 (shared with lb_order)
     lb::DBuf<lb::D4> &v4ref() { return *v4s; }
     lb::DBuf<float4> v4f;   // (nv) fp32 xyz + pad, only when v_dtype == LB_F32
     lb::DBuf<int4> t4;      // (nt) int32 x4, triangles padded with -1: one 16-byte load
-    // vertex -> (element, corner) incidence, built on first use: code = element*4 + corner,
-    // ascending per vertex (== COO input order of the reference's triplets)
+    // vertex -> (element, corner) incidence in the caller's numbering, built on first use by the
+    // divergence: code = element*4 + corner, ascending per vertex
     lb::DBuf<int32_t> inc_ptr;  // (nv+1)
     lb::DBuf<int32_t> inc;      // (k*nt)
     int64_t n_ref = 0;          // max referenced vertex + 1 (matrix dimension)
     bool has_inc = false;
+    // ---- solver layout, built once at upload (lb_mesh_create): the assembly reads and writes in
+    // the locality numbering `ord` (Morton order of the vertices), so that every gather of the
+    // element / row kernels stays inside a few cache lines and the matrices come out in the
+    // numbering the solvers iterate in
     std::shared_ptr<lb_order> ord;  // handed to the matrices assembled from this mesh
-};
-
-// row-grouped copy of a CSR matrix for the wide SpMM (blockvec.cu, LAPY_B200_SPMM=grouped): groups of
-// `rows` consecutive rows share the sorted union of their columns; entry e of a group holds one
-// column and `rows` values (0 where a row has no entry in that column)
-struct lb_grouped {
-    int rows = 0;
-    int64_t ngroups = 0, nent = 0;
-    lb::DBuf<int32_t> gptr;  // (ngroups + 1)
-    lb::DBuf<int32_t> gcol;  // (nent)
-    lb::DBuf<double> gval;   // (nent * rows), entry-major
+    lb::DBuf<lb::D4> v4m;           // (n_ref) vertices in the new numbering: v4m[r] = v4[order[r]]
+    lb::DBuf<float4> v4fm;          // fp32 twin
+    // (nt) elements with NEW vertex ids, sorted by their smallest new vertex id (ties by element id);
+    // triangles carry the caller's element id in .w
+    lb::DBuf<int4> t4m;
+    lb::DBuf<int32_t> eorig;        // (nt) caller's element id of every sorted element (sort key of the tet rows)
 };
 
 struct lb_mat {
@@ -253,8 +253,11 @@ struct lb_mat {
     lb::DBuf<int32_t> indices;  // (nnz) sorted, unique per row
     lb::DBuf<double> data;      // (nnz)
     bool diagonal = false;      // every stored entry is on the diagonal (lumped mass / identity)
-    // optional locality ordering (from the mesh the matrix was assembled on).  Solvers may
-    // renumber internally; results are always returned in the caller's order.
+    // Matrices assembled from a mesh are STORED in the mesh's locality numbering (Morton order of
+    // the vertices, `ord`): row / column r of the stored matrix is vertex ord->order[r] of the caller.
+    // The solvers iterate in that numbering; lb_mat_download, lb_spmm and the solver outputs convert
+    // to the caller's numbering.  Uploaded matrices (lb_mat_upload) are in the caller's numbering
+    // (permuted == false, ord == nullptr).
+    bool permuted = false;
     std::shared_ptr<lb_order> ord;
-    mutable std::shared_ptr<lb_grouped> grp;  // built on first use by the grouped SpMM (values are snapshotted)
 };

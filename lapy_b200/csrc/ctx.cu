@@ -6,7 +6,7 @@
 #include <cstdlib>
 #include <thread>
 
-#include "common.cuh"
+#include "amg.cuh"
 
 namespace lb {
 
@@ -413,6 +413,13 @@ int lb_mat_download(lb_mat *m, int32_t *indptr, int32_t *indices, double *data) 
     LB_REQUIRE(m, "matrix is NULL");
     lb_ctx *c = m->ctx;
     DeviceGuard g(c->device);
+    // matrices assembled on the device live in the mesh's locality numbering: the caller gets the
+    // canonical CSC of ITS numbering (rows / columns permuted back, rows sorted)
+    std::unique_ptr<lb_mat> plain;
+    if (m->permuted) {
+        plain = to_caller_order(c, m);
+        m = plain.get();
+    }
     if (indptr) d2h_large(c, indptr, m->indptr.p, (m->n + 1) * sizeof(int32_t));
     if (indices) d2h_large(c, indices, m->indices.p, m->nnz * sizeof(int32_t));
     if (data) d2h_large(c, data, m->data.p, m->nnz * sizeof(double));

@@ -662,21 +662,15 @@ static EigStats lobpcg(lb_ctx *c, const lb_mat *A0, const lb_mat *B0, int k, dou
                        double *h_evals, double *h_evecs) {
     const int64_t n = A0->n;
     phase(c, "(enter eigs)");
-    // solver-internal locality renumbering (Morton order of the mesh the matrices came from):
-    // neighbouring rows of X become neighbouring in memory, so the SpMM gathers hit L1/L2 instead
-    // of DRAM (ncu: 4.0x -> 1.1x of the algorithmic traffic).  Results return in the caller's order.
-    std::unique_ptr<lb_mat> Ap, Bp;
-    const lb_mat *A = A0, *B = B0;
-    const bool reorder = A0->ord && A0->ord == B0->ord && A0->ord->n == n && !getenv("LAPY_B200_NOREORDER");
-    if (reorder) {
-        ensure_order(*A0->ord);
-        Ap = permute_symmetric(c, A0, A0->ord->order.p, A0->ord->inv.p);
-        Bp = permute_symmetric(c, B0, A0->ord->order.p, A0->ord->inv.p);
-        A = Ap.get();
-        B = Bp.get();
-    }
+    // the solver iterates in the locality numbering the assembled matrices are stored in (Morton
+    // order of the mesh: the SpMM gathers hit L1/L2 instead of DRAM, ncu: 4.0x -> 1.1x of the
+    // algorithmic traffic); a user-assigned operand is permuted into it.  Results return in the
+    // caller's order.
+    MatView va, vb;
+    std::shared_ptr<lb_order> ord = common_numbering(c, A0, B0, va, vb);
+    const lb_mat *A = va.m, *B = vb.m;
+    const bool reorder = ord != nullptr;
     int m = ((k + std::max(6, (k + 3) / 4) + 7) / 8) * 8;
-    if (const char *e = getenv("LAPY_B200_BLOCK")) m = std::max(k + 1, atoi(e));
 
     // preconditioner on K = A - sigma*B (SPD for sigma < 0)
     const double shift = sigma < 0 ? -sigma : 1e-2;
@@ -730,7 +724,7 @@ static EigStats lobpcg(lb_ctx *c, const lb_mat *A0, const lb_mat *B0, int k, dou
     if (reorder) {
         // row i of the caller's numbering = row inv[i] of the renumbered block
         DBuf<double> out(c, (size_t)n * k);
-        gather_rows(c, n, k, A0->ord->inv.p, xout.p, m, out.p, k);
+        gather_rows(c, n, k, ord->inv.p, xout.p, m, out.p, k);
         d2h_large(c, h_evecs, out.p, (size_t)n * k * sizeof(double));
     } else {
         DBuf<double> out(c, (size_t)n * k);
@@ -750,16 +744,10 @@ static EigStats lobpcg(lb_ctx *c, const lb_mat *A0, const lb_mat *B0, int k, dou
 static EigStats lobpcg_dist(lb_ctx *c, const DistCtx *dist, const lb_mat *A0, const lb_mat *B0, int k, double sigma,
                             double tol, int maxit, double *h_evals, double *h_evecs) {
     const int64_t n = A0->n;
-    std::unique_ptr<lb_mat> Ap, Bp;
-    const lb_mat *A = A0, *B = B0;
-    const bool reorder = A0->ord && A0->ord == B0->ord && A0->ord->n == n;
-    if (reorder) {
-        ensure_order(*A0->ord);
-        Ap = permute_symmetric(c, A0, A0->ord->order.p, A0->ord->inv.p);
-        Bp = permute_symmetric(c, B0, A0->ord->order.p, A0->ord->inv.p);
-        A = Ap.get();
-        B = Bp.get();
-    }
+    MatView va, vb;
+    std::shared_ptr<lb_order> ord = common_numbering(c, A0, B0, va, vb);
+    const lb_mat *A = va.m, *B = vb.m;
+    const bool reorder = ord != nullptr;
     const int m = ((k + std::max(6, (k + 3) / 4) + 7) / 8) * 8;
     const int world = dist->world, rank = dist->rank;
     const int64_t rpr = (n + world - 1) / world;
@@ -808,8 +796,6 @@ static EigStats lobpcg_dist(lb_ctx *c, const DistCtx *dist, const lb_mat *A0, co
         }
     }
     Kfull.reset();
-    Ap.reset();  // the full renumbered copies are no longer needed
-    Bp.reset();
     auto amg = amg_setup(c, std::move(Kll), m, opt);
     DistOps D;
     D.d = dist;
@@ -842,7 +828,7 @@ static EigStats lobpcg_dist(lb_ctx *c, const DistCtx *dist, const lb_mat *A0, co
     DBuf<double> out(c, (size_t)n * k);
     copy_cols(c, r1 - r0, k, xloc.p, m, D.pack.p, k);
     dist_allgather(c, dist, D.pack.p, D.gath.p, (size_t)rpr * k);
-    if (reorder) gather_rows(c, n, k, A0->ord->inv.p, D.gath.p, k, out.p, k);
+    if (reorder) gather_rows(c, n, k, ord->inv.p, D.gath.p, k, out.p, k);
     else d2d(c, out.p, D.gath.p, (size_t)n * k * sizeof(double));
     d2h_large(c, h_evecs, out.p, (size_t)n * k * sizeof(double));
     return st;
@@ -962,7 +948,11 @@ extern "C" int lb_eigs(lb_ctx *c, lb_mat *a, lb_mat *b, int k, double sigma, dou
     EigStats st;
     const int m = ((k + std::max(6, (k + 3) / 4) + 7) / 8) * 8;
     if (a->n <= std::max<int64_t>(4 * m, 600)) {
-        dense_eigs(c, a, b, k, evals, evecs);
+        // tiny problem: dense solve in the caller's numbering
+        std::unique_ptr<lb_mat> pa, pb;
+        if (a->permuted) pa = to_caller_order(c, a);
+        if (b->permuted) pb = to_caller_order(c, b);
+        dense_eigs(c, pa ? pa.get() : a, pb ? pb.get() : b, k, evals, evecs);
         st.converged = k;
     } else if (c->dist && (c->dist->world > 1 || getenv("LAPY_B200_FORCE_DIST"))) {
         st = lobpcg_dist(c, c->dist, a, b, k, sigma, tol, maxit, evals, evecs);

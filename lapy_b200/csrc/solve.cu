@@ -15,12 +15,14 @@
 namespace lb {
 
 // ---- Dirichlet handling -----------------------------------------------------------------------
+// inv != NULL: the operator is stored in a locality numbering; idx are the caller's vertex ids
 __global__ void mark_fixed(int64_t nfix, const int64_t *__restrict__ idx, const double *__restrict__ val,
-                           int *__restrict__ is_fixed, double *__restrict__ dval) {
+                           const int32_t *__restrict__ inv, int *__restrict__ is_fixed, double *__restrict__ dval) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nfix) return;
-    is_fixed[idx[t]] = 1;
-    dval[idx[t]] = val[t];
+    const int64_t r = inv ? inv[idx[t]] : idx[t];
+    is_fixed[r] = 1;
+    dval[r] = val[t];
 }
 
 __global__ void broadcast_cols(int64_t n, int m, const double *__restrict__ d, double *__restrict__ out) {
@@ -470,8 +472,9 @@ static double avg_edge_length_device(lb_ctx *c, lb_mesh *mesh, lb_mat *pattern) 
     const int nb = 1024;
     DBuf<double> psum(c, nb);
     DBuf<unsigned long long> pcnt(c, nb);
-    LB_LAUNCH(c, edge_length_partial, nb, 256, 0, pattern->n, pattern->indptr.p, pattern->indices.p, mesh->v4s->p, psum.p,
-              pcnt.p);
+    // the pattern of an assembled matrix is in the mesh's locality numbering: use the vertices of that layout
+    const D4 *v4 = pattern->permuted ? mesh->v4m.p : mesh->v4s->p;
+    LB_LAUNCH(c, edge_length_partial, nb, 256, 0, pattern->n, pattern->indptr.p, pattern->indices.p, v4, psum.p, pcnt.p);
     std::vector<double> hs(nb);
     std::vector<unsigned long long> hc(nb);
     read_back(c, hs.data(), psum.p, nb);
@@ -499,7 +502,14 @@ int lb_spmm(lb_ctx *c, lb_mat *mat, const double *x, int64_t m, double *y) {
     const int64_t n = mat->n;
     DBuf<double> dx(c, (size_t)n * m), dy(c, (size_t)n * m);
     h2d(c, dx.p, x, (size_t)n * m * sizeof(double));
-    spmm(c, mat, dx.p, (int)m, dy.p, (int)m, (int)m);
+    if (mat->permuted) {  // stored in the mesh's locality numbering: permute x in, y out
+        DBuf<double> px(c, (size_t)n * m);
+        gather_rows(c, n, (int)m, mat->ord->order.p, dx.p, (int)m, px.p, (int)m);
+        spmm(c, mat, px.p, (int)m, dx.p, (int)m, (int)m);
+        gather_rows(c, n, (int)m, mat->ord->inv.p, dx.p, (int)m, dy.p, (int)m);
+    } else {
+        spmm(c, mat, dx.p, (int)m, dy.p, (int)m, (int)m);
+    }
     d2h(c, y, dy.p, (size_t)n * m * sizeof(double));
     sync(c);
     LB_API_END
@@ -511,11 +521,13 @@ int lb_spmm_benchmark(lb_ctx *c, lb_mat *mat0, int64_t m, int reps, int renumber
     LB_REQUIRE(c && mat0 && ms_per_launch && m >= 1 && m <= 1024 && reps >= 1, "lb_spmm_benchmark: bad argument");
     DeviceGuard g(c->device);
     const int64_t n = mat0->n;
+    // renumber != 0: the numbering the solvers work in = how assembled matrices are stored;
+    // renumber == 0: the same operator in the caller's numbering (diagnostic: what the locality
+    // numbering buys)
     std::unique_ptr<lb_mat> perm;
     lb_mat *mat = mat0;
-    if (renumber && mat0->ord && mat0->ord->n == n) {  // the numbering the solvers work in
-        ensure_order(*mat0->ord);
-        perm = permute_symmetric(c, mat0, mat0->ord->order.p, mat0->ord->inv.p);
+    if (!renumber && mat0->permuted) {
+        perm = to_caller_order(c, mat0);
         mat = perm.get();
     }
     DBuf<double> dx(c, (size_t)n * m), dy(c, (size_t)n * m);
@@ -534,7 +546,8 @@ int lb_spmm_benchmark(lb_ctx *c, lb_mat *mat0, int64_t m, int reps, int renumber
 int lb_avg_edge_length(lb_ctx *c, lb_mesh *mesh, lb_mat *pattern, double *out) {
     LB_API_BEGIN
     LB_REQUIRE(c && mesh && pattern && out, "lb_avg_edge_length: NULL argument");
-    LB_REQUIRE(pattern->n <= mesh->nv, "matrix does not belong to this mesh");
+    LB_REQUIRE(pattern->n <= mesh->nv && (!pattern->permuted || pattern->ord == mesh->ord),
+               "matrix does not belong to this mesh");
     DeviceGuard g(c->device);
     *out = avg_edge_length_device(c, mesh, pattern);
     LB_API_END
@@ -582,9 +595,20 @@ int lb_solve(lb_ctx *c, lb_mat *a, double alpha, lb_mat *b, double beta, const d
     const int mm = (int)m;
     for (int64_t i = 0; i < nfix; i++)
         LB_REQUIRE(fix_idx[i] >= 0 && fix_idx[i] < n, "Dirichlet index %lld out of range", (long long)fix_idx[i]);
-    auto K = mat_axpby(c, a, alpha, beta != 0.0 ? b : nullptr, beta);
-    DBuf<double> d_rhs(c, (size_t)n * mm), d_x(c, (size_t)n * mm);
-    h2d(c, d_rhs.p, rhs, (size_t)n * mm * sizeof(double));
+    // everything runs in the locality numbering of the assembled operator (Morton order of its mesh:
+    // the x gathers of the sweeps / SpMVs hit L1/L2); right-hand sides and Dirichlet indices are
+    // mapped in, the solution is mapped back to the caller's order
+    MatView va, vb;
+    std::shared_ptr<lb_order> ord = common_numbering(c, a, beta != 0.0 ? b : nullptr, va, vb);
+    const int32_t *to_new = ord ? ord->inv.p : nullptr;
+    auto K = mat_axpby(c, va.m, alpha, beta != 0.0 ? vb.m : nullptr, beta);
+    DBuf<double> d_rhs(c, (size_t)n * mm), d_x(c, (size_t)n * mm), d_sol(c, (size_t)n * mm);
+    if (ord) {
+        h2d(c, d_sol.p, rhs, (size_t)n * mm * sizeof(double));
+        gather_rows(c, n, mm, ord->order.p, d_sol.p, mm, d_rhs.p, mm);
+    } else {
+        h2d(c, d_rhs.p, rhs, (size_t)n * mm * sizeof(double));
+    }
     DBuf<int> is_fixed;
     DBuf<double> dval;
     if (nfix > 0) {
@@ -596,17 +620,14 @@ int lb_solve(lb_ctx *c, lb_mat *a, double alpha, lb_mat *b, double beta, const d
         DBuf<double> d_val(c, nfix);
         h2d(c, d_idx.p, fix_idx, nfix * sizeof(int64_t));
         h2d(c, d_val.p, fix_val, nfix * sizeof(double));
-        LB_LAUNCH(c, mark_fixed, cdiv(nfix, 256), 256, 0, nfix, d_idx.p, d_val.p, is_fixed.p, dval.p);
+        LB_LAUNCH(c, mark_fixed, cdiv(nfix, 256), 256, 0, nfix, d_idx.p, d_val.p, to_new, is_fixed.p, dval.p);
         // rhs <- rhs - K d  (solver.py:846), then eliminate: identity rows/cols, rhs_fixed = d
         DBuf<double> dblock(c, (size_t)n * mm);
         LB_LAUNCH(c, broadcast_cols, cdiv(n * mm, 256), 256, 0, n, mm, dval.p, dblock.p);
         spmm(c, K.get(), dblock.p, mm, d_rhs.p, mm, mm, 1, d_rhs.p, mm);
         LB_LAUNCH(c, mask_matrix, cdiv(n, 256), 256, 0, n, K->indptr.p, K->indices.p, K->data.p, is_fixed.p);
-        K->grp.reset();  // values changed in place: drop the row-grouped snapshot of the wide SpMM
         LB_LAUNCH(c, set_fixed_rows, cdiv(n * mm, 256), 256, 0, n, mm, is_fixed.p, dval.p, d_rhs.p);
     }
-    int force = 0;
-    if (const char *e = getenv("LAPY_B200_PREC")) force = !strcmp(e, "jacobi") ? 1 : !strcmp(e, "amg") ? 2 : 0;
     // project out the constants only if they ARE (numerically) in the null space: a user-assigned
     // nonsingular operator (A + c*B, screened Poisson) must be solved as it is, like splu does.
     // float32-assembled stiffness matrices have |A 1| ~ 1e-7 * diag: the threshold keeps them singular.
@@ -625,22 +646,10 @@ int lb_solve(lb_ctx *c, lb_mat *a, double alpha, lb_mat *b, double beta, const d
     }
     // mass-dominated operators (backward Euler heat step: diagonal B, beta != 0): componentwise Jacobi
     const bool try_jacobi = beta != 0.0 && b != nullptr && b->diagonal && nfix == 0;
-    // solver-internal locality renumbering (Morton order of the mesh the operator came from), as in
-    // lb_eigs: the x gathers of the sweeps / SpMVs hit L1/L2; the solution returns in the caller's order
-    const bool reorder = a->ord && a->ord->n == n && !getenv("LAPY_B200_NOREORDER");
-    SolveStats st;
-    if (reorder) {
-        ensure_order(*a->ord);
-        auto Kp = permute_symmetric(c, K.get(), a->ord->order.p, a->ord->inv.p);
-        K.reset();
-        DBuf<double> rhs_p(c, (size_t)n * mm);
-        gather_rows(c, n, mm, a->ord->order.p, d_rhs.p, mm, rhs_p.p, mm);
-        st = block_pcg(c, Kp.get(), rhs_p.p, d_rhs.p, mm, tol, maxit, project, force, try_jacobi);
-        gather_rows(c, n, mm, a->ord->inv.p, d_rhs.p, mm, d_x.p, mm);
-    } else {
-        st = block_pcg(c, K.get(), d_rhs.p, d_x.p, mm, tol, maxit, project, force, try_jacobi);
-    }
-    if (nfix > 0) LB_LAUNCH(c, set_fixed_rows, cdiv(n * mm, 256), 256, 0, n, mm, is_fixed.p, dval.p, d_x.p);
+    SolveStats st = block_pcg(c, K.get(), d_rhs.p, d_sol.p, mm, tol, maxit, project, 0, try_jacobi);
+    if (nfix > 0) LB_LAUNCH(c, set_fixed_rows, cdiv(n * mm, 256), 256, 0, n, mm, is_fixed.p, dval.p, d_sol.p);
+    if (ord) gather_rows(c, n, mm, ord->inv.p, d_sol.p, mm, d_x.p, mm);
+    else d2d(c, d_x.p, d_sol.p, (size_t)n * mm * sizeof(double));
     d2h(c, x, d_x.p, (size_t)n * mm * sizeof(double));
     sync(c);
     if (info) {
