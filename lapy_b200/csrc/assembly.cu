@@ -268,22 +268,83 @@ __global__ void incidence_fill(const int4 *__restrict__ t4, int64_t nt, int k,
 //   tet      corner 0: (t2,t3,t4) 1: (t1,t3,t4) 2: (t2,t1,t4) 3: (t1,t2,t3)   (solver.py:472-497)
 // `element` is the position in the sorted element array t4m; the reference's triplet order is the
 // CALLER's element order: triangles carry that id in .w, tets look it up in eorig[] (inc_key)
-__global__ void incidence_fill4(const int4 *__restrict__ t4, int64_t nt, int k,
-                                const int32_t *__restrict__ inc_ptr, int32_t *__restrict__ cursor,
-                                int4 *__restrict__ inc4) {
-    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= nt) return;
-    const int4 ti = __ldg(t4 + e);
-    const int code = (int)e * 4;
-    if (k == 3) {
-        inc4[inc_ptr[ti.x] + atomicAdd(cursor + ti.x, 1)] = make_int4(code, ti.y, ti.z, ti.w);
-        inc4[inc_ptr[ti.y] + atomicAdd(cursor + ti.y, 1)] = make_int4(code + 1, ti.x, ti.z, ti.w);
-        inc4[inc_ptr[ti.z] + atomicAdd(cursor + ti.z, 1)] = make_int4(code + 2, ti.y, ti.x, ti.w);
-    } else {
-        inc4[inc_ptr[ti.x] + atomicAdd(cursor + ti.x, 1)] = make_int4(code, ti.y, ti.z, ti.w);
-        inc4[inc_ptr[ti.y] + atomicAdd(cursor + ti.y, 1)] = make_int4(code + 1, ti.x, ti.z, ti.w);
-        inc4[inc_ptr[ti.z] + atomicAdd(cursor + ti.z, 1)] = make_int4(code + 2, ti.y, ti.x, ti.w);
-        inc4[inc_ptr[ti.w] + atomicAdd(cursor + ti.w, 1)] = make_int4(code + 3, ti.x, ti.y, ti.z);
+// The records of one vertex are placed by an atomic cursor.  ncu (round 2): with one global atomic
+// per incidence the kernel is latency bound (7 % issue utilisation, 113 us at level 9).  The elements
+// are sorted by their smallest (new) vertex id, so the vertices of a chunk of consecutive elements
+// lie in a narrow id window above the chunk's first key: ranks inside the chunk come from
+// shared-memory atomics and only ONE global atomic per (chunk, vertex) reserves the chunk's range of
+// the vertex's list; vertices outside the window fall back to a global atomic per incidence.  The
+// order inside a list is arbitrary either way - the row kernels sort by the caller's element id.
+constexpr int kIncWin = 2048;  // vertex window per chunk
+constexpr int kIncEpt = 4;     // elements per thread (chunk = 256 * 4 elements)
+
+__global__ void __launch_bounds__(256) incidence_fill4(const int4 *__restrict__ t4, int64_t nt, int k,
+                                                        const int32_t *__restrict__ inc_ptr,
+                                                        int32_t *__restrict__ cursor, int4 *__restrict__ inc4) {
+    __shared__ int s_cnt[kIncWin];
+    __shared__ int s_base[kIncWin];
+    __shared__ int s_vbase;
+    const int64_t e0 = (int64_t)blockIdx.x * (256 * kIncEpt);
+    for (int i = threadIdx.x; i < kIncWin; i += 256) s_cnt[i] = 0;
+    if (threadIdx.x == 0) {
+        const int4 f = __ldg(t4 + e0);  // e0 < nt by the grid size
+        int m = min(f.x, min(f.y, f.z));
+        if (k == 4) m = min(m, f.w);
+        s_vbase = m;
+    }
+    __syncthreads();
+    const int vbase = s_vbase;
+    int4 ti[kIncEpt];
+    int rk[kIncEpt][4];
+#pragma unroll
+    for (int j = 0; j < kIncEpt; j++) {
+        const int64_t e = e0 + (int64_t)j * 256 + threadIdx.x;
+        ti[j] = make_int4(0, 0, 0, 0);
+#pragma unroll
+        for (int cn = 0; cn < 4; cn++) rk[j][cn] = -1;
+        if (e < nt) {
+            ti[j] = __ldg(t4 + e);
+            const int vs[4] = {ti[j].x, ti[j].y, ti[j].z, ti[j].w};
+#pragma unroll
+            for (int cn = 0; cn < 4; cn++) {
+                if (cn < k) {
+                    const int lv = vs[cn] - vbase;
+                    if (lv >= 0 && lv < kIncWin) rk[j][cn] = atomicAdd(&s_cnt[lv], 1);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < kIncWin; i += 256) {
+        const int cnt = s_cnt[i];
+        if (cnt) s_base[i] = atomicAdd(cursor + vbase + i, cnt);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < kIncEpt; j++) {
+        const int64_t e = e0 + (int64_t)j * 256 + threadIdx.x;
+        if (e >= nt) continue;
+        const int code = (int)e * 4;
+        const int vs[4] = {ti[j].x, ti[j].y, ti[j].z, ti[j].w};
+        int pos[4];
+#pragma unroll
+        for (int cn = 0; cn < 4; cn++) {
+            pos[cn] = 0;
+            if (cn < k) {
+                const int v = vs[cn];
+                pos[cn] = inc_ptr[v] + (rk[j][cn] >= 0 ? s_base[v - vbase] + rk[j][cn] : atomicAdd(cursor + v, 1));
+            }
+        }
+        if (k == 3) {
+            inc4[pos[0]] = make_int4(code, ti[j].y, ti[j].z, ti[j].w);
+            inc4[pos[1]] = make_int4(code + 1, ti[j].x, ti[j].z, ti[j].w);
+            inc4[pos[2]] = make_int4(code + 2, ti[j].y, ti[j].x, ti[j].w);
+        } else {
+            inc4[pos[0]] = make_int4(code, ti[j].y, ti[j].z, ti[j].w);
+            inc4[pos[1]] = make_int4(code + 1, ti[j].x, ti[j].z, ti[j].w);
+            inc4[pos[2]] = make_int4(code + 2, ti[j].y, ti[j].x, ti[j].w);
+            inc4[pos[3]] = make_int4(code + 3, ti[j].x, ti[j].y, ti[j].z);
+        }
     }
 }
 
@@ -613,6 +674,234 @@ __global__ void __launch_bounds__(kRowThreads) row_fill_kernel(
         }
     }
 }
+
+// ---- fast triangle rows ---------------------------------------------------------------------------
+// ncu (round 2) on the per-thread kernels above at level 9: count 172 us, fill 590 us, both bound by
+// instruction issue - the sorted key set of a row was built by insertion into shared memory, one
+// dependent compare / move at a time.  Fast form for rows with <= 8 incident triangles (every row of
+// a regular surface mesh): the up to 16 neighbour ids of a row live in REGISTERS, packed with their
+// position in the reference's triplet order into one 32-bit word (id << 4 | position), and are
+// sorted by a 63-comparator odd-even merge network of min / max instructions - no branches, no
+// memory.  A walk over the sorted words yields the unique keys (the row's column indices), the
+// slot of the diagonal and, per triplet, the slot it adds into; the values are then accumulated in
+// triplet order (caller's element id ascending), so every entry is bit-identical to the sequential
+// model.  Rows with more incidences, a repeated vertex inside an element or ids >= 2^27 are flagged
+// and done by the per-thread kernels restricted to them (only_rows).
+#define LB_NET16(X)                                                                                              \
+    X(0, 1) X(2, 3) X(0, 2) X(1, 3) X(1, 2) X(4, 5) X(6, 7) X(4, 6) X(5, 7) X(5, 6) X(0, 4) X(2, 6) X(2, 4)    \
+    X(1, 5) X(3, 7) X(3, 5) X(1, 2) X(3, 4) X(5, 6) X(8, 9) X(10, 11) X(8, 10) X(9, 11) X(9, 10) X(12, 13)     \
+    X(14, 15) X(12, 14) X(13, 15) X(13, 14) X(8, 12) X(10, 14) X(10, 12) X(9, 13) X(11, 15) X(11, 13)           \
+    X(9, 10) X(11, 12) X(13, 14) X(0, 8) X(4, 12) X(4, 8) X(2, 10) X(6, 14) X(6, 10) X(2, 4) X(6, 8)            \
+    X(10, 12) X(1, 9) X(5, 13) X(5, 9) X(3, 11) X(7, 15) X(7, 11) X(3, 5) X(7, 9) X(11, 13) X(1, 2) X(3, 4)     \
+    X(5, 6) X(7, 8) X(9, 10) X(11, 12) X(13, 14)
+#define LB_MINMAX(i, j)                      \
+    {                                        \
+        const int lo_ = min(w[i], w[j]);     \
+        w[j] = max(w[i], w[j]);              \
+        w[i] = lo_;                          \
+    }
+constexpr int kFastInc = 8;  // incidences per row handled in registers
+
+__global__ void __launch_bounds__(kRowThreads) tria_row_count_fast(const int32_t *__restrict__ inc_ptr,
+                                                                   const int4 *__restrict__ inc4, int64_t n,
+                                                                   int32_t *__restrict__ row_nnz,
+                                                                   int32_t *__restrict__ row_has,
+                                                                   int32_t *__restrict__ row_big,
+                                                                   int32_t *__restrict__ nbig) {
+    const int64_t r = (int64_t)blockIdx.x * kRowThreads + threadIdx.x;
+    if (r >= n) return;
+    const int beg = inc_ptr[r], ninc = inc_ptr[r + 1] - beg;
+    bool big = ninc > kFastInc || n >= (1ll << 27);
+    int cnt = 0;
+    if (!big && ninc > 0) {
+        int w[16];
+#pragma unroll
+        for (int u = 0; u < kFastInc; u++) {
+            int4 q = make_int4(0, INT_MAX, INT_MAX, 0);
+            if (u < ninc) q = __ldg(inc4 + beg + u);
+            w[2 * u] = q.y;
+            w[2 * u + 1] = q.z;
+        }
+        LB_NET16(LB_MINMAX)
+        int prev = -1;
+        bool self = false;
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+            const int key = w[i];
+            if (key != INT_MAX && key != prev) cnt++;
+            self |= key == (int)r;
+            prev = key;
+        }
+        cnt++;  // the diagonal
+        big = self;  // a vertex repeated inside an element adds off-diagonal triplets to the diagonal
+    }
+    row_has[r] = ninc > 0;
+    row_big[r] = big;
+    row_nnz[r] = big ? 0 : cnt;  // flagged rows: row_count_kernel(only_rows) fills it in
+    if (big) atomicAdd(nbig, 1);
+}
+
+__global__ void __launch_bounds__(kRowThreads) tria_row_fill_fast(
+    const D4 *__restrict__ rec, const int32_t *__restrict__ inc_ptr, const int4 *__restrict__ inc4, int64_t n, int cap,
+    const ElemConsts *__restrict__ consts, int degen_div_f32, RowOut out, const int32_t *__restrict__ row_big) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *s_a = reinterpret_cast<double *>(smem_raw);
+    double *s_b = s_a + cap;
+    int32_t *s_k = reinterpret_cast<int32_t *>(s_b + cap);
+    unsigned char *s_slot = reinterpret_cast<unsigned char *>(s_k + cap);  // [16][T]: slot of triplet position c
+    constexpr int T = kRowThreads;
+    const int t = threadIdx.x;
+    const int64_t r0 = (int64_t)blockIdx.x * T, r = r0 + t;
+    const int64_t rlast = min(r0 + (int64_t)T, n);
+    const int blk_beg = out.indptr[r0], blk_nnz = out.indptr[rlast] - blk_beg;
+    const bool want_a = out.a_val != nullptr, want_b = out.b_val != nullptr;
+    const bool want_pat = want_a || want_b;
+    const bool use_smem = want_pat && blk_nnz <= cap;
+    if (r < n && !row_big[r]) {
+        const int beg = inc_ptr[r], ninc = inc_ptr[r + 1] - beg;
+        if (ninc > 0) {
+            const int rbeg = out.indptr[r];
+            // image of this row: shared memory (streamed out below) or, for an oversized block, the output itself
+            int32_t *keys = use_smem ? s_k + (rbeg - blk_beg) : (want_a ? out.a_idx : out.b_idx) + rbeg;
+            double *av = use_smem ? s_a + (rbeg - blk_beg) : out.a_val + rbeg;
+            double *bv = use_smem ? s_b + (rbeg - blk_beg) : out.b_val + rbeg;
+            // 1. incidence records in the reference's triplet order (caller's element id, then corner)
+            int4 qi[kFastInc];
+#pragma unroll
+            for (int u = 0; u < kFastInc; u++) qi[u] = u < ninc ? __ldg(inc4 + beg + u) : make_int4(INT_MAX, INT_MAX, INT_MAX, INT_MAX);
+#define LB_CSWAP(i, j)                                                              \
+    if (qi[i].w > qi[j].w || (qi[i].w == qi[j].w && qi[i].x > qi[j].x)) {           \
+        const int4 tmp_ = qi[i];                                                    \
+        qi[i] = qi[j];                                                              \
+        qi[j] = tmp_;                                                               \
+    }
+            LB_CSWAP(0, 1) LB_CSWAP(2, 3) LB_CSWAP(4, 5) LB_CSWAP(6, 7) LB_CSWAP(0, 2) LB_CSWAP(1, 3) LB_CSWAP(4, 6)
+            LB_CSWAP(5, 7) LB_CSWAP(1, 2) LB_CSWAP(5, 6) LB_CSWAP(0, 4) LB_CSWAP(3, 7) LB_CSWAP(1, 5) LB_CSWAP(2, 6)
+            LB_CSWAP(1, 4) LB_CSWAP(3, 6) LB_CSWAP(2, 4) LB_CSWAP(3, 5) LB_CSWAP(3, 4)
+#undef LB_CSWAP
+            // 2. element records: 8 independent 32-byte gathers (neighbouring rows share them: L1 / L2)
+            D4 er[kFastInc];
+#pragma unroll
+            for (int u = 0; u < kFastInc; u++)
+                if (u < ninc) er[u] = ldg_d4(rec + (qi[u].x >> 2));
+            // 3. sort (neighbour id << 4 | triplet position); position c = 2u + s is the reference order
+            int cnt = 0, dslot = 0;
+            if (want_pat) {
+                int w[16];
+#pragma unroll
+                for (int u = 0; u < kFastInc; u++) {
+                    w[2 * u] = u < ninc ? (qi[u].y << 4) | (2 * u) : INT_MAX;
+                    w[2 * u + 1] = u < ninc ? (qi[u].z << 4) | (2 * u + 1) : INT_MAX;
+                }
+                LB_NET16(LB_MINMAX)
+                // 4. unique keys -> slots; the diagonal takes the slot before the first larger key
+                int prev = -1;
+                bool dd = false;
+#pragma unroll
+                for (int i = 0; i < 16; i++) {
+                    if (w[i] != INT_MAX) {
+                        const int key = w[i] >> 4, cpos = w[i] & 15;
+                        if (key != prev) {
+                            if (!dd && key > (int)r) {
+                                dslot = cnt++;
+                                dd = true;
+                            }
+                            keys[cnt++] = key;
+                            prev = key;
+                        }
+                        s_slot[cpos * T + t] = (unsigned char)(cnt - 1);
+                    }
+                }
+                if (!dd) dslot = cnt++;
+                keys[dslot] = (int)r;
+            }
+            // 5. accumulate in triplet order; the first addend of a slot is stored as it is (keeps -0.0)
+            unsigned seen = 0;
+            double da = 0.0, db = 0.0, lump = 0.0;
+#pragma unroll
+            for (int u = 0; u < kFastInc; u++) {
+                if (u < ninc) {
+                    const int c = qi[u].x & 3;
+                    double a12 = er[u].x, a23 = er[u].y, a31 = er[u].z, bii = er[u].w;
+                    if (bii < 0.0) {  // clamped element (solver.py:159): divide by the global mean
+                        const double vm = consts->vol_mean;
+                        if (degen_div_f32) {
+                            a12 = (double)__fdiv_rn((float)a12, (float)vm);
+                            a23 = (double)__fdiv_rn((float)a23, (float)vm);
+                            a31 = (double)__fdiv_rn((float)a31, (float)vm);
+                        } else {
+                            a12 = __ddiv_rn(a12, vm);
+                            a23 = __ddiv_rn(a23, vm);
+                            a31 = __ddiv_rn(a31, vm);
+                        }
+                        bii = consts->bii_deg;
+                    }
+                    const double bij = 0.5 * bii;
+                    lump += 2.0 * bii;  // vol/12 (vol/3 for fem_tria_mass) == 2*bii exactly
+                    double x0, x1, m0, m1;
+                    if (c == 0) {
+                        x0 = a12; x1 = a31; m0 = a12; m1 = a31;
+                    } else if (c == 1) {
+                        x0 = a12; x1 = a23; m0 = a12; m1 = a23;
+                    } else {
+                        x0 = a23; x1 = a31; m0 = a31; m1 = a23;
+                    }
+                    // the diagonal (row sum = 0, solver.py:167-169) is formed in the element dtype
+                    const double xd = degen_div_f32 ? (double)__fsub_rn(-(float)m0, (float)m1) : __dsub_rn(-m0, m1);
+                    if (want_pat) {
+                        const int p0 = s_slot[(2 * u) * T + t], p1 = s_slot[(2 * u + 1) * T + t];
+                        if (seen >> p0 & 1u) {
+                            if (want_a) av[p0] = __dadd_rn(av[p0], x0);
+                            if (want_b) bv[p0] = __dadd_rn(bv[p0], bij);
+                        } else {
+                            if (want_a) av[p0] = x0;
+                            if (want_b) bv[p0] = bij;
+                            seen |= 1u << p0;
+                        }
+                        if (seen >> p1 & 1u) {
+                            if (want_a) av[p1] = __dadd_rn(av[p1], x1);
+                            if (want_b) bv[p1] = __dadd_rn(bv[p1], bij);
+                        } else {
+                            if (want_a) av[p1] = x1;
+                            if (want_b) bv[p1] = bij;
+                            seen |= 1u << p1;
+                        }
+                    }
+                    da = u == 0 ? xd : __dadd_rn(da, xd);
+                    db = u == 0 ? bii : __dadd_rn(db, bii);
+                }
+            }
+            if (want_pat) {
+                if (want_a) av[dslot] = da;
+                if (want_b) bv[dslot] = db;
+                if (!use_smem && want_a && want_b)
+                    for (int q = 0; q < cnt; q++) out.b_idx[rbeg + q] = keys[q];
+            }
+            if (out.lump_ptr) {
+                const int lp = out.lump_ptr[r];
+                out.lump_idx[lp] = (int)r;
+                out.lump_val[lp] = lump;
+            }
+        }
+    }
+    if (use_smem) {
+        __syncthreads();
+        // segments of flagged rows hold stale shared memory here; row_fill_kernel(only_rows) runs
+        // after this kernel and rewrites them
+        for (int q = t; q < blk_nnz; q += T) {
+            const int key = s_k[q];
+            if (want_a) {
+                out.a_idx[blk_beg + q] = key;
+                out.a_val[blk_beg + q] = s_a[q];
+            }
+            if (want_b) {
+                out.b_idx[blk_beg + q] = key;
+                out.b_val[blk_beg + q] = s_b[q];
+            }
+        }
+    }
+}
+#undef LB_MINMAX
 
 // ---- fused tet rows (the default for tets: 9.4 -> 4.4 ms at 121^3 in the caller's numbering) --------
 // ncu (round 1) on the per-thread tet kernels: count 1.5 ms + fill 6.9 ms at cube121, 9 % issue
@@ -1144,8 +1433,17 @@ static void run_rows(lb_mesh *mesh, const D4 *rec, const ElemConsts *consts, con
         LB_LAUNCH(c, row_accumulate_tet, nblocks, kRowThreads, kFusedSmemA, rec, aptr, inc4, eorig, n, consts,
                   (int)degen_f32, row_nnz.p, row_has.p, row_big.p, sc_key.p, sc_a.p, sc_b.p, sc_lump.p);
     }
+    // triangles: register fast path (tria_row_count_fast / tria_row_fill_fast), flagged rows by the
+    // per-thread kernels
+    const bool fast3 = K == 3;
+    DBuf<int32_t> nbig(c, 1);
+    if (fast3) {
+        row_big.alloc(c, n);
+        nbig.zero();
+        LB_LAUNCH(c, tria_row_count_fast, nblocks, kRowThreads, 0, aptr, inc4, n, row_nnz.p, row_has.p, row_big.p, nbig.p);
+    }
     LB_LAUNCH(c, row_count_kernel<K>, nblocks, kRowThreads, cap_keys * 4, aptr, inc4, n, cap_keys, scratch.p,
-              row_nnz.p, row_has.p, fused ? row_big.p : (const int32_t *)nullptr);
+              row_nnz.p, row_has.p, (fused || fast3) ? row_big.p : (const int32_t *)nullptr);
     phase(c, "row count");
     const bool full_b = !lump;
     lb_mat *A = nullptr, *B = nullptr;
@@ -1158,6 +1456,8 @@ static void run_rows(lb_mesh *mesh, const D4 *rec, const ElemConsts *consts, con
         read_back(c, &totals[1], lump_ptr.p + n, 1);
     }
     read_back(c, &totals[0], indptr.p + n, 1);
+    int32_t h_nbig = 0;
+    if (fast3) read_back(c, &h_nbig, nbig.p, 1);
     const int64_t nnz = totals[0];
     phase(c, "scan + nnz readback");
     try {
@@ -1188,7 +1488,14 @@ static void run_rows(lb_mesh *mesh, const D4 *rec, const ElemConsts *consts, con
             const int smem = cap * 20;
             if (smem > 40 * 1024)
                 LB_CUDA(cudaFuncSetAttribute(row_fill_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-            if (fused) {
+            if (fast3) {
+                const int smem_fast = cap * 20 + 16 * kRowThreads;
+                LB_LAUNCH(c, tria_row_fill_fast, nblocks, kRowThreads, smem_fast, rec, aptr, inc4, n, cap, consts,
+                          (int)degen_f32, out, (const int32_t *)row_big.p);
+                if (h_nbig > 0)
+                    LB_LAUNCH(c, row_fill_kernel<K>, nblocks, kRowThreads, 16, rec, aptr, inc4, eorig, n, cap, consts,
+                              (int)degen_f32, out, (const int32_t *)row_big.p);
+            } else if (fused) {
                 LB_LAUNCH(c, row_compact_kernel, nblocks, kRowThreads, 0, n, row_big.p, sc_key.p, sc_a.p, sc_b.p, sc_lump.p,
                           out);
                 LB_LAUNCH(c, row_fill_kernel<K>, nblocks, kRowThreads, 16, rec, aptr, inc4, eorig, n, cap, consts,
@@ -1198,10 +1505,18 @@ static void run_rows(lb_mesh *mesh, const D4 *rec, const ElemConsts *consts, con
                           (int)degen_f32, out, (const int32_t *)nullptr);
             }
         } else {
-            // mass only + lumped: no CSR pattern needed, but the same kernel does the sums
+            // mass only + lumped: no CSR pattern needed, but the same kernels do the sums
             const int cap = 0;
-            LB_LAUNCH(c, row_fill_kernel<K>, nblocks, kRowThreads, 16, rec, aptr, inc4, eorig, n, cap, consts,
-                      (int)degen_f32, out, (const int32_t *)nullptr);
+            if (fast3) {
+                LB_LAUNCH(c, tria_row_fill_fast, nblocks, kRowThreads, 16 * kRowThreads, rec, aptr, inc4, n, cap, consts,
+                          (int)degen_f32, out, (const int32_t *)row_big.p);
+                if (h_nbig > 0)
+                    LB_LAUNCH(c, row_fill_kernel<K>, nblocks, kRowThreads, 16, rec, aptr, inc4, eorig, n, cap, consts,
+                              (int)degen_f32, out, (const int32_t *)row_big.p);
+            } else {
+                LB_LAUNCH(c, row_fill_kernel<K>, nblocks, kRowThreads, 16, rec, aptr, inc4, eorig, n, cap, consts,
+                          (int)degen_f32, out, (const int32_t *)nullptr);
+            }
         }
     } catch (...) {
         delete A;
@@ -1348,7 +1663,7 @@ int lb_fem_assemble(lb_ctx *c, lb_mesh *mesh, int kind, int lump, const double *
     phase(c, "element pass");
     exclusive_scan_i32(c, deg.p, aptr.p, mesh->n_ref);
     deg.zero();
-    LB_LAUNCH(c, incidence_fill4, cdiv(nt, 256), 256, 0, mesh->t4m.p, nt, mesh->k, aptr.p, deg.p, inc4.p);
+    LB_LAUNCH(c, incidence_fill4, cdiv(nt, 256 * kIncEpt), 256, 0, mesh->t4m.p, nt, mesh->k, aptr.p, deg.p, inc4.p);
     phase(c, "incidence");
     if (a_out) *a_out = nullptr;
     // clamped elements: the aniso numerators are fp64 even for fp32 meshes (solver.py:278-280)
