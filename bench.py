@@ -427,6 +427,7 @@ def main():
     print(f"[bench] rank {rank}: per-step wall ms {[round(x, 1) for x in step_wall]}", file=sys.stderr)
     prof = ctx.profile_report()
     spmm_shapes = ctx.profile_shapes("spmm", 24)
+    dense_shapes = {cls: ctx.profile_shapes(cls, 8) for cls in ("gram", "update", "small_dense")}
     ctx.profile_enable(False)
     launches = ctx.launch_count() - l0
     parity = parity_record(ev, golden_spectrum(gkey, args.k), gkey)  # the LAST TIMED step's eigenvalues
@@ -550,6 +551,10 @@ def main():
                          "class_in_timed_region": {"launches": sp["launches"], "ms_per_step": sp["ms"] / args.steps, "avg_gb_per_s": class_rate,
                                                    "share_of_profiled_device_time": sp["ms"] / total_prof_ms if total_prof_ms else None}},
             "kernel_classes": classes,
+            "dense_shapes_in_timed_region": {
+                cls: [{"p": r["shape"][0], "q": r["shape"][1], "launches": r["launches"], "ms_per_step": r["ms"] / args.steps,
+                       "tflops": r["work"] / (r["ms"] * 1e-3) / 1e12 if r["ms"] else None} for r in rows]
+                for cls, rows in dense_shapes.items()},
             "configs": configs,
             "clocks": clk.summary(),
         }  # fmt: skip

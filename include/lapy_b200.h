@@ -127,7 +127,9 @@ int lb_mat_free(lb_mat *m);
 int lb_spmm(lb_ctx *ctx, lb_mat *mat, const double *x, int64_t m, double *y);
 
 /* device-resident timing of the SpMM kernel (x, y stay in HBM): ms per launch, CUDA events;
- * renumber != 0: on the locality-renumbered copy the solvers iterate with */
+ * renumber bit 0: in the locality numbering the solvers iterate in (how assembled matrices are
+ * stored) instead of the caller's; bit 1 (A/B aid): the plain gather kernel instead of the kernel
+ * that stages the strip's rows of X in shared memory */
 int lb_spmm_benchmark(lb_ctx *ctx, lb_mat *mat, int64_t m, int reps, int renumber,
                       double *ms_per_launch);
 
@@ -138,6 +140,12 @@ int lb_block_gram(lb_ctx *ctx, int64_t n, int64_t p, const double *x, int64_t q,
                   double *cmat);
 int lb_block_update(lb_ctx *ctx, int64_t n, int64_t p, const double *x, int64_t q,
                     const double *cmat, double alpha, double beta, double *y);
+
+/* device-resident timing of those kernels (operands stay in HBM): op 0 = Gram, 1 = update -> ms per
+ * launch; op 2 = register-only DMMA probe -> sustained fp64 tensor TFLOP/s (the roofline the dense
+ * products are quoted against).  variant 1 (A/B aid): the update with its 64-column tile for every q. */
+int lb_dense_benchmark(lb_ctx *ctx, int64_t n, int64_t p, int64_t q, int op, int variant, int reps,
+                       double *result);
 
 /* ---- solvers ------------------------------------------------------------------------------ */
 /* Solver.eigs (lapy/solver.py:667-716): k eigenpairs of A x = lambda B x nearest sigma (<= 0),
@@ -164,6 +172,12 @@ int lb_gradient(lb_ctx *ctx, lb_mesh *mesh, const double *f, int64_t nf, double 
 /* x (nt,nf,3) -> d (nv,nf): tria_compute_divergence lapy/diffgeo.py:303-387,
  * tet_compute_divergence :925-1006 */
 int lb_divergence(lb_ctx *ctx, lb_mesh *mesh, const double *x, int64_t nf, double *d);
+/* flux form of the same quantity on triangle meshes: tria_compute_divergence2 lapy/diffgeo.py:390-469 */
+int lb_divergence2(lb_ctx *ctx, lb_mesh *mesh, const double *x, int64_t nf, double *d);
+/* f (nv,nf) -> d (nv,nf) = divergence of the normalised gradient of f, all on the device: the
+ * right-hand side of compute_geodesic_f lapy/diffgeo.py:144-156 (gradient, g/|g| with nan_to_num,
+ * integrated divergence) */
+int lb_unit_gradient_divergence(lb_ctx *ctx, lb_mesh *mesh, const double *f, int64_t nf, double *d);
 /* mean length of the unique edges of the mesh `pattern` (a stiffness matrix) was assembled on:
  * TriaMesh.avg_edge_length lapy/tria_mesh.py:735-748, TetMesh lapy/tet_mesh.py:182-195 (fp64) */
 int lb_avg_edge_length(lb_ctx *ctx, lb_mesh *mesh, lb_mat *pattern, double *out);

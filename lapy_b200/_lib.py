@@ -69,11 +69,14 @@ SIGNATURES = {
     "lb_spmm_benchmark": [_vp, _vp, _i64, _int, _int, C.POINTER(_dbl)],
     "lb_block_gram": [_vp, _i64, _i64, _vp, _i64, _vp, _vp],
     "lb_block_update": [_vp, _i64, _i64, _vp, _i64, _vp, _dbl, _dbl, _vp],
+    "lb_dense_benchmark": [_vp, _i64, _i64, _i64, _int, _int, _int, C.POINTER(_dbl)],
     "lb_eigs": [_vp, _vp, _vp, _int, _dbl, _dbl, _int, _vp, _vp, C.POINTER(Info)],
     "lb_solve": [_vp, _vp, _dbl, _vp, _dbl, _vp, _i64, _vp, _i64, _vp, _dbl, _int, _int, _vp, C.POINTER(Info)],
     "lb_avg_edge_length": [_vp, _vp, _vp, C.POINTER(_dbl)],
     "lb_gradient": [_vp, _vp, _vp, _i64, _vp],
     "lb_divergence": [_vp, _vp, _vp, _i64, _vp],
+    "lb_divergence2": [_vp, _vp, _vp, _i64, _vp],
+    "lb_unit_gradient_divergence": [_vp, _vp, _vp, _i64, _vp],
 }
 STRING_GETTERS = ("lb_last_error", "lb_version")
 
@@ -166,8 +169,8 @@ class Context:
         self.world, self.rank = world, rank
 
     def init_row_partition_single(self):
-        """One-rank communicator (testing aid: exercises the row-partitioned code path on one GPU
-        together with LAPY_B200_FORCE_DIST=1)."""
+        """One-rank communicator (testing aid: a context with a communicator runs the row-partitioned
+        code path, here on one GPU)."""
         buf = np.zeros(128, np.uint8)
         check(lib().lb_nccl_unique_id(ptr(buf)))
         check(lib().lb_comm_init(self.handle, 1, 0, ptr(buf)))
@@ -263,6 +266,18 @@ class DeviceMesh:
 
     def drop_cache(self):
         check(lib().lb_mesh_drop_cache(self.handle))
+
+    def update_vertices(self, v: np.ndarray):
+        """New vertex positions on the same connectivity (lb_mesh_update_vertices): loop callers such
+        as the mean curvature flow re-assemble without re-uploading the elements."""
+        v = np.asarray(v)
+        if v.shape != (self.nv, 3):
+            raise ValueError("vertices must keep the shape (n, 3)")
+        if v.dtype != np.float32:
+            v = v.astype(np.float64, copy=False)
+        v = np.ascontiguousarray(v)
+        check(lib().lb_mesh_update_vertices(self.handle, ptr(v), F32 if v.dtype == np.float32 else F64))
+        self.v_dtype = v.dtype
 
     def close(self):
         if getattr(self, "handle", None):
@@ -393,11 +408,20 @@ def gradient(ctx: Context, mesh: DeviceMesh, f: np.ndarray) -> np.ndarray:
     return g
 
 
-def divergence(ctx: Context, mesh: DeviceMesh, x: np.ndarray) -> np.ndarray:
-    """x (nt, nf, 3) -> (nv, nf) (lb_divergence)."""
+def divergence(ctx: Context, mesh: DeviceMesh, x: np.ndarray, flux: bool = False) -> np.ndarray:
+    """x (nt, nf, 3) -> (nv, nf) (lb_divergence; flux=True: lb_divergence2, triangles only)."""
     x = np.ascontiguousarray(x, dtype=np.float64)
     d = np.empty((mesh.nv, x.shape[1]), np.float64)
-    check(lib().lb_divergence(ctx.handle, mesh.handle, ptr(x), x.shape[1], ptr(d)))
+    fn = lib().lb_divergence2 if flux else lib().lb_divergence
+    check(fn(ctx.handle, mesh.handle, ptr(x), x.shape[1], ptr(d)))
+    return d
+
+
+def unit_gradient_divergence(ctx: Context, mesh: DeviceMesh, f: np.ndarray) -> np.ndarray:
+    """f (nv, nf) -> div(grad f / |grad f|) (nv, nf) on the device (lb_unit_gradient_divergence)."""
+    f = np.ascontiguousarray(f, dtype=np.float64)
+    d = np.empty((mesh.nv, f.shape[1]), np.float64)
+    check(lib().lb_unit_gradient_divergence(ctx.handle, mesh.handle, ptr(f), f.shape[1], ptr(d)))
     return d
 
 
@@ -420,11 +444,20 @@ def block_update(ctx: Context, x: np.ndarray, cmat: np.ndarray, alpha=1.0, beta=
     return out
 
 
-def spmm_benchmark(ctx: Context, mat: DeviceMatrix, m: int = 1, reps: int = 20, renumber: bool = False) -> float:
-    """Device time (ms) of one y = M x launch with m columns, x / y resident in HBM."""
+def spmm_benchmark(ctx: Context, mat: DeviceMatrix, m: int = 1, reps: int = 20, renumber: int | bool = False) -> float:
+    """Device time (ms) of one y = M x launch with m columns, x / y resident in HBM.  renumber bit 0:
+    solver (locality) numbering instead of the caller's; bit 1: the plain gather kernel (A/B aid)."""
     ms = C.c_double()
     check(lib().lb_spmm_benchmark(ctx.handle, mat.handle, int(m), int(reps), int(renumber), C.byref(ms)))
     return ms.value
+
+
+def dense_benchmark(ctx: Context, n: int, p: int, q: int, op: int, variant: int = 0, reps: int = 10) -> float:
+    """ms per launch of the Gram (op 0) / update (op 1) kernel on resident operands; op 2: sustained
+    fp64 tensor TFLOP/s of a register-only DMMA probe (lb_dense_benchmark)."""
+    out = C.c_double()
+    check(lib().lb_dense_benchmark(ctx.handle, int(n), int(p), int(q), int(op), int(variant), int(reps), C.byref(out)))
+    return out.value
 
 
 def avg_edge_length(ctx: Context, mesh: DeviceMesh, pattern: DeviceMatrix) -> float:

@@ -20,6 +20,7 @@ struct SpmmEpilogue {
     double c1 = 0.0, c2 = 0.0;
     int overwrite = 0;  // mode 4: SOL = ... instead of SOL += ...
 };
+extern int g_spmm_variant;  // benchmark aid: 1 forces the plain gather kernel (lb_spmm_benchmark, renumber & 2)
 void spmm(lb_ctx *c, const lb_mat *a, const double *x, int ldx, double *y, int ldy, int m, int mode = 0,
           const double *b = nullptr, int ldb = 0, const SpmmEpilogue *epi = nullptr);
 
@@ -52,11 +53,14 @@ void gram(lb_ctx *c, int64_t n, int p, const double *x, int ldx, int q, const do
 void update(lb_ctx *c, int64_t n, int p, const double *x, int ldx, int q, const double *cmat, int ldc, double alpha,
             double beta, double *y, int ldy);
 
-// hand-written DMMA kernels (dmma.cu); gram()/update() dispatch to them unless LAPY_B200_DENSE=cublas
+// hand-written DMMA kernels (dmma.cu); gram()/update() always dispatch to them
 void gram_dmma(lb_ctx *c, int64_t n, int p, const double *x, int ldx, int q, const double *y, int ldy, double *cmat,
                bool symmetric);
 void update_dmma(lb_ctx *c, int64_t n, int p, const double *x, int ldx, int q, const double *cmat, int ldc,
                  double alpha, double beta, double *y, int ldy);
+
+// benchmark aid (lb_dense_benchmark): ms per launch of op 0 (Gram) / 1 (update), TFLOP/s for op 2 (DMMA peak probe)
+double dense_benchmark(lb_ctx *c, int64_t n, int p, int q, int op, int variant, int reps);
 
 // ---- small dense (device, cuSOLVER) ------------------------------------------------------------
 // in-place lower Cholesky of the row-major (q,q) SPD matrix g; returns LAPACK info (0 = ok)

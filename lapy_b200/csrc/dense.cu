@@ -89,30 +89,6 @@ int chol_lower(lb_ctx *c, int q, double *g) {
 int sym_eig(lb_ctx *c, int s, double *g, double *evals) {
     ProfScope prof(c, PROF_TRSM, 9.0 * s * s * s, s, 0);  // reported as class "small_dense" (syevd / coarse solves)
     int lwork = 0;
-    // opt-in A/B: cuSOLVER's Jacobi solver (LAPY_B200_EIG=syevj), usually quicker than the
-    // divide-and-conquer one below a few hundred rows; same output convention (ascending, vectors in g)
-    const char *eig = getenv("LAPY_B200_EIG");
-    if (eig && !strcmp(eig, "syevj")) {
-        syevjInfo_t params = nullptr;
-        LB_CUSOLVER(cusolverDnCreateSyevjInfo(&params));
-        cusolverDnXsyevjSetTolerance(params, 1e-15);
-        cusolverDnXsyevjSetMaxSweeps(params, 40);
-        cusolverDnXsyevjSetSortEig(params, 1);
-        cusolverStatus_t st = cusolverDnDsyevj_bufferSize(solver(c), CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_UPPER, s, g, s,
-                                                          evals, &lwork, params);
-        int h = -1;
-        if (st == CUSOLVER_STATUS_SUCCESS) {
-            DBuf<double> work(c, lwork);
-            DBuf<int> info(c, 1);
-            st = cusolverDnDsyevj(solver(c), CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_UPPER, s, g, s, evals, work.p, lwork,
-                                  info.p, params);
-            c->launches++;
-            if (st == CUSOLVER_STATUS_SUCCESS) read_back(c, &h, info.p, 1);
-        }
-        cusolverDnDestroySyevjInfo(params);
-        LB_REQUIRE(st == CUSOLVER_STATUS_SUCCESS, "cusolver syevj failed (%d)", (int)st);
-        return h;
-    }
     LB_CUSOLVER(cusolverDnDsyevd_bufferSize(solver(c), CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_UPPER, s, g, s, evals,
                                             &lwork));
     DBuf<double> work(c, lwork);

@@ -12,6 +12,7 @@
 // MMAs) so that the A operand of `update` is one 16-byte load per lane; a sum over k is
 // order-independent up to rounding and the order is fixed -> bit-reproducible.
 #include <cstdlib>
+#include <cstring>
 
 #include "blockvec.cuh"
 
@@ -124,32 +125,40 @@ __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;" ::"n"(N));
 }
 
+// Tile shapes: WCOLS x NJ 8-column blocks per CTA.  <2,4>: 128 rows x 64 columns (warps 4 x 2, the
+// wide products); <1,NJ>: 256 rows x 8*NJ columns (warps 8 x 1) for the narrow right-hand sides of
+// the late LOBPCG iterations (W -= [X P] G with 8..32 active columns): a 64-wide tile would spend
+// most of its DMMAs on padding (measured: q = 24 ran at 10 TFLOP/s, q = 64 at 25).
+// (Tried in round 2: several k-chunks per barrier - 2 changed nothing, 4 was 10 % slower.)
+template <int WCOLS, int NJ>
 __global__ void __launch_bounds__(256, 2)
     update_dmma_pipe_kernel(int64_t n, int p, const double *__restrict__ x, int ldx, int q,
                             const double *__restrict__ cmat, int ldc, double alpha, double beta, double *y, int ldy) {
+    constexpr int ROWS = WCOLS == 2 ? 128 : 256;
+    constexpr int COLS = WCOLS * NJ * 8;
     extern __shared__ __align__(16) double smem_pipe[];
-    double *xs = smem_pipe;                                 // [stages][128][8]
-    double *cs = smem_pipe + kUpdStages * 128 * 8;          // [stages][8][kUpdStride]
+    double *xs = smem_pipe;                                // [stages][ROWS][8]
+    double *cs = smem_pipe + kUpdStages * ROWS * 8;        // [stages][8][kUpdStride]
     const int p8 = (p + 7) & ~7, nchunk = p8 / 8;
-    const int col_tile = blockIdx.y * 64;
+    const int col_tile = blockIdx.y * COLS;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, t = lane & 3;
-    const int wr = (warp & 3) * 32, wc = (warp >> 2) * 32;
-    const int64_t ntiles = (n + 127) / 128;
+    const int wr = WCOLS == 2 ? (warp & 3) * 32 : warp * 32, wc = WCOLS == 2 ? (warp >> 2) * 32 : 0;
+    const int64_t ntiles = (n + ROWS - 1) / ROWS;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int64_t row_base = tile * 128;
+        const int64_t row_base = tile * ROWS;
         auto issue = [&](int chunk, int stage) {
             const int k8 = chunk * 8;
-            // X chunk: 128 rows x 64 B = 512 pieces of 16 B, two per thread
+            // X chunk: ROWS rows x 64 B = 4 * ROWS pieces of 16 B
 #pragma unroll
-            for (int it = 0; it < 2; it++) {
+            for (int it = 0; it < ROWS / 64; it++) {
                 const int piece = threadIdx.x + it * 256;
                 const int r = piece >> 2, part = piece & 3;
                 const int64_t row = row_base + r;
                 const int k = k8 + 2 * part;
                 const bool ok = row < n && k < p;
                 const double *src = x + (ok ? row : 0) * ldx + (ok ? k : 0);
-                double *dst = xs + ((size_t)stage * 128 + r) * 8 + 2 * part;
+                double *dst = xs + ((size_t)stage * ROWS + r) * 8 + 2 * part;
                 if (ok && k + 1 >= p) {  // last odd column: plain stores of the single valid value
                     dst[0] = __ldg(src);
                     dst[1] = 0.0;
@@ -157,9 +166,9 @@ __global__ void __launch_bounds__(256, 2)
                     cp_async16(dst, src, ok);
                 }
             }
-            // C chunk: 8 rows x 64 cols = 256 pieces of 16 B, one per thread
-            {
-                const int r = threadIdx.x >> 5, part = threadIdx.x & 31;
+            // C chunk: 8 rows x COLS columns = 4 * COLS pieces of 16 B
+            if (threadIdx.x < 4 * COLS) {
+                const int r = threadIdx.x / (COLS / 2), part = threadIdx.x % (COLS / 2);
                 const int k = k8 + r, col = col_tile + 2 * part;
                 const bool ok = k < p && col + 1 < q;
                 const double *src = cmat + (int64_t)(k < p ? k : 0) * ldc + (col + 1 < q ? col : 0);
@@ -172,11 +181,11 @@ __global__ void __launch_bounds__(256, 2)
                 }
             }
         };
-        double acc[4][4][2];
+        double acc[4][NJ][2];
 #pragma unroll
         for (int i = 0; i < 4; i++)
 #pragma unroll
-            for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+            for (int j = 0; j < NJ; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
         __syncthreads();  // the previous tile's readers are done with the ring
 #pragma unroll
         for (int s0 = 0; s0 < kUpdStages - 1; s0++) {
@@ -190,9 +199,9 @@ __global__ void __launch_bounds__(256, 2)
             if (nx < nchunk) issue(nx, nx % kUpdStages);
             cp_async_commit();
             const int stage = ch % kUpdStages;
-            const double *xst = xs + (size_t)stage * 128 * 8;
+            const double *xst = xs + (size_t)stage * ROWS * 8;
             const double *cst = cs + (size_t)stage * 8 * kUpdStride;
-            double a0[4], a1[4], b0[4], b1[4];
+            double a0[4], a1[4], b0[NJ], b1[NJ];
 #pragma unroll
             for (int i = 0; i < 4; i++) {
                 const double2 v = *reinterpret_cast<const double2 *>(xst + (wr + 8 * i + g) * 8 + 2 * t);
@@ -200,14 +209,14 @@ __global__ void __launch_bounds__(256, 2)
                 a1[i] = v.y;
             }
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
+            for (int j = 0; j < NJ; j++) {
                 b0[j] = cst[(2 * t) * kUpdStride + wc + 8 * j + g];
                 b1[j] = cst[(2 * t + 1) * kUpdStride + wc + 8 * j + g];
             }
 #pragma unroll
             for (int i = 0; i < 4; i++)
 #pragma unroll
-                for (int j = 0; j < 4; j++) {
+                for (int j = 0; j < NJ; j++) {
                     dmma884(acc[i][j][0], acc[i][j][1], a0[i], b0[j]);
                     dmma884(acc[i][j][0], acc[i][j][1], a1[i], b1[j]);
                 }
@@ -218,7 +227,7 @@ __global__ void __launch_bounds__(256, 2)
             const int64_t r = row_base + wr + 8 * i + g;
             if (r >= n) continue;
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
+            for (int j = 0; j < NJ; j++) {
                 const int col = col_tile + wc + 8 * j + 2 * t;
                 double *yp = y + r * ldy + col;
                 if (col < q) yp[0] = beta == 0.0 ? alpha * acc[i][j][0] : alpha * acc[i][j][0] + beta * yp[0];
@@ -228,24 +237,63 @@ __global__ void __launch_bounds__(256, 2)
     }
 }
 
+// peak probe: DMMAs on register operands only (no memory): what the fp64 tensor pipe sustains
+__global__ void __launch_bounds__(256) dmma_peak_kernel(int iters, double *out) {
+    double acc[4][4][2];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+    double a[4], b[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        a[i] = 1.0 + 1e-9 * (threadIdx.x + i);
+        b[i] = 1.0 - 1e-9 * (threadIdx.x + i);
+    }
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+                dmma884(acc[i][j][0], acc[i][j][1], b[i], a[j]);
+            }
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) s += acc[i][j][0] + acc[i][j][1];
+    if (s == 12345.678) out[0] = s;  // keeps the loop alive
+}
+
+// benchmark aid (lb_dense_benchmark): 1 forces the 64-column tile for every q
+static int g_update_wide_only = 0;
+
 void update_dmma(lb_ctx *c, int64_t n, int p, const double *x, int ldx, int q, const double *cmat, int ldc,
                  double alpha, double beta, double *y, int ldy) {
-    static int use_pipe = -1;
-    if (use_pipe < 0) {
-        const char *e = getenv("LAPY_B200_UPDATE");
-        use_pipe = (e && !strcmp(e, "direct")) ? 0 : 1;
-    }
     const bool aligned = (ldx % 2 == 0) && (ldc % 2 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) &&
                          ((reinterpret_cast<uintptr_t>(cmat) & 15) == 0);
-    if (use_pipe && aligned) {
-        const size_t smem = (size_t)kUpdStages * (128 * 8 + 8 * kUpdStride) * sizeof(double);
-        // per device (a process may drive several contexts): set every time, it is a cheap host call
-        LB_CUDA(cudaFuncSetAttribute(update_dmma_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        const int ytiles = cdiv(q, 64);
-        const int64_t ntiles = (n + 127) / 128;
+    if (aligned) {
+        // column tile: 64 for wide right-hand sides, 32 / 16 / 8 (256-row tiles) for narrow ones
+        const int cols = (q > 32 || g_update_wide_only) ? 64 : q > 16 ? 32 : q > 8 ? 16 : 8;
+        const int rows = cols == 64 ? 128 : 256;
+        const size_t smem = (size_t)kUpdStages * (rows * 8 + 8 * kUpdStride) * sizeof(double);
+        const int ytiles = cdiv(q, cols);
+        const int64_t ntiles = (n + rows - 1) / rows;
         const int gx = (int)std::min<int64_t>(ntiles, std::max(1, (kSMs * 2) / ytiles));
         dim3 grid(gx, ytiles);
-        LB_LAUNCH(c, update_dmma_pipe_kernel, grid, 256, smem, n, p, x, ldx, q, cmat, ldc, alpha, beta, y, ldy);
+        // per device (a process may drive several contexts): set every time, it is a cheap host call
+#define LB_UPD(WC, NJ)                                                                                                     \
+    do {                                                                                                                   \
+        LB_CUDA(cudaFuncSetAttribute(update_dmma_pipe_kernel<WC, NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        LB_LAUNCH(c, (update_dmma_pipe_kernel<WC, NJ>), grid, 256, smem, n, p, x, ldx, q, cmat, ldc, alpha, beta, y, ldy);      \
+    } while (0)
+        if (cols == 64) LB_UPD(2, 4);
+        else if (cols == 32) LB_UPD(1, 4);
+        else if (cols == 16) LB_UPD(1, 2);
+        else LB_UPD(1, 1);
+#undef LB_UPD
         return;
     }
     const int p8 = (p + 7) & ~7;
@@ -351,6 +399,44 @@ void gram_dmma(lb_ctx *c, int64_t n, int p, const double *x, int ldx, int q, con
               partial.p, ntile);
     LB_LAUNCH(c, gram_reduce_kernel, cdiv(p * q, 256), 256, 0, p, q, qtiles, ntile, nsplit, (int)symmetric, partial.p,
               cmat);
+}
+
+// device-resident timing of the dense block products (x, y, c resident): op 0 = Gram X^T Y (p x q),
+// 1 = update Y = X C, 2 = register-only DMMA peak probe (returns TFLOP/s); variant 1: the update with
+// the 64-column tile for every q (A/B aid for the narrow tiles)
+double dense_benchmark(lb_ctx *c, int64_t n, int p, int q, int op, int variant, int reps) {
+    float ms = 0;
+    if (op == 2) {
+        DBuf<double> out(c, 1);
+        const int iters = 4096;
+        LB_LAUNCH(c, dmma_peak_kernel, kSMs * 4, 256, 0, 16, out.p);
+        LB_CUDA(cudaEventRecord(c->ev0, c->stream));
+        for (int i = 0; i < reps; i++) LB_LAUNCH(c, dmma_peak_kernel, kSMs * 4, 256, 0, iters, out.p);
+        LB_CUDA(cudaEventRecord(c->ev1, c->stream));
+        LB_CUDA(cudaEventSynchronize(c->ev1));
+        LB_CUDA(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+        // flops per launch: blocks * warps * iters * 32 DMMA * (8*8*4*2)
+        const double flops = (double)kSMs * 4 * 8 * iters * 32.0 * 512.0;
+        return flops / (ms / reps * 1e-3) / 1e12;
+    }
+    DBuf<double> x(c, (size_t)n * p), y(c, (size_t)n * q), cm(c, (size_t)p * q);
+    fill_random(c, n, p, x.p, p, 7);
+    fill_random(c, n, q, y.p, q, 8);
+    fill_random(c, p, q, cm.p, q, 9);
+    const int saved = g_update_wide_only;
+    if (variant == 1) g_update_wide_only = 1;
+    auto run = [&]() {
+        if (op == 0) gram_dmma(c, n, p, x.p, p, q, y.p, q, cm.p, false);
+        else update_dmma(c, n, p, x.p, p, q, cm.p, q, 1.0, 0.0, y.p, q);
+    };
+    for (int i = 0; i < 2; i++) run();
+    LB_CUDA(cudaEventRecord(c->ev0, c->stream));
+    for (int i = 0; i < reps; i++) run();
+    LB_CUDA(cudaEventRecord(c->ev1, c->stream));
+    LB_CUDA(cudaEventSynchronize(c->ev1));
+    LB_CUDA(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    g_update_wide_only = saved;
+    return ms / reps;
 }
 
 }  // namespace lb

@@ -567,9 +567,7 @@ static EigStats lobpcg_core(lb_ctx *c, const lb_mat *A, const lb_mat *B, Amg *am
     double worst = 0.0;
     int nconv_k = 0;
     PhaseTimer pt(c);
-    int vcycles = 1, ortho_passes = 2;
-    if (const char *e = getenv("LAPY_B200_VCYCLES")) vcycles = std::max(1, atoi(e));
-    if (const char *e = getenv("LAPY_B200_ORTHO")) ortho_passes = std::max(1, atoi(e));
+    constexpr int ortho_passes = 2;  // block Gram-Schmidt against [X P]: "twice is enough" (one pass diverged, see below)
     for (int it = 0; it < maxit; it++) {
         st.iterations = it;
         pt.start();
@@ -598,6 +596,16 @@ static EigStats lobpcg_core(lb_ctx *c, const lb_mat *A, const lb_mat *B, Amg *am
             }
             if (!conv) idx[ma++] = j;
         }
+        // keep the active block even-sized: rows of the (n, ma) work blocks stay 16-byte aligned (bulk
+        // copies / 16-byte loads of the SpMM); the extra column is a converged one, harmless to refine
+        if ((ma & 1) && ma < m)
+            for (int j = 0; j < m; j++)
+                if (!act[j]) {
+                    act[j] = 1;
+                    idx[ma++] = j;
+                    std::sort(idx.begin(), idx.begin() + ma);
+                    break;
+                }
         if (c->trace)
             fprintf(stderr, "[lb trace] lobpcg it %3d: max res(first k) %.3e, converged %d/%d, active %d, P %d\n", it,
                     worst, nconv_k, k, ma, mp);
@@ -612,13 +620,6 @@ static EigStats lobpcg_core(lb_ctx *c, const lb_mat *A, const lb_mat *B, Amg *am
         double *W = S[cur].p + w0, *AW = AS[cur].p + w0, *BW = BS[cur].p + w0;
         if (D && D->full_amg) dist_precond(c, D, Rbuf.p, ma, W, ld, ma);
         else amg_apply(*amg, Rbuf.p, ma, W, ld, ma, lvl);
-        for (int vc = 1; vc < vcycles && !(D && D->full_amg); vc++) {
-            // second cycle on the residual of the first: W += V(R - K W)
-            spmm(c, amg->levels[lvl].K.get(), W, ld, tmp.p, ma, ma, 1, Rbuf.p, ma);
-            amg_apply(*amg, tmp.p, ma, Rbuf.p, ma, ma, lvl);  // Rbuf is free to overwrite only after use below
-            axpby_cols(c, n, ma, nullptr, 1.0, Rbuf.p, ma, nullptr, 1.0, W, ld);
-            residual_cols(c, n, ma, idx_d.p, lam_d.p, AS[cur].p, ld, BS[cur].p, ld, Rbuf.p, ma);
-        }
         pt.stop(1);
         // block Gram-Schmidt against [X P], twice ("twice is enough").  A single pass was measured to
         // lose orthogonality near convergence: the row-partitioned run (weaker block-Jacobi
@@ -675,8 +676,6 @@ static EigStats lobpcg(lb_ctx *c, const lb_mat *A0, const lb_mat *B0, int k, dou
     // preconditioner on K = A - sigma*B (SPD for sigma < 0)
     const double shift = sigma < 0 ? -sigma : 1e-2;
     AmgOptions opt;
-    if (const char *e = getenv("LAPY_B200_CHEB")) opt.cheb_deg = std::max(1, atoi(e));
-    if (const char *e = getenv("LAPY_B200_GAMMA")) opt.gamma = std::max(1, atoi(e));
     phase(c, "eigs: renumber A, B");
     auto amg = amg_setup(c, mat_axpby(c, A, 1.0, B, shift), m, opt);
     phase(c, "eigs: AMG setup");
@@ -685,9 +684,8 @@ static EigStats lobpcg(lb_ctx *c, const lb_mat *A0, const lb_mat *B0, int k, dou
     // K_l = A_l + shift*B_l has the eigenvectors of (A_l, B_l); only the vectors are carried up.
     const int nlev = (int)amg->levels.size();
     int depth = 0;  // number of coarse levels that get their own eigensolve
-    if (!getenv("LAPY_B200_NONESTED"))
-        // pays off only when the fine level dwarfs the per-iteration fixed cost (syevd, launches)
-        while (n >= 1000000 && depth + 1 < nlev - 1 && amg->levels[depth + 1].K->n >= std::max<int64_t>(8 * m, 4000)) depth++;
+    // pays off only when the fine level dwarfs the per-iteration fixed cost (syevd, launches)
+    while (n >= 1000000 && depth + 1 < nlev - 1 && amg->levels[depth + 1].K->n >= std::max<int64_t>(8 * m, 4000)) depth++;
     std::vector<std::unique_ptr<lb_mat>> Bl(depth + 1);
     for (int l = 0; l < depth; l++) {
         const lb_mat *bl = l == 0 ? B : Bl[l].get();
@@ -954,7 +952,7 @@ extern "C" int lb_eigs(lb_ctx *c, lb_mat *a, lb_mat *b, int k, double sigma, dou
         if (b->permuted) pb = to_caller_order(c, b);
         dense_eigs(c, pa ? pa.get() : a, pb ? pb.get() : b, k, evals, evecs);
         st.converged = k;
-    } else if (c->dist && (c->dist->world > 1 || getenv("LAPY_B200_FORCE_DIST"))) {
+    } else if (c->dist) {  // a communicator was attached (lb_comm_init): row-partitioned over its ranks
         st = lobpcg_dist(c, c->dist, a, b, k, sigma, tol, maxit, evals, evecs);
     } else {
         st = lobpcg(c, a, b, k, sigma, tol, maxit, evals, evecs);

@@ -526,6 +526,12 @@ int lb_spmm_benchmark(lb_ctx *c, lb_mat *mat0, int64_t m, int reps, int renumber
     // numbering buys)
     std::unique_ptr<lb_mat> perm;
     lb_mat *mat = mat0;
+    struct VariantGuard {
+        int saved;
+        ~VariantGuard() { g_spmm_variant = saved; }
+    } vg{g_spmm_variant};
+    if (renumber & 2) g_spmm_variant = 1;  // A/B aid: the plain gather kernel instead of the staged one
+    renumber &= 1;
     if (!renumber && mat0->permuted) {
         perm = to_caller_order(c, mat0);
         mat = perm.get();
@@ -540,6 +546,15 @@ int lb_spmm_benchmark(lb_ctx *c, lb_mat *mat0, int64_t m, int reps, int renumber
     float ms = 0;
     LB_CUDA(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
     *ms_per_launch = ms / reps;
+    LB_API_END
+}
+
+int lb_dense_benchmark(lb_ctx *c, int64_t n, int64_t p, int64_t q, int op, int variant, int reps, double *result) {
+    LB_API_BEGIN
+    LB_REQUIRE(c && result && n > 0 && p > 0 && q > 0 && p <= 384 && q <= 4096 && reps >= 1 && op >= 0 && op <= 2,
+               "lb_dense_benchmark: bad argument");
+    DeviceGuard g(c->device);
+    *result = dense_benchmark(c, n, (int)p, (int)q, op, variant, reps);
     LB_API_END
 }
 
@@ -644,8 +659,22 @@ int lb_solve(lb_ctx *c, lb_mat *a, double alpha, lb_mat *b, double beta, const d
         project = rs <= 1e-5 * dg;
         if (c->trace) fprintf(stderr, "[lb trace] solve: max |K 1| = %.3e, max diag = %.3e -> project = %d\n", rs, dg, (int)project);
     }
-    // mass-dominated operators (backward Euler heat step: diagonal B, beta != 0): componentwise Jacobi
-    const bool try_jacobi = beta != 0.0 && b != nullptr && b->diagonal && nfix == 0;
+    // mass-dominated operators (backward Euler heat step: diagonal B, beta != 0): componentwise Jacobi.
+    // Its contraction factor is ~ 1 - (mass share of the diagonal): the heat step t = m h^2 has a share
+    // of 0.2 (m = 1) ... 0.015 (m = 16), a mean-curvature-flow step (lapy/diffgeo.py:590) 1e-7 - there
+    // Jacobi would need millions of sweeps and the AMG-preconditioned CG below is used.
+    bool try_jacobi = beta != 0.0 && b != nullptr && b->diagonal && nfix == 0;
+    if (try_jacobi) {
+        DBuf<double> dk(c, n), db(c, n), sums(c, 2);
+        extract_diagonal(c, K.get(), dk.p);
+        extract_diagonal(c, vb.m, db.p);
+        col_dots(c, n, 1, dk.p, 1, nullptr, 0, sums.p);
+        col_dots(c, n, 1, db.p, 1, nullptr, 0, sums.p + 1);
+        double hs[2];
+        read_back(c, hs, sums.p, 2);
+        try_jacobi = std::fabs(beta) * hs[1] >= 1e-3 * hs[0];
+        if (c->trace) fprintf(stderr, "[lb trace] solve: mass share of the diagonal %.3e -> %s\n", std::fabs(beta) * hs[1] / hs[0], try_jacobi ? "componentwise Jacobi" : "AMG-PCG");
+    }
     SolveStats st = block_pcg(c, K.get(), d_rhs.p, d_sol.p, mm, tol, maxit, project, 0, try_jacobi);
     if (nfix > 0) LB_LAUNCH(c, set_fixed_rows, cdiv(n * mm, 256), 256, 0, n, mm, is_fixed.p, dval.p, d_sol.p);
     if (ord) gather_rows(c, n, mm, ord->inv.p, d_sol.p, mm, d_x.p, mm);

@@ -56,10 +56,10 @@ def diffusion(geometry, vids, m: float = 1.0, aniso=None, use_cholmod: bool = Fa
         if np.any(v < 0) or np.any(v >= nv):
             raise ValueError("vids contains out-of-range vertex indices")
     fem = Solver(geometry, lump=True, aniso=aniso)
-    if np.asarray(geometry.v).dtype == np.float64 and nv >= 100000:
-        # device kernel over the stiffness pattern (same edge set as triu(adj_sym, 1)); the host
-        # version costs seconds at millions of vertices.  float32 meshes keep the geometry's own
-        # (float32) arithmetic so that t is bit-identical to the reference's.
+    if np.asarray(geometry.v).dtype == np.float64:
+        # device kernel over the stiffness pattern (same edge set as triu(adj_sym, 1), lapy/tria_mesh.py:735-748,
+        # lapy/tet_mesh.py:182-195); the host version costs seconds at millions of vertices.  float32 meshes
+        # keep the geometry's own (float32, pairwise-summed) arithmetic so that t is bit-identical to the reference's.
         t = m * _lib.avg_edge_length(fem._ctx, fem._mesh, fem._device("a")) ** 2
     else:
         t = m * geometry.avg_edge_length() ** 2

@@ -6,8 +6,6 @@ the kernel's summation order (oracle.sparse_build.coo_to_csc_sequential), and wi
 1e-12 * (sum of |addends|) of SciPy's own result (equal entries where SciPy's order coincides).
 """
 
-import os
-
 import numpy as np
 import pytest
 from conftest import golden_csc, golden_mesh
@@ -194,66 +192,62 @@ def _tet_fan():
     return M.TetMesh(v, t)
 
 
-@pytest.mark.parametrize("mode", ["fused"])
-def test_tet_row_kernel_variants_match_default(monkeypatch, mode):
-    """LAPY_B200_TET_ROWS selects an alternative implementation of the tet row kernels: it must
-    reproduce the default kernels (and therefore the sequential model) bit for bit, including
-    flagged oversized rows, float32 meshes and the lumped mass."""
+def test_tet_fan_and_float32_rows_vs_oracle():
+    """Tet rows: the fused kernels handle <= 32 incidences / <= 16 entries per row, everything else is
+    flagged and done by the per-thread kernels: a vertex with 320 incident tets (162 neighbours), a
+    float32 cube and the lumped mass must all reproduce the sequential model bit for bit."""
     import lapy_b200
     from lapy_b200 import mesh as M
 
-    cube = M.cube_tets(13)
-    cube32 = M.TetMesh(cube.v.astype(np.float32), cube.t)
-    for mesh in (cube, cube32, _tet_fan()):
-        for lump in (False, True):
-            monkeypatch.delenv("LAPY_B200_TET_ROWS", raising=False)
-            ref = lapy_b200.Solver(mesh, lump=lump)
-            ra, rb = ref.stiffness, ref.mass
-            monkeypatch.setenv("LAPY_B200_TET_ROWS", mode)
-            alt = lapy_b200.Solver(mesh, lump=lump)
-            for x, y in ((alt.stiffness, ra), (alt.mass, rb)):
-                np.testing.assert_array_equal(x.indptr, y.indptr)
-                np.testing.assert_array_equal(x.indices, y.indices)
-                np.testing.assert_array_equal(x.data, y.data)
-    monkeypatch.delenv("LAPY_B200_TET_ROWS", raising=False)
     fan = _tet_fan()
     ta, tb, tl = _triplets(fan.v, fan.t, "tet")
     a_ref, b_ref = ofem.fem(fan)
     fem = lapy_b200.Solver(fan)
     _check(fem.stiffness, ta, a_ref, "fan A")
     _check(fem.mass, tb, b_ref, "fan B")
+    _check(lapy_b200.Solver(fan, lump=True).mass, tl, None, "fan Blump")
+    cube = M.cube_tets(13)
+    cube32 = M.TetMesh(cube.v.astype(np.float32), cube.t)
+    ta, tb, tl = _triplets(cube32.v, cube32.t, "tet")
+    a_ref, b_ref = ofem.fem(cube32)
+    fem = lapy_b200.Solver(cube32)
+    _check(fem.stiffness, ta, a_ref, "cube32 A")
+    _check(fem.mass, tb, b_ref, "cube32 B")
 
 
-def test_tria_row_kernel_variant_matches_default(monkeypatch):
-    """LAPY_B200_TRIA_ROWS=fused (written after round 1's GPU budget was spent): must reproduce the
-    default kernels bit for bit - closed and open meshes, float32, lumped mass, a 3000-triangle fan."""
+def test_triangle_fast_path_fallbacks_vs_oracle():
+    """Triangle rows: the register fast path handles <= 8 incident triangles; rows with more, a
+    non-manifold edge (three triangles on one edge: three addends, order matters) or a vertex repeated
+    inside a triangle go through the flagged path.  Open mesh, float32, lumped mass as well."""
     import lapy_b200
     from lapy_b200 import mesh as M
     from lapy_b200.mesh import TriaMesh
 
-    if not os.environ.get("LAPY_B200_TEST_EXPERIMENTAL"):
-        pytest.skip("opt-in kernel variant not yet validated on a GPU: set LAPY_B200_TEST_EXPERIMENTAL=1")
     ico = M.icosphere(4)
-    ico32 = TriaMesh(ico.v.astype(np.float32), ico.t)
     gx, gy = np.meshgrid(np.arange(40), np.arange(30), indexing="ij")
     gid = (gx * 30 + gy)[:-1, :-1].reshape(-1)
     square = TriaMesh(np.column_stack([gx.reshape(-1) * 0.1, gy.reshape(-1) * 0.13, np.zeros(gx.size)]),
                       np.vstack([np.column_stack([gid, gid + 30, gid + 31]), np.column_stack([gid, gid + 31, gid + 1])]))  # fmt: skip
-    n = 3000
+    # valence-12 vertices: a 12-triangle fan glued into a strip
+    n = 12
     ang = np.linspace(0, 2 * np.pi, n, endpoint=False)
-    fan = TriaMesh(np.vstack([[0, 0, 0.3], np.column_stack([np.cos(ang), np.sin(ang), np.zeros(n)])]),
-                   np.column_stack([np.zeros(n, int), 1 + np.arange(n), 1 + (np.arange(n) + 1) % n]))  # fmt: skip
-    for mesh in (ico, ico32, square, fan):
-        for lump in (False, True):
-            monkeypatch.delenv("LAPY_B200_TRIA_ROWS", raising=False)
-            ref = lapy_b200.Solver(mesh, lump=lump)
-            ra, rb = ref.stiffness, ref.mass
-            monkeypatch.setenv("LAPY_B200_TRIA_ROWS", "fused")
-            alt = lapy_b200.Solver(mesh, lump=lump)
-            for x, y in ((alt.stiffness, ra), (alt.mass, rb)):
-                np.testing.assert_array_equal(x.indptr, y.indptr)
-                np.testing.assert_array_equal(x.indices, y.indices)
-                np.testing.assert_array_equal(x.data, y.data)
+    fan12 = TriaMesh(np.vstack([[0, 0, 0.3], np.column_stack([np.cos(ang), np.sin(ang), np.zeros(n)])]),
+                     np.column_stack([np.zeros(n, int), 1 + np.arange(n), 1 + (np.arange(n) + 1) % n]))  # fmt: skip
+    # three triangles sharing the edge (0, 1) + one triangle with a repeated vertex
+    book = TriaMesh(np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [0, -1, 0.5], [0.3, 0.2, 1.0], [2, 2, 2]], float),
+                    np.array([[0, 1, 2], [1, 0, 3], [0, 1, 4], [2, 2, 5], [4, 1, 5]]))
+    for name, mesh in (("ico4", ico), ("ico4_f32", TriaMesh(ico.v.astype(np.float32), ico.t)), ("square", square),
+                       ("fan12", fan12), ("book", book)):  # fmt: skip
+        ta, tb, tl = _triplets(mesh.v, mesh.t, "tria")
+        a_ref, b_ref = ofem.fem(mesh)
+        fem = lapy_b200.Solver(mesh)
+        _check(fem.stiffness, ta, a_ref, name + " A")
+        _check(fem.mass, tb, b_ref, name + " B")
+        _, bl_ref = ofem.fem(mesh, lump=True)
+        _check(lapy_b200.Solver(mesh, lump=True).mass, tl, bl_ref, name + " Blump")
+        _, tbm, tlm = _triplets(mesh.v, mesh.t, "mass")
+        _check(lapy_b200.Solver.fem_tria_mass(mesh), tbm, None, name + " M")
+        _check(lapy_b200.Solver.fem_tria_mass(mesh, lump=True), tlm, None, name + " Mlump")
 
 
 def test_high_valence_fan():

@@ -79,8 +79,8 @@ def test_shapedna_post_processing_matches_the_reference():
         shapedna.compute_distance(ev, ev, dist="other")
     with pytest.raises(ValueError, match="Unknown normalization"):
         shapedna.normalize_ev(ico, ev, method="nope")
-    with pytest.raises(NotImplementedError):  # the minimal meshes carry no adjacency: volume needs a lapy mesh
-        shapedna.normalize_ev(ico, ev, method="volume")
+    # enclosed volume of the closed, oriented surface (lapy/shapedna.py:50-93, lapy/tria_mesh.py:671-702)
+    np.testing.assert_allclose(shapedna.normalize_ev(ico, ev, method="volume"), ev * ico.volume() ** (2.0 / 3.0), rtol=1e-15)
     tet = TetMesh(np.eye(4, 3), np.array([[0, 1, 2, 3]]))
     with pytest.raises(NotImplementedError):
         shapedna.normalize_ev(tet, ev)

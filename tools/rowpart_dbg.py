@@ -3,7 +3,7 @@
 Variants by environment: LAPY_B200_HALO=1 (boundary-only halo exchange), LAPY_B200_DIST_AMG=full (replicated
 hierarchy applied column-parallel + nested start)."""
 import os, sys, time, faulthandler
-faulthandler.dump_traceback_later(100, exit=True)
+faulthandler.dump_traceback_later(240, exit=True)
 os.environ.setdefault("LAPY_B200_TRACE", "1")
 os.environ.setdefault("NCCL_DEBUG", "WARN")
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -19,8 +19,9 @@ from lapy_b200 import _lib, mesh as M
 ctx = _lib.Context(local)
 ctx.init_row_partition()
 log("comm up")
-lvl = int(sys.argv[1]) if len(sys.argv) > 1 else 6
-mesh = M.icosphere(lvl)
+what = sys.argv[1] if len(sys.argv) > 1 else "6"
+lvl = int(what) if what.isdigit() else -1
+mesh = M.icosphere(lvl) if lvl >= 0 else M.cube_tets(int(what[4:]))
 fem = lapy_b200.Solver(mesh, ctx=ctx)
 log("assembled")
 errs = np.zeros(2)
@@ -32,6 +33,12 @@ try:
 except Exception as e:
     log('eigs failed', e); ev = np.zeros(50)
 log("eigs done", time.perf_counter() - t0, fem.last_info, ev[:4])
+t0 = time.perf_counter()
+try:
+    ev, evec = fem.eigs(k=50)
+    log("second eigs", time.perf_counter() - t0, fem.last_info, "lam1/pi^2", ev[1] / np.pi**2)
+except Exception as e:
+    log('second eigs failed', e)
 
 g = np.load(os.path.join(os.path.dirname(__file__), "..", "tests", "golden", "spectra.npz"))
 key = f"ico{lvl}_k50"

@@ -26,12 +26,14 @@ for name, msh, kind in (("ico%d" % level, M.icosphere(level), 0), ("cube%d" % cu
     a, b = _lib.assemble(ctx, dm, kind, False)
     for m in (1, 2, 4, 8, 12, 16, 20, 24, 32, 40, 48, 56, 64, 96, 128):
         nbytes = 12.0 * a.nnz + 4.0 * (a.n + 1) + 16.0 * a.n * m
-        for ren in (True, False):
-            if not ren and m not in (1, 16, 64):
+        for ren, label in ((1, "solver-order"), (3, "solver-order plain-gather-kernel"), (0, "caller-order")):
+            if ren == 0 and m not in (1, 16, 64):
+                continue
+            if ren == 3 and m < 8:
                 continue
             ms = _lib.spmm_benchmark(ctx, a, m, 20, renumber=ren)
-            out[f"{name} m={m} {'solver' if ren else 'caller'}-order"] = {"ms": ms, "gb_s": nbytes / ms / 1e6, "frac": nbytes / ms / 1e6 / PEAK}
-            print(name, m, "solver" if ren else "caller", f"{ms:.4f} ms  {nbytes / ms / 1e6:.0f} GB/s  {nbytes / ms / 1e6 / PEAK:.3f}", flush=True)
+            out[f"{name} m={m} {label}"] = {"ms": ms, "gb_s": nbytes / ms / 1e6, "frac": nbytes / ms / 1e6 / PEAK}
+            print(name, m, label, f"{ms:.4f} ms  {nbytes / ms / 1e6:.0f} GB/s  {nbytes / ms / 1e6 / PEAK:.3f}", flush=True)
     del a, b, dm
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump(out, open("gpurun_out/spmm_shapes.json", "w"), indent=1)
