@@ -27,6 +27,7 @@ level that fits a few minutes (level 8), one mesh per rank's worth of host proce
 from __future__ import annotations
 
 import argparse
+import faulthandler
 import json
 import os
 import sys
@@ -37,6 +38,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+faulthandler.enable()  # a crash inside the native library prints the Python stack on stderr
 
 PEAK_FALLBACK_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
 METRIC = "shapedna_k50_meshes_per_s"
@@ -349,6 +351,40 @@ def batch_record(world, workers=4, per_rank=12):
             "note": "BASELINE.json configs[4] unit (512 surfaces) scaled to %d per GPU; wall clock incl. H2D / D2H" % per_rank}  # fmt: skip
 
 
+def rowpart_record(local_rank, world, n_cube=121, k=50):
+    """N>1: ONE mesh (BASELINE.json configs[2]: the 121^3 tet cube, 1,771,561 v / 10,368,000 tets) solved
+    cooperatively by all ranks: contiguous row blocks of the locality-numbered operator per rank, NCCL
+    halo exchange in every SpMM, all-reduced Gram matrices, hierarchy applied column-parallel.  Seconds
+    are the max over ranks of the wall time of the second call (the first pays NCCL / cuSOLVER set-up)."""
+    import torch
+    import torch.distributed as dist
+
+    import lapy_b200
+    from lapy_b200 import _lib
+    from lapy_b200 import mesh as M
+
+    ctx = _lib.Context(local_rank)
+    ctx.init_row_partition()
+    mesh = M.cube_tets(n_cube)
+    mesh.v.flags.writeable = False
+    mesh.t.flags.writeable = False
+    fem = lapy_b200.Solver(mesh, ctx=ctx)
+    fem.eigs(k=k)
+    dist.barrier()
+    t0 = time.perf_counter()
+    ev, evec = fem.eigs(k=k)
+    dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+    dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    info = dict(fem.last_info)
+    ctx.leave_row_partition()
+    n = mesh.v.shape[0]
+    return {"workload": f"{n_cube}^3 tet cube, {n:,} v / {mesh.t.shape[0]:,} tets, eigs(k={k}) row-partitioned over {world} GPUs",
+            "seconds": float(dt.item()), "lobpcg_device_ms": info["solve_ms"], "iterations": info["iterations"],
+            "residual": info["residual"], "lam1_over_pi2": float(ev[1] / np.pi**2), "lam0": float(ev[0]),
+            "rows_per_rank": (n + world - 1) // world,
+            "note": "every rank receives the full (n, k) eigenvector array (708 MB D2H per rank, inside `seconds`)"}  # fmt: skip
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -486,6 +522,11 @@ def main():
             configs["batch_L7"] = batch_record(world)
         except Exception as e:
             configs["batch_L7"] = {"error": repr(e)}
+        if world > 1:
+            try:
+                configs["rowpart"] = rowpart_record(local_rank, world)
+            except Exception as e:
+                configs["rowpart"] = {"error": repr(e)}
 
     if rank == 0:
         sp = prof.get("spmm", {"launches": 0, "ms": 0.0, "work": 0.0})

@@ -127,9 +127,8 @@ int lb_mat_free(lb_mat *m);
 int lb_spmm(lb_ctx *ctx, lb_mat *mat, const double *x, int64_t m, double *y);
 
 /* device-resident timing of the SpMM kernel (x, y stay in HBM): ms per launch, CUDA events;
- * renumber bit 0: in the locality numbering the solvers iterate in (how assembled matrices are
- * stored) instead of the caller's; bit 1 (A/B aid): the plain gather kernel instead of the kernel
- * that stages the strip's rows of X in shared memory */
+ * renumber != 0: in the locality numbering the solvers iterate in (how assembled matrices are
+ * stored); 0: the same operator converted to the caller's numbering (what the numbering buys) */
 int lb_spmm_benchmark(lb_ctx *ctx, lb_mat *mat, int64_t m, int reps, int renumber,
                       double *ms_per_launch);
 

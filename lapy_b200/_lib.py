@@ -444,9 +444,9 @@ def block_update(ctx: Context, x: np.ndarray, cmat: np.ndarray, alpha=1.0, beta=
     return out
 
 
-def spmm_benchmark(ctx: Context, mat: DeviceMatrix, m: int = 1, reps: int = 20, renumber: int | bool = False) -> float:
-    """Device time (ms) of one y = M x launch with m columns, x / y resident in HBM.  renumber bit 0:
-    solver (locality) numbering instead of the caller's; bit 1: the plain gather kernel (A/B aid)."""
+def spmm_benchmark(ctx: Context, mat: DeviceMatrix, m: int = 1, reps: int = 20, renumber: bool = False) -> float:
+    """Device time (ms) of one y = M x launch with m columns, x / y resident in HBM; renumber: in the
+    solver (locality) numbering instead of the caller's."""
     ms = C.c_double()
     check(lib().lb_spmm_benchmark(ctx.handle, mat.handle, int(m), int(reps), int(renumber), C.byref(ms)))
     return ms.value

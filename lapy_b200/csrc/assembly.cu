@@ -757,130 +757,122 @@ __global__ void __launch_bounds__(kRowThreads) tria_row_fill_fast(
     const bool want_a = out.a_val != nullptr, want_b = out.b_val != nullptr;
     const bool want_pat = want_a || want_b;
     const bool use_smem = want_pat && blk_nnz <= cap;
-    if (r < n && !row_big[r]) {
-        const int beg = inc_ptr[r], ninc = inc_ptr[r + 1] - beg;
-        if (ninc > 0) {
-            const int rbeg = out.indptr[r];
-            // image of this row: shared memory (streamed out below) or, for an oversized block, the output itself
-            int32_t *keys = use_smem ? s_k + (rbeg - blk_beg) : (want_a ? out.a_idx : out.b_idx) + rbeg;
-            double *av = use_smem ? s_a + (rbeg - blk_beg) : out.a_val + rbeg;
-            double *bv = use_smem ? s_b + (rbeg - blk_beg) : out.b_val + rbeg;
-            // 1. incidence records in the reference's triplet order (caller's element id, then corner)
-            int4 qi[kFastInc];
+    // the row image lives in shared memory (streamed out below) or, for an oversized block, in the
+    // output itself: two instantiations of the same code so that the common case compiles to LDS / STS
+    // instead of generic loads and stores
+    auto process = [&](int32_t *keys, double *av, double *bv, const int rbeg, const int beg, const int ninc) {
+        // 1. incidence records in the reference's triplet order (caller's element id, then corner)
+        int4 qi[kFastInc];
 #pragma unroll
-            for (int u = 0; u < kFastInc; u++) qi[u] = u < ninc ? __ldg(inc4 + beg + u) : make_int4(INT_MAX, INT_MAX, INT_MAX, INT_MAX);
+        for (int u = 0; u < kFastInc; u++) qi[u] = u < ninc ? __ldg(inc4 + beg + u) : make_int4(INT_MAX, INT_MAX, INT_MAX, INT_MAX);
 #define LB_CSWAP(i, j)                                                              \
     if (qi[i].w > qi[j].w || (qi[i].w == qi[j].w && qi[i].x > qi[j].x)) {           \
         const int4 tmp_ = qi[i];                                                    \
         qi[i] = qi[j];                                                              \
         qi[j] = tmp_;                                                               \
     }
-            LB_CSWAP(0, 1) LB_CSWAP(2, 3) LB_CSWAP(4, 5) LB_CSWAP(6, 7) LB_CSWAP(0, 2) LB_CSWAP(1, 3) LB_CSWAP(4, 6)
-            LB_CSWAP(5, 7) LB_CSWAP(1, 2) LB_CSWAP(5, 6) LB_CSWAP(0, 4) LB_CSWAP(3, 7) LB_CSWAP(1, 5) LB_CSWAP(2, 6)
-            LB_CSWAP(1, 4) LB_CSWAP(3, 6) LB_CSWAP(2, 4) LB_CSWAP(3, 5) LB_CSWAP(3, 4)
+        LB_CSWAP(0, 1) LB_CSWAP(2, 3) LB_CSWAP(4, 5) LB_CSWAP(6, 7) LB_CSWAP(0, 2) LB_CSWAP(1, 3) LB_CSWAP(4, 6)
+        LB_CSWAP(5, 7) LB_CSWAP(1, 2) LB_CSWAP(5, 6) LB_CSWAP(0, 4) LB_CSWAP(3, 7) LB_CSWAP(1, 5) LB_CSWAP(2, 6)
+        LB_CSWAP(1, 4) LB_CSWAP(3, 6) LB_CSWAP(2, 4) LB_CSWAP(3, 5) LB_CSWAP(3, 4)
 #undef LB_CSWAP
-            // 2. element records: 8 independent 32-byte gathers (neighbouring rows share them: L1 / L2)
-            D4 er[kFastInc];
+        // 2. element records: 8 independent 32-byte gathers (neighbouring rows share them: L1 / L2)
+        D4 er[kFastInc];
 #pragma unroll
-            for (int u = 0; u < kFastInc; u++)
-                if (u < ninc) er[u] = ldg_d4(rec + (qi[u].x >> 2));
-            // 3. sort (neighbour id << 4 | triplet position); position c = 2u + s is the reference order
-            int cnt = 0, dslot = 0;
-            if (want_pat) {
-                int w[16];
-#pragma unroll
-                for (int u = 0; u < kFastInc; u++) {
-                    w[2 * u] = u < ninc ? (qi[u].y << 4) | (2 * u) : INT_MAX;
-                    w[2 * u + 1] = u < ninc ? (qi[u].z << 4) | (2 * u + 1) : INT_MAX;
-                }
-                LB_NET16(LB_MINMAX)
-                // 4. unique keys -> slots; the diagonal takes the slot before the first larger key
-                int prev = -1;
-                bool dd = false;
-#pragma unroll
-                for (int i = 0; i < 16; i++) {
-                    if (w[i] != INT_MAX) {
-                        const int key = w[i] >> 4, cpos = w[i] & 15;
-                        if (key != prev) {
-                            if (!dd && key > (int)r) {
-                                dslot = cnt++;
-                                dd = true;
-                            }
-                            keys[cnt++] = key;
-                            prev = key;
-                        }
-                        s_slot[cpos * T + t] = (unsigned char)(cnt - 1);
-                    }
-                }
-                if (!dd) dslot = cnt++;
-                keys[dslot] = (int)r;
-            }
-            // 5. accumulate in triplet order; the first addend of a slot is stored as it is (keeps -0.0)
-            unsigned seen = 0;
-            double da = 0.0, db = 0.0, lump = 0.0;
+        for (int u = 0; u < kFastInc; u++)
+            if (u < ninc) er[u] = ldg_d4(rec + (qi[u].x >> 2));
+        // 3. sort (neighbour id << 4 | triplet position); position c = 2u + s is the reference order
+        int cnt = 0, dslot = 0;
+        if (want_pat) {
+            int w[16];
 #pragma unroll
             for (int u = 0; u < kFastInc; u++) {
-                if (u < ninc) {
-                    const int c = qi[u].x & 3;
-                    double a12 = er[u].x, a23 = er[u].y, a31 = er[u].z, bii = er[u].w;
-                    if (bii < 0.0) {  // clamped element (solver.py:159): divide by the global mean
-                        const double vm = consts->vol_mean;
-                        if (degen_div_f32) {
-                            a12 = (double)__fdiv_rn((float)a12, (float)vm);
-                            a23 = (double)__fdiv_rn((float)a23, (float)vm);
-                            a31 = (double)__fdiv_rn((float)a31, (float)vm);
-                        } else {
-                            a12 = __ddiv_rn(a12, vm);
-                            a23 = __ddiv_rn(a23, vm);
-                            a31 = __ddiv_rn(a31, vm);
+                w[2 * u] = u < ninc ? (qi[u].y << 4) | (2 * u) : INT_MAX;
+                w[2 * u + 1] = u < ninc ? (qi[u].z << 4) | (2 * u + 1) : INT_MAX;
+            }
+            LB_NET16(LB_MINMAX)
+            // 4. unique keys -> slots (bit 7: first triplet of its key); the diagonal takes the slot
+            //    before the first larger key
+            int prev = -1;
+            bool dd = false;
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+                if (w[i] != INT_MAX) {
+                    const int key = w[i] >> 4, cpos = w[i] & 15;
+                    const bool first = key != prev;
+                    if (first) {
+                        if (!dd && key > (int)r) {
+                            dslot = cnt++;
+                            dd = true;
                         }
-                        bii = consts->bii_deg;
+                        keys[cnt++] = key;
+                        prev = key;
                     }
-                    const double bij = 0.5 * bii;
-                    lump += 2.0 * bii;  // vol/12 (vol/3 for fem_tria_mass) == 2*bii exactly
-                    double x0, x1, m0, m1;
-                    if (c == 0) {
-                        x0 = a12; x1 = a31; m0 = a12; m1 = a31;
-                    } else if (c == 1) {
-                        x0 = a12; x1 = a23; m0 = a12; m1 = a23;
-                    } else {
-                        x0 = a23; x1 = a31; m0 = a31; m1 = a23;
-                    }
-                    // the diagonal (row sum = 0, solver.py:167-169) is formed in the element dtype
-                    const double xd = degen_div_f32 ? (double)__fsub_rn(-(float)m0, (float)m1) : __dsub_rn(-m0, m1);
-                    if (want_pat) {
-                        const int p0 = s_slot[(2 * u) * T + t], p1 = s_slot[(2 * u + 1) * T + t];
-                        if (seen >> p0 & 1u) {
-                            if (want_a) av[p0] = __dadd_rn(av[p0], x0);
-                            if (want_b) bv[p0] = __dadd_rn(bv[p0], bij);
-                        } else {
-                            if (want_a) av[p0] = x0;
-                            if (want_b) bv[p0] = bij;
-                            seen |= 1u << p0;
-                        }
-                        if (seen >> p1 & 1u) {
-                            if (want_a) av[p1] = __dadd_rn(av[p1], x1);
-                            if (want_b) bv[p1] = __dadd_rn(bv[p1], bij);
-                        } else {
-                            if (want_a) av[p1] = x1;
-                            if (want_b) bv[p1] = bij;
-                            seen |= 1u << p1;
-                        }
-                    }
-                    da = u == 0 ? xd : __dadd_rn(da, xd);
-                    db = u == 0 ? bii : __dadd_rn(db, bii);
+                    s_slot[cpos * T + t] = (unsigned char)((cnt - 1) | (first ? 0x80 : 0));
                 }
             }
-            if (want_pat) {
-                if (want_a) av[dslot] = da;
-                if (want_b) bv[dslot] = db;
-                if (!use_smem && want_a && want_b)
-                    for (int q = 0; q < cnt; q++) out.b_idx[rbeg + q] = keys[q];
+            if (!dd) dslot = cnt++;
+            keys[dslot] = (int)r;
+        }
+        // 5. accumulate in triplet order; the first addend of a slot is stored as it is (keeps -0.0)
+        double da = 0.0, db = 0.0, lump = 0.0;
+#pragma unroll
+        for (int u = 0; u < kFastInc; u++) {
+            if (u < ninc) {
+                const int c = qi[u].x & 3;
+                double a12 = er[u].x, a23 = er[u].y, a31 = er[u].z, bii = er[u].w;
+                if (bii < 0.0) {  // clamped element (solver.py:159): divide by the global mean
+                    const double vm = consts->vol_mean;
+                    if (degen_div_f32) {
+                        a12 = (double)__fdiv_rn((float)a12, (float)vm);
+                        a23 = (double)__fdiv_rn((float)a23, (float)vm);
+                        a31 = (double)__fdiv_rn((float)a31, (float)vm);
+                    } else {
+                        a12 = __ddiv_rn(a12, vm);
+                        a23 = __ddiv_rn(a23, vm);
+                        a31 = __ddiv_rn(a31, vm);
+                    }
+                    bii = consts->bii_deg;
+                }
+                const double bij = 0.5 * bii;
+                lump += 2.0 * bii;  // vol/12 (vol/3 for fem_tria_mass) == 2*bii exactly
+                // column = corner c; rows in the reference's triplet order (solver.py:171-175)
+                const double x0 = c == 2 ? a23 : a12, x1 = c == 1 ? a23 : a31;
+                const double m0 = c == 2 ? a31 : a12, m1 = c == 0 ? a31 : a23;
+                // the diagonal (row sum = 0, solver.py:167-169) is formed in the element dtype
+                const double xd = degen_div_f32 ? (double)__fsub_rn(-(float)m0, (float)m1) : __dsub_rn(-m0, m1);
+                if (want_pat) {
+                    const int e0 = s_slot[(2 * u) * T + t], e1 = s_slot[(2 * u + 1) * T + t];
+                    const int p0 = e0 & 0x7f, p1 = e1 & 0x7f;
+                    if (want_a) av[p0] = (e0 & 0x80) ? x0 : __dadd_rn(av[p0], x0);
+                    if (want_b) bv[p0] = (e0 & 0x80) ? bij : __dadd_rn(bv[p0], bij);
+                    if (want_a) av[p1] = (e1 & 0x80) ? x1 : __dadd_rn(av[p1], x1);
+                    if (want_b) bv[p1] = (e1 & 0x80) ? bij : __dadd_rn(bv[p1], bij);
+                }
+                da = u == 0 ? xd : __dadd_rn(da, xd);
+                db = u == 0 ? bii : __dadd_rn(db, bii);
             }
-            if (out.lump_ptr) {
-                const int lp = out.lump_ptr[r];
-                out.lump_idx[lp] = (int)r;
-                out.lump_val[lp] = lump;
+        }
+        if (want_pat) {
+            if (want_a) av[dslot] = da;
+            if (want_b) bv[dslot] = db;
+            if (!use_smem && want_a && want_b)
+                for (int q = 0; q < cnt; q++) out.b_idx[rbeg + q] = keys[q];
+        }
+        if (out.lump_ptr) {
+            const int lp = out.lump_ptr[r];
+            out.lump_idx[lp] = (int)r;
+            out.lump_val[lp] = lump;
+        }
+    };
+    if (r < n && !row_big[r]) {
+        const int beg = inc_ptr[r], ninc = inc_ptr[r + 1] - beg;
+        if (ninc > 0) {
+            const int rbeg = out.indptr[r];
+            if (use_smem || !want_pat) {
+                const int off = want_pat ? rbeg - blk_beg : 0;
+                process(s_k + off, s_a + off, s_b + off, rbeg, beg, ninc);
+            } else {
+                process((want_a ? out.a_idx : out.b_idx) + rbeg, out.a_val + rbeg, out.b_val + rbeg, rbeg, beg, ninc);
             }
         }
     }

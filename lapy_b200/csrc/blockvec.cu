@@ -18,8 +18,6 @@ namespace lb {
 // X rows shared by neighbouring matrix rows (mesh neighbours after the locality renumbering) are
 // served by the SM's L1 instead of L2: the L2 -> SM traffic drops from ~nnz/row x to ~1-2x |X|.
 constexpr int kSpmmStrip = 128;
-// benchmark aid (lb_spmm_benchmark): 0 = production choice, 1 = force the plain gather kernel
-int g_spmm_variant = 0;
 
 template <int G, bool VEC>
 __global__ void __launch_bounds__(256) spmm_kernel(int64_t n, const int32_t *__restrict__ indptr,
@@ -133,166 +131,6 @@ __global__ void __launch_bounds__(256) spmm_kernel(int64_t n, const int32_t *__r
             if (ha) y[row * ldy + ca] = s0;
             if (hb) y[row * ldy + cb] = s1;
         }
-    }
-}
-
-// ---- SpMM with the strip's own X rows staged in shared memory by bulk copies ---------------------
-// ncu: spmm_kernel is bound by the L1/TEX data pipe - every nonzero is one 8m-byte gather and a warp
-// wide 16-byte load out of L1 moves 64 B per cycle.  Shared memory moves 128 B per cycle, and in the
-// locality numbering ~83 % of the column indices of a 128-row strip point into the strip itself
-// (profiles/study_row_groups_r1.txt).  This kernel therefore copies the strip's 128 rows of X into
-// shared memory with one cp.async.bulk per row (the copy engine writes shared memory directly:
-// no L1 wavefronts, no registers), completion tracked by an mbarrier, and serves the in-strip
-// gathers with LDS.128; only halo columns go through L1.  The CSR entries of the first rows are
-// fetched while the copies are in flight.  Square operators with 16-byte aligned rows of X only
-// (prolongators / restrictors and odd leading dimensions use spmm_kernel).
-__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
-
-template <int G>
-__global__ void __launch_bounds__(256) spmm_staged_kernel(int64_t n, const int32_t *__restrict__ indptr,
-                                                          const int32_t *__restrict__ indices,
-                                                          const double *__restrict__ val, const double *__restrict__ x,
-                                                          int ldx, double *y, int ldy, int m, int ms, int mode,
-                                                          const double *b, int ldb, SpmmEpilogue epi) {
-    extern __shared__ __align__(128) double s_x[];  // [kSpmmStrip][ms], ms = m (+2 pad when G < 32)
-    __shared__ __align__(8) unsigned long long s_bar;
-    constexpr int GROUPS = 256 / G;
-    const int grp = threadIdx.x / G, lane = threadIdx.x % G;
-    const unsigned gmask = G == 32 ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31) / G * G));
-    const int64_t strip0 = (int64_t)blockIdx.x * kSpmmStrip;
-    const int nrows = (int)(min(n, strip0 + kSpmmStrip) - strip0);
-    const unsigned bar = smem_u32(&s_bar);
-    if (threadIdx.x == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
-        asm volatile("fence.mbarrier_init.release.cluster;");
-    }
-    __syncthreads();
-    const unsigned row_bytes = (unsigned)m * 8u;
-    if (threadIdx.x == 0) {
-        unsigned long long st;
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 %0, [%1], %2;" : "=l"(st) : "r"(bar), "r"(row_bytes * (unsigned)nrows));
-        (void)st;
-    }
-    if (threadIdx.x < nrows) {
-        const double *src = x + (strip0 + threadIdx.x) * ldx;
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                         smem_u32(s_x + (size_t)threadIdx.x * ms)),
-                     "l"(src), "r"(row_bytes), "r"(bar)
-                     : "memory");
-    }
-    bool staged = false;
-    const int ca = 2 * lane, cb = ca + 1;  // lane owns columns ca, cb of the (<= 2G wide) block
-    const bool ha = ca < m, hb = cb < m;
-    for (int lr = grp; lr < nrows; lr += GROUPS) {
-        const int64_t row = strip0 + lr;
-        const int beg = __ldg(indptr + row), end = __ldg(indptr + row + 1);
-        double s0 = 0.0, s1 = 0.0;
-        for (int p0 = beg; p0 < end; p0 += G) {
-            const int cnt = min(G, end - p0);
-            int jl = 0;
-            double al = 0.0;
-            if (lane < cnt) {
-                jl = __ldg(indices + p0 + lane);
-                al = __ldg(val + p0 + lane);
-            }
-            if (!staged) {  // the first CSR fetch overlaps the bulk copies
-                unsigned done = 0;
-                while (!done)
-                    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
-                                 : "=r"(done)
-                                 : "r"(bar)
-                                 : "memory");
-                staged = true;
-            }
-            int q = 0;
-            for (; q + 3 < cnt; q += 4) {
-                int j[4];
-                double a[4], u0[4], u1[4];
-#pragma unroll
-                for (int w = 0; w < 4; w++) {
-                    j[w] = __shfl_sync(gmask, jl, q + w, G);
-                    a[w] = __shfl_sync(gmask, al, q + w, G);
-                }
-#pragma unroll
-                for (int w = 0; w < 4; w++) {
-                    const int64_t lj = (int64_t)j[w] - strip0;
-                    double2 v = make_double2(0.0, 0.0);
-                    if (lj >= 0 && lj < kSpmmStrip) {  // group-uniform: j is a broadcast value
-                        if (hb) v = *reinterpret_cast<const double2 *>(s_x + lj * ms + ca);
-                        else if (ha) v.x = s_x[lj * ms + ca];
-                    } else {
-                        const double *xr = x + (int64_t)j[w] * ldx;
-                        if (hb) v = __ldg(reinterpret_cast<const double2 *>(xr + ca));
-                        else if (ha) v.x = __ldg(xr + ca);
-                    }
-                    u0[w] = v.x;
-                    u1[w] = v.y;
-                }
-#pragma unroll
-                for (int w = 0; w < 4; w++) {
-                    s0 = fma(a[w], u0[w], s0);
-                    s1 = fma(a[w], u1[w], s1);
-                }
-            }
-            for (; q < cnt; q++) {
-                const int j0 = __shfl_sync(gmask, jl, q, G);
-                const double a0 = __shfl_sync(gmask, al, q, G);
-                const int64_t lj = (int64_t)j0 - strip0;
-                double2 v = make_double2(0.0, 0.0);
-                if (lj >= 0 && lj < kSpmmStrip) {
-                    if (hb) v = *reinterpret_cast<const double2 *>(s_x + lj * ms + ca);
-                    else if (ha) v.x = s_x[lj * ms + ca];
-                } else {
-                    const double *xr = x + (int64_t)j0 * ldx;
-                    if (hb) v = __ldg(reinterpret_cast<const double2 *>(xr + ca));
-                    else if (ha) v.x = __ldg(xr + ca);
-                }
-                s0 = fma(a0, v.x, s0);
-                s1 = fma(a0, v.y, s1);
-            }
-        }
-        if (mode == 1) {
-            if (ha) s0 = b[row * ldb + ca] - s0;
-            if (hb) s1 = b[row * ldb + cb] - s1;
-        } else if (mode == 2) {
-            if (ha) s0 = b[row * ldb + ca] + s0;
-            if (hb) s1 = b[row * ldb + cb] + s1;
-        } else if (mode == 3) {
-            const double di = epi.c2 * __ldg(epi.dinv + row);
-            if (ha) {
-                s0 = b[row * ldb + ca] - s0;
-                epi.out2[row * epi.ldout2 + ca] = di * s0;
-            }
-            if (hb) {
-                s1 = b[row * ldb + cb] - s1;
-                epi.out2[row * epi.ldout2 + cb] = di * s1;
-            }
-        } else if (mode == 4) {
-            const double di = epi.c2 * __ldg(epi.dinv + row);
-            if (ha) {
-                const double dold = x[row * ldx + ca];
-                const double dn = fma(epi.c1, dold, di * (b[row * ldb + ca] - s0));
-                double *sp = epi.out2 + row * epi.ldout2 + ca;
-                *sp = (epi.overwrite ? 0.0 : *sp) + dold + dn;
-            }
-            if (hb) {
-                const double dold = x[row * ldx + cb];
-                const double dn = fma(epi.c1, dold, di * (b[row * ldb + cb] - s1));
-                double *sp = epi.out2 + row * epi.ldout2 + cb;
-                *sp = (epi.overwrite ? 0.0 : *sp) + dold + dn;
-            }
-            continue;
-        }
-        if (hb) *reinterpret_cast<double2 *>(y + row * ldy + ca) = make_double2(s0, s1);
-        else if (ha) y[row * ldy + ca] = s0;
-    }
-    if (!staged) {  // rows without entries: the copies must still land before the CTA (its shared memory) retires
-        unsigned done = 0;
-        while (!done)
-            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
-                         : "=r"(done)
-                         : "r"(bar)
-                         : "memory");
     }
 }
 
@@ -411,49 +249,20 @@ void spmm(lb_ctx *c, const lb_mat *a, const double *x, int ldx, double *y, int l
     // 16-byte vector loads of X need even leading dimension and a 16-byte aligned base
     const bool vec = (ldx % 2 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
     const int grid = cdiv(n, kSpmmStrip);
-    auto launch_plain = [&](const double *xp, double *yp, int mp, const double *bp, const SpmmEpilogue &ep) {
-#define LB_SPMM(G)                                                                                                  \
-    do {                                                                                                            \
-        if (vec) LB_LAUNCH(c, (spmm_kernel<G, true>), grid, 256, 0, n, ip, ix, v, xp, ldx, yp, ldy, mp, mode, bp, ldb, ep); \
-        else LB_LAUNCH(c, (spmm_kernel<G, false>), grid, 256, 0, n, ip, ix, v, xp, ldx, yp, ldy, mp, mode, bp, ldb, ep);    \
+    // (Round 2 tried a variant that copies the strip's own 128 rows of X into shared memory with
+    // cp.async.bulk + mbarrier and serves the in-strip gathers with LDS.128: 1.45 ms instead of 1.11 ms
+    // at 64 columns, slower at every width - the copy latency is exposed at the head of every CTA and
+    // 64 KB of shared memory leave 3 CTAs per SM.  Removed; profiles/spmm_shapes_r2.json has both.)
+#define LB_SPMM(G)                                                                                       \
+    do {                                                                                                 \
+        if (vec) LB_LAUNCH(c, (spmm_kernel<G, true>), grid, 256, 0, n, ip, ix, v, x, ldx, y, ldy, m, mode, b, ldb, epi); \
+        else LB_LAUNCH(c, (spmm_kernel<G, false>), grid, 256, 0, n, ip, ix, v, x, ldx, y, ldy, m, mode, b, ldb, epi);    \
     } while (0)
-        if (mp <= 8) LB_SPMM(4);
-        else if (mp <= 16) LB_SPMM(8);
-        else if (mp <= 32) LB_SPMM(16);
-        else LB_SPMM(32);
+    if (m <= 8) LB_SPMM(4);
+    else if (m <= 16) LB_SPMM(8);
+    else if (m <= 32) LB_SPMM(16);
+    else LB_SPMM(32);
 #undef LB_SPMM
-    };
-    // staged form (see spmm_staged_kernel): square operator, 16-byte aligned rows of X and Y, column
-    // chunks of at most 64 with an even width (the bulk copies move multiples of 16 bytes); an odd
-    // tail chunk goes through the plain gather kernel
-    const bool y_ok = mode == 4 || ((ldy % 2 == 0) && ((reinterpret_cast<uintptr_t>(y) & 15) == 0));
-    if (g_spmm_variant != 1 && vec && y_ok && (a->ncols < 0 || a->ncols == n) && m >= 8 && y != x) {
-        for (int c0 = 0; c0 < m; c0 += 64) {
-            const int mc = std::min(64, m - c0);
-            SpmmEpilogue ep = epi;
-            if (ep.out2) ep.out2 += c0;
-            const double *bc = b ? b + c0 : b;
-            double *yc = y ? y + c0 : y;
-            if (mc % 2 != 0 || mc < 8) {
-                launch_plain(x + c0, yc, mc, bc, ep);
-                continue;
-            }
-            const int G = mc <= 16 ? 8 : mc <= 32 ? 16 : 32;
-            const int ms = G == 32 ? mc : mc + 2;
-            const size_t smem = (size_t)kSpmmStrip * ms * sizeof(double);
-#define LB_STAGED(GG)                                                                                                   \
-    do {                                                                                                                \
-        LB_CUDA(cudaFuncSetAttribute(spmm_staged_kernel<GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
-        LB_LAUNCH(c, (spmm_staged_kernel<GG>), grid, 256, smem, n, ip, ix, v, x + c0, ldx, yc, ldy, mc, ms, mode, bc, ldb, ep); \
-    } while (0)
-            if (G == 8) LB_STAGED(8);
-            else if (G == 16) LB_STAGED(16);
-            else LB_STAGED(32);
-#undef LB_STAGED
-        }
-        return;
-    }
-    launch_plain(x, y, m, b, epi);
 }
 
 // ---- column dots ------------------------------------------------------------------------------

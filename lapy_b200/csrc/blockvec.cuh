@@ -20,7 +20,6 @@ struct SpmmEpilogue {
     double c1 = 0.0, c2 = 0.0;
     int overwrite = 0;  // mode 4: SOL = ... instead of SOL += ...
 };
-extern int g_spmm_variant;  // benchmark aid: 1 forces the plain gather kernel (lb_spmm_benchmark, renumber & 2)
 void spmm(lb_ctx *c, const lb_mat *a, const double *x, int ldx, double *y, int ldy, int m, int mode = 0,
           const double *b = nullptr, int ldb = 0, const SpmmEpilogue *epi = nullptr);
 

@@ -10,6 +10,7 @@
 #include <cstring>
 #include <memory>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/lapy_b200.h"
@@ -156,6 +157,16 @@ inline void sync(lb_ctx *c) { LB_CUDA(cudaStreamSynchronize(c->stream)); }
 // large result download into pageable host memory: chunked through pinned staging buffers, the
 // host-side copy of chunk i (4 threads) overlaps the DMA of chunk i+1.  Synchronous.
 void d2h_large(lb_ctx *c, void *dst, const void *src, size_t bytes);
+// Touches every page of a large, freshly allocated host result buffer on helper threads WHILE the
+// device computes, so that the final download copies into resident pages.  (A fresh 1 GB NumPy array
+// is untouched anonymous memory: first-touch faults inside the download cost 0.1-0.5 s, box dependent -
+// measured as the step-to-step spread of the ShapeDNA bench.)  Joined by the destructor / wait().
+struct HostPrefault {
+    std::vector<std::thread> th;
+    HostPrefault(void *dst, size_t bytes, int nthreads = 2);
+    void wait();
+    ~HostPrefault() { wait(); }
+};
 
 // read back a few scalars (stream-ordered, then wait)
 template <class T>

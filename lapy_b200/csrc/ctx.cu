@@ -55,6 +55,27 @@ static void hint_huge_pages(void *dst, size_t bytes) {
 #endif
 }
 
+HostPrefault::HostPrefault(void *dst, size_t bytes, int nthreads) {
+    if (!dst || bytes < (32u << 20)) return;
+    hint_huge_pages(dst, bytes);
+    const size_t part = ((bytes / nthreads) + 4095) & ~size_t(4095);
+    for (int t = 0; t < nthreads; t++) {
+        const size_t off = std::min(bytes, part * t), len = std::min(part, bytes - off);
+        if (len == 0) continue;
+        th.emplace_back([=] {
+            volatile char *p = static_cast<volatile char *>(dst) + off;
+            for (size_t i = 0; i < len; i += 4096) p[i] = 0;  // the buffer is an output: its content is overwritten later
+            p[len - 1] = 0;
+        });
+    }
+}
+
+void HostPrefault::wait() {
+    for (auto &t : th)
+        if (t.joinable()) t.join();
+    th.clear();
+}
+
 void d2h_large(lb_ctx *c, void *dst, const void *src, size_t bytes) {
     if (bytes < (32u << 20)) {
         d2h(c, dst, src, bytes);

@@ -526,12 +526,6 @@ int lb_spmm_benchmark(lb_ctx *c, lb_mat *mat0, int64_t m, int reps, int renumber
     // numbering buys)
     std::unique_ptr<lb_mat> perm;
     lb_mat *mat = mat0;
-    struct VariantGuard {
-        int saved;
-        ~VariantGuard() { g_spmm_variant = saved; }
-    } vg{g_spmm_variant};
-    if (renumber & 2) g_spmm_variant = 1;  // A/B aid: the plain gather kernel instead of the staged one
-    renumber &= 1;
     if (!renumber && mat0->permuted) {
         perm = to_caller_order(c, mat0);
         mat = perm.get();

@@ -26,10 +26,8 @@ for name, msh, kind in (("ico%d" % level, M.icosphere(level), 0), ("cube%d" % cu
     a, b = _lib.assemble(ctx, dm, kind, False)
     for m in (1, 2, 4, 8, 12, 16, 20, 24, 32, 40, 48, 56, 64, 96, 128):
         nbytes = 12.0 * a.nnz + 4.0 * (a.n + 1) + 16.0 * a.n * m
-        for ren, label in ((1, "solver-order"), (3, "solver-order plain-gather-kernel"), (0, "caller-order")):
+        for ren, label in ((1, "solver-order"), (0, "caller-order")):
             if ren == 0 and m not in (1, 16, 64):
-                continue
-            if ren == 3 and m < 8:
                 continue
             ms = _lib.spmm_benchmark(ctx, a, m, 20, renumber=ren)
             out[f"{name} m={m} {label}"] = {"ms": ms, "gb_s": nbytes / ms / 1e6, "frac": nbytes / ms / 1e6 / PEAK}
