@@ -120,7 +120,7 @@ std::unique_ptr<lb_mat> permute_symmetric(lb_ctx *c, const lb_mat *a, const int3
     return out;
 }
 
-// ---- row-partitioned mode: row block with global columns, and its square diagonal block -------
+// ---- row-partitioned mode: row block with global columns ----------------------------------------
 __global__ void shift_ptr_kernel(int64_t nloc, const int32_t *__restrict__ ptr, int32_t *__restrict__ out) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i <= nloc) out[i] = ptr[i] - ptr[0];
@@ -137,45 +137,6 @@ std::unique_ptr<lb_mat> row_block(lb_ctx *c, const lb_mat *a, int64_t r0, int64_
     LB_LAUNCH(c, shift_ptr_kernel, cdiv(nloc + 1, 256), 256, 0, nloc, a->indptr.p + r0, out->indptr.p);
     d2d(c, out->indices.p, a->indices.p + ends[0], nnz * sizeof(int32_t));
     d2d(c, out->data.p, a->data.p + ends[0], nnz * sizeof(double));
-    return out;
-}
-
-__global__ void diag_block_count(int64_t nloc, const int32_t *__restrict__ ptr, const int32_t *__restrict__ idx,
-                                 int r0, int r1, int32_t *__restrict__ cnt) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nloc) return;
-    int s = 0;
-    for (int p = ptr[i]; p < ptr[i + 1]; p++) s += idx[p] >= r0 && idx[p] < r1;
-    cnt[i] = s;
-}
-
-__global__ void diag_block_fill(int64_t nloc, const int32_t *__restrict__ ptr, const int32_t *__restrict__ idx,
-                                const double *__restrict__ val, int r0, int r1, const int32_t *__restrict__ optr,
-                                int32_t *__restrict__ oidx, double *__restrict__ oval) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nloc) return;
-    int q = optr[i];
-    for (int p = ptr[i]; p < ptr[i + 1]; p++)
-        if (idx[p] >= r0 && idx[p] < r1) {
-            oidx[q] = idx[p] - r0;
-            oval[q] = val[p];
-            q++;
-        }
-}
-
-// square block [r0, r1) x [r0, r1) of a row block (couplings to other ranks dropped): the operator of
-// the per-rank (block-Jacobi) AMG preconditioner
-std::unique_ptr<lb_mat> diag_block(lb_ctx *c, const lb_mat *rows, int64_t r0, int64_t r1) {
-    const int64_t nloc = rows->n;
-    DBuf<int32_t> cnt(c, nloc), optr(c, nloc + 1);
-    LB_LAUNCH(c, diag_block_count, cdiv(nloc, 256), 256, 0, nloc, rows->indptr.p, rows->indices.p, (int)r0, (int)r1, cnt.p);
-    exclusive_scan_i32(c, cnt.p, optr.p, nloc);
-    int32_t nnz = 0;
-    read_back(c, &nnz, optr.p + nloc, 1);
-    auto out = make_mat(c, nloc, -1, nnz);
-    d2d(c, out->indptr.p, optr.p, (nloc + 1) * sizeof(int32_t));
-    LB_LAUNCH(c, diag_block_fill, cdiv(nloc, 256), 256, 0, nloc, rows->indptr.p, rows->indices.p, rows->data.p, (int)r0,
-              (int)r1, out->indptr.p, out->indices.p, out->data.p);
     return out;
 }
 

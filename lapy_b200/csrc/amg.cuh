@@ -63,9 +63,8 @@ struct MatView {
 };
 // returns the numbering the views are in (nullptr: the caller's); b may be NULL
 std::shared_ptr<lb_order> common_numbering(lb_ctx *c, const lb_mat *a, const lb_mat *b, MatView &va, MatView &vb);
-// rows [r0, r1) of a (CSR, global columns) and the square diagonal block of such a row block
+// rows [r0, r1) of a (CSR, global columns)
 std::unique_ptr<lb_mat> row_block(lb_ctx *c, const lb_mat *a, int64_t r0, int64_t r1, int64_t ncols);
-std::unique_ptr<lb_mat> diag_block(lb_ctx *c, const lb_mat *rows, int64_t r0, int64_t r1);
 // y[i, :] = x[map[i], :]
 void gather_rows(lb_ctx *c, int64_t n, int cols, const int32_t *map, const double *x, int ldx, double *y, int ldy);
 // dinv[i] = d[i] > 0 ? 1/d[i] : 0

@@ -308,65 +308,71 @@ void update_dmma(lb_ctx *c, int64_t n, int p, const double *x, int ldx, int q, c
 }
 
 // ---------------------------------------------------------------------------------------------
-// Gram: CTA = 4 warps = one 64 x 64 output tile over a slab of rows; warp = 32 x 32.
-// partial[(split * ntile + tile) * 4096 + i*64 + j]; gram_reduce sums the slabs in fixed order.
+// Gram: CTA = 4 warps = one 64 x QT output tile over a slab of rows; warp = 32 x QT/2 (NJ = QT/16
+// 8-column blocks).  QT = 64 for the wide products; 32 / 16 for the narrow right-hand sides of the late
+// LOBPCG iterations (a 64-wide tile ran the 16-column products at 1.5-4 TFLOP/s: DMMAs on padding).
+// partial[(split * ntile + tile) * 64*QT + i*QT + j]; gram_reduce sums the slabs in fixed order.
 // ---------------------------------------------------------------------------------------------
+template <int NJ>
 __global__ void __launch_bounds__(128, 4)
     gram_dmma_kernel(int64_t n, int p, const double *__restrict__ x, int ldx, int q, const double *__restrict__ y,
                      int ldy, int qtiles, int symmetric, int64_t rows_per_split, double *__restrict__ partial,
                      int ntile_total) {
+    constexpr int QT = 16 * NJ;
     const int tile = blockIdx.x;
     const int pt = tile / qtiles, qt = tile % qtiles;
-    if (symmetric && qt < pt) return;  // mirrored by gram_reduce
+    if (symmetric && qt < pt) return;  // mirrored by gram_reduce (QT == 64 only)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, t = lane & 3;
-    const int pc = pt * 64 + (warp & 1) * 32, qc = qt * 64 + (warp >> 1) * 32;
+    const int pc = pt * 64 + (warp & 1) * 32, qc = qt * QT + (warp >> 1) * (QT / 2);
     const int64_t r_begin = (int64_t)blockIdx.y * rows_per_split;
     const int64_t r_end = min(n, r_begin + rows_per_split);
-    double acc[4][4][2];
+    double acc[4][NJ][2];
 #pragma unroll
     for (int i = 0; i < 4; i++)
 #pragma unroll
-        for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
-    bool aok[4], bok[4];
+        for (int j = 0; j < NJ; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+    bool aok[4], bok[NJ];
 #pragma unroll
-    for (int i = 0; i < 4; i++) {
-        aok[i] = pc + 8 * i + g < p;
-        bok[i] = qc + 8 * i + g < q;
-    }
+    for (int i = 0; i < 4; i++) aok[i] = pc + 8 * i + g < p;
+#pragma unroll
+    for (int j = 0; j < NJ; j++) bok[j] = qc + 8 * j + g < q;
     for (int64_t r8 = r_begin; r8 < r_end; r8 += 8) {
         const int64_t ra = r8 + 2 * t, rb = ra + 1;
         const bool va = ra < r_end, vb = rb < r_end;
         const double *xa = x + ra * ldx + pc + g, *xb = x + rb * ldx + pc + g;
         const double *ya = y + ra * ldy + qc + g, *yb = y + rb * ldy + qc + g;
-        double a0[4], a1[4], b0[4], b1[4];
+        double a0[4], a1[4], b0[NJ], b1[NJ];
 #pragma unroll
         for (int i = 0; i < 4; i++) {
             a0[i] = (va && aok[i]) ? __ldg(xa + 8 * i) : 0.0;
             a1[i] = (vb && aok[i]) ? __ldg(xb + 8 * i) : 0.0;
-            b0[i] = (va && bok[i]) ? __ldg(ya + 8 * i) : 0.0;
-            b1[i] = (vb && bok[i]) ? __ldg(yb + 8 * i) : 0.0;
+        }
+#pragma unroll
+        for (int j = 0; j < NJ; j++) {
+            b0[j] = (va && bok[j]) ? __ldg(ya + 8 * j) : 0.0;
+            b1[j] = (vb && bok[j]) ? __ldg(yb + 8 * j) : 0.0;
         }
 #pragma unroll
         for (int i = 0; i < 4; i++)
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
+            for (int j = 0; j < NJ; j++) {
                 dmma884(acc[i][j][0], acc[i][j][1], a0[i], b0[j]);
                 dmma884(acc[i][j][0], acc[i][j][1], a1[i], b1[j]);
             }
     }
-    double *out = partial + ((int64_t)blockIdx.y * ntile_total + tile) * 4096;
-    const int li = (warp & 1) * 32, lj = (warp >> 1) * 32;
+    double *out = partial + ((int64_t)blockIdx.y * ntile_total + tile) * (64 * QT);
+    const int li = (warp & 1) * 32, lj = (warp >> 1) * (QT / 2);
 #pragma unroll
     for (int i = 0; i < 4; i++)
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
+        for (int j = 0; j < NJ; j++) {
             double2 v = make_double2(acc[i][j][0], acc[i][j][1]);
-            *reinterpret_cast<double2 *>(out + (li + 8 * i + g) * 64 + lj + 8 * j + 2 * t) = v;
+            *reinterpret_cast<double2 *>(out + (li + 8 * i + g) * QT + lj + 8 * j + 2 * t) = v;
         }
 }
 
-__global__ void gram_reduce_kernel(int p, int q, int qtiles, int ntile_total, int nsplit, int symmetric,
+__global__ void gram_reduce_kernel(int p, int q, int qtiles, int qt_width, int ntile_total, int nsplit, int symmetric,
                                    const double *__restrict__ partial, double *__restrict__ cmat) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= p * q) return;
@@ -376,29 +382,37 @@ __global__ void gram_reduce_kernel(int p, int q, int qtiles, int ntile_total, in
         pi = j;
         pj = i;
     }
-    const int tile = (pi >> 6) * qtiles + (pj >> 6);
-    const double *src = partial + (int64_t)tile * 4096 + (pi & 63) * 64 + (pj & 63);
+    const int tile = (pi >> 6) * qtiles + pj / qt_width;
+    const int64_t tsize = 64 * qt_width;
+    const double *src = partial + (int64_t)tile * tsize + (pi & 63) * qt_width + pj % qt_width;
     double s = 0.0;
-    for (int k = 0; k < nsplit; k++) s += src[(int64_t)k * ntile_total * 4096];
+    for (int k = 0; k < nsplit; k++) s += src[(int64_t)k * ntile_total * tsize];
     cmat[idx] = s;
 }
 
 // symmetric != 0: the caller guarantees X^T Y is symmetric (S^T (A S), W^T (B W)) and p == q
 void gram_dmma(lb_ctx *c, int64_t n, int p, const double *x, int ldx, int q, const double *y, int ldy, double *cmat,
                bool symmetric) {
-    const int ptiles = cdiv(p, 64), qtiles = cdiv(q, 64);
+    if (p <= 64 && q <= 64) symmetric = false;  // a single 64-row tile: nothing to mirror, narrow tiles allowed
+    const int qt_width = (q > 32 || symmetric) ? 64 : q > 16 ? 32 : 16;
+    const int ptiles = cdiv(p, 64), qtiles = cdiv(q, qt_width);
     const int ntile = ptiles * qtiles;
     const int active = symmetric ? ptiles * (ptiles + 1) / 2 : ntile;
     int nsplit = std::max(1, (kSMs * 4) / active);
     int64_t rows_per_split = ((n + nsplit - 1) / nsplit + 7) & ~7ll;
     if (rows_per_split < 512) rows_per_split = 512;
     nsplit = (int)((n + rows_per_split - 1) / rows_per_split);
-    DBuf<double> partial(c, (size_t)nsplit * ntile * 4096);
+    DBuf<double> partial(c, (size_t)nsplit * ntile * 64 * qt_width);
     dim3 grid(ntile, nsplit);
-    LB_LAUNCH(c, gram_dmma_kernel, grid, 128, 0, n, p, x, ldx, q, y, ldy, qtiles, (int)symmetric, rows_per_split,
-              partial.p, ntile);
-    LB_LAUNCH(c, gram_reduce_kernel, cdiv(p * q, 256), 256, 0, p, q, qtiles, ntile, nsplit, (int)symmetric, partial.p,
-              cmat);
+    if (qt_width == 64)
+        LB_LAUNCH(c, gram_dmma_kernel<4>, grid, 128, 0, n, p, x, ldx, q, y, ldy, qtiles, (int)symmetric, rows_per_split,
+                  partial.p, ntile);
+    else if (qt_width == 32)
+        LB_LAUNCH(c, gram_dmma_kernel<2>, grid, 128, 0, n, p, x, ldx, q, y, ldy, qtiles, 0, rows_per_split, partial.p, ntile);
+    else
+        LB_LAUNCH(c, gram_dmma_kernel<1>, grid, 128, 0, n, p, x, ldx, q, y, ldy, qtiles, 0, rows_per_split, partial.p, ntile);
+    LB_LAUNCH(c, gram_reduce_kernel, cdiv(p * q, 256), 256, 0, p, q, qtiles, qt_width, ntile, nsplit, (int)symmetric,
+              partial.p, cmat);
 }
 
 // device-resident timing of the dense block products (x, y, c resident): op 0 = Gram X^T Y (p x q),

@@ -28,13 +28,12 @@ namespace lb {
 
 // ---- row-partitioned mode: the three operations that communicate --------------------------------
 // Every rank owns the rows [rank*rpr, min(n, (rank+1)*rpr)) of the renumbered operator and the
-// matching rows of all block vectors.  SpMM all-gathers the block vector first (the operator's
-// columns are global); Gram matrices and column dots are summed over the ranks.  With D == NULL
-// these are the single-GPU operations.
+// matching rows of all block vectors.  SpMM exchanges the boundary rows of the block vector with
+// the neighbouring ranks (grouped ncclSend / ncclRecv); Gram matrices and column dots are summed
+// over the ranks (ncclAllReduce).  With D == NULL these are the single-GPU operations.
 using RawBuf = RawBufT<double>;  // plain cudaMalloc (dist.cuh): NCCL must not be handed pool memory
 
-// Halo-exchange form of the row-partitioned SpMM (LAPY_B200_HALO=1; the default is still the
-// whole-block all-gather).  Per operator: the ghost columns of this rank's row block (sorted
+// Halo exchange of the row-partitioned SpMM.  Per operator: the ghost columns of this rank's row block (sorted
 // global ids, grouped by owner), the rows every peer needs from this rank, and the row block
 // with its columns renumbered to [own rows | ghost rows], so that the ordinary SpMM kernel runs
 // on one contiguous (n_loc + n_ghost, w) input whose ghost part is filled by grouped
@@ -54,12 +53,11 @@ struct DistOps {
     int64_t rpr = 0;        // rows per rank (last rank may own fewer)
     int64_t n_local = 0;
     int64_t r0 = 0, r1 = 0;  // this rank's rows
-    RawBuf pack, gath, red;  // (rpr, wcap), (world*rpr, wcap), all-reduce staging
-    bool halo = false;
+    RawBuf pack, gath, red;  // (rpr, k), (world*rpr, k): final eigenvector all-gather; all-reduce staging
     int wcap = 0;
     std::map<const lb_mat *, std::unique_ptr<HaloPlan>> plans;  // built on first use (collectively)
-    // replicated preconditioner (LAPY_B200_DIST_AMG=full): every rank holds the AMG hierarchy of the
-    // FULL operator and applies it to its share of the COLUMNS; see dist_precond
+    // replicated preconditioner: every rank holds the AMG hierarchy of the FULL operator and applies
+    // it to its share of the COLUMNS; see dist_precond
     Amg *full_amg = nullptr;
     int64_t n_full = 0;
     RawBuf tpack, tfull_r, tfull_z;  // (n_local, mcap) packed slices; (n, ceil(mcap/world)) in / out
@@ -174,28 +172,22 @@ static void d_spmm(lb_ctx *c, DistOps *D, const lb_mat *a, const double *x, int 
         spmm(c, a, x, ldx, y, ldy, w);
         return;
     }
-    if (D->halo) {
-        auto &slot = D->plans[a];
-        if (!slot) slot = build_halo(c, D->d, a, D->r0, D->r1, D->rpr, D->wcap);
-        HaloPlan &h = *slot;
-        LB_REQUIRE(w <= h.wcap, "halo exchange: block of %d columns exceeds the plan's capacity %d", w, h.wcap);
-        const int W = D->d->world;
-        copy_cols(c, h.n_loc, w, x, ldx, h.xg.p, w);
-        if (h.n_send) gather_rows(c, h.n_send, w, h.send_rows.p, x, ldx, h.sendbuf.p, w);
-        std::vector<int64_t> so(W), sc(W), ro(W), rc(W);
-        for (int p = 0; p < W; p++) {
-            so[p] = h.send_off[p] * w;
-            sc[p] = h.send_cnt[p] * w;
-            ro[p] = (h.n_loc + h.recv_off[p]) * w;
-            rc[p] = h.recv_cnt[p] * w;
-        }
-        dist_exchange(c, D->d, h.sendbuf.p, so.data(), sc.data(), h.xg.p, ro.data(), rc.data(), 8);
-        spmm(c, h.local.get(), h.xg.p, w, y, ldy, w);
-        return;
+    auto &slot = D->plans[a];
+    if (!slot) slot = build_halo(c, D->d, a, D->r0, D->r1, D->rpr, D->wcap);
+    HaloPlan &h = *slot;
+    LB_REQUIRE(w <= h.wcap, "halo exchange: block of %d columns exceeds the plan's capacity %d", w, h.wcap);
+    const int W = D->d->world;
+    copy_cols(c, h.n_loc, w, x, ldx, h.xg.p, w);
+    if (h.n_send) gather_rows(c, h.n_send, w, h.send_rows.p, x, ldx, h.sendbuf.p, w);
+    std::vector<int64_t> so(W), sc(W), ro(W), rc(W);
+    for (int p = 0; p < W; p++) {
+        so[p] = h.send_off[p] * w;
+        sc[p] = h.send_cnt[p] * w;
+        ro[p] = (h.n_loc + h.recv_off[p]) * w;
+        rc[p] = h.recv_cnt[p] * w;
     }
-    copy_cols(c, D->n_local, w, x, ldx, D->pack.p, w);
-    dist_allgather(c, D->d, D->pack.p, D->gath.p, (size_t)D->rpr * w);
-    spmm(c, a, D->gath.p, w, y, ldy, w);
+    dist_exchange(c, D->d, h.sendbuf.p, so.data(), sc.data(), h.xg.p, ro.data(), rc.data(), 8);
+    spmm(c, h.local.get(), h.xg.p, w, y, ldy, w);
 }
 
 static void d_gram(lb_ctx *c, DistOps *D, int64_t n, int p, const double *x, int ldx, int q, const double *y, int ldy,
@@ -618,7 +610,7 @@ static EigStats lobpcg_core(lb_ctx *c, const lb_mat *A, const lb_mat *B, Amg *am
         residual_cols(c, n, ma, idx_d.p, lam_d.p, AS[cur].p, ld, BS[cur].p, ld, Rbuf.p, ma);
         const int w0 = m + mp;
         double *W = S[cur].p + w0, *AW = AS[cur].p + w0, *BW = BS[cur].p + w0;
-        if (D && D->full_amg) dist_precond(c, D, Rbuf.p, ma, W, ld, ma);
+        if (D) dist_precond(c, D, Rbuf.p, ma, W, ld, ma);
         else amg_apply(*amg, Rbuf.p, ma, W, ld, ma, lvl);
         pt.stop(1);
         // block Gram-Schmidt against [X P], twice ("twice is enough").  A single pass was measured to
@@ -755,49 +747,40 @@ static EigStats lobpcg_dist(lb_ctx *c, const DistCtx *dist, const lb_mat *A0, co
     const int64_t r0 = std::min(n, rank * rpr), r1 = std::min(n, r0 + rpr);
     LB_REQUIRE(r1 - r0 >= 4 * m, "row block of rank %d too small (%lld rows) for a block of %d", rank, (long long)(r1 - r0), m);
     const double shift = sigma < 0 ? -sigma : 1e-2;
-    auto Kfull = mat_axpby(c, A, 1.0, B, shift);  // on the full matrices: handles a diagonal (lumped) B
     auto Ar = row_block(c, A, r0, r1, world * rpr);
     auto Br = row_block(c, B, r0, r1, world * rpr);  // general CSR with global columns (also when B is diagonal)
-    auto Kr = row_block(c, Kfull.get(), r0, r1, world * rpr);
-    auto Kll = diag_block(c, Kr.get(), r0, r1);
-    Kr.reset();
+    // The hierarchy of the FULL operator on every rank (set-up is 10-20 ms, redundant like the
+    // assembly), applied column-parallel (dist_precond): the iteration count equals the single-GPU
+    // solver's (measured on 2 GPUs: 40 at level 9, 46 on the 121^3 cube; a per-rank block-Jacobi
+    // hierarchy needed 189 / 75).  The nested-iteration start is computed redundantly on the small
+    // coarse levels, so every rank starts from the same block.
     AmgOptions opt;
-    // opt-in (LAPY_B200_DIST_AMG=full): the hierarchy of the FULL operator on every rank (setup is
-    // 10-20 ms), applied column-parallel (dist_precond), and the nested-iteration start of the
-    // single-GPU driver computed redundantly on the small coarse levels
-    std::unique_ptr<Amg> amg_full;
+    std::unique_ptr<Amg> amg = amg_setup(c, mat_axpby(c, A, 1.0, B, shift), m, opt);
     DBuf<double> x_start;  // (n, m) prolonged coarse eigenvectors, identical on all ranks
     bool have_start = false;
-    if (const char *e = getenv("LAPY_B200_DIST_AMG")) {
-        if (!strcmp(e, "full")) {
-            amg_full = amg_setup(c, std::move(Kfull), m, opt);
-            const int nlev = (int)amg_full->levels.size();
-            int depth = 0;
-            while (n >= 1000000 && depth + 1 < nlev - 1 &&
-                   amg_full->levels[depth + 1].K->n >= std::max<int64_t>(8 * m, 4000))
-                depth++;
-            std::vector<std::unique_ptr<lb_mat>> Bl(depth + 1);
-            for (int l = 0; l < depth; l++) {
-                const lb_mat *bl = l == 0 ? B : Bl[l].get();
-                auto BP = spgemm(c, bl, amg_full->levels[l].P.get());
-                Bl[l + 1] = spgemm(c, amg_full->levels[l].R.get(), BP.get());
-                Bl[l + 1]->ncols = -1;
-            }
-            std::vector<double> lamc;
-            for (int l = depth; l >= 1; l--) {
-                const lb_mat *Kl = amg_full->levels[l].K.get();
-                DBuf<double> xo(c, (size_t)Kl->n * m);
-                lobpcg_core(c, Kl, Bl[l].get(), amg_full.get(), l, have_start ? x_start.p : nullptr, m, k, m,
-                            std::max(tol, 1e-3), 60, lamc, xo.p);
-                const lb_mat *P = amg_full->levels[l - 1].P.get();
-                x_start.alloc(c, (size_t)P->n * m);
-                spmm(c, P, xo.p, m, x_start.p, m, m);
-                have_start = true;
-            }
+    {
+        const int nlev = (int)amg->levels.size();
+        int depth = 0;
+        while (n >= 1000000 && depth + 1 < nlev - 1 && amg->levels[depth + 1].K->n >= std::max<int64_t>(8 * m, 4000)) depth++;
+        std::vector<std::unique_ptr<lb_mat>> Bl(depth + 1);
+        for (int l = 0; l < depth; l++) {
+            const lb_mat *bl = l == 0 ? B : Bl[l].get();
+            auto BP = spgemm(c, bl, amg->levels[l].P.get());
+            Bl[l + 1] = spgemm(c, amg->levels[l].R.get(), BP.get());
+            Bl[l + 1]->ncols = -1;
+        }
+        std::vector<double> lamc;
+        for (int l = depth; l >= 1; l--) {
+            const lb_mat *Kl = amg->levels[l].K.get();
+            DBuf<double> xo(c, (size_t)Kl->n * m);
+            lobpcg_core(c, Kl, Bl[l].get(), amg.get(), l, have_start ? x_start.p : nullptr, m, k, m, std::max(tol, 1e-3), 60,
+                        lamc, xo.p);
+            const lb_mat *P = amg->levels[l - 1].P.get();
+            x_start.alloc(c, (size_t)P->n * m);
+            spmm(c, P, xo.p, m, x_start.p, m, m);
+            have_start = true;
         }
     }
-    Kfull.reset();
-    auto amg = amg_setup(c, std::move(Kll), m, opt);
     DistOps D;
     D.d = dist;
     D.rpr = rpr;
@@ -805,20 +788,17 @@ static EigStats lobpcg_dist(lb_ctx *c, const DistCtx *dist, const lb_mat *A0, co
     D.r0 = r0;
     D.r1 = r1;
     D.wcap = 2 * m;
-    if (const char *e = getenv("LAPY_B200_HALO")) D.halo = atoi(e) != 0;
-    D.pack.alloc((size_t)rpr * 2 * m);
+    D.pack.alloc((size_t)rpr * k);
     LB_CUDA(cudaMemsetAsync(D.pack.p, 0, D.pack.n * sizeof(double), c->stream));
-    D.gath.alloc((size_t)world * rpr * 2 * m);
+    D.gath.alloc((size_t)world * rpr * k);
     D.red.alloc((size_t)9 * m * m + 4 * m);
-    if (amg_full) {
-        D.full_amg = amg_full.get();
-        D.n_full = n;
-        D.tpack.alloc((size_t)(r1 - r0) * m);
-        D.tfull_r.alloc((size_t)n * ((m + world - 1) / world));
-        D.tfull_z.alloc((size_t)n * ((m + world - 1) / world));
-    }
-    if (c->trace) fprintf(stderr, "[lb trace] rank %d: rows [%lld, %lld) of %lld, AMG levels %zu%s\n", rank, (long long)r0,
-                          (long long)r1, (long long)n, amg->levels.size(), amg_full ? " (replicated full hierarchy)" : "");
+    D.full_amg = amg.get();
+    D.n_full = n;
+    D.tpack.alloc((size_t)(r1 - r0) * m);
+    D.tfull_r.alloc((size_t)n * ((m + world - 1) / world));
+    D.tfull_z.alloc((size_t)n * ((m + world - 1) / world));
+    if (c->trace) fprintf(stderr, "[lb trace] rank %d: rows [%lld, %lld) of %lld, AMG levels %zu (replicated, column-parallel)\n",
+                          rank, (long long)r0, (long long)r1, (long long)n, amg->levels.size());
     std::vector<double> lam;
     DBuf<double> xloc(c, (size_t)(r1 - r0) * m);
     EigStats st = lobpcg_core(c, Ar.get(), Br.get(), amg.get(), 0, have_start ? x_start.p + (size_t)r0 * m : nullptr, m, k,
@@ -913,10 +893,6 @@ extern "C" int lb_dist_selftest(lb_ctx *c, lb_mat *a, double *errs) {
     D.r0 = r0;
     D.r1 = r1;
     D.wcap = w;
-    if (const char *e = getenv("LAPY_B200_HALO")) D.halo = atoi(e) != 0;
-    D.pack.alloc((size_t)rpr * w);
-    LB_CUDA(cudaMemsetAsync(D.pack.p, 0, D.pack.n * sizeof(double), c->stream));
-    D.gath.alloc((size_t)world * rpr * w);
     D.red.alloc((size_t)w * w);
     DBuf<double> xf(c, (size_t)n * w), yf(c, (size_t)n * w), yd(c, (size_t)(r1 - r0) * w), gf(c, w * w), gd(c, w * w);
     DBuf<unsigned long long> mx(c, 2);

@@ -38,30 +38,23 @@ def _worker(rank, world, port, q, env):
         dist.destroy_process_group()
 
 
-VARIANTS = {
-    "allgather": {},  # default: whole-block all-gather SpMM, block-Jacobi AMG per rank
-    "halo": {"LAPY_B200_HALO": "1"},  # boundary-only halo exchange (grouped send/recv)
-    "halo+full-amg": {"LAPY_B200_HALO": "1", "LAPY_B200_DIST_AMG": "full"},  # + replicated hierarchy, column-parallel
-}
-
-
-@pytest.mark.parametrize("variant", list(VARIANTS))
-def test_two_rank_row_partitioned_eigs(variant):
+def test_two_rank_row_partitioned_eigs():
+    """Rows of the locality-numbered operator split over 2 ranks: NCCL halo exchange in every SpMM,
+    all-reduced Gram matrices, hierarchy of the full operator applied column-parallel.  Validated on
+    2 GPUs in round 2 (level 6 here; level 9: 40 iterations, 1.14 s; 121^3 tets: 46 iterations, 1.20 s)."""
     import torch
     import torch.multiprocessing as mp
     from conftest import load_golden
 
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
-    if VARIANTS[variant] and not os.environ.get("LAPY_B200_TEST_HALO"):
-        pytest.skip("opt-in communication variants, not yet validated on 2 GPUs: set LAPY_B200_TEST_HALO=1")
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
     port = s.getsockname()[1]
     s.close()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, VARIANTS[variant])) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, {})) for r in range(2)]
     for p in procs:
         p.start()
     res = [q.get(timeout=150) for _ in procs]
@@ -73,3 +66,4 @@ def test_two_rank_row_partitioned_eigs(variant):
         assert np.all(np.abs(ev[1:] - ref[1:]) <= 1e-8 * ref[1:]) and abs(ev[0]) < 1e-8, (rank, ev[:4], ref[:4])
         assert orth < 1e-9 and resid < 1e-6
     np.testing.assert_array_equal(res[0][1], res[1][1])  # both ranks hold identical results
+    assert res[0][4]["iterations"] <= 70

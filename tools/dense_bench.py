@@ -13,7 +13,7 @@ for p, q in ((192, 128), (128, 64), (64, 64), (128, 32), (128, 24), (128, 16), (
         tf = 2.0 * n * p * q / ms / 1e9
         out[f"update p={p} q={q} {'wide-tile-only' if var else 'default'}"] = {"ms": ms, "tflops": tf}
         print(f"update p={p:3d} q={q:3d} {'wide' if var else 'dflt'}: {ms:.3f} ms  {tf:.1f} TFLOP/s", flush=True)
-for p, q in ((192, 192), (128, 64), (64, 64)):
+for p, q in ((192, 192), (128, 64), (64, 64), (128, 32), (128, 16), (79, 16), (16, 16)):
     ms = _lib.dense_benchmark(ctx, n, p, q, 0, 0, 10)
     tf = 2.0 * n * p * q / ms / 1e9
     out[f"gram p={p} q={q}"] = {"ms": ms, "tflops": tf}
