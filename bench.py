@@ -451,7 +451,7 @@ def main():
         ev, evec, info, nnz = step()
     barrier()
     l0 = ctx.launch_count()
-    ctx.profile_enable(True)
+    ctx.profile_enable(2)  # CUDA-event pairs around the SpMM launches only (the kernel the roofline is quoted on)
     with ClockSampler(local_rank) as clk:
         ctx.timer_start()  # CUDA events on the library's stream (the stream every kernel runs on)
         step_wall = []
@@ -461,13 +461,21 @@ def main():
             step_wall.append((time.perf_counter() - t_s) * 1e3)
         dev_ms = ctx.timer_stop()
     print(f"[bench] rank {rank}: per-step wall ms {[round(x, 1) for x in step_wall]}", file=sys.stderr)
-    prof = ctx.profile_report()
+    spmm_prof = ctx.profile_report().get("spmm", {"launches": 0, "ms": 0.0, "work": 0.0})
     spmm_shapes = ctx.profile_shapes("spmm", 24)
-    dense_shapes = {cls: ctx.profile_shapes(cls, 8) for cls in ("gram", "update", "small_dense")}
     ctx.profile_enable(False)
     launches = ctx.launch_count() - l0
     parity = parity_record(ev, golden_spectrum(gkey, args.k), gkey)  # the LAST TIMED step's eigenvalues
     barrier()
+    # per-class breakdown from ONE extra step with event pairs around every hot launch (outside the
+    # timed region: ~30k event records per step cost device and host time)
+    ctx.profile_enable(1)
+    ctx.timer_start()
+    step()
+    prof_step_ms = ctx.timer_stop()
+    prof = ctx.profile_report()
+    dense_shapes = {cls: ctx.profile_shapes(cls, 8) for cls in ("gram", "update", "small_dense")}
+    ctx.profile_enable(False)
     # assembly alone (device time), outside the timed region
     for _ in range(5):
         dmesh.drop_cache()
@@ -529,11 +537,11 @@ def main():
                 configs["rowpart"] = {"error": repr(e)}
 
     if rank == 0:
-        sp = prof.get("spmm", {"launches": 0, "ms": 0.0, "work": 0.0})
+        sp = spmm_prof
         class_rate = sp["work"] / (sp["ms"] * 1e-3) / 1e9 if sp["ms"] else 0.0
         total_prof_ms = sum(v["ms"] for v in prof.values())
         classes = {
-            k: {"launches": v["launches"], "ms_per_step": v["ms"] / args.steps,
+            k: {"launches": v["launches"], "ms_per_step": v["ms"],
                 "rate": v["work"] / (v["ms"] * 1e-3) / 1e9 if v["ms"] else None,
                 "rate_unit": "GB/s" if k in ("spmm", "col_dots", "elementwise") else "GFLOP/s"}
             for k, v in prof.items()
@@ -590,10 +598,12 @@ def main():
                              {"columns": s["shape"][0], "nnz": s["shape"][1], "launches": s["launches"], "ms_per_step": s["ms"] / args.steps,
                               "gb_per_s": s["work"] / (s["ms"] * 1e-3) / 1e9 if s["ms"] else None} for s in spmm_shapes[:12]],
                          "class_in_timed_region": {"launches": sp["launches"], "ms_per_step": sp["ms"] / args.steps, "avg_gb_per_s": class_rate,
-                                                   "share_of_profiled_device_time": sp["ms"] / total_prof_ms if total_prof_ms else None}},
+                                                   "share_of_step": sp["ms"] / args.steps / ms_step}},
             "kernel_classes": classes,
+            "kernel_classes_note": f"CUDA-event totals per kernel class over ONE extra step outside the timed region ({prof_step_ms:.0f} ms with "
+                                   f"event pairs around every hot launch; profiled classes sum to {total_prof_ms:.0f} ms)",
             "dense_shapes_in_timed_region": {
-                cls: [{"p": r["shape"][0], "q": r["shape"][1], "launches": r["launches"], "ms_per_step": r["ms"] / args.steps,
+                cls: [{"p": r["shape"][0], "q": r["shape"][1], "launches": r["launches"], "ms_per_step": r["ms"],
                        "tflops": r["work"] / (r["ms"] * 1e-3) / 1e12 if r["ms"] else None} for r in rows]
                 for cls, rows in dense_shapes.items()},
             "configs": configs,

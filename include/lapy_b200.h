@@ -77,8 +77,10 @@ int lb_timer_stop(lb_ctx *ctx, double *ms);
 /* per-kernel-class device timing (CUDA events around the hot launches): classes are
  * 0 SpMM, 1 Gram (X^T Y), 2 block update (X C), 3 small dense (syevd, coarse solves), 4 column
  * dots, 5 elementwise block kernels.
- * enable clears the records; report fills arrays of 6: launches, device ms, work (algorithmic
- * bytes for classes 0/4/5, flops for 1-3). */
+ * enable clears the records (on: 0 = off, 1 = all classes, 2 = the SpMM class only - two event
+ * records per launch are not free, so a timed region records only the class its roofline is quoted
+ * on); report fills arrays of 6: launches, device ms, work (algorithmic bytes for classes 0/4/5,
+ * flops for 1-3). */
 int lb_profile_enable(lb_ctx *ctx, int on);
 int lb_profile_report(lb_ctx *ctx, int64_t *count, double *ms, double *work);
 /* the records of one class aggregated by launch shape (SpMM: shape0 = columns, shape1 = nnz of the

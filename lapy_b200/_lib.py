@@ -189,7 +189,8 @@ class Context:
 
     PROFILE_CLASSES = ("spmm", "gram", "update", "small_dense", "col_dots", "elementwise")
 
-    def profile_enable(self, on: bool = True):
+    def profile_enable(self, on: bool | int = True):
+        """0 / False: off; 1 / True: every kernel class; 2: the SpMM class only (cheap enough for a timed region)."""
         check(lib().lb_profile_enable(self.handle, int(on)))
 
     def profile_report(self) -> dict:

@@ -532,6 +532,11 @@ __global__ void densify(int64_t n, const int32_t *__restrict__ ptr, const int32_
     for (int p = ptr[i]; p < ptr[i + 1]; p++) dense[i * n + idx[p]] = val[p];
 }
 
+__global__ void set_identity(int64_t n, double *__restrict__ dense, int ld) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dense[i * ld + i] = 1.0;
+}
+
 __global__ void fix_empty_diag(int64_t n, double *__restrict__ dense) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n && dense[i * n + i] <= 0.0) dense[i * n + i] = 1.0;
@@ -565,6 +570,12 @@ std::unique_ptr<Amg> amg_setup(lb_ctx *c, std::unique_ptr<lb_mat> K0, int mcap, 
             LB_LAUNCH(c, densify, cdiv(n, 128), 128, 0, n, K->indptr.p, K->indices.p, K->data.p, amg->coarse_chol.p);
             LB_LAUNCH(c, fix_empty_diag, cdiv(n, 128), 128, 0, n, amg->coarse_chol.p);
             dense_chol_solve_prepare(c, (int)n, amg->coarse_chol.p);
+            // inverse = solve with the identity (once per hierarchy; symmetric, so row- == column-major)
+            amg->coarse_ld = ((int)n + 1) & ~1;
+            amg->coarse_inv.alloc(c, (size_t)n * amg->coarse_ld);
+            amg->coarse_inv.zero();
+            LB_LAUNCH(c, set_identity, cdiv(n, 128), 128, 0, n, amg->coarse_inv.p, amg->coarse_ld);
+            dense_chol_solve(c, (int)n, amg->coarse_chol.p, (int)n, amg->coarse_inv.p, amg->coarse_ld);
             L.K = std::move(K);
             L.x.alloc(c, (size_t)n * mcap);
             L.b.alloc(c, (size_t)n * mcap);
@@ -727,6 +738,12 @@ static void cycle(Amg &amg, int l, const double *b, int ldb, double *x, int ldx,
     lb_ctx *c = amg.ctx;
     AmgLevel &L = amg.levels[l];
     if (l == (int)amg.levels.size() - 1) {
+        const bool aligned = (ldb % 2 == 0) && ((reinterpret_cast<uintptr_t>(b) & 15) == 0) && b != x;
+        if (aligned) {  // x = K^-1 b as one tall-skinny DMMA product with the explicit inverse
+            ProfScope prof(c, PROF_TRSM, 2.0 * amg.coarse_n * amg.coarse_n * m, amg.coarse_n, m);
+            update_dmma(c, amg.coarse_n, amg.coarse_n, amg.coarse_inv.p, amg.coarse_ld, m, b, ldb, 1.0, 0.0, x, ldx);
+            return;
+        }
         copy_cols(c, L.K->n, m, b, ldb, x, ldx);
         dense_chol_solve(c, amg.coarse_n, amg.coarse_chol.p, m, x, ldx);
         return;

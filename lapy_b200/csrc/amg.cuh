@@ -25,6 +25,11 @@ struct Amg {
     lb_ctx *ctx = nullptr;
     std::vector<AmgLevel> levels;
     DBuf<double> coarse_chol;  // dense Cholesky factor of the coarsest operator
+    // explicit inverse of the coarsest operator, row-major (coarse_n, coarse_ld) with an even leading
+    // dimension: the coarse solve of an aligned block is ONE DMMA block product instead of two
+    // latency-bound cuBLAS trsm (0.41 ms -> ~0.05 ms per visit at 561 unknowns x 64 columns)
+    DBuf<double> coarse_inv;
+    int coarse_ld = 0;
     int coarse_n = 0;
     int cheb_deg = 2;
     int gamma = 2;  // cycle index: 1 = V, 2 = W

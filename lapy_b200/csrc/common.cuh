@@ -76,7 +76,7 @@ struct lb_ctx {
     bool trace = false;        // LAPY_B200_TRACE=1: per-phase wall clock (synchronising!) on stderr
     double trace_t0 = 0;
     // per-kernel-class device timing (lb_profile_enable): event pairs around the hot launches
-    bool profile = false;
+    int profile = 0;  // 0 off, 1 all classes, 2 SpMM class only (cheap enough for a timed region)
     struct ProfRec {
         int cls;
         cudaEvent_t e0, e1;

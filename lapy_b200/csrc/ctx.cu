@@ -117,7 +117,7 @@ static cudaEvent_t prof_event(lb_ctx *c) {
 }
 
 ProfScope::ProfScope(lb_ctx *ctx, int cls, double work, int64_t shape0, int64_t shape1) : c(ctx) {
-    if (!c->profile) return;
+    if (c->profile == 0 || (c->profile == 2 && cls != PROF_SPMM)) return;
     lb_ctx::ProfRec r{cls, prof_event(c), prof_event(c), work, {shape0, shape1}};
     cudaEventRecord(r.e0, c->stream);
     idx = (int)c->prof.size();
@@ -351,7 +351,7 @@ int lb_profile_enable(lb_ctx *c, int on) {
         c->prof_pool.push_back(r.e1);
     }
     c->prof.clear();
-    c->profile = on != 0;
+    c->profile = on;
     LB_API_END
 }
 

@@ -283,10 +283,14 @@ void update_dmma(lb_ctx *c, int64_t n, int p, const double *x, int ldx, int q, c
         const int64_t ntiles = (n + rows - 1) / rows;
         const int gx = (int)std::min<int64_t>(ntiles, std::max(1, (kSMs * 2) / ytiles));
         dim3 grid(gx, ytiles);
-        // per device (a process may drive several contexts): set every time, it is a cheap host call
+        // the dynamic shared memory limit is a per-device, per-instantiation setting: once per (device, tile)
 #define LB_UPD(WC, NJ)                                                                                                     \
     do {                                                                                                                   \
-        LB_CUDA(cudaFuncSetAttribute(update_dmma_pipe_kernel<WC, NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        static bool attr_set[64] = {};                                                                                     \
+        if (c->device >= 64 || !attr_set[c->device]) {                                                                     \
+            LB_CUDA(cudaFuncSetAttribute(update_dmma_pipe_kernel<WC, NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            if (c->device < 64) attr_set[c->device] = true;                                                                \
+        }                                                                                                                  \
         LB_LAUNCH(c, (update_dmma_pipe_kernel<WC, NJ>), grid, 256, smem, n, p, x, ldx, q, cmat, ldc, alpha, beta, y, ldy);      \
     } while (0)
         if (cols == 64) LB_UPD(2, 4);

@@ -132,6 +132,7 @@ __global__ void pcg_beta(int m, double *__restrict__ rz, const double *__restric
 // diagonal entries are zeroed (voff), with the Jacobi update as the row epilogue.
 constexpr int kJacCap = 2944;
 constexpr int kJacBatch = 2;
+constexpr int kJacDepCap = 24;  // neighbour strips tracked per strip (active set)
 
 // voff <- off-diagonal part of K (diagonal entries set to +0.0), kdiag <- diagonal of K
 __global__ void split_diagonal(int64_t n, const int32_t *__restrict__ indptr, const int32_t *__restrict__ indices,
@@ -154,9 +155,33 @@ __global__ void __launch_bounds__(256) jacobi_stream_kernel(int64_t n, const int
                                                             const double *__restrict__ kdiag,
                                                             const double *__restrict__ x, const double *__restrict__ b,
                                                             double *__restrict__ y, int ld,
-                                                            unsigned long long *__restrict__ max_rel) {
+                                                            unsigned long long *__restrict__ max_rel,
+                                                            const unsigned char *__restrict__ age_in,
+                                                            unsigned char *__restrict__ age_out,
+                                                            const int32_t *__restrict__ dep,
+                                                            const int32_t *__restrict__ dep_cnt, double thr) {
     __shared__ double s_prod[MC][kJacCap];
     __shared__ int32_t s_ptr[ROWS + 1];
+    // Active set: a strip is swept only if one of the strips its columns point into (itself included)
+    // changed by more than thr (relative) in one of the last two sweeps.  Ahead of the diffusion front
+    // everything is still exactly 0, behind it the values have converged: only the band in between is
+    // worked on.  age = sweeps since the strip last changed (two ping-pong buffers: after two quiet
+    // sweeps both hold the same values to within thr).  dep_cnt < 0: too many neighbour strips, always swept.
+    if (dep) {
+        __shared__ int s_active;
+        if (threadIdx.x == 0) s_active = dep_cnt[blockIdx.x] < 0;
+        __syncthreads();
+        const int nd = dep_cnt[blockIdx.x];
+        if (threadIdx.x < nd && age_in[dep[(int64_t)blockIdx.x * kJacDepCap + threadIdx.x]] <= 1) s_active = 1;
+        __syncthreads();
+        if (!s_active) {
+            if (threadIdx.x == 0) {
+                const int a = age_in[blockIdx.x];
+                age_out[blockIdx.x] = (unsigned char)min(a + 1, 255);
+            }
+            return;
+        }
+    }
     const int64_t strip0 = (int64_t)blockIdx.x * ROWS;
     const int nrows = (int)(min(n, strip0 + ROWS) - strip0);
     for (int i = threadIdx.x; i <= nrows; i += 256) s_ptr[i] = __ldg(indptr + strip0 + i);
@@ -206,23 +231,102 @@ __global__ void __launch_bounds__(256) jacobi_stream_kernel(int64_t n, const int
             else if (xn != 0.0) rel = fmax(rel, fabs(xn - xo) / fabs(xn));
         }
     }
+    if (dep) {
+        const int changed = __syncthreads_or(rel > thr);
+        if (threadIdx.x == 0) {
+            const int a = age_in[blockIdx.x];
+            age_out[blockIdx.x] = changed ? 0 : (unsigned char)min(a + 1, 255);
+        }
+    }
 #pragma unroll
     for (int o = 16; o; o >>= 1) rel = fmax(rel, __shfl_xor_sync(0xffffffffu, rel, o));
     if ((threadIdx.x & 31) == 0 && rel > 0.0) atomicMax(max_rel, (unsigned long long)__double_as_longlong(rel));
 }
 
+// neighbour strips of every strip of ROWS rows: the distinct values of column / ROWS over the
+// strip's entries (bitmap in shared memory, then compaction); more than kJacDepCap -> dep_cnt = -1
+template <int ROWS>
+__global__ void __launch_bounds__(256) strip_deps_kernel(int64_t n, const int32_t *__restrict__ indptr,
+                                                         const int32_t *__restrict__ indices, int nstrips,
+                                                         int32_t *__restrict__ dep, int32_t *__restrict__ dep_cnt) {
+    extern __shared__ unsigned s_bits[];  // ceil(nstrips / 32) words
+    __shared__ int s_cnt;
+    const int nwords = (nstrips + 31) / 32;
+    for (int i = threadIdx.x; i < nwords; i += 256) s_bits[i] = 0u;
+    if (threadIdx.x == 0) s_cnt = 0;
+    __syncthreads();
+    const int64_t strip0 = (int64_t)blockIdx.x * ROWS;
+    const int64_t rlast = min(n, strip0 + ROWS);
+    const int beg = indptr[strip0], end = indptr[rlast];
+    for (int p = beg + threadIdx.x; p < end; p += 256) {
+        const int sj = indices[p] / ROWS;
+        atomicOr(&s_bits[sj >> 5], 1u << (sj & 31));
+    }
+    if (threadIdx.x == 0) atomicOr(&s_bits[blockIdx.x >> 5], 1u << (blockIdx.x & 31));  // itself
+    __syncthreads();
+    for (int i = threadIdx.x; i < nwords; i += 256) {
+        unsigned w = s_bits[i];
+        while (w) {
+            const int bit = __ffs(w) - 1;
+            w &= w - 1;
+            const int slot = atomicAdd(&s_cnt, 1);
+            if (slot < kJacDepCap) dep[(int64_t)blockIdx.x * kJacDepCap + slot] = i * 32 + bit;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) dep_cnt[blockIdx.x] = s_cnt <= kJacDepCap ? s_cnt : -1;
+}
+
+// active-set state of one componentwise Jacobi solve (see jacobi_stream_kernel)
+struct JacobiActive {
+    int rows = 0, nstrips = 0;
+    DBuf<int32_t> dep, dep_cnt;
+    DBuf<unsigned char> age[2];
+    int cur = 0;
+    bool on = false;
+};
+
+static void jacobi_active_setup(lb_ctx *c, const lb_mat *K, JacobiActive &ja) {
+    const int64_t n = K->n;
+    ja.rows = K->nnz <= 10 * n ? 256 : 128;  // the strip size jacobi_sweep picks
+    ja.nstrips = cdiv(n, ja.rows);
+    ja.on = ja.nstrips >= 64 && ja.nstrips <= 8 * 48 * 1024;  // bitmap <= 48 KB of shared memory
+    if (!ja.on) return;
+    ja.dep.alloc(c, (size_t)ja.nstrips * kJacDepCap);
+    ja.dep_cnt.alloc(c, ja.nstrips);
+    ja.age[0].alloc(c, ja.nstrips);
+    ja.age[1].alloc(c, ja.nstrips);
+    const size_t smem = (size_t)((ja.nstrips + 31) / 32) * sizeof(unsigned);
+    if (ja.rows == 256)
+        LB_LAUNCH(c, strip_deps_kernel<256>, ja.nstrips, 256, smem, n, K->indptr.p, K->indices.p, ja.nstrips, ja.dep.p, ja.dep_cnt.p);
+    else
+        LB_LAUNCH(c, strip_deps_kernel<128>, ja.nstrips, 256, smem, n, K->indptr.p, K->indices.p, ja.nstrips, ja.dep.p, ja.dep_cnt.p);
+}
+
+static void jacobi_active_reset(lb_ctx *c, JacobiActive &ja) {  // new right-hand sides: everything is swept twice
+    if (!ja.on) return;
+    ja.age[0].zero();
+    ja.age[1].zero();
+    ja.cur = 0;
+}
+
 static void jacobi_sweep(lb_ctx *c, const lb_mat *K, const double *voff, const double *kdiag, const double *x,
-                         const double *b, double *y, int ld, int mc, unsigned long long *max_rel) {
+                         const double *b, double *y, int ld, int mc, unsigned long long *max_rel, JacobiActive &ja,
+                         double thr) {
     const int64_t n = K->n;
     const bool wide = K->nnz <= 10 * n;  // 256 rows per CTA fit the staging buffer on average
+    const unsigned char *age_in = ja.on ? ja.age[ja.cur].p : nullptr;
+    unsigned char *age_out = ja.on ? ja.age[ja.cur ^ 1].p : nullptr;
+    const int32_t *dep = ja.on ? ja.dep.p : nullptr, *dep_cnt = ja.on ? ja.dep_cnt.p : nullptr;
 #define LB_JAC(MC, ROWS)                                                                                              \
     LB_LAUNCH(c, (jacobi_stream_kernel<MC, ROWS>), cdiv(n, ROWS), 256, 0, n, K->indptr.p, K->indices.p, voff, kdiag, x, b, y, \
-              ld, max_rel)
+              ld, max_rel, age_in, age_out, dep, dep_cnt, thr)
     if (mc == 1 && wide) LB_JAC(1, 256);
     else if (mc == 1) LB_JAC(1, 128);
     else if (wide) LB_JAC(2, 256);
     else LB_JAC(2, 128);
 #undef LB_JAC
+    ja.cur ^= 1;
 }
 
 struct SolveStats {
@@ -265,12 +369,16 @@ static SolveStats block_pcg(lb_ctx *c, lb_mat *K, const double *rhs, double *x, 
         d2d(c, voff.p, K->data.p, (size_t)K->nnz * sizeof(double));
         LB_LAUNCH(c, split_diagonal, cdiv(n, 256), 256, 0, n, K->indptr.p, K->indices.p, voff.p, kdiag.p);
         const double jtol = std::max(0.1 * tol, 1e-13);  // on the relative increment per sweep
+        JacobiActive ja;
+        jacobi_active_setup(c, K, ja);
         bool ok = true;
         int sweeps_max = 0;
         double rel_max = 0.0;
         for (int c0 = 0; c0 < m && ok; c0 += 2) {
             const int mc = std::min(2, m - c0);
             xa.zero();
+            xb.zero();  // strips that are never swept (ahead of the front) must read 0 in both buffers
+            jacobi_active_reset(c, ja);
             double *cur = xa.p + c0, *nxt = xb.p + c0;
             const double *bb = rhs + c0;
             double rel = 1.0, prev = 2.0;
@@ -279,11 +387,11 @@ static SolveStats block_pcg(lb_ctx *c, lb_mat *K, const double *rhs, double *x, 
             ok = false;
             while (sweeps < 100000) {
                 for (int i = 0; i < 63; i++) {
-                    jacobi_sweep(c, K, voff.p, kdiag.p, cur, bb, nxt, m, mc, mr.p);
+                    jacobi_sweep(c, K, voff.p, kdiag.p, cur, bb, nxt, m, mc, mr.p, ja, jtol);
                     std::swap(cur, nxt);
                 }
                 mr.zero();
-                jacobi_sweep(c, K, voff.p, kdiag.p, cur, bb, nxt, m, mc, mr.p);
+                jacobi_sweep(c, K, voff.p, kdiag.p, cur, bb, nxt, m, mc, mr.p, ja, jtol);
                 std::swap(cur, nxt);
                 sweeps += 64;
                 unsigned long long bits2 = 0;
