@@ -89,6 +89,10 @@ int lb_profile_shapes(lb_ctx *ctx, int cls, int cap, int64_t *shape0, int64_t *s
                       double *ms, double *work, int *nshapes);
 /* number of kernels this library has launched on ctx since creation */
 int lb_launch_count(lb_ctx *ctx, int64_t *count);
+/* out4: [0] kernels launched, [1] assemblies done by the strip-cooperative triangle kernels, [2] by
+ * the record pipeline (tets; triangle meshes with valence > 8, repeated vertices or degenerate
+ * elements), [3] reserved.  Lets a test assert that the fast path is the one that runs. */
+int lb_ctx_counters(lb_ctx *ctx, int64_t *out4);
 
 /* ---- row-partitioned multi-GPU mode (one process per GPU, NCCL) -------------------------------
  * rank 0 creates an id (128 bytes), the host program broadcasts it (torch.distributed, MPI, ...),

@@ -49,6 +49,7 @@ SIGNATURES = {
     "lb_timer_start": [_vp],
     "lb_timer_stop": [_vp, C.POINTER(_dbl)],
     "lb_launch_count": [_vp, C.POINTER(_i64)],
+    "lb_ctx_counters": [_vp, _vp],
     "lb_profile_enable": [_vp, _int],
     "lb_profile_report": [_vp, _vp, _vp, _vp],
     "lb_profile_shapes": [_vp, _int, _int, _vp, _vp, _vp, _vp, _vp, C.POINTER(_int)],
@@ -216,6 +217,12 @@ class Context:
             {"shape": (int(s0[i]), int(s1[i])), "launches": int(cnt[i]), "ms": float(ms[i]), "work": float(work[i])}
             for i in range(n.value)
         ]
+
+    def counters(self) -> dict:
+        """{launches, strip_assemblies, record_assemblies} since the context was created."""
+        out = np.zeros(4, np.int64)
+        check(lib().lb_ctx_counters(self.handle, ptr(out)))
+        return {"launches": int(out[0]), "strip_assemblies": int(out[1]), "record_assemblies": int(out[2])}
 
     def launch_count(self) -> int:
         n = C.c_int64()

@@ -104,57 +104,67 @@ struct ElemConsts {
     double lump_deg;  // lumped mass contribution of a clamped element (tets)
 };
 
+// local entries of one triangle (solver.py:145-169, :259-280, :342-358) in the dtype of the vertices:
+// q12, q23, q31 (divided by vol unless degenerate), bii (-1 marks a degenerate element), vol
+template <class T, int MODE>
+__device__ __forceinline__ void tria_local(const Vec3<T> &p1, const Vec3<T> &p2, const Vec3<T> &p3, int64_t eo,
+                                           const double *__restrict__ u1, const double *__restrict__ u2,
+                                           const double *__restrict__ am, double &q12, double &q23, double &q31,
+                                           double &bii, double &vol_d) {
+    using E = Ex<T>;
+    using ED = Ex<double>;
+    Vec3<T> ec = vsub(p2, p1), ea = vsub(p3, p2), eb = vsub(p1, p3);  // v2mv1, v3mv2, v1mv3
+    Vec3<T> cr = vcross(ea, eb);
+    T s = E::sqrt(vdot(cr, cr));
+    T vol = MODE == MODE_MASS ? E::mul((T)0.5, s) : E::mul((T)2, s);
+    vol_d = (double)vol;
+    const bool degen = vol < E::eps();
+    if (MODE == MODE_FEM) {
+        T d12 = vdot(ea, eb), d23 = vdot(eb, ec), d31 = vdot(ec, ea);
+        if (!degen) {
+            d12 = E::div(d12, vol);
+            d23 = E::div(d23, vol);
+            d31 = E::div(d31, vol);
+        }
+        q12 = (double)d12; q23 = (double)d23; q31 = (double)d31;
+    } else if (MODE == MODE_ANISO) {
+        // projections and the weighted dot run in fp64 (u1, u2, aniso_mat are fp64 arrays of the caller,
+        // indexed by the CALLER's element id eo)
+        Vec3<double> a = vwiden(ea), b = vwiden(eb), c = vwiden(ec);
+        Vec3<double> w1 = {u1[3 * eo], u1[3 * eo + 1], u1[3 * eo + 2]};
+        Vec3<double> w2 = {u2[3 * eo], u2[3 * eo + 1], u2[3 * eo + 2]};
+        double m0 = am[2 * eo], m1 = am[2 * eo + 1];
+        double a0 = vdot(w1, a), a1 = vdot(w2, a), b0 = vdot(w1, b), b1 = vdot(w2, b);
+        double c0 = vdot(w1, c), c1 = vdot(w2, c);
+        auto adot = [&](double x0, double x1, double y0, double y1) {
+            return ED::add(ED::mul(ED::mul(x0, m0), y0), ED::mul(ED::mul(x1, m1), y1));
+        };
+        q12 = adot(a0, a1, b0, b1);
+        q23 = adot(b0, b1, c0, c1);
+        q31 = adot(c0, c1, a0, a1);
+        if (!degen) {
+            q12 = ED::div(q12, vol_d);
+            q23 = ED::div(q23, vol_d);
+            q31 = ED::div(q31, vol_d);
+        }
+    } else {
+        q12 = q23 = q31 = 0.0;
+    }
+    bii = degen ? -1.0 : (double)E::div(vol, MODE == MODE_MASS ? (T)6 : (T)24);
+}
+
 template <class T, int MODE>
 __global__ void __launch_bounds__(256) tria_element_kernel(
     const typename Ex<T>::V4 *__restrict__ v4, const int4 *__restrict__ t4, int64_t nt,
     const double *__restrict__ u1, const double *__restrict__ u2, const double *__restrict__ am,
     D4 *__restrict__ rec, int32_t *__restrict__ deg, double *__restrict__ partial) {
-    using E = Ex<T>;
-    using ED = Ex<double>;
     int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     double vol_d = 0.0;
     if (e < nt) {
         int4 ti = __ldg(t4 + e);
         Vec3<T> p1 = load_vertex<T>(v4, ti.x), p2 = load_vertex<T>(v4, ti.y), p3 = load_vertex<T>(v4, ti.z);
-        Vec3<T> ec = vsub(p2, p1), ea = vsub(p3, p2), eb = vsub(p1, p3);  // v2mv1, v3mv2, v1mv3
-        Vec3<T> cr = vcross(ea, eb);
-        T s = E::sqrt(vdot(cr, cr));
-        T vol = MODE == MODE_MASS ? E::mul((T)0.5, s) : E::mul((T)2, s);
-        vol_d = (double)vol;
-        bool degen = vol < E::eps();
-        double q12, q23, q31;
-        if (MODE == MODE_FEM) {
-            T d12 = vdot(ea, eb), d23 = vdot(eb, ec), d31 = vdot(ec, ea);
-            if (!degen) {
-                d12 = E::div(d12, vol);
-                d23 = E::div(d23, vol);
-                d31 = E::div(d31, vol);
-            }
-            q12 = (double)d12; q23 = (double)d23; q31 = (double)d31;
-        } else if (MODE == MODE_ANISO) {
-            // projections and the weighted dot run in fp64 (u1, u2, aniso_mat are fp64 arrays)
-            Vec3<double> a = vwiden(ea), b = vwiden(eb), c = vwiden(ec);
-            const int64_t eo = ti.w;  // caller's element id (t4m is sorted): u1 / u2 / aniso_mat are the caller's arrays
-            Vec3<double> w1 = {u1[3 * eo], u1[3 * eo + 1], u1[3 * eo + 2]};
-            Vec3<double> w2 = {u2[3 * eo], u2[3 * eo + 1], u2[3 * eo + 2]};
-            double m0 = am[2 * eo], m1 = am[2 * eo + 1];
-            double a0 = vdot(w1, a), a1 = vdot(w2, a), b0 = vdot(w1, b), b1 = vdot(w2, b);
-            double c0 = vdot(w1, c), c1 = vdot(w2, c);
-            auto adot = [&](double x0, double x1, double y0, double y1) {
-                return ED::add(ED::mul(ED::mul(x0, m0), y0), ED::mul(ED::mul(x1, m1), y1));
-            };
-            q12 = adot(a0, a1, b0, b1);
-            q23 = adot(b0, b1, c0, c1);
-            q31 = adot(c0, c1, a0, a1);
-            if (!degen) {
-                q12 = ED::div(q12, vol_d);
-                q23 = ED::div(q23, vol_d);
-                q31 = ED::div(q31, vol_d);
-            }
-        } else {
-            q12 = q23 = q31 = 0.0;
-        }
-        double bii = degen ? -1.0 : (double)E::div(vol, MODE == MODE_MASS ? (T)6 : (T)24);
+        double q12, q23, q31, bii;
+        tria_local<T, MODE>(p1, p2, p3, ti.w, u1, u2, am, q12, q23, q31, bii, vol_d);
         st_d4(rec + e, q12, q23, q31, bii);
         if (deg) {
             atomicAdd(deg + ti.x, 1);
@@ -893,6 +903,224 @@ __global__ void __launch_bounds__(kRowThreads) tria_row_fill_fast(
         }
     }
 }
+
+// ---- strip-cooperative triangle rows -----------------------------------------------------------
+// ncu (round 2) on the pipeline above at level 9: 1.8 GB of DRAM traffic for 0.59 GB of compulsory
+// bytes - 1.1 GB of it are intermediates the design itself creates (16-byte incidence records written
+// once and read twice, 32-byte element records written and gathered) - and ~1600 instructions per
+// row in the fill.  Strip form: a CTA owns 128 consecutive rows of the locality numbering.  The
+// elements that touch those rows are (a) the contiguous range of the sorted element array whose
+// smallest vertex lies in the strip and (b) a short list of "halo" elements whose smallest vertex
+// lies in an earlier strip (lb_mesh::hptr / hlist, part of the solver layout built at upload).  The
+// CTA loads them once, computes the element matrices INTO SHARED MEMORY, builds the strip-local
+// vertex -> element incidence with shared-memory atomics, and every thread then merges one row out of
+// shared memory with the same register sorting networks as tria_row_fill_fast.  No incidence or
+// element records ever reach DRAM; the count pass (FILL = false) is the same traversal without
+// the vertex loads and the arithmetic.
+// Anything the fast path does not cover raises a flag and the whole assembly falls back to the
+// record pipeline above: a row with > 8 incident triangles or a vertex repeated inside a triangle,
+// a strip with > kStripElems elements, a degenerate element (its clamp needs the global mean of vol).
+constexpr int kStripRows = 128;
+constexpr int kStripElems = 448;
+
+struct StripLayout {
+    const int4 *t4m;
+    const int32_t *kptr;   // (n + 1) first sorted element whose smallest vertex is >= v
+    const int32_t *hptr;   // (nstrips + 1)
+    const int32_t *hlist;  // halo elements per strip
+    int64_t n;
+};
+
+template <bool FILL, class T, int MODE>
+__global__ void __launch_bounds__(kStripRows) strip_rows_kernel(
+    StripLayout L, const typename Ex<T>::V4 *__restrict__ v4m, const double *__restrict__ u1,
+    const double *__restrict__ u2, const double *__restrict__ am, int cap, RowOut out, int32_t *__restrict__ row_nnz,
+    int32_t *__restrict__ row_has, int32_t *__restrict__ flags) {
+    constexpr int R = kStripRows;
+    extern __shared__ __align__(32) unsigned char smem_raw[];
+    // layout: s_rec [E] D4 | s_el [E] int4 | s_a [cap] | s_b [cap] | s_k [cap] | s_cnt [R] | s_inc [8][R] u16 | s_slot [16][R] u8
+    D4 *s_rec = reinterpret_cast<D4 *>(smem_raw);
+    int4 *s_el = reinterpret_cast<int4 *>(s_rec + (FILL ? kStripElems : 0));
+    double *s_a = reinterpret_cast<double *>(s_el + kStripElems);
+    double *s_b = s_a + (FILL ? cap : 0);
+    int32_t *s_k = reinterpret_cast<int32_t *>(s_b + (FILL ? cap : 0));
+    int32_t *s_cnt = s_k + (FILL ? cap : 0);
+    unsigned short *s_inc = reinterpret_cast<unsigned short *>(s_cnt + R);
+    unsigned char *s_slot = reinterpret_cast<unsigned char *>(s_inc + 8 * R);
+    const int t = threadIdx.x;
+    const int64_t r0 = (int64_t)blockIdx.x * R, r = r0 + t;
+    const int nrows = (int)(min(L.n, r0 + R) - r0);
+    const int eb = L.kptr[r0], nown = L.kptr[r0 + nrows] - eb;
+    const int hb = L.hptr[blockIdx.x], ne = nown + (L.hptr[blockIdx.x + 1] - hb);
+    if (ne > kStripElems) {  // uniform
+        if (t == 0) atomicOr(flags, 1);
+        return;
+    }
+    s_cnt[t] = 0;
+    __syncthreads();
+    // ---- phase 1: elements -> shared memory, strip-local incidence
+    for (int le = t; le < ne; le += R) {
+        const int e = le < nown ? eb + le : __ldg(L.hlist + hb + (le - nown));
+        const int4 ti = __ldg(L.t4m + e);
+        s_el[le] = ti;
+        if (FILL) {
+            const Vec3<T> p1 = load_vertex<T>(v4m, ti.x), p2 = load_vertex<T>(v4m, ti.y), p3 = load_vertex<T>(v4m, ti.z);
+            double q12, q23, q31, bii, vol_d;
+            tria_local<T, MODE>(p1, p2, p3, ti.w, u1, u2, am, q12, q23, q31, bii, vol_d);
+            st_d4(s_rec + le, q12, q23, q31, bii);
+            if (bii < 0.0) atomicOr(flags + 1, 1);  // degenerate: needs the global clamp -> record pipeline
+        }
+        const int vs[3] = {ti.x, ti.y, ti.z};
+#pragma unroll
+        for (int cn = 0; cn < 3; cn++) {
+            const int64_t lv = (int64_t)vs[cn] - r0;
+            if (lv >= 0 && lv < nrows) {
+                const int slot = atomicAdd(&s_cnt[lv], 1);
+                if (slot < kFastInc) s_inc[slot * R + lv] = (unsigned short)(le * 4 + cn);
+            }
+        }
+    }
+    __syncthreads();
+    // ---- phase 2: one row per thread out of shared memory
+    const int blk_beg = FILL ? out.indptr[r0] : 0, blk_nnz = FILL ? out.indptr[r0 + nrows] - blk_beg : 0;
+    const bool want_a = FILL && out.a_val != nullptr, want_b = FILL && out.b_val != nullptr;
+    const bool want_pat = want_a || want_b;
+    const bool use_smem = want_pat && blk_nnz <= cap;
+    auto process = [&](int32_t *keys, double *av, double *bv, const int rbeg, const int ninc) {
+        // incidences in the reference's triplet order: (caller's element id, corner)
+        int w8[kFastInc];
+#pragma unroll
+        for (int u = 0; u < kFastInc; u++) {
+            w8[u] = INT_MAX;
+            if (u < ninc) {
+                const int code = s_inc[u * R + t];
+                w8[u] = (s_el[code >> 2].w << 5) | ((code & 3) << 3) | u;
+            }
+        }
+#define LB_MM8(i, j)                      \
+    {                                     \
+        const int lo_ = min(w8[i], w8[j]); \
+        w8[j] = max(w8[i], w8[j]);         \
+        w8[i] = lo_;                      \
+    }
+        LB_MM8(0, 1) LB_MM8(2, 3) LB_MM8(4, 5) LB_MM8(6, 7) LB_MM8(0, 2) LB_MM8(1, 3) LB_MM8(4, 6) LB_MM8(5, 7) LB_MM8(1, 2)
+        LB_MM8(5, 6) LB_MM8(0, 4) LB_MM8(3, 7) LB_MM8(1, 5) LB_MM8(2, 6) LB_MM8(1, 4) LB_MM8(3, 6) LB_MM8(2, 4) LB_MM8(3, 5)
+        LB_MM8(3, 4)
+#undef LB_MM8
+        int code[kFastInc], w[16];
+        bool self = false;
+#pragma unroll
+        for (int i = 0; i < kFastInc; i++) {
+            code[i] = 0;
+            w[2 * i] = w[2 * i + 1] = INT_MAX;
+            if (i < ninc) {
+                code[i] = s_inc[(w8[i] & 7) * R + t];
+                const int4 el = s_el[code[i] >> 2];
+                const int cn = code[i] & 3;
+                // neighbours in the triplet order of this column: corner 0: (t2, t3), 1: (t1, t3), 2: (t2, t1)
+                const int k0 = cn == 1 ? el.x : el.y, k1 = cn == 2 ? el.x : el.z;
+                self |= k0 == (int)r || k1 == (int)r;
+                w[2 * i] = (k0 << 4) | (2 * i);
+                w[2 * i + 1] = (k1 << 4) | (2 * i + 1);
+            }
+        }
+        LB_NET16(LB_MINMAX)
+        int cnt = 0, dslot = 0, prev = -1;
+        bool dd = false;
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+            if (w[i] != INT_MAX) {
+                const int key = w[i] >> 4, cpos = w[i] & 15;
+                const bool first = key != prev;
+                if (first) {
+                    if (!dd && key > (int)r) {
+                        dslot = cnt++;
+                        dd = true;
+                    }
+                    if (FILL && want_pat) keys[cnt] = key;
+                    cnt++;
+                    prev = key;
+                }
+                if (FILL) s_slot[cpos * R + t] = (unsigned char)((cnt - 1) | (first ? 0x80 : 0));
+            }
+        }
+        if (!dd) dslot = cnt++;
+        if (!FILL) {
+            if (self) atomicOr(flags, 1);
+            row_nnz[r] = cnt;
+            return;
+        }
+        if (want_pat) keys[dslot] = (int)r;
+        double da = 0.0, db = 0.0, lump = 0.0;
+#pragma unroll
+        for (int i = 0; i < kFastInc; i++) {
+            if (i < ninc) {
+                const int cn = code[i] & 3;
+                const D4 er = s_rec[code[i] >> 2];
+                const double a12 = er.x, a23 = er.y, a31 = er.z, bii = er.w;
+                const double bij = 0.5 * bii;
+                lump += 2.0 * bii;  // vol/12 (vol/3 for fem_tria_mass) == 2*bii exactly
+                const double x0 = cn == 2 ? a23 : a12, x1 = cn == 1 ? a23 : a31;
+                const double m0 = cn == 2 ? a31 : a12, m1 = cn == 0 ? a31 : a23;
+                // the diagonal (row sum = 0, solver.py:167-169) is formed in the element dtype
+                const double xd = sizeof(T) == 4 && MODE != MODE_ANISO ? (double)__fsub_rn(-(float)m0, (float)m1) : __dsub_rn(-m0, m1);
+                if (want_pat) {
+                    const int e0 = s_slot[(2 * i) * R + t], e1 = s_slot[(2 * i + 1) * R + t];
+                    const int p0 = e0 & 0x7f, p1 = e1 & 0x7f;
+                    if (want_a) av[p0] = (e0 & 0x80) ? x0 : __dadd_rn(av[p0], x0);
+                    if (want_b) bv[p0] = (e0 & 0x80) ? bij : __dadd_rn(bv[p0], bij);
+                    if (want_a) av[p1] = (e1 & 0x80) ? x1 : __dadd_rn(av[p1], x1);
+                    if (want_b) bv[p1] = (e1 & 0x80) ? bij : __dadd_rn(bv[p1], bij);
+                }
+                da = i == 0 ? xd : __dadd_rn(da, xd);
+                db = i == 0 ? bii : __dadd_rn(db, bii);
+            }
+        }
+        if (want_pat) {
+            if (want_a) av[dslot] = da;
+            if (want_b) bv[dslot] = db;
+            if (!use_smem && want_a && want_b)
+                for (int q = 0; q < cnt; q++) out.b_idx[rbeg + q] = keys[q];
+        }
+        if (out.lump_ptr) {
+            const int lp = out.lump_ptr[r];
+            out.lump_idx[lp] = (int)r;
+            out.lump_val[lp] = lump;
+        }
+    };
+    if (t < nrows) {
+        const int ninc = s_cnt[t];
+        if (!FILL) {
+            row_has[r] = ninc > 0;
+            if (ninc > kFastInc) atomicOr(flags, 1);
+            if (ninc == 0 || ninc > kFastInc) row_nnz[r] = 0;
+            else process(nullptr, nullptr, nullptr, 0, ninc);
+        } else if (ninc > 0 && ninc <= kFastInc) {
+            const int rbeg = out.indptr[r];
+            if (use_smem || !want_pat) {
+                const int off = want_pat ? rbeg - blk_beg : 0;
+                process(s_k + off, s_a + off, s_b + off, rbeg, ninc);
+            } else {
+                process((want_a ? out.a_idx : out.b_idx) + rbeg, out.a_val + rbeg, out.b_val + rbeg, rbeg, ninc);
+            }
+        }
+    }
+    if (FILL && use_smem) {
+        __syncthreads();
+        for (int q = t; q < blk_nnz; q += R) {
+            const int key = s_k[q];
+            if (want_a) {
+                out.a_idx[blk_beg + q] = key;
+                out.a_val[blk_beg + q] = s_a[q];
+            }
+            if (want_b) {
+                out.b_idx[blk_beg + q] = key;
+                out.b_val[blk_beg + q] = s_b[q];
+            }
+        }
+    }
+}
+
 #undef LB_MINMAX
 
 // ---- fused tet rows (the default for tets: 9.4 -> 4.4 ms at 121^3 in the caller's numbering) --------
@@ -1317,6 +1545,27 @@ __global__ void element_renumber_kernel(int64_t nt, int k, const int32_t *__rest
     t4m[pos] = make_int4(inv[ti.x], inv[ti.y], inv[ti.z], k == 4 ? inv[ti.w] : e);
 }
 
+// halo elements of the strips: element e (sorted, new vertex ids) belongs to the strip of its smallest
+// vertex; every OTHER strip one of its vertices lies in gets it as a halo element.  ptr == NULL: count.
+__global__ void halo_list_kernel(const int4 *__restrict__ t4m, int64_t nt, int32_t *__restrict__ cursor,
+                                 const int32_t *__restrict__ ptr, int32_t *__restrict__ list) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= nt) return;
+    const int4 ti = __ldg(t4m + e);
+    const int s0 = min(ti.x, min(ti.y, ti.z)) / kStripRows;
+    const int sa = ti.x / kStripRows, sb = ti.y / kStripRows, sc = ti.z / kStripRows;
+    const int cand[3] = {sa, sb, sc};
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        const int sj = cand[i];
+        bool dup = sj == s0;
+        for (int j = 0; j < i; j++) dup |= cand[j] == sj;
+        if (dup) continue;
+        const int pos = atomicAdd(cursor + sj, 1);
+        if (ptr) list[ptr[sj] + pos] = (int)e;
+    }
+}
+
 static void refresh_layout_vertices(lb_mesh *m) {
     lb_ctx *c = m->ctx;
     const int64_t n = m->n_ref;
@@ -1338,16 +1587,35 @@ static void build_layout(lb_mesh *m) {
     m->ord->n = n;
     ensure_order(*m->ord);
     refresh_layout_vertices(m);
-    DBuf<int32_t> key(c, nt), hist(c, n), kptr(c, n + 1);
+    DBuf<int32_t> key(c, nt), hist(c, n);
+    m->kptr.alloc(c, n + 1);
     hist.zero();
     LB_LAUNCH(c, element_key_kernel, cdiv(nt, 256), 256, 0, m->t4.p, nt, m->k, m->ord->inv.p, key.p, hist.p);
-    exclusive_scan_i32(c, hist.p, kptr.p, n);
+    exclusive_scan_i32(c, hist.p, m->kptr.p, n);
     hist.zero();
     m->eorig.alloc(c, nt);
-    LB_LAUNCH(c, element_fill_kernel, cdiv(nt, 256), 256, 0, nt, key.p, kptr.p, hist.p, m->eorig.p);
-    LB_LAUNCH(c, incidence_sort, cdiv(n, 128), 128, 0, kptr.p, m->eorig.p, n);
+    LB_LAUNCH(c, element_fill_kernel, cdiv(nt, 256), 256, 0, nt, key.p, m->kptr.p, hist.p, m->eorig.p);
+    LB_LAUNCH(c, incidence_sort, cdiv(n, 128), 128, 0, m->kptr.p, m->eorig.p, n);
     m->t4m.alloc(c, nt);
     LB_LAUNCH(c, element_renumber_kernel, cdiv(nt, 256), 256, 0, nt, m->k, m->eorig.p, m->t4.p, m->ord->inv.p, m->t4m.p);
+    // triangles: per strip of 128 rows the "halo" elements (they touch the strip, their smallest vertex
+    // lies in an earlier strip); ids fit the packed words of the strip kernel below 2^26 elements / 2^27 rows
+    m->has_strips = false;
+    if (m->k == 3 && nt < (1ll << 26) && n < (1ll << 27)) {
+        const int ns = cdiv(n, kStripRows);
+        DBuf<int32_t> hcnt(c, ns);
+        hcnt.zero();
+        m->hptr.alloc(c, ns + 1);
+        LB_LAUNCH(c, halo_list_kernel, cdiv(nt, 256), 256, 0, m->t4m.p, nt, hcnt.p, (const int32_t *)nullptr, (int32_t *)nullptr);
+        exclusive_scan_i32(c, hcnt.p, m->hptr.p, ns);
+        int32_t total = 0;
+        read_back(c, &total, m->hptr.p + ns, 1);
+        m->hlist.alloc(c, (size_t)std::max(1, total));
+        hcnt.zero();
+        LB_LAUNCH(c, halo_list_kernel, cdiv(nt, 256), 256, 0, m->t4m.p, nt, hcnt.p, m->hptr.p, m->hlist.p);
+        LB_LAUNCH(c, incidence_sort, cdiv(ns, 128), 128, 0, m->hptr.p, m->hlist.p, (int64_t)ns);  // deterministic order
+        m->has_strips = true;
+    }
 }
 
 template <class T>
@@ -1520,6 +1788,88 @@ static void run_rows(lb_mesh *mesh, const D4 *rec, const ElemConsts *consts, con
     *b_out = B;
 }
 
+// strip-cooperative triangle assembly (strip_rows_kernel): count pass, scan, fill pass.  Returns false
+// - with nothing allocated - when the mesh needs the record pipeline (flags raised by the kernels).
+template <class T>
+static bool run_strip_rows(lb_mesh *mesh, int kind, const double *u1, const double *u2, const double *am, bool want_a,
+                           bool lump, lb_mat **a_out, lb_mat **b_out) {
+    lb_ctx *c = mesh->ctx;
+    const int64_t n = mesh->n_ref;
+    const int ns = cdiv(n, kStripRows);
+    StripLayout L{mesh->t4m.p, mesh->kptr.p, mesh->hptr.p, mesh->hlist.p, n};
+    const typename Ex<T>::V4 *v4;
+    if constexpr (sizeof(T) == 4) v4 = mesh->v4fm.p;
+    else v4 = mesh->v4m.p;
+    DBuf<int32_t> row_nnz(c, n), row_has(c, n), flags(c, 2), indptr(c, n + 1), lump_ptr;
+    flags.zero();
+    RowOut none{};
+    const size_t smem_count = (size_t)kStripElems * 16 + kStripRows * 4 + 8 * kStripRows * 2;
+    LB_LAUNCH(c, (strip_rows_kernel<false, double, MODE_FEM>), ns, kStripRows, smem_count, L, (const D4 *)nullptr, u1, u2, am, 0,
+              none, row_nnz.p, row_has.p, flags.p);
+    exclusive_scan_i32(c, row_nnz.p, indptr.p, n);
+    if (lump) {
+        lump_ptr.alloc(c, n + 1);
+        exclusive_scan_i32(c, row_has.p, lump_ptr.p, n);
+    }
+    int32_t hflags[2] = {0, 0}, nnz32 = 0, nlump = 0;
+    read_back(c, hflags, flags.p, 2);
+    if (hflags[0]) return false;
+    read_back(c, &nnz32, indptr.p + n, 1);
+    if (lump) read_back(c, &nlump, lump_ptr.p + n, 1);
+    const int64_t nnz = nnz32;
+    const bool full_b = !lump;
+    lb_mat *A = nullptr, *B = nullptr;
+    try {
+        RowOut out{};
+        out.indptr = indptr.p;
+        if (want_a) {
+            A = new_mat(c, n, nnz);
+            d2d(c, A->indptr.p, indptr.p, (n + 1) * sizeof(int32_t));
+            out.a_idx = A->indices.p;
+            out.a_val = A->data.p;
+        }
+        if (full_b) {
+            B = new_mat(c, n, nnz);
+            d2d(c, B->indptr.p, indptr.p, (n + 1) * sizeof(int32_t));
+            out.b_idx = B->indices.p;
+            out.b_val = B->data.p;
+        } else {
+            B = new_mat(c, n, nlump);
+            B->diagonal = true;
+            d2d(c, B->indptr.p, lump_ptr.p, (n + 1) * sizeof(int32_t));
+            out.lump_ptr = lump_ptr.p;
+            out.lump_idx = B->indices.p;
+            out.lump_val = B->data.p;
+        }
+        const int cap = (want_a || full_b) ? 1280 : 0;  // CSR entries of shared memory per strip
+        const size_t smem = (size_t)kStripElems * 48 + (size_t)cap * 20 + kStripRows * 4 + 8 * kStripRows * 2 + 16 * kStripRows;
+#define LB_STRIP(MODE)                                                                                                   \
+    do {                                                                                                                 \
+        LB_CUDA(cudaFuncSetAttribute(strip_rows_kernel<true, T, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        LB_LAUNCH(c, (strip_rows_kernel<true, T, MODE>), ns, kStripRows, smem, L, v4, u1, u2, am, cap, out, (int32_t *)nullptr,  \
+                  (int32_t *)nullptr, flags.p);                                                                          \
+    } while (0)
+        if (kind == LB_FEM_TRIA) LB_STRIP(MODE_FEM);
+        else if (kind == LB_FEM_TRIA_ANISO) LB_STRIP(MODE_ANISO);
+        else LB_STRIP(MODE_MASS);
+#undef LB_STRIP
+        read_back(c, hflags, flags.p, 2);  // a degenerate element: its clamp needs the global mean of vol
+        if (hflags[1]) {
+            delete A;
+            delete B;
+            return false;
+        }
+    } catch (...) {
+        delete A;
+        delete B;
+        throw;
+    }
+    if (a_out) *a_out = A;
+    else delete A;
+    *b_out = B;
+    return true;
+}
+
 }  // namespace lb
 
 using namespace lb;
@@ -1634,8 +1984,6 @@ int lb_fem_assemble(lb_ctx *c, lb_mesh *mesh, int kind, int lump, const double *
     phase(c, "(enter assemble)");
     const int64_t nt = mesh->nt;
     const bool want_a = kind != LB_FEM_TRIA_MASS && a_out != nullptr;
-    DBuf<D4> rec(c, (size_t)nt * (mesh->k == 4 ? 3 : 1));
-    DBuf<ElemConsts> consts(c, 1);
     DBuf<double> d_u1, d_u2, d_am;
     if (kind == LB_FEM_TRIA_ANISO) {
         d_u1.alloc(c, 3 * nt);
@@ -1645,6 +1993,32 @@ int lb_fem_assemble(lb_ctx *c, lb_mesh *mesh, int kind, int lump, const double *
         h2d(c, d_u2.p, u2, 3 * nt * sizeof(double));
         h2d(c, d_am.p, aniso_mat, 2 * nt * sizeof(double));
     }
+    if (a_out) *a_out = nullptr;
+    auto tag = [&]() {  // the matrices are stored in the mesh's locality numbering (lb_mat::permuted)
+        if (a_out && *a_out) {
+            (*a_out)->ord = mesh->ord;
+            (*a_out)->permuted = true;
+        }
+        (*b_out)->ord = mesh->ord;
+        (*b_out)->permuted = true;
+    };
+    // triangles: strip-cooperative kernels (no record arrays in DRAM); anything they do not cover
+    // (valence > 8, repeated vertex, degenerate element, oversized strip) falls through to the record pipeline
+    if (mesh->k == 3 && mesh->has_strips) {
+        const bool ok = mesh->v_dtype == LB_F32
+                            ? run_strip_rows<float>(mesh, kind, d_u1.p, d_u2.p, d_am.p, want_a, lump != 0, a_out, b_out)
+                            : run_strip_rows<double>(mesh, kind, d_u1.p, d_u2.p, d_am.p, want_a, lump != 0, a_out, b_out);
+        phase(c, ok ? "strip rows" : "strip rows (fell back)");
+        if (ok) {
+            tag();
+            c->n_strip_assemblies++;
+            sync(c);  // u1/u2/aniso_mat are borrowed host buffers
+            return LB_OK;
+        }
+    }
+    c->n_record_assemblies++;
+    DBuf<D4> rec(c, (size_t)nt * (mesh->k == 4 ? 3 : 1));
+    DBuf<ElemConsts> consts(c, 1);
     DBuf<int32_t> deg(c, mesh->n_ref), aptr(c, mesh->n_ref + 1);
     DBuf<int4> inc4(c, (size_t)mesh->k * nt);
     deg.zero();
@@ -1657,18 +2031,11 @@ int lb_fem_assemble(lb_ctx *c, lb_mesh *mesh, int kind, int lump, const double *
     deg.zero();
     LB_LAUNCH(c, incidence_fill4, cdiv(nt, 256 * kIncEpt), 256, 0, mesh->t4m.p, nt, mesh->k, aptr.p, deg.p, inc4.p);
     phase(c, "incidence");
-    if (a_out) *a_out = nullptr;
     // clamped elements: the aniso numerators are fp64 even for fp32 meshes (solver.py:278-280)
     const bool degen_f32 = mesh->v_dtype == LB_F32 && kind != LB_FEM_TRIA_ANISO;
     if (mesh->k == 3) run_rows<3>(mesh, rec.p, consts.p, aptr.p, inc4.p, want_a, lump != 0, degen_f32, a_out, b_out);
     else run_rows<4>(mesh, rec.p, consts.p, aptr.p, inc4.p, want_a, lump != 0, degen_f32, a_out, b_out);
-    // the matrices are stored in the mesh's locality numbering (lb_mat::permuted)
-    if (a_out && *a_out) {
-        (*a_out)->ord = mesh->ord;
-        (*a_out)->permuted = true;
-    }
-    (*b_out)->ord = mesh->ord;
-    (*b_out)->permuted = true;
+    tag();
     sync(c);  // u1/u2/aniso_mat are borrowed host buffers
     phase(c, "rows");
     LB_API_END

@@ -69,6 +69,7 @@ struct lb_ctx {
     bool own_stream = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int64_t launches = 0;
+    int64_t n_strip_assemblies = 0, n_record_assemblies = 0;  // which assembly pipeline ran (lb_ctx_counters)
     void *pinned = nullptr;  // small pinned staging area for scalar read-backs
     size_t pinned_bytes = 0;
     void *cusolver = nullptr;  // cusolverDnHandle_t, created lazily (dense Rayleigh-Ritz only)
@@ -254,6 +255,10 @@ struct lb_mesh {
     // triangles carry the caller's element id in .w
     lb::DBuf<int4> t4m;
     lb::DBuf<int32_t> eorig;        // (nt) caller's element id of every sorted element (sort key of the tet rows)
+    // triangles: strips of 128 consecutive rows for the strip-cooperative assembly (assembly.cu)
+    lb::DBuf<int32_t> kptr;         // (n_ref + 1) first sorted element whose smallest vertex is >= v
+    lb::DBuf<int32_t> hptr, hlist;  // per strip: the elements touching it whose smallest vertex lies in an earlier strip
+    bool has_strips = false;
 };
 
 struct lb_mat {

@@ -420,6 +420,18 @@ int lb_launch_count(lb_ctx *c, int64_t *count) {
     LB_API_END
 }
 
+// [0] kernels launched, [1] assemblies done by the strip-cooperative kernels, [2] assemblies done by
+// the record pipeline (tets, and triangle meshes the strip kernels do not cover), [3] reserved
+int lb_ctx_counters(lb_ctx *c, int64_t *out4) {
+    LB_API_BEGIN
+    LB_REQUIRE(c && out4, "ctx/out is NULL");
+    out4[0] = c->launches;
+    out4[1] = c->n_strip_assemblies;
+    out4[2] = c->n_record_assemblies;
+    out4[3] = 0;
+    LB_API_END
+}
+
 // ---- matrices ---------------------------------------------------------------------------
 int lb_mat_info(lb_mat *m, int64_t *n, int64_t *nnz) {
     LB_API_BEGIN

@@ -346,3 +346,29 @@ def test_cube121_sampled_columns_vs_oracle():
             r0, r1 = indptr[col], indptr[col + 1]
             assert np.array_equal(got.indices[g0:g1], indices[r0:r1]), (name, col)
             assert np.array_equal(got.data[g0:g1], data[r0:r1]), (name, col)
+
+
+def test_which_assembly_pipeline_runs():
+    """Regular triangle meshes (valence <= 8, no repeated vertex, no degenerate element) must take the
+    strip-cooperative kernels - a silent fallback to the record pipeline would be a 3x slowdown nobody
+    notices; tets and irregular triangle meshes take the record pipeline."""
+    import lapy_b200
+    from lapy_b200 import _lib
+    from lapy_b200 import mesh as M
+    from lapy_b200.mesh import TriaMesh
+
+    ctx = _lib.default_context()
+    c0 = ctx.counters()
+    lapy_b200.Solver(M.icosphere(5))
+    lapy_b200.Solver(M.icosphere(5), lump=True)
+    lapy_b200.Solver.fem_tria_mass(M.icosphere(4))
+    c1 = ctx.counters()
+    assert c1["strip_assemblies"] - c0["strip_assemblies"] == 3 and c1["record_assemblies"] == c0["record_assemblies"]
+    lapy_b200.Solver(M.cube_tets(6))
+    n = 12
+    ang = np.linspace(0, 2 * np.pi, n, endpoint=False)
+    fan = TriaMesh(np.vstack([[0, 0, 0.3], np.column_stack([np.cos(ang), np.sin(ang), np.zeros(n)])]),
+                   np.column_stack([np.zeros(n, int), 1 + np.arange(n), 1 + (np.arange(n) + 1) % n]))  # fmt: skip
+    lapy_b200.Solver(fan)  # valence 12
+    c2 = ctx.counters()
+    assert c2["record_assemblies"] - c1["record_assemblies"] == 2 and c2["strip_assemblies"] == c1["strip_assemblies"]
