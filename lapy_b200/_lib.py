@@ -377,10 +377,18 @@ def spmm(ctx: Context, mat: DeviceMatrix, x: np.ndarray) -> np.ndarray:
     return y[:, 0] if one_d else y
 
 
-def eigs(ctx: Context, a: DeviceMatrix, b: DeviceMatrix, k: int, sigma: float, tol: float = 0.0, maxit: int = 0):
-    """lb_eigs -> (evals (k,), evecs (n,k), info dict)."""
+def eigs(ctx: Context, a: DeviceMatrix, b: DeviceMatrix, k: int, sigma: float, tol: float = 0.0, maxit: int = 0,
+         out_evecs: np.ndarray | None = None):
+    """lb_eigs -> (evals (k,), evecs (n,k), info dict).  ``out_evecs``: a C-contiguous float64 (n, k) array
+    to receive the eigenvectors (a throughput loop re-uses one buffer instead of allocating - and page
+    faulting - a fresh gigabyte per call)."""
     evals = np.empty(k, np.float64)
-    evecs = np.empty((a.n, k), np.float64)
+    if out_evecs is None:
+        evecs = np.empty((a.n, k), np.float64)
+    else:
+        evecs = out_evecs
+        if evecs.shape != (a.n, k) or evecs.dtype != np.float64 or not evecs.flags.c_contiguous:
+            raise ValueError("out_evecs must be a C-contiguous float64 array of shape (n, k)")
     info = Info()
     check(lib().lb_eigs(ctx.handle, a.handle, b.handle, int(k), float(sigma), float(tol), int(maxit),
                         ptr(evals), ptr(evecs), C.byref(info)))  # fmt: skip

@@ -921,7 +921,7 @@ __global__ void __launch_bounds__(kRowThreads) tria_row_fill_fast(
 // record pipeline above: a row with > 8 incident triangles or a vertex repeated inside a triangle,
 // a strip with > kStripElems elements, a degenerate element (its clamp needs the global mean of vol).
 constexpr int kStripRows = 128;
-constexpr int kStripElems = 448;
+constexpr int kStripElems = 576;  // measured: 410 at most on a level-8 icosphere (mean 334 = 256 own + 78 halo)
 
 struct StripLayout {
     const int4 *t4m;
@@ -1841,7 +1841,7 @@ static bool run_strip_rows(lb_mesh *mesh, int kind, const double *u1, const doub
             out.lump_idx = B->indices.p;
             out.lump_val = B->data.p;
         }
-        const int cap = (want_a || full_b) ? 1280 : 0;  // CSR entries of shared memory per strip
+        const int cap = (want_a || full_b) ? 1152 : 0;  // CSR entries of shared memory per strip (9 per row)
         const size_t smem = (size_t)kStripElems * 48 + (size_t)cap * 20 + kStripRows * 4 + 8 * kStripRows * 2 + 16 * kStripRows;
 #define LB_STRIP(MODE)                                                                                                   \
     do {                                                                                                                 \

@@ -427,7 +427,10 @@ __global__ void __launch_bounds__(1024) rr_coef_kernel(const double *__restrict_
         if (tid == 0 && keep) s_kept = kept + 1;
         __syncthreads();
     }
-    const int kept = s_kept, w = m + kept;
+    // an even number of P columns: the W block that follows [X P] in the basis then starts at a 16-byte
+    // aligned column (vector loads of the SpMM, cp.async of the block update) and the coefficient matrix
+    // has an even leading dimension; the dropped direction is the one of the last active column
+    const int kept = s_kept & ~1, w = m + kept;
     for (int i = tid; i < s * w; i += blockDim.x) {
         const int r = i / w, cidx = i - r * w;
         coef[i] = cidx < m ? cx[(size_t)cidx * s + r] : qq[(size_t)(cidx - m) * s + r];
@@ -529,7 +532,7 @@ static EigStats lobpcg_core(lb_ctx *c, const lb_mat *A, const lb_mat *B, Amg *am
                 hQ.assign((size_t)s * q, 0.0);
                 for (int a = 0; a < q; a++)
                     for (int i = m; i < s; i++) hQ[(size_t)i * q + a] = hC[(size_t)i * m + active_cols[a]];
-                mp_new = host_orth(s, m, hC, q, hQ);
+                mp_new = host_orth(s, m, hC, q, hQ) & ~1;  // even, like rr_coef_kernel
             }
             w = m + mp_new;
             coefh.assign((size_t)s * w, 0.0);
