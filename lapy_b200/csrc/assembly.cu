@@ -921,6 +921,7 @@ __global__ void __launch_bounds__(kRowThreads) tria_row_fill_fast(
 // record pipeline above: a row with > 8 incident triangles or a vertex repeated inside a triangle,
 // a strip with > kStripElems elements, a degenerate element (its clamp needs the global mean of vol).
 constexpr int kStripRows = 128;
+constexpr int kStripThreads = 256;  // phase 1 (element loads + arithmetic) uses all of them, phase 2 one thread per row
 constexpr int kStripElems = 576;  // measured: 410 at most on a level-8 icosphere (mean 334 = 256 own + 78 halo)
 
 struct StripLayout {
@@ -932,7 +933,7 @@ struct StripLayout {
 };
 
 template <bool FILL, class T, int MODE>
-__global__ void __launch_bounds__(kStripRows) strip_rows_kernel(
+__global__ void __launch_bounds__(kStripThreads) strip_rows_kernel(
     StripLayout L, const typename Ex<T>::V4 *__restrict__ v4m, const double *__restrict__ u1,
     const double *__restrict__ u2, const double *__restrict__ am, int cap, RowOut out, int32_t *__restrict__ row_nnz,
     int32_t *__restrict__ row_has, int32_t *__restrict__ flags) {
@@ -956,10 +957,10 @@ __global__ void __launch_bounds__(kStripRows) strip_rows_kernel(
         if (t == 0) atomicOr(flags, 1);
         return;
     }
-    s_cnt[t] = 0;
+    if (t < R) s_cnt[t] = 0;
     __syncthreads();
     // ---- phase 1: elements -> shared memory, strip-local incidence
-    for (int le = t; le < ne; le += R) {
+    for (int le = t; le < ne; le += kStripThreads) {
         const int e = le < nown ? eb + le : __ldg(L.hlist + hb + (le - nown));
         const int4 ti = __ldg(L.t4m + e);
         s_el[le] = ti;
@@ -1107,7 +1108,7 @@ __global__ void __launch_bounds__(kStripRows) strip_rows_kernel(
     }
     if (FILL && use_smem) {
         __syncthreads();
-        for (int q = t; q < blk_nnz; q += R) {
+        for (int q = t; q < blk_nnz; q += kStripThreads) {
             const int key = s_k[q];
             if (want_a) {
                 out.a_idx[blk_beg + q] = key;
@@ -1804,7 +1805,7 @@ static bool run_strip_rows(lb_mesh *mesh, int kind, const double *u1, const doub
     flags.zero();
     RowOut none{};
     const size_t smem_count = (size_t)kStripElems * 16 + kStripRows * 4 + 8 * kStripRows * 2;
-    LB_LAUNCH(c, (strip_rows_kernel<false, double, MODE_FEM>), ns, kStripRows, smem_count, L, (const D4 *)nullptr, u1, u2, am, 0,
+    LB_LAUNCH(c, (strip_rows_kernel<false, double, MODE_FEM>), ns, kStripThreads, smem_count, L, (const D4 *)nullptr, u1, u2, am, 0,
               none, row_nnz.p, row_has.p, flags.p);
     exclusive_scan_i32(c, row_nnz.p, indptr.p, n);
     if (lump) {
@@ -1846,7 +1847,7 @@ static bool run_strip_rows(lb_mesh *mesh, int kind, const double *u1, const doub
 #define LB_STRIP(MODE)                                                                                                   \
     do {                                                                                                                 \
         LB_CUDA(cudaFuncSetAttribute(strip_rows_kernel<true, T, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        LB_LAUNCH(c, (strip_rows_kernel<true, T, MODE>), ns, kStripRows, smem, L, v4, u1, u2, am, cap, out, (int32_t *)nullptr,  \
+        LB_LAUNCH(c, (strip_rows_kernel<true, T, MODE>), ns, kStripThreads, smem, L, v4, u1, u2, am, cap, out, (int32_t *)nullptr,  \
                   (int32_t *)nullptr, flags.p);                                                                          \
     } while (0)
         if (kind == LB_FEM_TRIA) LB_STRIP(MODE_FEM);

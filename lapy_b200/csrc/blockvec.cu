@@ -25,47 +25,23 @@ __global__ void __launch_bounds__(256) spmm_kernel(int64_t n, const int32_t *__r
                                                    const double *__restrict__ val, const double *__restrict__ x,
                                                    int ldx, double *y, int ldy, int m, int mode,
                                                    const double *b, int ldb, SpmmEpilogue epi) {
-    // ncu (round 1): L1/TEX-throughput bound (73 %), every nonzero cost one 512-byte X request plus two
-    // broadcast requests for (index, value) -> the group fetches a row's (index, value) pairs with ONE
-    // coalesced load each (lane q holds entry q) and broadcasts them by warp shuffle.
-    // ncu (round 2, source view): the stall samples sit on the first shuffle (waiting for the index
-    // load) and on the first fma (waiting for the X rows): three dependent memory latencies per row
-    // (row pointers -> entries -> X rows), one row in flight per group.  The loop is therefore software
-    // pipelined: the row pointers are fetched two rows ahead and the first G entries one row ahead, so
-    // that only the X gathers of the current row are on the critical path.
+    // ncu (round 1): this kernel is L1/TEX-throughput bound (73 %), not DRAM bound (44 %): every
+    // nonzero cost one 512-byte X request plus two broadcast requests for (index, value).  The
+    // group now fetches a row's (index, value) pairs with ONE coalesced load each (lane q holds
+    // entry q) and broadcasts them by warp shuffle, leaving only the X gathers on the L1 pipe.
+    // (Staging the strip's CSR segment in shared memory instead was measured 14 % slower.)
+    // Round 2, ncu source view: 302 warp instructions per row, stall samples on the first shuffle (index
+    // load) and the first fma (X rows) = three dependent latencies per row.  Software pipelining the
+    // row loop (row pointers two rows ahead, entries one row ahead) was measured SLOWER (1.25 vs 1.11 ms
+    // at 64 columns, every width): the extra live registers cost more occupancy than the overlap wins.
     constexpr int GROUPS = 256 / G;  // rows in flight per CTA
     const int grp = threadIdx.x / G, lane = threadIdx.x % G;
     const unsigned gmask = G == 32 ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31) / G * G));
     const int64_t strip0 = (int64_t)blockIdx.x * kSpmmStrip;
     const int nrows = (int)(min(n, strip0 + kSpmmStrip) - strip0);
-    // pipeline registers: current row (beg, end, first chunk jl / al), next row's pointers
-    int beg = 0, end = 0, nbeg = 0, nend = 0, jl = 0;
-    double al = 0.0;
-    if (grp < nrows) {
-        beg = __ldg(indptr + strip0 + grp);
-        end = __ldg(indptr + strip0 + grp + 1);
-        if (lane < end - beg) {
-            jl = __ldg(indices + beg + lane);
-            al = __ldg(val + beg + lane);
-        }
-    }
-    if (grp + GROUPS < nrows) {
-        nbeg = __ldg(indptr + strip0 + grp + GROUPS);
-        nend = __ldg(indptr + strip0 + grp + GROUPS + 1);
-    }
     for (int lr = grp; lr < nrows; lr += GROUPS) {
         const int64_t row = strip0 + lr;
-        // prefetch: first chunk of the next row (its pointers arrived an iteration ago), pointers of the row after
-        int njl = 0, nnbeg = 0, nnend = 0;
-        double nal = 0.0;
-        if (lr + GROUPS < nrows && lane < nend - nbeg) {
-            njl = __ldg(indices + nbeg + lane);
-            nal = __ldg(val + nbeg + lane);
-        }
-        if (lr + 2 * GROUPS < nrows) {
-            nnbeg = __ldg(indptr + row + 2 * GROUPS);
-            nnend = __ldg(indptr + row + 2 * GROUPS + 1);
-        }
+        const int beg = __ldg(indptr + row), end = __ldg(indptr + row + 1);
         // VEC: lane owns columns c0 + 2*lane, +1 (one 16-byte load); else c0 + lane, c0 + lane + G
         for (int c0 = 0; c0 < m; c0 += 2 * G) {
             const int ca = VEC ? c0 + 2 * lane : c0 + lane;
@@ -74,15 +50,11 @@ __global__ void __launch_bounds__(256) spmm_kernel(int64_t n, const int32_t *__r
             double s0 = 0.0, s1 = 0.0;
             for (int p0 = beg; p0 < end; p0 += G) {
                 const int cnt = min(G, end - p0);
-                int jc = jl;
-                double ac = al;
-                if (p0 != beg) {  // rows longer than G entries: further chunks are fetched in place
-                    jc = 0;
-                    ac = 0.0;
-                    if (lane < cnt) {
-                        jc = __ldg(indices + p0 + lane);
-                        ac = __ldg(val + p0 + lane);
-                    }
+                int jl = 0;
+                double al = 0.0;
+                if (lane < cnt) {
+                    jl = __ldg(indices + p0 + lane);
+                    al = __ldg(val + p0 + lane);
                 }
                 int q = 0;
                 for (; q + 3 < cnt; q += 4) {
@@ -90,8 +62,8 @@ __global__ void __launch_bounds__(256) spmm_kernel(int64_t n, const int32_t *__r
                     double a[4], u0[4], u1[4];
 #pragma unroll
                     for (int w = 0; w < 4; w++) {
-                        j[w] = __shfl_sync(gmask, jc, q + w, G);
-                        a[w] = __shfl_sync(gmask, ac, q + w, G);
+                        j[w] = __shfl_sync(gmask, jl, q + w, G);
+                        a[w] = __shfl_sync(gmask, al, q + w, G);
                     }
 #pragma unroll
                     for (int w = 0; w < 4; w++) {
@@ -112,8 +84,8 @@ __global__ void __launch_bounds__(256) spmm_kernel(int64_t n, const int32_t *__r
                     }
                 }
                 for (; q < cnt; q++) {
-                    const int j0 = __shfl_sync(gmask, jc, q, G);
-                    const double a0 = __shfl_sync(gmask, ac, q, G);
+                    const int j0 = __shfl_sync(gmask, jl, q, G);
+                    const double a0 = __shfl_sync(gmask, al, q, G);
                     const double *xr = x + (int64_t)j0 * ldx;
                     if (VEC && hb) {
                         const double2 v = __ldg(reinterpret_cast<const double2 *>(xr + ca));
@@ -163,12 +135,6 @@ __global__ void __launch_bounds__(256) spmm_kernel(int64_t n, const int32_t *__r
             if (ha) y[row * ldy + ca] = s0;
             if (hb) y[row * ldy + cb] = s1;
         }
-        beg = nbeg;
-        end = nend;
-        jl = njl;
-        al = nal;
-        nbeg = nnbeg;
-        nend = nnend;
     }
 }
 
