@@ -460,11 +460,14 @@ def block_update(ctx: Context, x: np.ndarray, cmat: np.ndarray, alpha=1.0, beta=
     return out
 
 
-def spmm_benchmark(ctx: Context, mat: DeviceMatrix, m: int = 1, reps: int = 20, renumber: bool = False) -> float:
+def spmm_benchmark(ctx: Context, mat: DeviceMatrix, m: int = 1, reps: int = 20, renumber: bool = False,
+                   variant: int = 0) -> float:
     """Device time (ms) of one y = M x launch with m columns, x / y resident in HBM; renumber: in the
-    solver (locality) numbering instead of the caller's."""
+    solver (locality) numbering instead of the caller's.  variant (development aid): 1 = the row-wise
+    fallback kernel, 2 = the single-precision strip kernel of the preconditioner."""
     ms = C.c_double()
-    check(lib().lb_spmm_benchmark(ctx.handle, mat.handle, int(m), int(reps), int(renumber), C.byref(ms)))
+    check(lib().lb_spmm_benchmark(ctx.handle, mat.handle, int(m), int(reps), int(bool(renumber)) | (int(variant) << 8),
+                                  C.byref(ms)))
     return ms.value
 
 

@@ -638,22 +638,28 @@ std::unique_ptr<Amg> amg_setup(lb_ctx *c, std::unique_ptr<lb_mat> K0, int mcap, 
 }
 
 // =============================================================================================
-// V-cycle
+// V-cycle / W-cycle, in double or single precision
 // =============================================================================================
-__global__ void cheb_first(int64_t n, int m, const double *__restrict__ dinv, const double *__restrict__ src,
-                           int ldsrc, double scale, double *__restrict__ d, double *x, int ldx, int zero_guess) {
+// The eigensolver applies the cycle in SINGLE precision (amg_apply_f32): a preconditioner only has to
+// be a good approximate inverse, LOBPCG's residuals, Gram matrices and Rayleigh-Ritz stay in double.
+// Half the bytes per gathered X row and per matrix value -> the cycle's SpMMs run 1.65-1.85x faster
+// (profiles/spmm_variants_r2.json).  The linear solves (lb_solve) keep the double-precision cycle.
+template <typename T>
+__global__ void cheb_first(int64_t n, int m, const T *__restrict__ dinv, const T *__restrict__ src, int ldsrc, T scale,
+                           T *__restrict__ d, T *x, int ldx, int zero_guess) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n * m) return;
     const int64_t row = t / m;
     const int col = (int)(t - row * m);
-    const double dv = scale * dinv[row] * src[row * ldsrc + col];
+    const T dv = scale * dinv[row] * src[row * ldsrc + col];
     d[row * m + col] = dv;
-    double *xp = x + row * ldx + col;
+    T *xp = x + row * ldx + col;
     *xp = zero_guess ? dv : *xp + dv;
 }
 
-__global__ void cheb_d_only(int64_t n, int m, const double *__restrict__ dinv, const double *__restrict__ src,
-                            int ldsrc, double scale, double *__restrict__ d) {
+template <typename T>
+__global__ void cheb_d_only(int64_t n, int m, const T *__restrict__ dinv, const T *__restrict__ src, int ldsrc, T scale,
+                            T *__restrict__ d) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n * m) return;
     const int64_t row = t / m;
@@ -661,18 +667,93 @@ __global__ void cheb_d_only(int64_t n, int m, const double *__restrict__ dinv, c
     d[t] = scale * dinv[row] * src[row * ldsrc + col];
 }
 
-__global__ void cheb_next(int64_t n, int m, const double *__restrict__ dinv, const double *__restrict__ r, double c1,
-                          double c2, double *__restrict__ d, double *x, int ldx) {
+template <typename T>
+__global__ void cheb_next(int64_t n, int m, const T *__restrict__ dinv, const T *__restrict__ r, T c1, T c2,
+                          T *__restrict__ d, T *x, int ldx) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n * m) return;
     const int64_t row = t / m;
     const int col = (int)(t - row * m);
-    const double dv = c1 * d[t] + c2 * dinv[row] * r[t];
+    const T dv = c1 * d[t] + c2 * dinv[row] * r[t];
     d[t] = dv;
     x[row * ldx + col] += dv;
 }
 
-static void smooth(Amg &amg, int l, double *x, int ldx, const double *b, int ldb, int m, bool zero_guess) {
+// x(n, m) = inv(n, n) b(n, m), single precision: the coarsest level of the fp32 cycle (<= 2000 unknowns)
+__global__ void __launch_bounds__(256) coarse_apply_f32(int n, int m, const float *__restrict__ inv, int ldinv,
+                                                        const float *__restrict__ b, int ldb, float *__restrict__ x,
+                                                        int ldx) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * m) return;
+    const int row = t / m, col = t - row * m;
+    const float *ir = inv + (size_t)row * ldinv;
+    float s0 = 0.f, s1 = 0.f;
+    int k = 0;
+    for (; k + 1 < n; k += 2) {
+        s0 = fmaf(ir[k], b[(size_t)k * ldb + col], s0);
+        s1 = fmaf(ir[k + 1], b[(size_t)(k + 1) * ldb + col], s1);
+    }
+    if (k < n) s0 = fmaf(ir[k], b[(size_t)k * ldb + col], s0);
+    x[(size_t)row * ldx + col] = s0 + s1;
+}
+
+__global__ void f32_to_f64_cols(int64_t n, int m, const float *__restrict__ x, int ldx, double *__restrict__ y, int ldy) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * m) return;
+    const int64_t row = t / m;
+    const int col = (int)(t - row * m);
+    y[row * ldy + col] = (double)x[row * ldx + col];
+}
+
+__global__ void f64_to_f32_cols(int64_t n, int m, int mpad, const double *__restrict__ x, int ldx, float *__restrict__ y,
+                                int ldy) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * mpad) return;
+    const int64_t row = t / mpad;
+    const int col = (int)(t - row * mpad);
+    y[row * ldy + col] = col < m ? (float)x[row * ldx + col] : 0.f;
+}
+
+void convert_cols_f32(lb_ctx *c, int64_t n, int m, const double *x, int ldx, float *y, int ldy) {
+    const int mpad = (m + 3) & ~3;
+    if (n * mpad == 0) return;
+    ProfScope prof(c, PROF_ELEMENTWISE, 12.0 * n * m);
+    LB_LAUNCH(c, f64_to_f32_cols, cdiv(n * mpad, 256), 256, 0, n, m, mpad, x, ldx, y, ldy);
+}
+
+// per-type views of a level
+template <typename T>
+struct LevelView;
+template <>
+struct LevelView<double> {
+    static double *x(AmgLevel &L) { return L.x.p; }
+    static double *b(AmgLevel &L) { return L.b.p; }
+    static double *r(AmgLevel &L) { return L.r.p; }
+    static double *d(AmgLevel &L) { return L.d.p; }
+    static const double *dinv(AmgLevel &L) { return L.dinv.p; }
+    static void mm(lb_ctx *c, const lb_mat *a, const double *x, int ldx, double *y, int ldy, int m, int mode,
+                   const double *b, int ldb, const SpmmEpilogueT<double> *e) {
+        spmm(c, a, x, ldx, y, ldy, m, mode, b, ldb, e);
+    }
+};
+template <>
+struct LevelView<float> {
+    static float *x(AmgLevel &L) { return L.x32.p; }
+    static float *b(AmgLevel &L) { return L.b32.p; }
+    static float *r(AmgLevel &L) { return L.r32.p; }
+    static float *d(AmgLevel &L) { return L.d32.p; }
+    static const float *dinv(AmgLevel &L) { return L.dinv32.p; }
+    static void mm(lb_ctx *c, const lb_mat *a, const float *x, int ldx, float *y, int ldy, int m, int mode,
+                   const float *b, int ldb, const SpmmEpilogueT<float> *e) {
+        spmm_f32(c, a, x, ldx, y, ldy, m, mode, b, ldb, e);
+    }
+};
+
+// returns true when the result was written to out64 (fused exit of the single-precision cycle)
+template <typename T>
+static bool smooth(Amg &amg, int l, T *x, int ldx, const T *b, int ldb, int m, bool zero_guess, double *out64 = nullptr,
+                   int ldout64 = 0) {
+    typedef LevelView<T> LV;
     lb_ctx *c = amg.ctx;
     AmgLevel &L = amg.levels[l];
     const int64_t n = L.K->n;
@@ -680,88 +761,166 @@ static void smooth(Amg &amg, int l, double *x, int ldx, const double *b, int ldb
     const double theta = 0.5 * (hi + lo), delta = 0.5 * (hi - lo), sigma = theta / delta;
     double rho_k = 1.0 / sigma;
     const int grid = cdiv(n * m, 256);
+    T *Lr = LV::r(L), *Ld = LV::d(L);
+    const T *dinv = LV::dinv(L);
     if (amg.cheb_deg == 2 && m > 2 && !L.K->diagonal) {
         // fused form: the elementwise Chebyshev updates ride in the SpMM epilogues (36 % less HBM
         // traffic per cycle on the finest level than the separate kernels below)
         const double rho_n = 1.0 / (2.0 * sigma - rho_k);
-        SpmmEpilogue e{};
-        e.dinv = L.dinv.p;
-        const double *src = b;
+        SpmmEpilogueT<T> e{};
+        e.dinv = dinv;
+        const T *src = b;
         int ldsrc = ldb;
         if (zero_guess) {
-            ProfScope prof(c, PROF_ELEMENTWISE, 16.0 * n * m);
-            LB_LAUNCH(c, cheb_d_only, grid, 256, 0, n, m, L.dinv.p, b, ldb, 1.0 / theta, L.d.p);  // d = dinv o b / theta
+            ProfScope prof(c, PROF_ELEMENTWISE, 2.0 * sizeof(T) * n * m);
+            LB_LAUNCH(c, cheb_d_only<T>, grid, 256, 0, n, m, dinv, b, ldb, (T)(1.0 / theta), Ld);  // d = dinv o b / theta
         } else {
-            e.out2 = L.d.p;
+            e.out2 = Ld;
             e.ldout2 = m;
-            e.c2 = 1.0 / theta;
-            spmm(c, L.K.get(), x, ldx, L.r.p, m, m, 3, b, ldb, &e);  // r = b - K x, d = dinv o r / theta
-            src = L.r.p;
+            e.c2 = (T)(1.0 / theta);
+            LV::mm(c, L.K.get(), x, ldx, Lr, m, m, 3, b, ldb, &e);  // r = b - K x, d = dinv o r / theta
+            src = Lr;
             ldsrc = m;
         }
         e.out2 = x;
         e.ldout2 = ldx;
-        e.c1 = rho_n * rho_k;
-        e.c2 = 2.0 * rho_n / delta;
+        e.c1 = (T)(rho_n * rho_k);
+        e.c2 = (T)(2.0 * rho_n / delta);
         e.overwrite = zero_guess ? 1 : 0;
-        spmm(c, L.K.get(), L.d.p, m, nullptr, 0, m, 4, src, ldsrc, &e);  // x (+)= d + [c1 d + c2 dinv o (src - K d)]
-        return;
+        e.out64 = out64;
+        e.ldout64 = ldout64;
+        LV::mm(c, L.K.get(), Ld, m, nullptr, 0, m, 4, src, ldsrc, &e);  // x (+)= d + [c1 d + c2 dinv o (src - K d)]
+        return out64 != nullptr;
     }
-    const double *src = b;
+    const T *src = b;
     int ldsrc = ldb;
     if (!zero_guess) {
-        spmm(c, L.K.get(), x, ldx, L.r.p, m, m, 1, b, ldb);  // r = b - K x
-        src = L.r.p;
+        LV::mm(c, L.K.get(), x, ldx, Lr, m, m, 1, b, ldb, nullptr);  // r = b - K x
+        src = Lr;
         ldsrc = m;
     }
     {
-        ProfScope prof(c, PROF_ELEMENTWISE, (zero_guess ? 24.0 : 32.0) * n * m);
-        LB_LAUNCH(c, cheb_first, grid, 256, 0, n, m, L.dinv.p, src, ldsrc, 1.0 / theta, L.d.p, x, ldx, (int)zero_guess);
+        ProfScope prof(c, PROF_ELEMENTWISE, (zero_guess ? 3.0 : 4.0) * sizeof(T) * n * m);
+        LB_LAUNCH(c, cheb_first<T>, grid, 256, 0, n, m, dinv, src, ldsrc, (T)(1.0 / theta), Ld, x, ldx, (int)zero_guess);
     }
     for (int k = 1; k < amg.cheb_deg; k++) {
-        spmm(c, L.K.get(), L.d.p, m, L.r.p, m, m, 1, src, ldsrc);  // r = r_prev - K d
-        src = L.r.p;
+        LV::mm(c, L.K.get(), Ld, m, Lr, m, m, 1, src, ldsrc, nullptr);  // r = r_prev - K d
+        src = Lr;
         ldsrc = m;
         const double rho_n = 1.0 / (2.0 * sigma - rho_k);
         {
-            ProfScope prof(c, PROF_ELEMENTWISE, 40.0 * n * m);
-            LB_LAUNCH(c, cheb_next, grid, 256, 0, n, m, L.dinv.p, L.r.p, rho_n * rho_k, 2.0 * rho_n / delta, L.d.p, x, ldx);
+            ProfScope prof(c, PROF_ELEMENTWISE, 5.0 * sizeof(T) * n * m);
+            LB_LAUNCH(c, cheb_next<T>, grid, 256, 0, n, m, dinv, Lr, (T)(rho_n * rho_k), (T)(2.0 * rho_n / delta), Ld, x, ldx);
         }
         rho_k = rho_n;
     }
+    return false;
+}
+
+static void coarse_solve(Amg &amg, AmgLevel &L, const double *b, int ldb, double *x, int ldx, int m) {
+    lb_ctx *c = amg.ctx;
+    const bool aligned = (ldb % 2 == 0) && ((reinterpret_cast<uintptr_t>(b) & 15) == 0) && b != x;
+    if (aligned) {  // x = K^-1 b as one tall-skinny DMMA product with the explicit inverse
+        ProfScope prof(c, PROF_TRSM, 2.0 * amg.coarse_n * amg.coarse_n * m, amg.coarse_n, m);
+        update_dmma(c, amg.coarse_n, amg.coarse_n, amg.coarse_inv.p, amg.coarse_ld, m, b, ldb, 1.0, 0.0, x, ldx);
+        return;
+    }
+    copy_cols(c, L.K->n, m, b, ldb, x, ldx);
+    dense_chol_solve(c, amg.coarse_n, amg.coarse_chol.p, m, x, ldx);
+}
+
+static void coarse_solve(Amg &amg, AmgLevel &, const float *b, int ldb, float *x, int ldx, int m) {
+    lb_ctx *c = amg.ctx;
+    ProfScope prof(c, PROF_TRSM, 2.0 * amg.coarse_n * amg.coarse_n * m, amg.coarse_n, kProfF32 + m);
+    LB_LAUNCH(c, coarse_apply_f32, cdiv((int64_t)amg.coarse_n * m, 256), 256, 0, amg.coarse_n, m, amg.coarse_inv32.p,
+              amg.coarse_ld32, b, ldb, x, ldx);
 }
 
 // one multigrid cycle on level l: x <- x + cycle(b - K x) (x = 0 on entry when zero_guess).
 // amg.gamma = 1: V-cycle; 2: W-cycle (the coarse problem is visited twice - cheap, levels shrink
 // ~10x - which keeps the convergence factor level-independent for MIS-2 aggregates)
-static void cycle(Amg &amg, int l, const double *b, int ldb, double *x, int ldx, int m, bool zero_guess) {
+template <typename T>
+static bool cycle(Amg &amg, int l, const T *b, int ldb, T *x, int ldx, int m, bool zero_guess, double *out64 = nullptr,
+                  int ldout64 = 0) {
+    typedef LevelView<T> LV;
     lb_ctx *c = amg.ctx;
     AmgLevel &L = amg.levels[l];
     if (l == (int)amg.levels.size() - 1) {
-        const bool aligned = (ldb % 2 == 0) && ((reinterpret_cast<uintptr_t>(b) & 15) == 0) && b != x;
-        if (aligned) {  // x = K^-1 b as one tall-skinny DMMA product with the explicit inverse
-            ProfScope prof(c, PROF_TRSM, 2.0 * amg.coarse_n * amg.coarse_n * m, amg.coarse_n, m);
-            update_dmma(c, amg.coarse_n, amg.coarse_n, amg.coarse_inv.p, amg.coarse_ld, m, b, ldb, 1.0, 0.0, x, ldx);
-            return;
-        }
-        copy_cols(c, L.K->n, m, b, ldb, x, ldx);
-        dense_chol_solve(c, amg.coarse_n, amg.coarse_chol.p, m, x, ldx);
-        return;
+        coarse_solve(amg, L, b, ldb, x, ldx, m);
+        return false;
     }
     AmgLevel &C = amg.levels[l + 1];
-    smooth(amg, l, x, ldx, b, ldb, m, zero_guess);
-    spmm(c, L.K.get(), x, ldx, L.r.p, m, m, 1, b, ldb);       // r = b - K x
-    spmm(c, L.R.get(), L.r.p, m, C.b.p, m, m, 0);             // b_c = R r
+    smooth<T>(amg, l, x, ldx, b, ldb, m, zero_guess);
+    LV::mm(c, L.K.get(), x, ldx, LV::r(L), m, m, 1, b, ldb, nullptr);          // r = b - K x
+    LV::mm(c, L.R.get(), LV::r(L), m, LV::b(C), m, m, 0, nullptr, 0, nullptr);  // b_c = R r
     const bool coarsest_next = l + 1 == (int)amg.levels.size() - 1;
     const int visits = coarsest_next ? 1 : amg.gamma;
-    for (int g = 0; g < visits; g++) cycle(amg, l + 1, C.b.p, m, C.x.p, m, m, g == 0);
-    spmm(c, L.P.get(), C.x.p, m, x, ldx, m, 2, x, ldx);       // x += P x_c
-    smooth(amg, l, x, ldx, b, ldb, m, false);
+    for (int g = 0; g < visits; g++) cycle<T>(amg, l + 1, LV::b(C), m, LV::x(C), m, m, g == 0);
+    LV::mm(c, L.P.get(), LV::x(C), m, x, ldx, m, 2, x, ldx, nullptr);  // x += P x_c
+    return smooth<T>(amg, l, x, ldx, b, ldb, m, false, out64, ldout64);
 }
 
 void amg_apply(Amg &amg, const double *r, int ldr, double *z, int ldz, int m, int level) {
     LB_REQUIRE(m <= amg.mcap, "AMG applied to %d columns but sized for %d", m, amg.mcap);
-    cycle(amg, level, r, ldr, z, ldz, m, true);
+    cycle<double>(amg, level, r, ldr, z, ldz, m, true);
+}
+
+__global__ void to_f32_vec(int64_t n, const double *__restrict__ in, float *__restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (float)in[i];
+}
+
+// single-precision mirrors of the hierarchy (values, diagonals, coarse inverse, work blocks): made on
+// the first single-precision application.  Returns false when a level does not fit the strip SpMM.
+bool amg_prepare_f32(Amg &amg) {
+    if (amg.f32_state) return amg.f32_state > 0;
+    lb_ctx *c = amg.ctx;
+    amg.f32_state = -1;
+    if (amg.cheb_deg != 2 || amg.levels.size() < 2) return false;
+    const int nl = (int)amg.levels.size();
+    for (int l = 0; l < nl; l++) {
+        AmgLevel &L = amg.levels[l];
+        if (l + 1 < nl && (!spmm_f32_supported(c, L.K.get()) || !spmm_f32_supported(c, L.P.get()) ||
+                           !spmm_f32_supported(c, L.R.get())))
+            return false;
+    }
+    const int mc = (amg.mcap + 3) & ~3;
+    for (int l = 0; l < nl; l++) {
+        AmgLevel &L = amg.levels[l];
+        const int64_t n = L.K->n;
+        L.dinv32.alloc(c, n);
+        LB_LAUNCH(c, to_f32_vec, cdiv(n, 256), 256, 0, n, L.dinv.p, L.dinv32.p);
+        L.x32.alloc(c, (size_t)n * mc);
+        L.b32.alloc(c, (size_t)n * mc);
+        if (l + 1 < nl) {
+            L.r32.alloc(c, (size_t)n * mc);
+            L.d32.alloc(c, (size_t)n * mc);
+            mat_values_f32(c, L.K.get());
+            mat_values_f32(c, L.P.get());
+            mat_values_f32(c, L.R.get());
+        }
+    }
+    amg.coarse_ld32 = (amg.coarse_n + 3) & ~3;
+    amg.coarse_inv32.alloc(c, (size_t)amg.coarse_n * amg.coarse_ld32);
+    amg.coarse_inv32.zero();
+    f64_to_f32_cols<<<cdiv((int64_t)amg.coarse_n * amg.coarse_ld32, 256), 256, 0, c->stream>>>(
+        amg.coarse_n, amg.coarse_n, amg.coarse_ld32, amg.coarse_inv.p, amg.coarse_ld, amg.coarse_inv32.p, amg.coarse_ld32);
+    c->launches++;
+    LB_CUDA(cudaGetLastError());
+    amg.f32_state = 1;
+    return true;
+}
+
+void amg_apply_f32(Amg &amg, const float *r, int ldr, double *z, int ldz, int m, int level) {
+    LB_REQUIRE(amg.f32_state > 0, "single-precision hierarchy not prepared");
+    LB_REQUIRE(m % 4 == 0 && m <= ((amg.mcap + 3) & ~3) && ldr % 4 == 0, "single-precision cycle: bad block shape");
+    AmgLevel &L = amg.levels[level];
+    const bool direct = (ldz % 2 == 0) && ((reinterpret_cast<uintptr_t>(z) & 15) == 0);
+    const bool done = cycle<float>(amg, level, r, ldr, L.x32.p, m, m, true, direct ? z : nullptr, ldz);
+    if (!done) {
+        ProfScope prof(amg.ctx, PROF_ELEMENTWISE, 12.0 * L.K->n * m);
+        LB_LAUNCH(amg.ctx, f32_to_f64_cols, cdiv(L.K->n * m, 256), 256, 0, L.K->n, m, L.x32.p, m, z, ldz);
+    }
 }
 
 }  // namespace lb

@@ -19,6 +19,8 @@ struct AmgLevel {
     double rho = 2.0;            // upper bound of the spectral radius of D^-1 K (Gershgorin)
     // V-cycle work blocks (n_l, mcap): solution, right-hand side, residual, Chebyshev direction
     DBuf<double> x, b, r, d;
+    // single-precision twins (amg_prepare_f32)
+    DBuf<float> dinv32, x32, b32, r32, d32;
 };
 
 struct Amg {
@@ -34,6 +36,9 @@ struct Amg {
     int cheb_deg = 2;
     int gamma = 2;  // cycle index: 1 = V, 2 = W
     int mcap = 0;  // block width the work arrays are sized for
+    DBuf<float> coarse_inv32;  // single-precision copy of coarse_inv, leading dimension coarse_ld32
+    int coarse_ld32 = 0;
+    int f32_state = 0;  // 0: not prepared, 1: single-precision mirrors ready, -1: not supported for this hierarchy
     double setup_ms = 0;
 };
 
@@ -49,6 +54,13 @@ struct AmgOptions {
 std::unique_ptr<Amg> amg_setup(lb_ctx *c, std::unique_ptr<lb_mat> K, int mcap, const AmgOptions &opt);
 // z (n_level, m) = cycle(r) starting at `level` (0 = finest); r is not modified
 void amg_apply(Amg &amg, const double *r, int ldr, double *z, int ldz, int m, int level = 0);
+// The same cycle in single precision (the eigensolver's preconditioner).  amg_prepare_f32 builds the
+// float mirrors once and says whether the hierarchy supports it.  r: (n_level, ldr) floats with
+// m % 4 == 0 columns (callers pad with zero columns) and ldr % 4 == 0; z: doubles, columns 0..m-1 written.
+bool amg_prepare_f32(Amg &amg);
+void amg_apply_f32(Amg &amg, const float *r, int ldr, double *z, int ldz, int m, int level = 0);
+// y(n, ldy) floats = x(n, ldx) doubles, columns m..roundup4(m)-1 zero-filled
+void convert_cols_f32(lb_ctx *c, int64_t n, int m, const double *x, int ldx, float *y, int ldy);
 
 // C = alpha*A + beta*B for matrices with identical pattern or diagonal B (new matrix)
 std::unique_ptr<lb_mat> mat_axpby(lb_ctx *c, const lb_mat *a, double alpha, const lb_mat *b, double beta);

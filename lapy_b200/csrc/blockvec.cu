@@ -207,6 +207,279 @@ __global__ void __launch_bounds__(256) spmv_stream_kernel(int64_t n, const int32
     }
 }
 
+// ---- SpMM, strip-staged form --------------------------------------------------------------------
+// Round-2 finding (profiles/spmm_shapes_r2.json): the time of spmm_kernel above is rows x 0.28 us/Mrow +
+// nnz x 0.029 us/Mnnz - at 7 entries per row (triangle meshes) 58 % of it is per-ROW cost: three
+// dependent latencies (row pointers -> entries -> X rows) and 302 warp instructions per row.
+// Here a CTA stages the CSR segment of its strip of R rows in shared memory with two coalesced
+// passes (the only dependent latencies, paid once per CTA and hidden by the other resident CTAs),
+// after which a row costs one shared-memory read per entry (broadcast), up to 8 independent 16-byte
+// X gathers in flight, and the epilogue.  Same summation order as spmm_kernel (CSR order, one fma
+// per entry) -> bit-identical results.  T = double (double2 per lane) or float (float4 per lane:
+// the single-precision multigrid cycle of the eigensolver's preconditioner, amg.cu).
+template <typename T>
+struct VecT;
+template <>
+struct VecT<double> {
+    typedef double2 V;
+    static constexpr int W = 2;
+};
+template <>
+struct VecT<float> {
+    typedef float4 V;
+    static constexpr int W = 4;
+};
+__device__ __forceinline__ void vfma(double2 &acc, double a, const double2 &u) {
+    acc.x = fma(a, u.x, acc.x);
+    acc.y = fma(a, u.y, acc.y);
+}
+__device__ __forceinline__ void vfma(float4 &acc, float a, const float4 &u) {
+    acc.x = fmaf(a, u.x, acc.x);
+    acc.y = fmaf(a, u.y, acc.y);
+    acc.z = fmaf(a, u.z, acc.z);
+    acc.w = fmaf(a, u.w, acc.w);
+}
+template <typename T, typename V>
+__device__ __forceinline__ void vunpack(const V &v, T *s);
+template <>
+__device__ __forceinline__ void vunpack<double, double2>(const double2 &v, double *s) {
+    s[0] = v.x;
+    s[1] = v.y;
+}
+template <>
+__device__ __forceinline__ void vunpack<float, float4>(const float4 &v, float *s) {
+    s[0] = v.x;
+    s[1] = v.y;
+    s[2] = v.z;
+    s[3] = v.w;
+}
+__device__ __forceinline__ double2 vpack(const double *s) { return make_double2(s[0], s[1]); }
+__device__ __forceinline__ float4 vpack(const float *s) { return make_float4(s[0], s[1], s[2], s[3]); }
+
+constexpr int kStripPad = 8;  // entries the 8-wide inner loop may address past the end of the strip
+
+template <typename T, int G, int MODE, int CH, int MINB>
+__global__ void __launch_bounds__(256, MINB) spmm_strip_kernel(int64_t n, int R, int cap, const int32_t *__restrict__ indptr,
+                                                         const int32_t *__restrict__ indices,
+                                                         const T *__restrict__ val, const T *__restrict__ x, int ldx,
+                                                         T *y, int ldy, int m, const T *b, int ldb,
+                                                         SpmmEpilogueT<T> epi) {
+    using V = typename VecT<T>::V;
+    constexpr int W = VecT<T>::W;
+    constexpr int GROUPS = 256 / G;
+    extern __shared__ __align__(16) unsigned char strip_smem[];
+    int32_t *s_ptr = reinterpret_cast<int32_t *>(strip_smem);  // R + 1 row pointers
+    T *s_val = reinterpret_cast<T *>(strip_smem + (size_t)((R + 4) & ~3) * 4);
+    int32_t *s_idx = reinterpret_cast<int32_t *>(s_val + cap + kStripPad);
+    const int64_t strip0 = (int64_t)blockIdx.x * R;
+    const int nrows = (int)min((int64_t)R, n - strip0);
+    for (int i = threadIdx.x; i <= nrows; i += 256) s_ptr[i] = __ldg(indptr + strip0 + i);
+    __syncthreads();
+    const int base = s_ptr[0], total = s_ptr[nrows] - base;  // <= cap (host-side strip statistics)
+    for (int i = threadIdx.x; i < total; i += 256) {
+        s_idx[i] = __ldcs(indices + base + i);
+        s_val[i] = __ldcs(val + base + i);
+    }
+    if (threadIdx.x < kStripPad) s_idx[total + threadIdx.x] = 0;
+    __syncthreads();
+    const int grp = threadIdx.x / G, lane = threadIdx.x % G;
+    const unsigned xstride = (unsigned)ldx * (unsigned)sizeof(T);
+    for (int c0 = 0; c0 < m; c0 += G * W) {
+        const int col = c0 + lane * W;
+        if (col >= m) continue;
+        const char *xl = reinterpret_cast<const char *>(x + col);
+        for (int lr = grp; lr < nrows; lr += GROUPS) {
+            const int beg = s_ptr[lr] - base, end = s_ptr[lr + 1] - base;
+            const int64_t row = strip0 + lr;
+            V bv, dold;
+            T di = 0;
+            if (MODE >= 1) bv = *reinterpret_cast<const V *>(b + row * ldb + col);
+            if (MODE >= 3) di = epi.c2 * __ldg(epi.dinv + row);
+            if (MODE == 4) dold = *reinterpret_cast<const V *>(x + row * ldx + col);
+            V acc;
+            {
+                T z[W] = {};
+                acc = vpack(z);
+            }
+            for (int p = beg; p < end; p += CH) {
+                // the gathers are unconditional and issued back to back: slots past the end of the row
+                // address the next row's columns (valid X rows, usually the next gathers anyway; the pad
+                // after the strip holds column 0), only the fmas are predicated - no predicate is live
+                // across the loads, which is what let the compiler serialise them
+                V u[CH];
+#pragma unroll
+                for (int q = 0; q < CH; q++)
+                    u[q] = __ldg(reinterpret_cast<const V *>(xl + (size_t)((uint64_t)(uint32_t)s_idx[p + q] * xstride)));
+                asm volatile("" ::: "memory");
+#pragma unroll
+                for (int q = 0; q < CH; q++)
+                    if (p + q < end) vfma(acc, s_val[p + q], u[q]);
+            }
+            T s[W], bb[W], out[W];
+            vunpack<T, V>(acc, s);
+            if (MODE >= 1) vunpack<T, V>(bv, bb);
+            if (MODE == 0) {
+                *reinterpret_cast<V *>(y + row * ldy + col) = acc;
+            } else if (MODE == 1 || MODE == 3) {  // residual (3: + first Chebyshev direction d = c2 dinv o r)
+#pragma unroll
+                for (int e = 0; e < W; e++) out[e] = bb[e] - s[e];
+                *reinterpret_cast<V *>(y + row * ldy + col) = vpack(out);
+                if (MODE == 3) {
+#pragma unroll
+                    for (int e = 0; e < W; e++) out[e] = di * out[e];
+                    *reinterpret_cast<V *>(epi.out2 + row * epi.ldout2 + col) = vpack(out);
+                }
+            } else if (MODE == 2) {
+#pragma unroll
+                for (int e = 0; e < W; e++) out[e] = bb[e] + s[e];
+                *reinterpret_cast<V *>(y + row * ldy + col) = vpack(out);
+            } else {  // 4: last Chebyshev step, x gathers d: sol (+)= d + [c1 d + c2 dinv o (b - K d)]
+                T dd[W], sp[W] = {};
+                vunpack<T, V>(dold, dd);
+                if (!epi.overwrite) vunpack<T, V>(*reinterpret_cast<const V *>(epi.out2 + row * epi.ldout2 + col), sp);
+#pragma unroll
+                for (int e = 0; e < W; e++) {
+                    const T dn = fma(epi.c1, dd[e], di * (bb[e] - s[e]));
+                    out[e] = sp[e] + dd[e] + dn;
+                }
+                if (epi.out64) {  // result leaves the single-precision cycle as doubles
+                    double *o = epi.out64 + row * epi.ldout64 + col;
+#pragma unroll
+                    for (int e = 0; e < W; e += 2) *reinterpret_cast<double2 *>(o + e) = make_double2((double)out[e], (double)out[e + 1]);
+                } else {
+                    *reinterpret_cast<V *>(epi.out2 + row * epi.ldout2 + col) = vpack(out);
+                }
+            }
+        }
+    }
+}
+
+// max number of stored entries in any strip of R = 8, 16, 32, 64, 128 consecutive rows
+__global__ void strip_stats_kernel(int64_t n, const int32_t *__restrict__ indptr, int32_t *__restrict__ out) {
+    const int64_t s = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 8;
+    if (s >= n) return;
+    const int beg = indptr[s];
+#pragma unroll
+    for (int k = 0; k < 5; k++) {
+        const int R = 8 << k;
+        if (s % R == 0) atomicMax(out + k, indptr[min(n, s + R)] - beg);
+    }
+}
+
+static void ensure_strip_stats(lb_ctx *c, const lb_mat *a) {
+    if (a->strip_ready) return;
+    DBuf<int32_t> d(c, 5);
+    d.zero();
+    LB_LAUNCH(c, strip_stats_kernel, cdiv(cdiv(a->n, 8), 256), 256, 0, a->n, a->indptr.p, d.p);
+    read_back(c, a->strip_cap, d.p, 5);
+    a->strip_ready = true;
+}
+
+constexpr size_t kStripSmemBudget = 32 * 1024;
+
+// rows per CTA the strip kernel would use for this matrix and value type (0: does not fit)
+template <typename T>
+static int strip_rows(lb_ctx *c, const lb_mat *a, int *cap_out) {
+    ensure_strip_stats(c, a);
+    for (int k = 4; k >= 0; k--) {
+        const int R = 8 << k;
+        const size_t bytes = (size_t)((R + 4) & ~3) * 4 + (size_t)(a->strip_cap[k] + kStripPad) * (4 + sizeof(T));
+        if (bytes <= kStripSmemBudget) {
+            *cap_out = a->strip_cap[k];
+            return R;
+        }
+    }
+    return 0;
+}
+
+bool spmm_f32_supported(lb_ctx *c, const lb_mat *a) {
+    int cap;
+    return !a->diagonal && strip_rows<float>(c, a, &cap) > 0;
+}
+
+static inline bool aligned16(const void *p, int ld, int w) {
+    return p == nullptr || ((reinterpret_cast<uintptr_t>(p) & 15) == 0 && ld % w == 0);
+}
+
+extern int g_spmm_variant;
+template <typename T, int G>
+static void launch_strip(lb_ctx *c, int grid, size_t smem, int64_t n, int R, int cap, const lb_mat *a, const T *val,
+                         const T *x, int ldx, T *y, int ldy, int m, int mode, const T *b, int ldb,
+                         const SpmmEpilogueT<T> &epi) {
+    // gathers per chunk: 4 for short rows (prolongators, ~3 entries), else 8
+    const bool narrow = a->nnz <= 4 * a->n;
+    // resident CTAs the kernel is compiled for (register budget vs gathers in flight), measured
+    // (profiles/spmm_variants_r2.json): one row per warp (G = 32) wants 4, several rows per warp 5
+    const int minb = g_spmm_variant ? g_spmm_variant : (G == 32 ? 4 : 5);
+#define LB_STRIP3(MODE, CH, MINB)                                                                                   \
+    LB_LAUNCH(c, (spmm_strip_kernel<T, G, MODE, CH, MINB>), grid, 256, smem, n, R, cap, a->indptr.p, a->indices.p, val, x, \
+              ldx, y, ldy, m, b, ldb, epi)
+#define LB_STRIP(MODE)                                                                                              \
+    do {                                                                                                            \
+        if (narrow) LB_STRIP3(MODE, 4, 4);                                                                          \
+        else if (minb == 3) LB_STRIP3(MODE, 8, 3);                                                                  \
+        else if (minb == 5) LB_STRIP3(MODE, 8, 5);                                                                  \
+        else LB_STRIP3(MODE, 8, 4);                                                                                 \
+    } while (0)
+    switch (mode) {
+        case 0: LB_STRIP(0); break;
+        case 1: LB_STRIP(1); break;
+        case 2: LB_STRIP(2); break;
+        case 3: LB_STRIP(3); break;
+        default: LB_STRIP(4); break;
+    }
+#undef LB_STRIP
+#undef LB_STRIP3
+}
+
+// returns false when the operands do not meet the strip kernel's requirements (16-byte aligned
+// rows, column count a multiple of the vector width, strip fits the shared-memory budget)
+template <typename T>
+static bool spmm_strip(lb_ctx *c, const lb_mat *a, const T *val, const T *x, int ldx, T *y, int ldy, int m, int mode,
+                       const T *b, int ldb, const SpmmEpilogueT<T> &epi) {
+    constexpr int W = VecT<T>::W;
+    if (m % W || !aligned16(x, ldx, W) || !aligned16(y, ldy, W) || !aligned16(b, ldb, W) ||
+        !aligned16(epi.out2, epi.ldout2, W) || !aligned16(epi.out64, epi.ldout64, 2))
+        return false;
+    int cap = 0;
+    const int R = strip_rows<T>(c, a, &cap);
+    if (R == 0) return false;
+    const size_t smem = (size_t)((R + 4) & ~3) * 4 + (size_t)(cap + kStripPad) * (4 + sizeof(T));
+    const int grid = cdiv(a->n, R);
+    const int lanes = m / W;
+    if (lanes <= 4) launch_strip<T, 4>(c, grid, smem, a->n, R, cap, a, val, x, ldx, y, ldy, m, mode, b, ldb, epi);
+    else if (lanes <= 8) launch_strip<T, 8>(c, grid, smem, a->n, R, cap, a, val, x, ldx, y, ldy, m, mode, b, ldb, epi);
+    else if (lanes <= 16) launch_strip<T, 16>(c, grid, smem, a->n, R, cap, a, val, x, ldx, y, ldy, m, mode, b, ldb, epi);
+    else launch_strip<T, 32>(c, grid, smem, a->n, R, cap, a, val, x, ldx, y, ldy, m, mode, b, ldb, epi);
+    return true;
+}
+
+// single-precision copy of the values of a matrix (made once, kept with the matrix)
+__global__ void to_f32_kernel(int64_t n, const double *__restrict__ in, float *__restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (float)in[i];
+}
+
+const float *mat_values_f32(lb_ctx *c, const lb_mat *a) {
+    if (a->data32.n != (size_t)a->nnz || a->data32.p == nullptr) {
+        a->data32.alloc(c, (size_t)a->nnz);
+        if (a->nnz) LB_LAUNCH(c, to_f32_kernel, cdiv(a->nnz, 256), 256, 0, a->nnz, a->data.p, a->data32.p);
+    }
+    return a->data32.p;
+}
+
+void spmm_f32(lb_ctx *c, const lb_mat *a, const float *x, int ldx, float *y, int ldy, int m, int mode, const float *b,
+              int ldb, const SpmmEpilogueT<float> *epi_in) {
+    SpmmEpilogueT<float> epi{};
+    if (epi_in) epi = *epi_in;
+    const int64_t n = a->n;
+    if (n == 0 || m == 0) return;
+    const int64_t xrows = a->ncols < 0 ? a->n : a->ncols;
+    ProfScope prof(c, PROF_SPMM, 8.0 * a->nnz + 4.0 * (n + 1) + 4.0 * m * (xrows + n * (mode ? 2 : 1)), kProfF32 + m, a->nnz);
+    const bool ok = !a->diagonal && spmm_strip<float>(c, a, mat_values_f32(c, a), x, ldx, y, ldy, m, mode, b, ldb, epi);
+    LB_REQUIRE(ok, "single-precision SpMM: operands not aligned or strip too long (internal error)");
+}
+
 // diagonal matrix (lumped mass, identity): entries only on the diagonal, possibly missing rows
 __global__ void diag_spmm_kernel(int64_t n, const int32_t *__restrict__ indptr, const double *__restrict__ val,
                                  const double *__restrict__ x, int ldx, double *y, int ldy, int m,
@@ -221,6 +494,9 @@ __global__ void diag_spmm_kernel(int64_t n, const int32_t *__restrict__ indptr, 
     else if (mode == 2) s = b[row * ldb + col] + s;
     y[row * ldy + col] = s;
 }
+
+int g_spmm_force_rowwise = 0;
+int g_spmm_variant = 0;  // benchmark aid (lb_spmm_benchmark variant 1): time the row-wise kernel
 
 void spmm(lb_ctx *c, const lb_mat *a, const double *x, int ldx, double *y, int ldy, int m, int mode, const double *b,
           int ldb, const SpmmEpilogue *epi_in) {
@@ -250,6 +526,8 @@ void spmm(lb_ctx *c, const lb_mat *a, const double *x, int ldx, double *y, int l
 #undef LB_SPMV
         return;
     }
+    if (!g_spmm_force_rowwise && spmm_strip<double>(c, a, v, x, ldx, y, ldy, m, mode, b, ldb, epi)) return;
+    // fallback (odd column counts, unaligned operands, strips beyond the shared-memory budget):
     // 16-byte vector loads of X need even leading dimension and a 16-byte aligned base
     const bool vec = (ldx % 2 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
     const int grid = cdiv(n, kSpmmStrip);
@@ -352,6 +630,32 @@ void residual_cols(lb_ctx *c, int64_t n, int ncols, const int *idx, const double
     if (n * ncols == 0) return;
     ProfScope prof(c, PROF_ELEMENTWISE, 24.0 * n * ncols);
     LB_LAUNCH(c, residual_cols_kernel, cdiv(n * ncols, 256), 256, 0, n, ncols, idx, lam, ax, ldax, mx, ldmx, out, ldout);
+}
+
+// single-precision output with the column count padded to a multiple of 4 (zero columns): the input
+// block of the single-precision multigrid cycle
+__global__ void residual_cols_f32_kernel(int64_t n, int ncols, int npad, const int *__restrict__ idx,
+                                         const double *__restrict__ lam, const double *__restrict__ ax, int ldax,
+                                         const double *__restrict__ mx, int ldmx, float *__restrict__ out, int ldout) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * npad) return;
+    const int64_t row = t / npad;
+    const int a = (int)(t - row * npad);
+    float v = 0.f;
+    if (a < ncols) {
+        const int col = idx[a];
+        v = (float)fma(-lam[col], mx[row * ldmx + col], ax[row * ldax + col]);
+    }
+    out[row * ldout + a] = v;
+}
+
+void residual_cols_f32(lb_ctx *c, int64_t n, int ncols, const int *idx, const double *lam, const double *ax, int ldax,
+                       const double *mx, int ldmx, float *out, int ldout) {
+    const int npad = (ncols + 3) & ~3;
+    if (n * npad == 0) return;
+    ProfScope prof(c, PROF_ELEMENTWISE, 20.0 * n * ncols);
+    LB_LAUNCH(c, residual_cols_f32_kernel, cdiv(n * npad, 256), 256, 0, n, ncols, npad, idx, lam, ax, ldax, mx, ldmx, out,
+              ldout);
 }
 
 void copy_cols(lb_ctx *c, int64_t n, int cols, const double *x, int ldx, double *y, int ldy) {

@@ -13,15 +13,31 @@ namespace lb {
 // Y(n,m) = B + A X                   (mode 2; B may alias Y)
 // Y(n,m) = B - A X and D = c2 * dinv o Y               (mode 3, fused first Chebyshev step)
 // SOL (+)= X + c1 X + c2 * dinv o (B - A X)              (mode 4, fused last Chebyshev step; Y unused)
-struct SpmmEpilogue {
-    const double *dinv = nullptr;
-    double *out2 = nullptr;  // D (mode 3) / SOL (mode 4)
+template <typename T>
+struct SpmmEpilogueT {
+    const T *dinv = nullptr;
+    T *out2 = nullptr;  // D (mode 3) / SOL (mode 4)
     int ldout2 = 0;
-    double c1 = 0.0, c2 = 0.0;
+    T c1 = 0, c2 = 0;
     int overwrite = 0;  // mode 4: SOL = ... instead of SOL += ...
+    // mode 4 of the strip kernel: when set, the result is written here as doubles (old SOL still read
+    // from out2): the exit of the single-precision multigrid cycle
+    double *out64 = nullptr;
+    int ldout64 = 0;
 };
+typedef SpmmEpilogueT<double> SpmmEpilogue;
+constexpr int64_t kProfF32 = 100000;  // added to the column count in the profile shape of single-precision launches
 void spmm(lb_ctx *c, const lb_mat *a, const double *x, int ldx, double *y, int ldy, int m, int mode = 0,
           const double *b = nullptr, int ldb = 0, const SpmmEpilogue *epi = nullptr);
+
+// single-precision twin (strip kernel only; values = a lazily made float copy kept with the matrix):
+// the multigrid cycle that preconditions the eigensolver runs in fp32 (amg.cu).  All operands must have
+// 16-byte aligned rows and m % 4 == 0; spmm_f32_supported(): the matrix fits the strip kernel.
+void spmm_f32(lb_ctx *c, const lb_mat *a, const float *x, int ldx, float *y, int ldy, int m, int mode = 0,
+              const float *b = nullptr, int ldb = 0, const SpmmEpilogueT<float> *epi = nullptr);
+bool spmm_f32_supported(lb_ctx *c, const lb_mat *a);
+const float *mat_values_f32(lb_ctx *c, const lb_mat *a);
+extern int g_spmm_force_rowwise, g_spmm_variant;
 
 // out[j] = sum_i X[i,j] * Y[i,j], j < cols  (deterministic two-stage reduction), device output
 void col_dots(lb_ctx *c, int64_t n, int cols, const double *x, int ldx, const double *y, int ldy, double *out);
@@ -33,6 +49,10 @@ void axpby_cols(lb_ctx *c, int64_t n, int cols, const double *a, double a_const,
 // Y[:, j] = X[:, idx[j]] - lam[idx[j]] * Z[:, idx[j]]   (compacting gather of active columns)
 void residual_cols(lb_ctx *c, int64_t n, int ncols, const int *idx, const double *lam, const double *ax, int ldax,
                    const double *mx, int ldmx, double *out, int ldout);
+
+// the same in single precision, columns padded with zeros to a multiple of 4 (ldout % 4 == 0)
+void residual_cols_f32(lb_ctx *c, int64_t n, int ncols, const int *idx, const double *lam, const double *ax, int ldax,
+                       const double *mx, int ldmx, float *out, int ldout);
 
 void copy_cols(lb_ctx *c, int64_t n, int cols, const double *x, int ldx, double *y, int ldy);
 void scale_rows(lb_ctx *c, int64_t n, int cols, const double *d, const double *x, int ldx, double *y, int ldy);

@@ -276,4 +276,9 @@ struct lb_mat {
     // (permuted == false, ord == nullptr).
     bool permuted = false;
     std::shared_ptr<lb_order> ord;
+    // caches of the strip-staged SpMM (blockvec.cu), filled on first use: the largest number of entries
+    // in any strip of 8 / 16 / 32 / 64 / 128 consecutive rows, and a single-precision copy of the values
+    mutable int32_t strip_cap[5] = {0, 0, 0, 0, 0};
+    mutable bool strip_ready = false;
+    mutable lb::DBuf<float> data32;
 };

@@ -558,6 +558,7 @@ static EigStats lobpcg_core(lb_ctx *c, const lb_mat *A, const lb_mat *B, Amg *am
         std::vector<int> none;
         rayleigh_ritz(m, 0, none, mp);
     }
+    const bool f32_cycle = !D && amg_prepare_f32(*amg);
 
     double worst = 0.0;
     int nconv_k = 0;
@@ -610,11 +611,20 @@ static EigStats lobpcg_core(lb_ctx *c, const lb_mat *A, const lb_mat *B, Amg *am
         // ---- W = precond(R_active), orthogonalised against [X P], B-orthonormalised
         std::vector<int> active_cols(idx.begin(), idx.begin() + ma);
         h2d(c, idx_d.p, idx.data(), ma * sizeof(int));
-        residual_cols(c, n, ma, idx_d.p, lam_d.p, AS[cur].p, ld, BS[cur].p, ld, Rbuf.p, ma);
         const int w0 = m + mp;
         double *W = S[cur].p + w0, *AW = AS[cur].p + w0, *BW = BS[cur].p + w0;
-        if (D) dist_precond(c, D, Rbuf.p, ma, W, ld, ma);
-        else amg_apply(*amg, Rbuf.p, ma, W, ld, ma, lvl);
+        if (!D && f32_cycle) {
+            // single-precision multigrid cycle: the residual block is converted as it is compacted, the
+            // cycle's last kernel writes W in double (amg.cu)
+            const int mpad = (ma + 3) & ~3;
+            float *Rf = reinterpret_cast<float *>(Rbuf.p);
+            residual_cols_f32(c, n, ma, idx_d.p, lam_d.p, AS[cur].p, ld, BS[cur].p, ld, Rf, mpad);
+            amg_apply_f32(*amg, Rf, mpad, W, ld, mpad, lvl);
+        } else {
+            residual_cols(c, n, ma, idx_d.p, lam_d.p, AS[cur].p, ld, BS[cur].p, ld, Rbuf.p, ma);
+            if (D) dist_precond(c, D, Rbuf.p, ma, W, ld, ma);
+            else amg_apply(*amg, Rbuf.p, ma, W, ld, ma, lvl);
+        }
         pt.stop(1);
         // block Gram-Schmidt against [X P], twice ("twice is enough").  A single pass was measured to
         // lose orthogonality near convergence: the row-partitioned run (weaker block-Jacobi

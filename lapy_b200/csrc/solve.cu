@@ -634,17 +634,37 @@ int lb_spmm_benchmark(lb_ctx *c, lb_mat *mat0, int64_t m, int reps, int renumber
     // numbering buys)
     std::unique_ptr<lb_mat> perm;
     lb_mat *mat = mat0;
-    if (!renumber && mat0->permuted) {
+    if (!(renumber & 1) && mat0->permuted) {
         perm = to_caller_order(c, mat0);
         mat = perm.get();
     }
+    // bits 8.. of `renumber`: kernel variant (development aid): 1 = row-wise kernel, 2 = single precision,
+    // 3 / 4 / 5 = strip kernel compiled for that many resident CTAs (23 / 24 / 25: in single precision)
+    const int variant = renumber >> 8;
+    const bool f32 = variant == 2 || variant >= 20;
+    g_spmm_force_rowwise = variant == 1;
+    g_spmm_variant = variant >= 20 ? variant - 20 : (variant >= 3 ? variant : 0);
     DBuf<double> dx(c, (size_t)n * m), dy(c, (size_t)n * m);
     fill_random(c, n, (int)m, dx.p, (int)m, 42);
-    for (int i = 0; i < 3; i++) spmm(c, mat, dx.p, (int)m, dy.p, (int)m, (int)m);
+    DBuf<float> fx, fy;
+    const int m4 = ((int)m + 3) & ~3;
+    if (f32) {
+        LB_REQUIRE(spmm_f32_supported(c, mat), "matrix not supported by the single-precision SpMM");
+        fx.alloc(c, (size_t)n * m4);
+        fy.alloc(c, (size_t)n * m4);
+        fx.zero();
+    }
+    auto once = [&]() {
+        if (f32) spmm_f32(c, mat, fx.p, m4, fy.p, m4, m4);
+        else spmm(c, mat, dx.p, (int)m, dy.p, (int)m, (int)m);
+    };
+    for (int i = 0; i < 3; i++) once();
     LB_CUDA(cudaEventRecord(c->ev0, c->stream));
-    for (int i = 0; i < reps; i++) spmm(c, mat, dx.p, (int)m, dy.p, (int)m, (int)m);
+    for (int i = 0; i < reps; i++) once();
     LB_CUDA(cudaEventRecord(c->ev1, c->stream));
     LB_CUDA(cudaEventSynchronize(c->ev1));
+    g_spmm_force_rowwise = 0;
+    g_spmm_variant = 0;
     float ms = 0;
     LB_CUDA(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
     *ms_per_launch = ms / reps;
