@@ -43,7 +43,7 @@ faulthandler.enable()  # a crash inside the native library prints the Python sta
 PEAK_FALLBACK_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
 METRIC = "shapedna_k50_meshes_per_s"
 PARITY_RTOL = 1e-8  # BASELINE.json north_star
-ROWPART_WORLDS = {2}  # world sizes the row-partitioned solve has been validated on (profiles/rowpart_*_r2.log)
+ROWPART_WORLDS = {2, 4}  # world sizes the row-partitioned solve has been validated on (profiles/rowpart_*_r2.log)
 
 
 def measured_peak():

@@ -911,15 +911,16 @@ bool amg_prepare_f32(Amg &amg) {
     return true;
 }
 
-void amg_apply_f32(Amg &amg, const float *r, int ldr, double *z, int ldz, int m, int level) {
+void amg_apply_f32(Amg &amg, const float *r, int ldr, double *z, int ldz, int m, int mz, int level) {
     LB_REQUIRE(amg.f32_state > 0, "single-precision hierarchy not prepared");
-    LB_REQUIRE(m % 4 == 0 && m <= ((amg.mcap + 3) & ~3) && ldr % 4 == 0, "single-precision cycle: bad block shape");
+    LB_REQUIRE(m % 4 == 0 && m <= ((amg.mcap + 3) & ~3) && ldr % 4 == 0 && mz <= m, "single-precision cycle: bad block shape");
     AmgLevel &L = amg.levels[level];
-    const bool direct = (ldz % 2 == 0) && ((reinterpret_cast<uintptr_t>(z) & 15) == 0);
+    // the fused exit writes all m (padded) columns: only when the caller's rows have room for them
+    const bool direct = (mz == m || ldz >= m) && (ldz % 2 == 0) && ((reinterpret_cast<uintptr_t>(z) & 15) == 0);
     const bool done = cycle<float>(amg, level, r, ldr, L.x32.p, m, m, true, direct ? z : nullptr, ldz);
     if (!done) {
-        ProfScope prof(amg.ctx, PROF_ELEMENTWISE, 12.0 * L.K->n * m);
-        LB_LAUNCH(amg.ctx, f32_to_f64_cols, cdiv(L.K->n * m, 256), 256, 0, L.K->n, m, L.x32.p, m, z, ldz);
+        ProfScope prof(amg.ctx, PROF_ELEMENTWISE, 12.0 * L.K->n * mz);
+        LB_LAUNCH(amg.ctx, f32_to_f64_cols, cdiv(L.K->n * mz, 256), 256, 0, L.K->n, mz, L.x32.p, m, z, ldz);
     }
 }
 

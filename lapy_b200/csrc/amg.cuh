@@ -56,9 +56,10 @@ std::unique_ptr<Amg> amg_setup(lb_ctx *c, std::unique_ptr<lb_mat> K, int mcap, c
 void amg_apply(Amg &amg, const double *r, int ldr, double *z, int ldz, int m, int level = 0);
 // The same cycle in single precision (the eigensolver's preconditioner).  amg_prepare_f32 builds the
 // float mirrors once and says whether the hierarchy supports it.  r: (n_level, ldr) floats with
-// m % 4 == 0 columns (callers pad with zero columns) and ldr % 4 == 0; z: doubles, columns 0..m-1 written.
+// m % 4 == 0 columns (callers pad with zero columns) and ldr % 4 == 0; z: doubles, columns 0..mz-1 valid
+// (when ldz >= m the padding columns mz..m-1 of a row of z are overwritten with zeros as well).
 bool amg_prepare_f32(Amg &amg);
-void amg_apply_f32(Amg &amg, const float *r, int ldr, double *z, int ldz, int m, int level = 0);
+void amg_apply_f32(Amg &amg, const float *r, int ldr, double *z, int ldz, int m, int mz, int level = 0);
 // y(n, ldy) floats = x(n, ldx) doubles, columns m..roundup4(m)-1 zero-filled
 void convert_cols_f32(lb_ctx *c, int64_t n, int m, const double *x, int ldx, float *y, int ldy);
 

@@ -231,7 +231,14 @@ static void dist_precond(lb_ctx *c, DistOps *D, const double *r, int ldr, double
         else copy_cols(c, nl, cw(p), r + c0(p), ldr, D->tpack.p + so[p], cw(p));
     }
     dist_exchange(c, D->d, D->tpack.p, so.data(), sc.data(), D->tfull_r.p, ro.data(), rc.data(), 8);
-    if (mine) amg_apply(*D->full_amg, D->tfull_r.p, mine, D->tfull_z.p, mine, mine, 0);
+    if (mine && amg_prepare_f32(*D->full_amg)) {  // single-precision cycle, like the single-GPU solver
+        const int mpad = (mine + 3) & ~3;
+        DBuf<float> rf(c, (size_t)D->n_full * mpad);
+        convert_cols_f32(c, D->n_full, mine, D->tfull_r.p, mine, rf.p, mpad);
+        amg_apply_f32(*D->full_amg, rf.p, mpad, D->tfull_z.p, mine, mpad, mine, 0);
+    } else if (mine) {
+        amg_apply(*D->full_amg, D->tfull_r.p, mine, D->tfull_z.p, mine, mine, 0);
+    }
     // reverse: rows [row0(p), ...) of my result slice -> rank p; rank p's slice of MY rows -> tpack -> z
     dist_exchange(c, D->d, D->tfull_z.p, ro.data(), rc.data(), D->tpack.p, so.data(), sc.data(), 8);
     for (int p = 0; p < W; p++) {
@@ -619,7 +626,7 @@ static EigStats lobpcg_core(lb_ctx *c, const lb_mat *A, const lb_mat *B, Amg *am
             const int mpad = (ma + 3) & ~3;
             float *Rf = reinterpret_cast<float *>(Rbuf.p);
             residual_cols_f32(c, n, ma, idx_d.p, lam_d.p, AS[cur].p, ld, BS[cur].p, ld, Rf, mpad);
-            amg_apply_f32(*amg, Rf, mpad, W, ld, mpad, lvl);
+            amg_apply_f32(*amg, Rf, mpad, W, ld, mpad, ma, lvl);
         } else {
             residual_cols(c, n, ma, idx_d.p, lam_d.p, AS[cur].p, ld, BS[cur].p, ld, Rbuf.p, ma);
             if (D) dist_precond(c, D, Rbuf.p, ma, W, ld, ma);
