@@ -917,7 +917,13 @@ void amg_apply_f32(Amg &amg, const float *r, int ldr, double *z, int ldz, int m,
     AmgLevel &L = amg.levels[level];
     // the fused exit writes all m (padded) columns: only when the caller's rows have room for them
     const bool direct = (mz == m || ldz >= m) && (ldz % 2 == 0) && ((reinterpret_cast<uintptr_t>(z) & 15) == 0);
-    const bool done = cycle<float>(amg, level, r, ldr, L.x32.p, m, m, true, direct ? z : nullptr, ldz);
+    // kF32Cycles cycles per application: z_{k+1} = z_k + cycle(r - K z_k).  At ~3.5 ms per cycle (level 9,
+    // 64 columns) against ~22 ms for the rest of a LOBPCG iteration a stronger preconditioner pays:
+    // measured 40 / 31 / 27 iterations and 1117 / 938 / 885 ms for 1 / 2 / 3 cycles (level-9 icosphere),
+    // 47 / 34 / 28 iterations and 1152 / 977 / 927 ms on the 121^3 tet cube
+    constexpr int ncyc = kF32Cycles;
+    for (int k = 0; k + 1 < ncyc; k++) cycle<float>(amg, level, r, ldr, L.x32.p, m, m, k == 0);
+    const bool done = cycle<float>(amg, level, r, ldr, L.x32.p, m, m, ncyc == 1, direct ? z : nullptr, ldz);
     if (!done) {
         ProfScope prof(amg.ctx, PROF_ELEMENTWISE, 12.0 * L.K->n * mz);
         LB_LAUNCH(amg.ctx, f32_to_f64_cols, cdiv(L.K->n * mz, 256), 256, 0, L.K->n, mz, L.x32.p, m, z, ldz);

@@ -58,6 +58,7 @@ void amg_apply(Amg &amg, const double *r, int ldr, double *z, int ldz, int m, in
 // float mirrors once and says whether the hierarchy supports it.  r: (n_level, ldr) floats with
 // m % 4 == 0 columns (callers pad with zero columns) and ldr % 4 == 0; z: doubles, columns 0..mz-1 valid
 // (when ldz >= m the padding columns mz..m-1 of a row of z are overwritten with zeros as well).
+constexpr int kF32Cycles = 3;  // multigrid cycles per single-precision application (amg.cu)
 bool amg_prepare_f32(Amg &amg);
 void amg_apply_f32(Amg &amg, const float *r, int ldr, double *z, int ldz, int m, int mz, int level = 0);
 // y(n, ldy) floats = x(n, ldx) doubles, columns m..roundup4(m)-1 zero-filled

@@ -19,21 +19,28 @@ namespace lb {
 // served by the SM's L1 instead of L2: the L2 -> SM traffic drops from ~nnz/row x to ~1-2x |X|.
 constexpr int kSpmmStrip = 128;
 
-template <int G, bool VEC>
+template <typename T>
+struct Vec2T;
+template <>
+struct Vec2T<double> {
+    typedef double2 V;
+};
+template <>
+struct Vec2T<float> {
+    typedef float2 V;
+};
+
+template <typename T, int G, bool VEC>
 __global__ void __launch_bounds__(256) spmm_kernel(int64_t n, const int32_t *__restrict__ indptr,
-                                                   const int32_t *__restrict__ indices,
-                                                   const double *__restrict__ val, const double *__restrict__ x,
-                                                   int ldx, double *y, int ldy, int m, int mode,
-                                                   const double *b, int ldb, SpmmEpilogue epi) {
-    // ncu (round 1): this kernel is L1/TEX-throughput bound (73 %), not DRAM bound (44 %): every
-    // nonzero cost one 512-byte X request plus two broadcast requests for (index, value).  The
-    // group now fetches a row's (index, value) pairs with ONE coalesced load each (lane q holds
-    // entry q) and broadcasts them by warp shuffle, leaving only the X gathers on the L1 pipe.
-    // (Staging the strip's CSR segment in shared memory instead was measured 14 % slower.)
-    // Round 2, ncu source view: 302 warp instructions per row, stall samples on the first shuffle (index
-    // load) and the first fma (X rows) = three dependent latencies per row.  Software pipelining the
-    // row loop (row pointers two rows ahead, entries one row ahead) was measured SLOWER (1.25 vs 1.11 ms
-    // at 64 columns, every width): the extra live registers cost more occupancy than the overlap wins.
+                                                   const int32_t *__restrict__ indices, const T *__restrict__ val,
+                                                   const T *__restrict__ x, int ldx, T *y, int ldy, int m, int mode,
+                                                   const T *b, int ldb, SpmmEpilogueT<T> epi) {
+    // Row-wise form: the general fallback of the strip-staged kernel below (odd column counts, unaligned
+    // operands, rows too long for the strip's shared-memory budget).  The group fetches a row's (index,
+    // value) pairs with ONE coalesced load each (lane q holds entry q) and broadcasts them by warp shuffle,
+    // leaving only the X gathers on the L1 pipe.  ncu (round 2): 302 warp instructions per row and three
+    // dependent latencies per row (row pointers -> entries -> X rows) - what the strip kernel removes.
+    typedef typename Vec2T<T>::V V2;
     constexpr int GROUPS = 256 / G;  // rows in flight per CTA
     const int grp = threadIdx.x / G, lane = threadIdx.x % G;
     const unsigned gmask = G == 32 ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31) / G * G));
@@ -42,16 +49,16 @@ __global__ void __launch_bounds__(256) spmm_kernel(int64_t n, const int32_t *__r
     for (int lr = grp; lr < nrows; lr += GROUPS) {
         const int64_t row = strip0 + lr;
         const int beg = __ldg(indptr + row), end = __ldg(indptr + row + 1);
-        // VEC: lane owns columns c0 + 2*lane, +1 (one 16-byte load); else c0 + lane, c0 + lane + G
+        // VEC: lane owns columns c0 + 2*lane, +1 (one vector load); else c0 + lane, c0 + lane + G
         for (int c0 = 0; c0 < m; c0 += 2 * G) {
             const int ca = VEC ? c0 + 2 * lane : c0 + lane;
             const int cb = VEC ? ca + 1 : ca + G;
             const bool ha = ca < m, hb = cb < m;
-            double s0 = 0.0, s1 = 0.0;
+            T s0 = 0, s1 = 0;
             for (int p0 = beg; p0 < end; p0 += G) {
                 const int cnt = min(G, end - p0);
                 int jl = 0;
-                double al = 0.0;
+                T al = 0;
                 if (lane < cnt) {
                     jl = __ldg(indices + p0 + lane);
                     al = __ldg(val + p0 + lane);
@@ -59,7 +66,7 @@ __global__ void __launch_bounds__(256) spmm_kernel(int64_t n, const int32_t *__r
                 int q = 0;
                 for (; q + 3 < cnt; q += 4) {
                     int j[4];
-                    double a[4], u0[4], u1[4];
+                    T a[4], u0[4], u1[4];
 #pragma unroll
                     for (int w = 0; w < 4; w++) {
                         j[w] = __shfl_sync(gmask, jl, q + w, G);
@@ -67,14 +74,14 @@ __global__ void __launch_bounds__(256) spmm_kernel(int64_t n, const int32_t *__r
                     }
 #pragma unroll
                     for (int w = 0; w < 4; w++) {
-                        const double *xr = x + (int64_t)j[w] * ldx;
+                        const T *xr = x + (int64_t)j[w] * ldx;
                         if (VEC && hb) {
-                            const double2 v = __ldg(reinterpret_cast<const double2 *>(xr + ca));
+                            const V2 v = __ldg(reinterpret_cast<const V2 *>(xr + ca));
                             u0[w] = v.x;
                             u1[w] = v.y;
                         } else {
-                            u0[w] = ha ? __ldg(xr + ca) : 0.0;
-                            u1[w] = hb ? __ldg(xr + cb) : 0.0;
+                            u0[w] = ha ? __ldg(xr + ca) : (T)0;
+                            u1[w] = hb ? __ldg(xr + cb) : (T)0;
                         }
                     }
 #pragma unroll
@@ -85,10 +92,10 @@ __global__ void __launch_bounds__(256) spmm_kernel(int64_t n, const int32_t *__r
                 }
                 for (; q < cnt; q++) {
                     const int j0 = __shfl_sync(gmask, jl, q, G);
-                    const double a0 = __shfl_sync(gmask, al, q, G);
-                    const double *xr = x + (int64_t)j0 * ldx;
+                    const T a0 = __shfl_sync(gmask, al, q, G);
+                    const T *xr = x + (int64_t)j0 * ldx;
                     if (VEC && hb) {
-                        const double2 v = __ldg(reinterpret_cast<const double2 *>(xr + ca));
+                        const V2 v = __ldg(reinterpret_cast<const V2 *>(xr + ca));
                         s0 = fma(a0, v.x, s0);
                         s1 = fma(a0, v.y, s1);
                     } else {
@@ -105,7 +112,7 @@ __global__ void __launch_bounds__(256) spmm_kernel(int64_t n, const int32_t *__r
                 if (hb) s1 = b[row * ldb + cb] + s1;
             } else if (mode == 3) {
                 // fused first Chebyshev step: r = b - K x (written to y), d = c2 * dinv o r (out2)
-                const double di = epi.c2 * __ldg(epi.dinv + row);
+                const T di = epi.c2 * __ldg(epi.dinv + row);
                 if (ha) {
                     s0 = b[row * ldb + ca] - s0;
                     epi.out2[row * epi.ldout2 + ca] = di * s0;
@@ -117,18 +124,22 @@ __global__ void __launch_bounds__(256) spmm_kernel(int64_t n, const int32_t *__r
             } else if (mode == 4) {
                 // fused last Chebyshev step (x gathers d): rr = b - K d; dn = c1 d + c2 dinv o rr;
                 // sol (+)= d + dn; neither the residual nor dn is written
-                const double di = epi.c2 * __ldg(epi.dinv + row);
+                const T di = epi.c2 * __ldg(epi.dinv + row);
                 if (ha) {
-                    const double dold = x[row * ldx + ca];
-                    const double dn = fma(epi.c1, dold, di * (b[row * ldb + ca] - s0));
-                    double *sp = epi.out2 + row * epi.ldout2 + ca;
-                    *sp = (epi.overwrite ? 0.0 : *sp) + dold + dn;
+                    const T dold = x[row * ldx + ca];
+                    const T dn = fma(epi.c1, dold, di * (b[row * ldb + ca] - s0));
+                    T *sp = epi.out2 + row * epi.ldout2 + ca;
+                    const T v = (epi.overwrite ? (T)0 : *sp) + dold + dn;
+                    if (epi.out64) epi.out64[row * epi.ldout64 + ca] = (double)v;
+                    else *sp = v;
                 }
                 if (hb) {
-                    const double dold = x[row * ldx + cb];
-                    const double dn = fma(epi.c1, dold, di * (b[row * ldb + cb] - s1));
-                    double *sp = epi.out2 + row * epi.ldout2 + cb;
-                    *sp = (epi.overwrite ? 0.0 : *sp) + dold + dn;
+                    const T dold = x[row * ldx + cb];
+                    const T dn = fma(epi.c1, dold, di * (b[row * ldb + cb] - s1));
+                    T *sp = epi.out2 + row * epi.ldout2 + cb;
+                    const T v = (epi.overwrite ? (T)0 : *sp) + dold + dn;
+                    if (epi.out64) epi.out64[row * epi.ldout64 + cb] = (double)v;
+                    else *sp = v;
                 }
                 continue;
             }
@@ -136,6 +147,27 @@ __global__ void __launch_bounds__(256) spmm_kernel(int64_t n, const int32_t *__r
             if (hb) y[row * ldy + cb] = s1;
         }
     }
+}
+
+// fallback launch for either value type
+template <typename T>
+static void spmm_rowwise(lb_ctx *c, const lb_mat *a, const T *v, const T *x, int ldx, T *y, int ldy, int m, int mode,
+                         const T *b, int ldb, const SpmmEpilogueT<T> &epi) {
+    const int32_t *ip = a->indptr.p, *ix = a->indices.p;
+    const int64_t n = a->n;
+    // vector loads of X need an even leading dimension and an aligned base
+    const bool vec = (ldx % 2 == 0) && ((reinterpret_cast<uintptr_t>(x) & (2 * sizeof(T) - 1)) == 0);
+    const int grid = cdiv(n, kSpmmStrip);
+#define LB_SPMM(G)                                                                                                        \
+    do {                                                                                                                  \
+        if (vec) LB_LAUNCH(c, (spmm_kernel<T, G, true>), grid, 256, 0, n, ip, ix, v, x, ldx, y, ldy, m, mode, b, ldb, epi);  \
+        else LB_LAUNCH(c, (spmm_kernel<T, G, false>), grid, 256, 0, n, ip, ix, v, x, ldx, y, ldy, m, mode, b, ldb, epi);     \
+    } while (0)
+    if (m <= 8) LB_SPMM(4);
+    else if (m <= 16) LB_SPMM(8);
+    else if (m <= 32) LB_SPMM(16);
+    else LB_SPMM(32);
+#undef LB_SPMM
 }
 
 // ---- SpMV, CSR-stream form: the CTA stages the products a_ij * x_j of a strip of rows in shared
@@ -392,10 +424,7 @@ static int strip_rows(lb_ctx *c, const lb_mat *a, int *cap_out) {
     return 0;
 }
 
-bool spmm_f32_supported(lb_ctx *c, const lb_mat *a) {
-    int cap;
-    return !a->diagonal && strip_rows<float>(c, a, &cap) > 0;
-}
+bool spmm_f32_supported(lb_ctx *, const lb_mat *a) { return !a->diagonal; }
 
 static inline bool aligned16(const void *p, int ld, int w) {
     return p == nullptr || ((reinterpret_cast<uintptr_t>(p) & 15) == 0 && ld % w == 0);
@@ -476,8 +505,10 @@ void spmm_f32(lb_ctx *c, const lb_mat *a, const float *x, int ldx, float *y, int
     if (n == 0 || m == 0) return;
     const int64_t xrows = a->ncols < 0 ? a->n : a->ncols;
     ProfScope prof(c, PROF_SPMM, 8.0 * a->nnz + 4.0 * (n + 1) + 4.0 * m * (xrows + n * (mode ? 2 : 1)), kProfF32 + m, a->nnz);
-    const bool ok = !a->diagonal && spmm_strip<float>(c, a, mat_values_f32(c, a), x, ldx, y, ldy, m, mode, b, ldb, epi);
-    LB_REQUIRE(ok, "single-precision SpMM: operands not aligned or strip too long (internal error)");
+    LB_REQUIRE(!a->diagonal, "single-precision SpMM: diagonal matrices are not supported (internal error)");
+    const float *v = mat_values_f32(c, a);
+    // rows too long for the strip's shared-memory budget (the near-dense coarse levels of tet meshes): row-wise kernel
+    if (!spmm_strip<float>(c, a, v, x, ldx, y, ldy, m, mode, b, ldb, epi)) spmm_rowwise<float>(c, a, v, x, ldx, y, ldy, m, mode, b, ldb, epi);
 }
 
 // diagonal matrix (lumped mass, identity): entries only on the diagonal, possibly missing rows
@@ -527,24 +558,7 @@ void spmm(lb_ctx *c, const lb_mat *a, const double *x, int ldx, double *y, int l
         return;
     }
     if (!g_spmm_force_rowwise && spmm_strip<double>(c, a, v, x, ldx, y, ldy, m, mode, b, ldb, epi)) return;
-    // fallback (odd column counts, unaligned operands, strips beyond the shared-memory budget):
-    // 16-byte vector loads of X need even leading dimension and a 16-byte aligned base
-    const bool vec = (ldx % 2 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
-    const int grid = cdiv(n, kSpmmStrip);
-    // (Round 2 tried a variant that copies the strip's own 128 rows of X into shared memory with
-    // cp.async.bulk + mbarrier and serves the in-strip gathers with LDS.128: 1.45 ms instead of 1.11 ms
-    // at 64 columns, slower at every width - the copy latency is exposed at the head of every CTA and
-    // 64 KB of shared memory leave 3 CTAs per SM.  Removed; profiles/spmm_shapes_r2.json has both.)
-#define LB_SPMM(G)                                                                                       \
-    do {                                                                                                 \
-        if (vec) LB_LAUNCH(c, (spmm_kernel<G, true>), grid, 256, 0, n, ip, ix, v, x, ldx, y, ldy, m, mode, b, ldb, epi); \
-        else LB_LAUNCH(c, (spmm_kernel<G, false>), grid, 256, 0, n, ip, ix, v, x, ldx, y, ldy, m, mode, b, ldb, epi);    \
-    } while (0)
-    if (m <= 8) LB_SPMM(4);
-    else if (m <= 16) LB_SPMM(8);
-    else if (m <= 32) LB_SPMM(16);
-    else LB_SPMM(32);
-#undef LB_SPMM
+    spmm_rowwise<double>(c, a, v, x, ldx, y, ldy, m, mode, b, ldb, epi);
 }
 
 // ---- column dots ------------------------------------------------------------------------------

@@ -81,13 +81,16 @@ __global__ void __launch_bounds__(256, 2)
                 b0[j] = cs[ka * kUpdStride + wc + 8 * j + g];
                 b1[j] = cs[(ka + 1) * kUpdStride + wc + 8 * j + g];
             }
+            // the two DMMAs of an accumulator are issued a full sweep apart (asm volatile keeps this order):
+            // back to back they are a dependent pair and the warp idles for the DMMA latency after every other issue
 #pragma unroll
             for (int i = 0; i < 4; i++)
 #pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    dmma884(acc[i][j][0], acc[i][j][1], a0[i], b0[j]);
-                    dmma884(acc[i][j][0], acc[i][j][1], a1[i], b1[j]);
-                }
+                for (int j = 0; j < 4; j++) dmma884(acc[i][j][0], acc[i][j][1], a0[i], b0[j]);
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) dmma884(acc[i][j][0], acc[i][j][1], a1[i], b1[j]);
         }
 #pragma unroll
         for (int i = 0; i < 4; i++) {
@@ -213,13 +216,16 @@ __global__ void __launch_bounds__(256, 2)
                 b0[j] = cst[(2 * t) * kUpdStride + wc + 8 * j + g];
                 b1[j] = cst[(2 * t + 1) * kUpdStride + wc + 8 * j + g];
             }
+            // the two DMMAs of an accumulator are issued a full sweep apart (asm volatile keeps this order):
+            // back to back they are a dependent pair and the warp idles for the DMMA latency after every other issue
 #pragma unroll
             for (int i = 0; i < 4; i++)
 #pragma unroll
-                for (int j = 0; j < NJ; j++) {
-                    dmma884(acc[i][j][0], acc[i][j][1], a0[i], b0[j]);
-                    dmma884(acc[i][j][0], acc[i][j][1], a1[i], b1[j]);
-                }
+                for (int j = 0; j < NJ; j++) dmma884(acc[i][j][0], acc[i][j][1], a0[i], b0[j]);
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+#pragma unroll
+                for (int j = 0; j < NJ; j++) dmma884(acc[i][j][0], acc[i][j][1], a1[i], b1[j]);
         }
         cp_async_wait<0>();
 #pragma unroll
@@ -228,6 +234,115 @@ __global__ void __launch_bounds__(256, 2)
             if (r >= n) continue;
 #pragma unroll
             for (int j = 0; j < NJ; j++) {
+                const int col = col_tile + wc + 8 * j + 2 * t;
+                double *yp = y + r * ldy + col;
+                if (col < q) yp[0] = beta == 0.0 ? alpha * acc[i][j][0] : alpha * acc[i][j][0] + beta * yp[0];
+                if (col + 1 < q) yp[1] = beta == 0.0 ? alpha * acc[i][j][1] : alpha * acc[i][j][1] + beta * yp[1];
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// update, resident-C form (the wide shapes: q > 32, p <= kResMaxP).  Round-2 finding: the cp.async
+// ring above synchronises the CTA once per 8-wide k-chunk; the two resident CTAs fall into lockstep
+// (round-robin issue makes them finish a chunk together), so the tensor pipe idles for barrier +
+// shared-memory latency once per chunk: 71 % of the DMMA peak.  Here the whole coefficient slice
+// C[:, 64 columns] sits in shared memory for the CTA's lifetime, the A fragments come straight from
+// global memory (64-byte row pieces, sector-exact) one chunk ahead in registers (two spill), and there is NO
+// barrier inside the k loop: every warp free-runs, the scheduler interleaves warps at different
+// phases.
+// ---------------------------------------------------------------------------------------------
+constexpr int kResMaxP = 192;
+
+__global__ void __launch_bounds__(256, 2)
+    update_dmma_res_kernel(int64_t n, int p, const double *__restrict__ x, int ldx, int q,
+                           const double *__restrict__ cmat, int ldc, double alpha, double beta, double *y, int ldy) {
+    extern __shared__ __align__(16) double cres[];  // (p8, kUpdStride): C[:, col tile], zero padded
+    const int p8 = (p + 7) & ~7;
+    const int col_tile = blockIdx.y * 64;
+    for (int i = threadIdx.x; i < p8 * 64; i += blockDim.x) {
+        const int k = i >> 6, cc = i & 63;
+        const int col = col_tile + cc;
+        cres[k * kUpdStride + cc] = (k < p && col < q) ? __ldg(cmat + (int64_t)k * ldc + col) : 0.0;
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const int wr = (warp & 3) * 32, wc = (warp >> 2) * 32;
+    const int64_t ntiles = (n + 127) / 128;
+    const int nfull = p / 8;  // chunks whose 8 columns all exist; a ragged last chunk is loaded with guards
+    const double *cb = cres + (2 * t) * kUpdStride + wc + g;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t r0 = tile * 128 + wr;
+        const double *xr[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int64_t r = r0 + 8 * i + g;
+            xr[i] = x + (r < n ? r : n - 1) * ldx + 2 * t;  // rows past the end read the last row, never stored
+        }
+        auto load = [&](int ch, double2 (&a)[4]) {
+            if (ch < nfull) {
+#pragma unroll
+                for (int i = 0; i < 4; i++) a[i] = __ldg(reinterpret_cast<const double2 *>(xr[i] + ch * 8));
+            } else {
+                const int ka = ch * 8 + 2 * t;
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    a[i].x = ka < p ? __ldg(xr[i] + ch * 8) : 0.0;
+                    a[i].y = ka + 1 < p ? __ldg(xr[i] + ch * 8 + 1) : 0.0;
+                }
+            }
+        };
+        const int nchunk = p8 / 8;
+        double acc[4][4][2];
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+        // lane l also pulls the 128-byte lines of row l of the warp's 32 rows into L2 kPf chunks ahead
+        // (one line = two chunks): the register prefetch below then waits for an L2 hit, not for DRAM
+        constexpr int kPf = 6;
+        const int64_t prow = r0 + lane;
+        const double *pf = x + (prow < n ? prow : n - 1) * ldx;
+        {  // ... and the head of the NEXT row tile of this CTA (its first kPf chunks)
+            const int64_t nrow = prow + (int64_t)gridDim.x * 128;
+            if (nrow < n) {
+                const double *npf = x + nrow * ldx;
+#pragma unroll
+                for (int c2 = 0; c2 < kPf; c2 += 2)
+                    if (c2 * 8 < p) asm volatile("prefetch.global.L2 [%0];" ::"l"(npf + c2 * 8));
+            }
+        }
+        double2 a0[4], a1[4];
+        load(0, a0);
+        for (int ch = 0; ch < nchunk; ch++) {
+            if (!(ch & 1) && (ch + kPf) * 8 < p) asm volatile("prefetch.global.L2 [%0];" ::"l"(pf + (ch + kPf) * 8));
+            if (ch + 1 < nchunk) load(ch + 1, a1);
+            const double *cc = cb + (size_t)ch * 8 * kUpdStride;
+            double b0[4], b1[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                b0[j] = cc[8 * j];
+                b1[j] = cc[kUpdStride + 8 * j];
+            }
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) dmma884(acc[i][j][0], acc[i][j][1], a0[i].x, b0[j]);
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) dmma884(acc[i][j][0], acc[i][j][1], a0[i].y, b1[j]);
+#pragma unroll
+            for (int i = 0; i < 4; i++) a0[i] = a1[i];
+        }
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int64_t r = r0 + 8 * i + g;
+            if (r >= n) continue;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
                 const int col = col_tile + wc + 8 * j + 2 * t;
                 double *yp = y + r * ldy + col;
                 if (col < q) yp[0] = beta == 0.0 ? alpha * acc[i][j][0] : alpha * acc[i][j][0] + beta * yp[0];
@@ -251,13 +366,16 @@ __global__ void __launch_bounds__(256) dmma_peak_kernel(int iters, double *out) 
         b[i] = 1.0 - 1e-9 * (threadIdx.x + i);
     }
     for (int it = 0; it < iters; it++) {
+        // the two DMMAs of an accumulator are issued a full sweep apart (asm volatile keeps this order):
+        // back to back they are a dependent pair and the warp idles for the DMMA latency after every other issue
 #pragma unroll
         for (int i = 0; i < 4; i++)
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
-                dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
-                dmma884(acc[i][j][0], acc[i][j][1], b[i], a[j]);
-            }
+            for (int j = 0; j < 4; j++) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) dmma884(acc[i][j][0], acc[i][j][1], b[i], a[j]);
     }
     double s = 0.0;
 #pragma unroll
@@ -269,6 +387,7 @@ __global__ void __launch_bounds__(256) dmma_peak_kernel(int iters, double *out) 
 
 // benchmark aid (lb_dense_benchmark): 1 forces the 64-column tile for every q
 static int g_update_wide_only = 0;
+static int g_update_variant = 0;  // 2: the cp.async ring kernel for the wide shapes too (A/B aid)
 
 void update_dmma(lb_ctx *c, int64_t n, int p, const double *x, int ldx, int q, const double *cmat, int ldc,
                  double alpha, double beta, double *y, int ldy) {
@@ -277,6 +396,28 @@ void update_dmma(lb_ctx *c, int64_t n, int p, const double *x, int ldx, int q, c
     if (aligned) {
         // column tile: 64 for wide right-hand sides, 32 / 16 / 8 (256-row tiles) for narrow ones
         const int cols = (q > 32 || g_update_wide_only) ? 64 : q > 16 ? 32 : q > 8 ? 16 : 8;
+        // q = 64 a + r with 0 < r <= 32 (late iterations: 78, 92 active columns): the 64-wide tiles take
+        // the first 64 a columns, a narrow tile the rest - a full tile on r columns is mostly padding
+        if (cols == 64 && q > 64 && q % 64 != 0 && q % 64 <= 32 && !g_update_wide_only) {
+            const int qm = q / 64 * 64;
+            update_dmma(c, n, p, x, ldx, qm, cmat, ldc, alpha, beta, y, ldy);
+            update_dmma(c, n, p, x, ldx, q - qm, cmat + qm, ldc, alpha, beta, y + qm, ldy);
+            return;
+        }
+        if (cols == 64 && p <= kResMaxP && g_update_variant != 2) {
+            const size_t smem_res = (size_t)((p + 7) & ~7) * kUpdStride * sizeof(double);
+            static bool res_attr[64] = {};
+            if (c->device >= 64 || !res_attr[c->device]) {
+                LB_CUDA(cudaFuncSetAttribute(update_dmma_res_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)((size_t)kResMaxP * kUpdStride * sizeof(double))));
+                if (c->device < 64) res_attr[c->device] = true;
+            }
+            const int yt = cdiv(q, 64);
+            const int64_t nt = (n + 127) / 128;
+            dim3 grid_res((int)std::min<int64_t>(nt, std::max(1, (kSMs * 2) / yt)), yt);
+            LB_LAUNCH(c, update_dmma_res_kernel, grid_res, 256, smem_res, n, p, x, ldx, q, cmat, ldc, alpha, beta, y, ldy);
+            return;
+        }
         const int rows = cols == 64 ? 128 : 256;
         const size_t smem = (size_t)kUpdStages * (rows * 8 + 8 * kUpdStride) * sizeof(double);
         const int ytiles = cdiv(q, cols);
@@ -316,6 +457,7 @@ void update_dmma(lb_ctx *c, int64_t n, int p, const double *x, int ldx, int q, c
 // 8-column blocks).  QT = 64 for the wide products; 32 / 16 for the narrow right-hand sides of the late
 // LOBPCG iterations (a 64-wide tile ran the 16-column products at 1.5-4 TFLOP/s: DMMAs on padding).
 // partial[(split * ntile + tile) * 64*QT + i*QT + j]; gram_reduce sums the slabs in fixed order.
+// (Round 2: an L2 prefetch of the rows 128 ahead, the trick that helped the update, cost 15 % here.)
 // ---------------------------------------------------------------------------------------------
 template <int NJ>
 __global__ void __launch_bounds__(128, 4)
@@ -331,6 +473,7 @@ __global__ void __launch_bounds__(128, 4)
     const int pc = pt * 64 + (warp & 1) * 32, qc = qt * QT + (warp >> 1) * (QT / 2);
     const int64_t r_begin = (int64_t)blockIdx.y * rows_per_split;
     const int64_t r_end = min(n, r_begin + rows_per_split);
+    if (pc >= p || qc >= q) return;  // this warp's 32 x QT/2 piece is all padding (gram_reduce never reads it)
     double acc[4][NJ][2];
 #pragma unroll
     for (int i = 0; i < 4; i++)
@@ -357,13 +500,16 @@ __global__ void __launch_bounds__(128, 4)
             b0[j] = (va && bok[j]) ? __ldg(ya + 8 * j) : 0.0;
             b1[j] = (vb && bok[j]) ? __ldg(yb + 8 * j) : 0.0;
         }
+        // the two DMMAs of an accumulator are issued a full sweep apart (asm volatile keeps this order):
+        // back to back they are a dependent pair and the warp idles for the DMMA latency after every other issue
 #pragma unroll
         for (int i = 0; i < 4; i++)
 #pragma unroll
-            for (int j = 0; j < NJ; j++) {
-                dmma884(acc[i][j][0], acc[i][j][1], a0[i], b0[j]);
-                dmma884(acc[i][j][0], acc[i][j][1], a1[i], b1[j]);
-            }
+            for (int j = 0; j < NJ; j++) dmma884(acc[i][j][0], acc[i][j][1], a0[i], b0[j]);
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+            for (int j = 0; j < NJ; j++) dmma884(acc[i][j][0], acc[i][j][1], a1[i], b1[j]);
     }
     double *out = partial + ((int64_t)blockIdx.y * ntile_total + tile) * (64 * QT);
     const int li = (warp & 1) * 32, lj = (warp >> 1) * (QT / 2);
@@ -443,6 +589,7 @@ double dense_benchmark(lb_ctx *c, int64_t n, int p, int q, int op, int variant, 
     fill_random(c, p, q, cm.p, q, 9);
     const int saved = g_update_wide_only;
     if (variant == 1) g_update_wide_only = 1;
+    g_update_variant = variant == 2 ? 2 : 0;
     auto run = [&]() {
         if (op == 0) gram_dmma(c, n, p, x.p, p, q, y.p, q, cm.p, false);
         else update_dmma(c, n, p, x.p, p, q, cm.p, q, 1.0, 0.0, y.p, q);
@@ -454,6 +601,7 @@ double dense_benchmark(lb_ctx *c, int64_t n, int p, int q, int op, int variant, 
     LB_CUDA(cudaEventSynchronize(c->ev1));
     LB_CUDA(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
     g_update_wide_only = saved;
+    g_update_variant = 0;
     return ms / reps;
 }
 
