@@ -439,7 +439,8 @@ def main():
     # host result buffer of the throughput loop, allocated (and touched) once: a fresh 1 GB NumPy array per
     # step costs 0.1-0.8 s of page faults / munmap on the host, box dependent (measured as step-to-step
     # spread 1.80 .. 2.64 s); the end-to-end number below goes through the public API and allocates per call
-    evec_buf = np.zeros((mesh.v.shape[0], args.k), np.float64)
+    # ... and page-locked: the library then downloads with one DMA instead of staging through its own pinned buffers
+    evec_buf = torch.zeros((mesh.v.shape[0], args.k), dtype=torch.float64).pin_memory().numpy()
 
     def step():
         dmesh.drop_cache()  # the vertex->element incidence is part of the assembly work
@@ -494,9 +495,13 @@ def main():
     spmv_ren_ms = _lib.spmm_benchmark(ctx, a_dev, 1, 50, renumber=True)
     spmm64_ren_ms = _lib.spmm_benchmark(ctx, a_dev, 64, 20, renumber=True)
     # the instantiation that took the most device time inside the timed region (level-0 operators only)
+    # shape[0] = columns (+ 100000 for the single-precision launches of the multigrid cycle), shape[1] = nnz
+    for s in spmm_shapes:
+        s["f32"] = s["shape"][0] >= 100000
+        s["cols"] = s["shape"][0] % 100000
     lvl0 = [s for s in spmm_shapes if s["shape"][1] == nnz]
     dom = max(lvl0, key=lambda s: s["ms"]) if lvl0 else None
-    dom_iso_ms = _lib.spmm_benchmark(ctx, a_dev, dom["shape"][0], 20, renumber=True) if dom else None
+    dom_iso_ms = _lib.spmm_benchmark(ctx, a_dev, dom["cols"], 20, renumber=True, variant=2 if dom["f32"] else 0) if dom else None
     del _b
     t_ms = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -558,20 +563,22 @@ def main():
         # roofline of the dominant kernel: algorithmic bytes of its launches in the timed region
         # (12 nnz + 4 (V+1) + 8 m (rows of X + rows of Y [+ rows of B])) / their summed CUDA-event time
         if dom:
-            m_dom = dom["shape"][0]
+            m_dom, dom_f32 = dom["cols"], dom["f32"]
             achieved = dom["work"] / (dom["ms"] * 1e-3) / 1e9
             per_launch_bytes = dom["work"] / dom["launches"]
-            kernel = (f"spmm_kernel, level-0 operator (nnz {nnz:,}) x (n,{m_dom}) block: the SpMM instantiation with the largest "
+            kernel = (f"spmm_strip_kernel<{'float' if dom_f32 else 'double'}>, level-0 operator (nnz {nnz:,}) x (n,{m_dom}) block"
+                      f"{' of the single-precision multigrid cycle' if dom_f32 else ''}: the SpMM instantiation with the largest "
                       f"summed device time in the timed region ({dom['launches']} launches, {dom['ms'] / args.steps:.1f} ms/step)")
         else:
-            m_dom, achieved, per_launch_bytes, kernel = 64, 0.0, 0.0, "spmm_kernel (no launches recorded)"
+            m_dom, dom_f32, achieved, per_launch_bytes, kernel = 64, False, 0.0, 0.0, "spmm_strip_kernel (no launches recorded)"
+        es_dom = 4 if dom_f32 else 8
         spmm64_bytes = 12 * nnz + 4 * (nv + 1) + 16 * nv * 64
         traffic, traffic_src = None, None
         tp = os.path.join(ROOT, "profiles", "ncu_dominant_kernel_r2.json")
         if os.path.exists(tp):
             try:
                 tj = json.load(open(tp))
-                if int(tj.get("columns", -1)) == int(m_dom):
+                if int(tj.get("columns", -1)) == int(m_dom) and tj.get("dtype", "f64") == ("f32" if dom_f32 else "f64"):
                     traffic, traffic_src = float(tj["dram_bytes_per_launch"]), tj.get("source")
             except Exception:
                 pass
@@ -582,6 +589,7 @@ def main():
             "metric": METRIC, "value": world / (ms_step * 1e-3), "unit": "meshes/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "dtype_note": "assembly, operators, LOBPCG blocks, Gram / Rayleigh-Ritz, residuals and results in f64; only the multigrid cycle applied to the residual block (the preconditioner) runs in f32",
             "config": {"workload": desc, "step": "FEM assembly (A, B full) + block-LOBPCG/AMG eigensolve, mesh resident in HBM",
                        "k": args.k, "sigma": -0.01, "tol": "1e-9 scaled residual", "parallelism": f"mesh-parallel x{world}",
                        "l2": "working set per step (S/AS/BS blocks 24 GB at level 9) exceeds the 126 MB L2"},
@@ -602,9 +610,11 @@ def main():
                          "traffic": traffic, "traffic_source": traffic_src, "peak_kind": peak_kind, "kernel": kernel,
                          "algorithmic_bytes": int(per_launch_bytes), "ms_per_launch": dom["ms"] / dom["launches"] if dom else None,
                          "isolated_ms_per_launch": dom_iso_ms,
-                         "isolated_frac": (12 * nnz + 4 * (nv + 1) + 16 * nv * m_dom) / (dom_iso_ms * 1e-3) / 1e9 / peak if dom_iso_ms else None,
+                         "isolated_frac": ((4 + es_dom) * nnz + 4 * (nv + 1) + 2 * es_dom * nv * m_dom) / (dom_iso_ms * 1e-3) / 1e9 / peak if dom_iso_ms else None,
+                         "isolated_note": "y = K x alone (mode 0); the launches in the timed region also read b / write the Chebyshev direction (their bytes are counted)",
+                         "dtype": "f32" if dom_f32 else "f64",
                          "spmm_shapes_in_timed_region": [
-                             {"columns": s["shape"][0], "nnz": s["shape"][1], "launches": s["launches"], "ms_per_step": s["ms"] / args.steps,
+                             {"columns": s["cols"], "dtype": "f32" if s["f32"] else "f64", "nnz": s["shape"][1], "launches": s["launches"], "ms_per_step": s["ms"] / args.steps,
                               "gb_per_s": s["work"] / (s["ms"] * 1e-3) / 1e9 if s["ms"] else None} for s in spmm_shapes[:12]],
                          "class_in_timed_region": {"launches": sp["launches"], "ms_per_step": sp["ms"] / args.steps, "avg_gb_per_s": class_rate,
                                                    "share_of_step": sp["ms"] / args.steps / ms_step}},

@@ -921,6 +921,7 @@ void amg_apply_f32(Amg &amg, const float *r, int ldr, double *z, int ldz, int m,
     // 64 columns) against ~22 ms for the rest of a LOBPCG iteration a stronger preconditioner pays:
     // measured 40 / 31 / 27 iterations and 1117 / 938 / 885 ms for 1 / 2 / 3 cycles (level-9 icosphere),
     // 47 / 34 / 28 iterations and 1152 / 977 / 927 ms on the 121^3 tet cube
+    // (V-cycles instead of W-cycles: 37 / 33 / 31 iterations with 3 / 4 / 5 of them, all slower in total)
     constexpr int ncyc = kF32Cycles;
     for (int k = 0; k + 1 < ncyc; k++) cycle<float>(amg, level, r, ldr, L.x32.p, m, m, k == 0);
     const bool done = cycle<float>(amg, level, r, ldr, L.x32.p, m, m, ncyc == 1, direct ? z : nullptr, ldz);

@@ -607,6 +607,52 @@ void col_dots(lb_ctx *c, int64_t n, int cols, const double *x, int ldx, const do
     LB_LAUNCH(c, col_dots_final, cdiv(cols, 64), 64, 0, nb, cols, partial.p, out);
 }
 
+// residual norms without materialising the residual: out[j] = sum_i (AX[i,j] - lam[j] BX[i,j])^2 and
+// out[cols + j] = sum_i BX[i,j]^2 in one pass over the two blocks (the convergence test of every LOBPCG
+// iteration; the separate residual block + two dot passes moved 2.5x the bytes)
+__global__ void __launch_bounds__(kDotCW *kDotRY) residual_norms_partial(int64_t n, int cols, const double *__restrict__ lam,
+                                                                         const double *__restrict__ ax, int ldax,
+                                                                         const double *__restrict__ bx, int ldbx,
+                                                                         double *__restrict__ partial) {
+    __shared__ double red[2][kDotRY][kDotCW + 1];
+    const int tx = threadIdx.x % kDotCW, ty = threadIdx.x / kDotCW;
+    const int64_t chunk = (n + gridDim.x - 1) / gridDim.x;
+    const int64_t r0 = (int64_t)blockIdx.x * chunk, r1 = min(n, r0 + chunk);
+    for (int c0 = 0; c0 < cols; c0 += kDotCW) {
+        const int col = c0 + tx;
+        double s = 0.0, sb = 0.0;
+        if (col < cols) {
+            const double l = lam[col];
+            for (int64_t r = r0 + ty; r < r1; r += kDotRY) {
+                const double b = bx[r * ldbx + col];
+                const double res = fma(-l, b, ax[r * ldax + col]);
+                s = fma(res, res, s);
+                sb = fma(b, b, sb);
+            }
+        }
+        red[0][ty][tx] = s;
+        red[1][ty][tx] = sb;
+        __syncthreads();
+        if (ty < 2 && col < cols) {
+            double t = 0.0;
+#pragma unroll
+            for (int k = 0; k < kDotRY; k++) t += red[ty][k][tx];
+            partial[(int64_t)blockIdx.x * 2 * cols + ty * cols + col] = t;
+        }
+        __syncthreads();
+    }
+}
+
+void residual_norms(lb_ctx *c, int64_t n, int cols, const double *lam, const double *ax, int ldax, const double *bx,
+                    int ldbx, double *out) {
+    if (cols == 0) return;
+    ProfScope prof(c, PROF_DOTS, 16.0 * n * cols);
+    const int nb = (int)std::min<int64_t>(kDotBlocks, std::max<int64_t>(1, n / 64));
+    DBuf<double> partial(c, (size_t)nb * 2 * cols);
+    LB_LAUNCH(c, residual_norms_partial, nb, kDotCW * kDotRY, 0, n, cols, lam, ax, ldax, bx, ldbx, partial.p);
+    LB_LAUNCH(c, col_dots_final, cdiv(2 * cols, 64), 64, 0, nb, 2 * cols, partial.p, out);
+}
+
 // ---- elementwise block kernels -------------------------------------------------------------------
 __global__ void axpby_cols_kernel(int64_t n, int cols, const double *__restrict__ a, double a_const,
                                   const double *__restrict__ x, int ldx, const double *__restrict__ b, double b_const,

@@ -42,6 +42,10 @@ extern int g_spmm_force_rowwise, g_spmm_variant;
 // out[j] = sum_i X[i,j] * Y[i,j], j < cols  (deterministic two-stage reduction), device output
 void col_dots(lb_ctx *c, int64_t n, int cols, const double *x, int ldx, const double *y, int ldy, double *out);
 
+// out[j] = ||AX[:,j] - lam[j] BX[:,j]||^2, out[cols + j] = ||BX[:,j]||^2 (one pass, deterministic)
+void residual_norms(lb_ctx *c, int64_t n, int cols, const double *lam, const double *ax, int ldax, const double *bx,
+                    int ldbx, double *out);
+
 // Y[:,j] = a[j]*X[:,j] + b[j]*Y[:,j]; a / b device arrays or NULL (then a_const / b_const)
 void axpby_cols(lb_ctx *c, int64_t n, int cols, const double *a, double a_const, const double *x, int ldx,
                 const double *b, double b_const, double *y, int ldy);
@@ -77,6 +81,9 @@ void gram_dmma(lb_ctx *c, int64_t n, int p, const double *x, int ldx, int q, con
                bool symmetric);
 void update_dmma(lb_ctx *c, int64_t n, int p, const double *x, int ldx, int q, const double *cmat, int ldc,
                  double alpha, double beta, double *y, int ldy);
+
+// X <- X C in place (p <= 64, aligned operands); false: not possible, nothing done
+bool update_dmma_inplace(lb_ctx *c, int64_t n, int p, double *x, int ldx, const double *cmat, int ldc);
 
 // benchmark aid (lb_dense_benchmark): ms per launch of op 0 (Gram) / 1 (update), TFLOP/s for op 2 (DMMA peak probe)
 double dense_benchmark(lb_ctx *c, int64_t n, int p, int q, int op, int variant, int reps);

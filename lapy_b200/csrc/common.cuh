@@ -86,6 +86,11 @@ struct lb_ctx {
     };
     std::vector<ProfRec> prof;
     std::vector<cudaEvent_t> prof_pool;
+    // eigensolver work blocks ([X P W], A., B. double-buffered: 24 GB at level 9), kept between calls: the
+    // stream-ordered pool re-maps physical memory to satisfy a fresh 4 GB request after the small
+    // allocations of the multigrid setup split its free blocks (measured: 0.03 - 0.5 s per solve)
+    void *ws = nullptr;
+    size_t ws_bytes = 0;
     lb_dist *dist = nullptr;  // NCCL communicator of the row-partitioned mode (lb_comm_init)
     // two pinned staging buffers for large device -> pageable-host results (eigenvectors)
     void *stage[2] = {nullptr, nullptr};
@@ -177,6 +182,9 @@ inline void read_back(lb_ctx *c, T *host, const T *dev, size_t count) {
     sync(c);
     std::memcpy(host, c->pinned, count * sizeof(T));
 }
+
+// the context's persistent workspace, grown on demand (contents undefined)
+void *ctx_workspace(lb_ctx *c, size_t bytes);
 
 double wall_ms();
 // development aid: prints the wall time since the previous phase mark (after a stream sync)

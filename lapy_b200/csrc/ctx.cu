@@ -82,6 +82,15 @@ void d2h_large(lb_ctx *c, void *dst, const void *src, size_t bytes) {
         sync(c);
         return;
     }
+    {  // page-locked destination (cudaHostAlloc / cudaHostRegister, e.g. a pinned torch tensor): one DMA, no staging
+        cudaPointerAttributes attr{};
+        if (cudaPointerGetAttributes(&attr, dst) == cudaSuccess && attr.type == cudaMemoryTypeHost) {
+            d2h(c, dst, src, bytes);
+            sync(c);
+            return;
+        }
+        cudaGetLastError();  // an unregistered pointer is not an error here
+    }
     hint_huge_pages(dst, bytes);
     for (int i = 0; i < 2; i++) {
         if (!c->stage[i]) {
@@ -114,6 +123,17 @@ static cudaEvent_t prof_event(lb_ctx *c) {
     cudaEvent_t e;
     cudaEventCreate(&e);
     return e;
+}
+
+void *ctx_workspace(lb_ctx *c, size_t bytes) {
+    if (bytes > c->ws_bytes) {
+        if (c->ws) LB_CUDA(cudaFreeAsync(c->ws, c->stream));
+        c->ws = nullptr;
+        c->ws_bytes = 0;
+        LB_CUDA(cudaMallocAsync(&c->ws, bytes, c->stream));
+        c->ws_bytes = bytes;
+    }
+    return c->ws;
 }
 
 ProfScope::ProfScope(lb_ctx *ctx, int cls, double work, int64_t shape0, int64_t shape1) : c(ctx) {
@@ -305,6 +325,7 @@ int lb_ctx_destroy(lb_ctx *c) {
         if (c->stage[i]) cudaFreeHost(c->stage[i]);
         if (c->stage_ev[i]) cudaEventDestroy(c->stage_ev[i]);
     }
+    if (c->ws) cudaFreeAsync(c->ws, c->stream);
     cudaEventDestroy(c->ev0);
     cudaEventDestroy(c->ev1);
     cudaFreeHost(c->pinned);

@@ -135,7 +135,7 @@ __device__ __forceinline__ void cp_async_wait() {
 // (Tried in round 2: several k-chunks per barrier - 2 changed nothing, 4 was 10 % slower.)
 template <int WCOLS, int NJ>
 __global__ void __launch_bounds__(256, 2)
-    update_dmma_pipe_kernel(int64_t n, int p, const double *__restrict__ x, int ldx, int q,
+    update_dmma_pipe_kernel(int64_t n, int p, const double *x, int ldx, int q,  // x may alias y (in place, one column tile)
                             const double *__restrict__ cmat, int ldc, double alpha, double beta, double *y, int ldy) {
     constexpr int ROWS = WCOLS == 2 ? 128 : 256;
     constexpr int COLS = WCOLS * NJ * 8;
@@ -255,9 +255,12 @@ __global__ void __launch_bounds__(256, 2)
 // ---------------------------------------------------------------------------------------------
 constexpr int kResMaxP = 192;
 
+// inplace != 0: y aliases x (q <= 64, one column tile): the two warps that share a row block must both
+// have read their A fragments before either stores
 __global__ void __launch_bounds__(256, 2)
-    update_dmma_res_kernel(int64_t n, int p, const double *__restrict__ x, int ldx, int q,
-                           const double *__restrict__ cmat, int ldc, double alpha, double beta, double *y, int ldy) {
+    update_dmma_res_kernel(int64_t n, int p, const double *x, int ldx, int q,
+                           const double *__restrict__ cmat, int ldc, double alpha, double beta, double *y, int ldy,
+                           int inplace) {
     extern __shared__ __align__(16) double cres[];  // (p8, kUpdStride): C[:, col tile], zero padded
     const int p8 = (p + 7) & ~7;
     const int col_tile = blockIdx.y * 64;
@@ -337,6 +340,7 @@ __global__ void __launch_bounds__(256, 2)
 #pragma unroll
             for (int i = 0; i < 4; i++) a0[i] = a1[i];
         }
+        if (inplace) __syncthreads();
 #pragma unroll
         for (int i = 0; i < 4; i++) {
             const int64_t r = r0 + 8 * i + g;
@@ -415,7 +419,8 @@ void update_dmma(lb_ctx *c, int64_t n, int p, const double *x, int ldx, int q, c
             const int yt = cdiv(q, 64);
             const int64_t nt = (n + 127) / 128;
             dim3 grid_res((int)std::min<int64_t>(nt, std::max(1, (kSMs * 2) / yt)), yt);
-            LB_LAUNCH(c, update_dmma_res_kernel, grid_res, 256, smem_res, n, p, x, ldx, q, cmat, ldc, alpha, beta, y, ldy);
+            LB_LAUNCH(c, update_dmma_res_kernel, grid_res, 256, smem_res, n, p, x, ldx, q, cmat, ldc, alpha, beta, y, ldy,
+                      (int)(x == y));
             return;
         }
         const int rows = cols == 64 ? 128 : 256;
@@ -450,6 +455,17 @@ void update_dmma(lb_ctx *c, int64_t n, int p, const double *x, int ldx, int q, c
     const int gx = (int)std::min<int64_t>(ntiles, std::max(1, (kSMs * 2) / ytiles));
     dim3 grid(gx, ytiles);
     LB_LAUNCH(c, update_dmma_kernel, grid, 256, smem, n, p, x, ldx, q, cmat, ldc, alpha, beta, y, ldy);
+}
+
+// X(n, p) <- X C(p, p) in place.  Possible when one column tile covers all p columns (every CTA then
+// reads the rows of its tile completely before it writes them) and the aligned kernels apply;
+// returns false otherwise (the caller goes through a scratch block).
+bool update_dmma_inplace(lb_ctx *c, int64_t n, int p, double *x, int ldx, const double *cmat, int ldc) {
+    const bool aligned = (ldx % 2 == 0) && (ldc % 2 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) &&
+                         ((reinterpret_cast<uintptr_t>(cmat) & 15) == 0);
+    if (!aligned || p > 64 || g_update_wide_only) return false;
+    update_dmma(c, n, p, x, ldx, p, cmat, ldc, 1.0, 0.0, x, ldx);
+    return true;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -263,21 +263,45 @@ static int b_orthonormalize(lb_ctx *c, DistOps *D, const lb_mat *B, int64_t n, i
     for (int rep = 0; rep < 2; rep++) {
         d_spmm(c, D, B, w, ldw, bw, ldbw, kept);
         d_gram(c, D, n, kept, w, ldw, kept, bw, ldbw, G.p, true);
-        DBuf<double> Gc(c, (size_t)kept * kept);
-        d2d(c, Gc.p, G.p, (size_t)kept * kept * sizeof(double));
-        int info = chol_lower(c, kept, Gc.p);
+        // Cholesky of the diagonally scaled Gram matrix G' = D G D (D = diag(G)^-1/2) on the HOST: q <= m,
+        // O(q^3 / 3) flops, identical on every rank (G is all-reduced).  The columns of W = T(residual)
+        // differ in norm by orders of magnitude; without the scaling the pivot ratio below measured the
+        // column scaling instead of the conditioning, so nearly every iteration paid a second pass.
+        std::vector<double> hL((size_t)kept * kept), hT((size_t)kept * kept, 0.0), dsc(kept);
+        d2h(c, hL.data(), G.p, hL.size() * sizeof(double));
+        sync(c);
+        int info = 0;
+        for (int i = 0; i < kept; i++) {
+            const double gii = hL[(size_t)i * kept + i];
+            if (!(gii > 0.0) || !std::isfinite(gii)) info = i + 1;
+            dsc[i] = info ? 1.0 : 1.0 / std::sqrt(gii);
+        }
+        double dmin = 1e300, dmax = 0;
+        std::vector<double> hGs;  // the scaled matrix, kept for the whitening fallback
         if (info == 0) {
-            // W <- W L^-T as a block update with the explicit (kept x kept) inverse built on the
-            // host (O(q^3), q <= m): one tensor-core product instead of a triangular solve
-            std::vector<double> hL((size_t)kept * kept), hT((size_t)kept * kept, 0.0);
-            d2h(c, hL.data(), Gc.p, hL.size() * sizeof(double));
-            sync(c);
-            double dmin = 1e300, dmax = 0;
-            for (int i = 0; i < kept; i++) {
-                dmin = std::min(dmin, hL[(size_t)i * kept + i]);
-                dmax = std::max(dmax, hL[(size_t)i * kept + i]);
+            for (int i = 0; i < kept; i++)
+                for (int j = 0; j < kept; j++) hL[(size_t)i * kept + j] *= dsc[i] * dsc[j];
+            hGs = hL;
+            for (int j = 0; j < kept && info == 0; j++) {  // row-major lower Cholesky, in place
+                double djj = hL[(size_t)j * kept + j];
+                for (int t = 0; t < j; t++) djj -= hL[(size_t)j * kept + t] * hL[(size_t)j * kept + t];
+                if (!(djj > 1e-12)) {  // cond(G') > ~1e12: whitening instead
+                    info = j + 1;
+                    break;
+                }
+                djj = std::sqrt(djj);
+                hL[(size_t)j * kept + j] = djj;
+                dmin = std::min(dmin, djj);
+                dmax = std::max(dmax, djj);
+                for (int i = j + 1; i < kept; i++) {
+                    double v = hL[(size_t)i * kept + j];
+                    for (int t = 0; t < j; t++) v -= hL[(size_t)i * kept + t] * hL[(size_t)j * kept + t];
+                    hL[(size_t)i * kept + j] = v / djj;
+                }
             }
-            // Linv (lower) by forward substitution, T = Linv^T (upper): T[j][i] = Linv[i][j]
+        }
+        if (info == 0) {
+            // W <- W D L'^-T as ONE block update with the explicit (kept x kept) matrix T = D L'^-T
             std::vector<double> Li((size_t)kept * kept, 0.0);
             for (int j = 0; j < kept; j++) {
                 Li[(size_t)j * kept + j] = 1.0 / hL[(size_t)j * kept + j];
@@ -288,18 +312,26 @@ static int b_orthonormalize(lb_ctx *c, DistOps *D, const lb_mat *B, int64_t n, i
                 }
             }
             for (int i = 0; i < kept; i++)
-                for (int j = 0; j <= i; j++) hT[(size_t)j * kept + i] = Li[(size_t)i * kept + j];
+                for (int j = 0; j <= i; j++) hT[(size_t)j * kept + i] = dsc[j] * Li[(size_t)i * kept + j];
             DBuf<double> dT(c, hT.size());
             h2d(c, dT.p, hT.data(), hT.size() * sizeof(double));
-            update(c, n, kept, w, ldw, kept, dT.p, kept, 1.0, 0.0, tmp, q);
-            copy_cols(c, n, kept, tmp, q, w, ldw);
+            bool inplace = false;
+            {
+                ProfScope prof(c, PROF_UPDATE, 2.0 * n * kept * kept, kept, kept);
+                inplace = update_dmma_inplace(c, n, kept, w, ldw, dT.p, kept);
+            }
+            if (!inplace) {
+                update(c, n, kept, w, ldw, kept, dT.p, kept, 1.0, 0.0, tmp, q);
+                copy_cols(c, n, kept, tmp, q, w, ldw);
+            }
             sync(c);
             // cond(G) ~ (dmax/dmin)^2: one pass leaves an orthogonality error ~ eps*cond(G)
             if (rep == 0 && (dmax / dmin) * (dmax / dmin) < 1e3) break;
             continue;
         }
-        // SVQB: G = V diag(e) V^T; W <- W V diag(e)^-1/2 over the columns with e > eps * e_max
+        // SVQB on the scaled matrix: G' = V diag(e) V^T; W <- W D V diag(e)^-1/2 over the columns with e > eps * e_max
         std::vector<double> hV((size_t)kept * kept), hE(kept);
+        if (!hGs.empty()) h2d(c, G.p, hGs.data(), hGs.size() * sizeof(double));  // whiten the scaled matrix (else dsc = 1)
         info = sym_eig(c, kept, G.p, ev.p);
         LB_REQUIRE(info == 0, "whitening eigen-decomposition failed (info=%d)", info);
         d2h(c, hV.data(), G.p, hV.size() * sizeof(double));
@@ -315,7 +347,7 @@ static int b_orthonormalize(lb_ctx *c, DistOps *D, const lb_mat *B, int64_t n, i
         int col = 0;
         for (int j = kept - 1; j >= 0 && col < newq; j--, col++) {
             const double s = 1.0 / std::sqrt(hE[j]);
-            for (int i = 0; i < kept; i++) T[(size_t)i * newq + col] = hV[(size_t)j * kept + i] * s;  // row j = evec j
+            for (int i = 0; i < kept; i++) T[(size_t)i * newq + col] = dsc[i] * hV[(size_t)j * kept + i] * s;  // row j = evec j
         }
         DBuf<double> dT(c, T.size());
         h2d(c, dT.p, T.data(), T.size() * sizeof(double));
@@ -485,11 +517,14 @@ static EigStats lobpcg_core(lb_ctx *c, const lb_mat *A, const lb_mat *B, Amg *am
     LB_CUDA(cudaEventCreate(&e1));
     LB_CUDA(cudaEventRecord(e0, c->stream));
 
-    const size_t blk = (size_t)n * ld;
-    DBuf<double> S[2] = {DBuf<double>(c, blk), DBuf<double>(c, blk)};
-    DBuf<double> AS[2] = {DBuf<double>(c, blk), DBuf<double>(c, blk)};
-    DBuf<double> BS[2] = {DBuf<double>(c, blk), DBuf<double>(c, blk)};
-    DBuf<double> Rbuf(c, (size_t)n * m), tmp(c, (size_t)n * m);
+    // the eight big blocks live in the context's persistent workspace (common.cuh)
+    const size_t blk = ((size_t)n * ld + 31) & ~(size_t)31, small = ((size_t)n * m + 31) & ~(size_t)31;
+    struct Blk {
+        double *p;
+    };
+    double *wsp = static_cast<double *>(ctx_workspace(c, (6 * blk + 2 * small) * sizeof(double)));
+    Blk S[2] = {{wsp}, {wsp + blk}}, AS[2] = {{wsp + 2 * blk}, {wsp + 3 * blk}}, BS[2] = {{wsp + 4 * blk}, {wsp + 5 * blk}};
+    Blk Rbuf{wsp + 6 * blk}, tmp{wsp + 6 * blk + small};
     DBuf<double> G(c, (size_t)ld * ld), evd(c, ld), lam_d(c, m), coef(c, (size_t)ld * 2 * m), dots(c, 2 * m);
     DBuf<int> idx_d(c, m), kept_d(c, 1);
     std::vector<double> hG, hC, hQ, coefh, rr(2 * m);
@@ -497,6 +532,7 @@ static EigStats lobpcg_core(lb_ctx *c, const lb_mat *A, const lb_mat *B, Amg *am
     std::vector<int> act(m), idx(m);
     int cur = 0;
 
+    phase(c, "lobpcg: work blocks allocated");
     // ---- initial block: constants + pseudo-random, B-orthonormalised, one Rayleigh-Ritz
     if (x0) {
         copy_cols(c, n, m, x0, ldx0, S[0].p, ld);  // prolonged coarse-level eigenvectors
@@ -506,6 +542,7 @@ static EigStats lobpcg_core(lb_ctx *c, const lb_mat *A, const lb_mat *B, Amg *am
     }
     int kept = b_orthonormalize(c, D, B, n, m, S[0].p, ld, BS[0].p, ld, tmp.p);
     LB_REQUIRE(kept == m, "initial block is rank deficient");
+    phase(c, "lobpcg: initial block orthonormalised");
     d_spmm(c, D, A, S[0].p, ld, AS[0].p, ld, m);
     auto rayleigh_ritz = [&](int s, int mp_hint, const std::vector<int> &active_cols, int &mp_new) {
         // G = S^T A S (s x s); eigenvectors -> Cx; Cp from the active columns
@@ -565,7 +602,9 @@ static EigStats lobpcg_core(lb_ctx *c, const lb_mat *A, const lb_mat *B, Amg *am
         std::vector<int> none;
         rayleigh_ritz(m, 0, none, mp);
     }
+    phase(c, "lobpcg: first Rayleigh-Ritz");
     const bool f32_cycle = !D && amg_prepare_f32(*amg);
+    phase(c, "lobpcg: single-precision hierarchy");
 
     double worst = 0.0;
     int nconv_k = 0;
@@ -575,11 +614,8 @@ static EigStats lobpcg_core(lb_ctx *c, const lb_mat *A, const lb_mat *B, Amg *am
         st.iterations = it;
         pt.start();
         // ---- residual norms of all m columns
-        std::iota(idx.begin(), idx.end(), 0);
-        h2d(c, idx_d.p, idx.data(), m * sizeof(int));
-        residual_cols(c, n, m, idx_d.p, lam_d.p, AS[cur].p, ld, BS[cur].p, ld, Rbuf.p, m);
-        d_dots(c, D, n, m, Rbuf.p, m, Rbuf.p, m, dots.p);
-        d_dots(c, D, n, m, BS[cur].p, ld, BS[cur].p, ld, dots.p + m);
+        residual_norms(c, n, m, lam_d.p, AS[cur].p, ld, BS[cur].p, ld, dots.p);
+        if (D) d_allreduce(c, D, dots.p, 2 * m);
         read_back(c, rr.data(), dots.p, 2 * m);
         double lam_mean = 0;
         for (int j = 0; j < k; j++) lam_mean += std::fabs(lam[j]);
@@ -653,6 +689,7 @@ static EigStats lobpcg_core(lb_ctx *c, const lb_mat *A, const lb_mat *B, Amg *am
     if (c->trace)
         fprintf(stderr, "[lb trace] lobpcg phases (ms): residual %.1f | precond %.1f | ortho-vs-XP %.1f | B-orthonormalize %.1f | A*W %.1f | Rayleigh-Ritz+update %.1f\n",
                 pt.acc[0], pt.acc[1], pt.acc[2], pt.acc[3], pt.acc[4], pt.acc[5]);
+    phase(c, "lobpcg: iterations");
     st.iterations += 1;
     st.converged = nconv_k;
     st.residual = worst;

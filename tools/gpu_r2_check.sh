@@ -3,9 +3,8 @@ cd "${GRAFT_REPO_ROOT:-/root/repo}"
 mkdir -p gpurun_out
 ( time timeout 1500 python -m pytest tests -m gpu -q -x --durations=5 ) > gpurun_out/k_pytest.log 2>&1
 tail -12 gpurun_out/k_pytest.log
-timeout 300 python tools/time_assembly.py 9 121 > gpurun_out/k_asm.log 2>&1; tail -4 gpurun_out/k_asm.log
-LAPY_B200_TRACE=1 timeout 120 python tools/asm_once.py ico9 2 2>&1 | grep -E "lb trace|assemble" | tail -6
-timeout 300 python tools/spmm_shapes.py 9 121 > gpurun_out/k_spmm_shapes.log 2>&1; grep -E " (1|8|16|32|64|128) (solver|caller)" gpurun_out/k_spmm_shapes.log | head -30
+LAPY_B200_TRACE=1 timeout 300 python tools/eigs_loop.py ico9 2 2>&1 | grep -E "phases|step|nested" | tail -4
+LAPY_B200_TRACE=1 timeout 300 python tools/eigs_loop.py cube121 2 2>&1 | grep -E "phases|step|nested" | tail -2
 timeout 900 python bench.py --steps 5 --warmup 3 > gpurun_out/k_bench.json 2> gpurun_out/k_bench.err; echo "bench rc $?"; tail -5 gpurun_out/k_bench.err; python - <<'PY'
 import json
 try:

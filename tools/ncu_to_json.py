@@ -9,13 +9,13 @@ def val(r, name):
     return v * (1e9 if u.startswith("gbyte") else 1e6 if u.startswith("mbyte") else 1e3 if u.startswith("kbyte") else 1.0)
 best = None
 for r in rows[2:]:
-    if "spmm_kernel" in r[idx["Kernel Name"]]:
+    if "spmm_strip_kernel" in r[idx["Kernel Name"]] or "spmm_kernel" in r[idx["Kernel Name"]]:
         best = r
-out = {"kernel": best[idx["Kernel Name"]], "columns": int(sys.argv[2]),
+out = {"kernel": best[idx["Kernel Name"]], "columns": int(sys.argv[2]), "dtype": "f32" if "<float" in best[idx["Kernel Name"]] else "f64",
        "dram_bytes_per_launch": val(best, "dram__bytes_read.sum") + val(best, "dram__bytes_write.sum"),
        "dram_read_bytes": val(best, "dram__bytes_read.sum"), "dram_write_bytes": val(best, "dram__bytes_write.sum"),
        "duration_us_under_ncu": float(best[idx["gpu__time_duration.sum"]]),
        "l1_hit_pct": float(best[idx["l1tex__t_sector_hit_rate.pct"]]), "l2_hit_pct": float(best[idx["lts__t_sector_hit_rate.pct"]]),
-       "source": "ncu --set full --clock-control none, last spmm_kernel launch of tools/spmm_once.py (level-9 stiffness, solver numbering)"}
+       "source": "ncu --set full --clock-control none, last SpMM launch of tools/spmm_once.py (level-9 stiffness, solver numbering)"}
 json.dump(out, open(sys.argv[3], "w"), indent=1)
 print(out)
