@@ -43,7 +43,7 @@ faulthandler.enable()  # a crash inside the native library prints the Python sta
 PEAK_FALLBACK_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
 METRIC = "shapedna_k50_meshes_per_s"
 PARITY_RTOL = 1e-8  # BASELINE.json north_star
-ROWPART_WORLDS = {2, 4}  # world sizes the row-partitioned solve has been validated on (profiles/rowpart_*_r2.log)
+ROWPART_WORLDS = {2, 4, 8}  # world sizes the row-partitioned solve has been validated on (profiles/rowpart_*_r2.log)
 
 
 def measured_peak():
@@ -336,6 +336,9 @@ def batch_record(world, workers=4, per_rank=12):
     from lapy_b200.batch import batched_shapedna
 
     rank = dist.get_rank() if world > 1 else 0
+    # every worker thread spins on its stream while the GPU iterates: never more workers than this
+    # rank's share of the host cores (an 8-GPU box of this pool has 32 cores)
+    workers = max(1, min(workers, (os.cpu_count() or 4) // max(world, 1) - 1))
     total = per_rank * world
     cache = {i: M.perturbed_sphere(7, seed=i) for i in range(rank, total, world)}
     for m in cache.values():

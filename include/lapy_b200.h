@@ -154,8 +154,9 @@ int lb_dense_benchmark(lb_ctx *ctx, int64_t n, int64_t p, int64_t q, int op, int
 
 /* ---- solvers ------------------------------------------------------------------------------ */
 /* Solver.eigs (lapy/solver.py:667-716): k eigenpairs of A x = lambda B x nearest sigma (<= 0),
- * ascending, B-orthonormal.  evals (k), evecs (n,k) row-major.  tol <= 0 / maxit <= 0 pick
- * defaults (1e-9 relative residual, 200). */
+ * ascending, B-orthonormal.  evals (k), evecs (n,k) row-major or NULL (eigenvalues only: the
+ * ShapeDNA of a batch needs no eigenvectors, lapy/shapedna.py:160-164 keeps them optional downstream).
+ * tol <= 0 / maxit <= 0 pick defaults (1e-9 relative residual, 200). */
 int lb_eigs(lb_ctx *ctx, lb_mat *a, lb_mat *b, int k, double sigma, double tol, int maxit,
             double *evals, double *evecs, lb_info *info);
 

@@ -378,11 +378,16 @@ def spmm(ctx: Context, mat: DeviceMatrix, x: np.ndarray) -> np.ndarray:
 
 
 def eigs(ctx: Context, a: DeviceMatrix, b: DeviceMatrix, k: int, sigma: float, tol: float = 0.0, maxit: int = 0,
-         out_evecs: np.ndarray | None = None):
+         out_evecs: np.ndarray | None = None, vectors: bool = True):
     """lb_eigs -> (evals (k,), evecs (n,k), info dict).  ``out_evecs``: a C-contiguous float64 (n, k) array
     to receive the eigenvectors (a throughput loop re-uses one buffer instead of allocating - and page
-    faulting - a fresh gigabyte per call)."""
+    faulting - a fresh gigabyte per call).  ``vectors=False``: eigenvalues only (evecs is None)."""
     evals = np.empty(k, np.float64)
+    if not vectors:
+        info = Info()
+        check(lib().lb_eigs(ctx.handle, a.handle, b.handle, int(k), float(sigma), float(tol), int(maxit),
+                            ptr(evals), None, C.byref(info)))  # fmt: skip
+        return evals, None, info.as_dict()
     if out_evecs is None:
         evecs = np.empty((a.n, k), np.float64)
     else:

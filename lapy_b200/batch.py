@@ -68,7 +68,7 @@ def batched_shapedna(
         from .solver import Solver
 
         def compute(mesh, k, lump, ctx=None):
-            return Solver(mesh, lump=lump, ctx=ctx).eigs(k=k)[0]
+            return Solver(mesh, lump=lump, ctx=ctx).eigs(k=k, vectors=False)[0]  # the batch returns eigenvalues only
 
         takes_ctx = True
     else:

@@ -679,22 +679,40 @@ __global__ void cheb_next(int64_t n, int m, const T *__restrict__ dinv, const T 
     x[row * ldx + col] += dv;
 }
 
-// x(n, m) = inv(n, n) b(n, m), single precision: the coarsest level of the fp32 cycle (<= 2000 unknowns)
+// x(n, m) = inv(n, n) b(n, m), single precision: the coarsest level of the fp32 cycle (<= 2000 unknowns,
+// visited 4 x 3 times per preconditioner application).  CTA = 16 rows x 64 columns, 4 outputs per thread,
+// inv / b tiles of 64 k-values staged in shared memory (round 2: the one-output-per-thread version took
+// 79 us at 561 x 64 = 3.4 % of a ShapeDNA step).
 __global__ void __launch_bounds__(256) coarse_apply_f32(int n, int m, const float *__restrict__ inv, int ldinv,
                                                         const float *__restrict__ b, int ldb, float *__restrict__ x,
                                                         int ldx) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n * m) return;
-    const int row = t / m, col = t - row * m;
-    const float *ir = inv + (size_t)row * ldinv;
-    float s0 = 0.f, s1 = 0.f;
-    int k = 0;
-    for (; k + 1 < n; k += 2) {
-        s0 = fmaf(ir[k], b[(size_t)k * ldb + col], s0);
-        s1 = fmaf(ir[k + 1], b[(size_t)(k + 1) * ldb + col], s1);
+    __shared__ float s_inv[16][65];
+    __shared__ float s_b[64][64];
+    const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+    const int row0 = blockIdx.x * 16, col = blockIdx.y * 64 + tx;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int k0 = 0; k0 < n; k0 += 64) {
+        for (int i = threadIdx.x; i < 16 * 64; i += 256) {
+            const int r = i >> 6, k = i & 63;
+            s_inv[r][k] = (row0 + r < n && k0 + k < n) ? inv[(size_t)(row0 + r) * ldinv + k0 + k] : 0.f;
+        }
+        for (int i = threadIdx.x; i < 64 * 64; i += 256) {
+            const int k = i >> 6, c2 = i & 63;
+            s_b[k][c2] = (k0 + k < n && blockIdx.y * 64 + c2 < m) ? b[(size_t)(k0 + k) * ldb + blockIdx.y * 64 + c2] : 0.f;
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int k = 0; k < 64; k++) {
+            const float bv = s_b[k][tx];
+#pragma unroll
+            for (int r = 0; r < 4; r++) acc[r] = fmaf(s_inv[ty * 4 + r][k], bv, acc[r]);
+        }
+        __syncthreads();
     }
-    if (k < n) s0 = fmaf(ir[k], b[(size_t)k * ldb + col], s0);
-    x[(size_t)row * ldx + col] = s0 + s1;
+    if (col < m)
+#pragma unroll
+        for (int r = 0; r < 4; r++)
+            if (row0 + ty * 4 + r < n) x[(size_t)(row0 + ty * 4 + r) * ldx + col] = acc[r];
 }
 
 __global__ void f32_to_f64_cols(int64_t n, int m, const float *__restrict__ x, int ldx, double *__restrict__ y, int ldy) {
@@ -832,7 +850,7 @@ static void coarse_solve(Amg &amg, AmgLevel &L, const double *b, int ldb, double
 static void coarse_solve(Amg &amg, AmgLevel &, const float *b, int ldb, float *x, int ldx, int m) {
     lb_ctx *c = amg.ctx;
     ProfScope prof(c, PROF_TRSM, 2.0 * amg.coarse_n * amg.coarse_n * m, amg.coarse_n, kProfF32 + m);
-    LB_LAUNCH(c, coarse_apply_f32, cdiv((int64_t)amg.coarse_n * m, 256), 256, 0, amg.coarse_n, m, amg.coarse_inv32.p,
+    LB_LAUNCH(c, coarse_apply_f32, dim3(cdiv(amg.coarse_n, 16), cdiv(m, 64)), 256, 0, amg.coarse_n, m, amg.coarse_inv32.p,
               amg.coarse_ld32, b, ldb, x, ldx);
 }
 

@@ -770,6 +770,10 @@ static EigStats lobpcg(lb_ctx *c, const lb_mat *A0, const lb_mat *B0, int k, dou
 
     for (int j = 0; j < k; j++) h_evals[j] = lam[j];
     prefault.wait();
+    if (!h_evecs) {  // eigenvalues only (batched ShapeDNA): no gather, no download
+        sync(c);
+        return st;
+    }
     if (reorder) {
         // row i of the caller's numbering = row inv[i] of the renumbered block
         DBuf<double> out(c, (size_t)n * k);
@@ -862,6 +866,10 @@ static EigStats lobpcg_dist(lb_ctx *c, const DistCtx *dist, const lb_mat *A0, co
                               m, tol, maxit, lam, xloc.p, &D, r0);
     st.setup_ms = amg->setup_ms;
     for (int j = 0; j < k; j++) h_evals[j] = lam[j];
+    if (!h_evecs) {
+        sync(c);
+        return st;
+    }
     // all-gather the k eigenvector columns, undo the renumbering, return the full array on every rank
     DBuf<double> out(c, (size_t)n * k);
     copy_cols(c, r1 - r0, k, xloc.p, m, D.pack.p, k);
@@ -911,6 +919,10 @@ static void dense_eigs(lb_ctx *c, const lb_mat *A, const lb_mat *B, int k, doubl
         throw Error{LB_ERR_NOCONV};
     }
     d2h(c, h_evals, w.p, k * sizeof(double));
+    if (!h_evecs) {
+        sync(c);
+        return;
+    }
     // eigenvector j = column j column-major = row j row-major: transpose the first k rows into (n,k)
     std::vector<double> rows((size_t)k * n);
     d2h(c, rows.data(), dA.p, rows.size() * sizeof(double));
@@ -970,7 +982,7 @@ extern "C" int lb_dist_selftest(lb_ctx *c, lb_mat *a, double *errs) {
 extern "C" int lb_eigs(lb_ctx *c, lb_mat *a, lb_mat *b, int k, double sigma, double tol, int maxit, double *evals,
                        double *evecs, lb_info *info) {
     LB_API_BEGIN
-    LB_REQUIRE(c && a && b && evals && evecs, "lb_eigs: NULL argument");
+    LB_REQUIRE(c && a && b && evals, "lb_eigs: NULL argument");  // evecs == NULL: eigenvalues only
     LB_REQUIRE(a->n == b->n, "stiffness and mass must have the same dimension");
     LB_REQUIRE(k >= 1 && k < a->n, "k must satisfy 1 <= k < n (n = %lld)", (long long)a->n);
     if (sigma > 0) {

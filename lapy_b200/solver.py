@@ -156,12 +156,13 @@ class Solver:
         return tuple(Solver._assemble_static(tetra, _lib.FEM_TETRA, lump, dtype))
 
     # -- Solver.eigs (lapy/solver.py:667-716) ----------------------------------------------------
-    def eigs(self, k: int = 10, sigma: float = -0.01, *, tol: float = 0.0, maxit: int = 0):
+    def eigs(self, k: int = 10, sigma: float = -0.01, *, tol: float = 0.0, maxit: int = 0, vectors: bool = True):
         """k eigenpairs of ``A x = lambda B x`` nearest ``sigma`` (sigma <= 0: the k smallest).
 
         Returns ``(eigenvalues (k,), eigenvectors (n, k))``, ascending, B-orthonormal like ARPACK's.
         ``tol`` / ``maxit`` (extensions) bound the block-LOBPCG iteration; ``self.last_info`` holds
-        the iteration report.  sigma > 0 raises ``NotImplementedError``.
+        the iteration report.  sigma > 0 raises ``NotImplementedError``.  ``vectors=False``
+        (extension) skips the eigenvector download and returns ``(eigenvalues, None)``.
         """
         n = self._shape0()
         if k >= n:  # SciPy ARPACK wrapper raises the same for sparse input (arpack.py:1691-1699)
@@ -169,7 +170,8 @@ class Solver:
         if k <= 0:
             raise ValueError(f"k must be greater than 0. k={k}")
         logger.info("Solver: block LOBPCG + smoothed-aggregation AMG on the GPU ...")
-        evals, evecs, info = _lib.eigs(self._ctx, self._device("a"), self._device("b"), k, sigma, tol, maxit)
+        evals, evecs, info = _lib.eigs(self._ctx, self._device("a"), self._device("b"), k, sigma, tol, maxit,
+                                       vectors=vectors)
         self.last_info = info
         return evals, evecs
 

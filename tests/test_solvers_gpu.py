@@ -153,6 +153,13 @@ def test_k50_lumped_and_small_k():
     check_evals(fem.eigs(k=50)[0], ref)
     check_evals(fem.eigs(k=3)[0], ref[:3])
     check_evals(fem.eigensystem(k=11)[0], ref[:11])
+    # eigenvalues only (what batched_shapedna asks for): same spectrum, no eigenvector array
+    ev, vec = fem.eigs(k=50, vectors=False)
+    assert vec is None
+    check_evals(ev, ref)
+    tiny = lapy_b200.Solver(M.icosphere(1), lump=True)  # dense path
+    ev_t, vec_t = tiny.eigs(k=5, vectors=False)
+    assert vec_t is None and np.allclose(ev_t, tiny.eigs(k=5)[0], rtol=0, atol=1e-12)
 
 
 def test_eigs_tiny_mesh_and_errors():

@@ -3,7 +3,7 @@
 cd "${GRAFT_REPO_ROOT:-/root/repo}"
 mkdir -p gpurun_out
 nvidia-smi -L | wc -l; nproc; free -g | head -2 | tail -1
-timeout 700 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29519 bench.py --gpus 8 --steps 2 --warmup 3 > gpurun_out/n8_bench.json 2> gpurun_out/n8_bench.err; echo "bench rc $?"; grep -v "^\*\*\*\|OMP_NUM" gpurun_out/n8_bench.err | tail -12
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29519 bench.py --gpus 8 --steps 3 --warmup 3 > gpurun_out/n8_bench.json 2> gpurun_out/n8_bench.err; echo "bench rc $?"; grep -v "^\*\*\*\|OMP_NUM" gpurun_out/n8_bench.err | tail -12
 python - <<'PY'
 import json
 try:
@@ -14,4 +14,3 @@ try:
 except Exception as e:
     print("bench parse failed", e); print(open("gpurun_out/n8_bench.json").read()[:3000])
 PY
-timeout 300 python bench.py --impl reference --gpus 8 --ref-level 6 2>&1 | tail -1 | cut -c1-700

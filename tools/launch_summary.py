@@ -4,7 +4,13 @@ rows = [r for r in csv.reader(open(sys.argv[1])) if len(r) > 5]
 hdr = rows[0]
 ik, iv, iu = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
 tot = collections.Counter(); cnt = collections.Counter()
-for r in rows[1:]:
+body = rows[1:]
+if "--after-last" in sys.argv:  # keep the launches from the last occurrence of a kernel on (one bench step)
+    pat = sys.argv[sys.argv.index("--after-last") + 1]
+    last = max((i for i, r in enumerate(body) if pat in r[ik]), default=0)
+    body = body[last:]
+    print(f"# launches from the last '{pat}' on")
+for r in body:
     try:
         v = float(r[iv].replace(",", ""))
     except ValueError:
