@@ -138,6 +138,12 @@ int lb_spmm(lb_ctx *ctx, lb_mat *mat, const double *x, int64_t m, double *y);
 int lb_spmm_benchmark(lb_ctx *ctx, lb_mat *mat, int64_t m, int reps, int renumber,
                       double *ms_per_launch);
 
+/* kernel-level parity of the SpMM forms on resident random blocks of m (% 4 == 0) columns: errs[0..4] = max
+ * |strip-staged - row-wise| per epilogue mode in double (same summation order: 0.0 expected), errs[5..9] =
+ * max |single-precision strip - double| / max |double| (the multigrid cycle of the preconditioner).
+ * The row-wise kernel is the one pinned against scipy's csr_matvecs (lapy/solver.py:844-846) since round 1. */
+int lb_spmm_selftest(lb_ctx *ctx, lb_mat *mat, int64_t m, double *errs);
+
 /* dense tall-skinny block products on the fp64 tensor cores (hand-written DMMA kernels), the
  * contractions LAPACK performs inside ARPACK for the reference (lapy/solver.py:713); row-major:
  * C(p,q) = X(n,p)^T Y(n,q)   and   Y(n,q) = alpha X(n,p) C(p,q) + beta Y */

@@ -71,6 +71,7 @@ SIGNATURES = {
     "lb_block_gram": [_vp, _i64, _i64, _vp, _i64, _vp, _vp],
     "lb_block_update": [_vp, _i64, _i64, _vp, _i64, _vp, _dbl, _dbl, _vp],
     "lb_dense_benchmark": [_vp, _i64, _i64, _i64, _int, _int, _int, C.POINTER(_dbl)],
+    "lb_spmm_selftest": [_vp, _vp, _i64, C.POINTER(C.c_double)],
     "lb_eigs": [_vp, _vp, _vp, _int, _dbl, _dbl, _int, _vp, _vp, C.POINTER(Info)],
     "lb_solve": [_vp, _vp, _dbl, _vp, _dbl, _vp, _i64, _vp, _i64, _vp, _dbl, _int, _int, _vp, C.POINTER(Info)],
     "lb_avg_edge_length": [_vp, _vp, _vp, C.POINTER(_dbl)],
@@ -474,6 +475,14 @@ def spmm_benchmark(ctx: Context, mat: DeviceMatrix, m: int = 1, reps: int = 20, 
     check(lib().lb_spmm_benchmark(ctx.handle, mat.handle, int(m), int(reps), int(bool(renumber)) | (int(variant) << 8),
                                   C.byref(ms)))
     return ms.value
+
+
+def spmm_selftest(ctx: Context, mat: DeviceMatrix, m: int = 64) -> np.ndarray:
+    """(10,) errors of lb_spmm_selftest: [0:5] strip-staged vs row-wise SpMM per epilogue mode (double, expected
+    0.0), [5:10] single-precision strip kernel vs double, relative."""
+    errs = np.zeros(10)
+    check(lib().lb_spmm_selftest(ctx.handle, mat.handle, int(m), errs.ctypes.data_as(C.POINTER(C.c_double))))
+    return errs
 
 
 def dense_benchmark(ctx: Context, n: int, p: int, q: int, op: int, variant: int = 0, reps: int = 10) -> float:

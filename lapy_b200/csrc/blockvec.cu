@@ -561,6 +561,96 @@ void spmm(lb_ctx *c, const lb_mat *a, const double *x, int ldx, double *y, int l
     spmm_rowwise<double>(c, a, v, x, ldx, y, ldy, m, mode, b, ldb, epi);
 }
 
+// ---- self-test of the SpMM kernels (lb_spmm_selftest) --------------------------------------------
+__global__ void max_diff_kernel(int64_t cnt, const double *__restrict__ a, const double *__restrict__ b,
+                                unsigned long long *out /* [0] max |a-b|, [1] max |b| as double bits */) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= cnt) return;
+    const double d = fabs(a[i] - b[i]), r = fabs(b[i]);
+    if (!(d == 0.0)) atomicMax(out, (unsigned long long)__double_as_longlong(d == d ? d : 1e300));
+    if (r > 0.0) atomicMax(out + 1, (unsigned long long)__double_as_longlong(r));
+}
+__global__ void f64_to_f32_kernel(int64_t cnt, const double *__restrict__ a, float *__restrict__ b) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < cnt) b[i] = (float)a[i];
+}
+__global__ void f32_to_f64_kernel(int64_t cnt, const float *__restrict__ a, double *__restrict__ b) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < cnt) b[i] = (double)a[i];
+}
+__global__ void abs_plus_one_kernel(int64_t cnt, double *a) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < cnt) a[i] = 1.0 + fabs(a[i]);
+}
+
+// errs[mode] (mode 0..4): max |strip - row-wise| over all outputs of that mode in double precision (the two
+// kernels sum in the same order: expected 0); errs[5 + mode]: max |single-precision strip - double| / max |double|
+void spmm_selftest(lb_ctx *c, const lb_mat *a, int m, double *errs) {
+    LB_REQUIRE(!a->diagonal && m % 4 == 0 && m >= 4 && (a->ncols < 0 || a->ncols == a->n), "spmm_selftest: square general matrix, m % 4 == 0");
+    const int64_t n = a->n;
+    const size_t cnt = (size_t)n * m;
+    const int grid = cdiv(cnt, 256);
+    DBuf<double> x(c, cnt), b(c, cnt), sol0(c, cnt), dinv(c, n);
+    fill_random(c, n, m, x.p, m, 11);
+    fill_random(c, n, m, b.p, m, 12);
+    fill_random(c, n, m, sol0.p, m, 13);
+    fill_random(c, n, 1, dinv.p, 1, 14);
+    LB_LAUNCH(c, abs_plus_one_kernel, cdiv(n, 256), 256, 0, n, dinv.p);
+    DBuf<float> xf(c, cnt), bf(c, cnt), dinvf(c, n), yf(c, cnt), o2f(c, cnt);
+    LB_LAUNCH(c, f64_to_f32_kernel, grid, 256, 0, (int64_t)cnt, x.p, xf.p);
+    LB_LAUNCH(c, f64_to_f32_kernel, grid, 256, 0, (int64_t)cnt, b.p, bf.p);
+    LB_LAUNCH(c, f64_to_f32_kernel, cdiv(n, 256), 256, 0, n, dinv.p, dinvf.p);
+    DBuf<double> y[2] = {DBuf<double>(c, cnt), DBuf<double>(c, cnt)}, o2[2] = {DBuf<double>(c, cnt), DBuf<double>(c, cnt)};
+    DBuf<double> conv(c, cnt);
+    DBuf<unsigned long long> mx(c, 2);
+    auto diff = [&](const double *p, const double *q, double *dmax, double *rmax) {
+        mx.zero();
+        LB_LAUNCH(c, max_diff_kernel, grid, 256, 0, (int64_t)cnt, p, q, mx.p);
+        unsigned long long h[2];
+        read_back(c, h, mx.p, 2);
+        double d, r;
+        std::memcpy(&d, &h[0], 8);
+        std::memcpy(&r, &h[1], 8);
+        *dmax = std::max(*dmax, d);
+        *rmax = std::max(*rmax, r);
+    };
+    for (int mode = 0; mode <= 4; mode++) {
+        for (int v = 0; v < 2; v++) {  // 0: strip, 1: row-wise
+            SpmmEpilogue e{};
+            e.dinv = dinv.p;
+            e.c1 = 0.375;
+            e.c2 = 0.8125;
+            e.out2 = o2[v].p;
+            e.ldout2 = m;
+            y[v].zero();
+            d2d(c, o2[v].p, sol0.p, cnt * sizeof(double));
+            g_spmm_force_rowwise = v;
+            spmm(c, a, x.p, m, y[v].p, m, m, mode, mode ? b.p : nullptr, m, mode >= 3 ? &e : nullptr);
+            g_spmm_force_rowwise = 0;
+        }
+        double d = 0, r = 0;
+        diff(y[0].p, y[1].p, &d, &r);
+        diff(o2[0].p, o2[1].p, &d, &r);
+        errs[mode] = d;
+        // single precision against the double row-wise result
+        SpmmEpilogueT<float> ef{};
+        ef.dinv = dinvf.p;
+        ef.c1 = 0.375f;
+        ef.c2 = 0.8125f;
+        ef.out2 = o2f.p;
+        ef.ldout2 = m;
+        yf.zero();
+        LB_LAUNCH(c, f64_to_f32_kernel, grid, 256, 0, (int64_t)cnt, sol0.p, o2f.p);
+        spmm_f32(c, a, xf.p, m, yf.p, m, m, mode, mode ? bf.p : nullptr, m, mode >= 3 ? &ef : nullptr);
+        double df = 0, rf = 0;
+        LB_LAUNCH(c, f32_to_f64_kernel, grid, 256, 0, (int64_t)cnt, yf.p, conv.p);
+        diff(conv.p, y[1].p, &df, &rf);
+        LB_LAUNCH(c, f32_to_f64_kernel, grid, 256, 0, (int64_t)cnt, o2f.p, conv.p);
+        diff(conv.p, o2[1].p, &df, &rf);
+        errs[5 + mode] = rf > 0 ? df / rf : df;
+    }
+}
+
 // ---- column dots ------------------------------------------------------------------------------
 constexpr int kDotBlocks = kSMs * 4;
 constexpr int kDotCW = 32;  // columns per pass

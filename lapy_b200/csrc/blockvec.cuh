@@ -38,6 +38,8 @@ void spmm_f32(lb_ctx *c, const lb_mat *a, const float *x, int ldx, float *y, int
 bool spmm_f32_supported(lb_ctx *c, const lb_mat *a);
 const float *mat_values_f32(lb_ctx *c, const lb_mat *a);
 extern int g_spmm_force_rowwise, g_spmm_variant;
+// kernel-level parity of the SpMM forms (lb_spmm_selftest): see blockvec.cu
+void spmm_selftest(lb_ctx *c, const lb_mat *a, int m, double *errs);
 
 // out[j] = sum_i X[i,j] * Y[i,j], j < cols  (deterministic two-stage reduction), device output
 void col_dots(lb_ctx *c, int64_t n, int cols, const double *x, int ldx, const double *y, int ldy, double *out);

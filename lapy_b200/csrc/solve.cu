@@ -671,6 +671,16 @@ int lb_spmm_benchmark(lb_ctx *c, lb_mat *mat0, int64_t m, int reps, int renumber
     LB_API_END
 }
 
+// errs (10): the strip-staged SpMM against the row-wise kernel for the five epilogue modes (double:
+// expected 0.0, same summation order) and the single-precision strip kernel against double (relative)
+int lb_spmm_selftest(lb_ctx *c, lb_mat *mat, int64_t m, double *errs) {
+    LB_API_BEGIN
+    LB_REQUIRE(c && mat && errs && m >= 4 && m <= 1024, "lb_spmm_selftest: bad argument");
+    DeviceGuard g(c->device);
+    spmm_selftest(c, mat, (int)m, errs);
+    LB_API_END
+}
+
 int lb_dense_benchmark(lb_ctx *c, int64_t n, int64_t p, int64_t q, int op, int variant, int reps, double *result) {
     LB_API_BEGIN
     LB_REQUIRE(c && result && n > 0 && p > 0 && q > 0 && p <= 384 && q <= 4096 && reps >= 1 && op >= 0 && op <= 2,

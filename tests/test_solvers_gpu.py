@@ -74,6 +74,23 @@ def test_spmm_matches_scipy(golden, m):
     assert np.abs(_lib.spmm(ctx, dl, x) - bl @ x).max() <= 1e-16
 
 
+@pytest.mark.parametrize("maker,m", [("ico6", 64), ("ico6", 24), ("ico6", 128), ("cube15", 64), ("cube15", 8)])
+def test_spmm_kernel_forms_agree(maker, m):
+    """The strip-staged SpMM (default) against the row-wise kernel that test_spmm_matches_scipy pins, for all
+    five epilogue modes: bit-identical in double (same summation order); the single-precision strip kernel of
+    the preconditioner's multigrid cycle within float rounding of the double result."""
+    from lapy_b200 import _lib
+    from lapy_b200 import mesh as M
+
+    mesh = M.icosphere(6) if maker == "ico6" else M.cube_tets(15)
+    ctx = _lib.default_context()
+    dm = _lib.DeviceMesh(ctx, mesh.v, mesh.t)
+    a, _b = _lib.assemble(ctx, dm, _lib.FEM_TETRA if mesh.t.shape[1] == 4 else _lib.FEM_TRIA, False)
+    errs = _lib.spmm_selftest(ctx, a, m)
+    assert np.all(errs[:5] == 0.0), errs
+    assert np.all(errs[5:] < 5e-6), errs
+
+
 @pytest.mark.parametrize("name,k,lump", [("cubeTria", 10, False), ("squareMesh", 10, True), ("ico3", 20, False),
                                            ("cube9", 12, False), ("cubeTetra", 10, False), ("torus", 10, False)])  # fmt: skip
 def test_eigs_vs_reference_golden(golden, name, k, lump):
