@@ -336,15 +336,12 @@ def batch_record(world, workers=4, per_rank=12):
     from lapy_b200.batch import batched_shapedna
 
     rank = dist.get_rank() if world > 1 else 0
-    # every worker thread spins on its stream while the GPU iterates: never more workers than this
-    # rank's share of the host cores (an 8-GPU box of this pool has 32 cores)
-    workers = max(1, min(workers, (os.cpu_count() or 4) // max(world, 1) - 1))
     total = per_rank * world
     cache = {i: M.perturbed_sphere(7, seed=i) for i in range(rank, total, world)}
     for m in cache.values():
         m.v.flags.writeable = False
         m.t.flags.writeable = False
-    batched_shapedna(cache.__getitem__, n_meshes=min(total, 2 * world), k=50, workers=workers)  # warm-up
+    batched_shapedna(cache.__getitem__, n_meshes=min(total, max(2, workers) * world), k=50, workers=workers)  # warm-up: every worker context once
     if world > 1:
         dist.barrier()
     t0 = time.perf_counter()

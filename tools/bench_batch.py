@@ -46,7 +46,7 @@ def factory(i):
 mine = range(rank, args.meshes, world)
 for i in mine:
     factory(i)
-batched_shapedna(factory, n_meshes=min(args.meshes, 2 * world), k=args.k, workers=args.workers)  # warm-up
+batched_shapedna(factory, n_meshes=min(args.meshes, max(2, args.workers) * world), k=args.k, workers=args.workers)  # warm-up: every worker context once
 if world > 1:
     dist.barrier()
 t0 = time.perf_counter()
