@@ -430,7 +430,7 @@ static inline bool aligned16(const void *p, int ld, int w) {
     return p == nullptr || ((reinterpret_cast<uintptr_t>(p) & 15) == 0 && ld % w == 0);
 }
 
-extern int g_spmm_variant;
+extern thread_local int g_spmm_variant;
 template <typename T, int G>
 static void launch_strip(lb_ctx *c, int grid, size_t smem, int64_t n, int R, int cap, const lb_mat *a, const T *val,
                          const T *x, int ldx, T *y, int ldy, int m, int mode, const T *b, int ldb,
@@ -526,8 +526,8 @@ __global__ void diag_spmm_kernel(int64_t n, const int32_t *__restrict__ indptr, 
     y[row * ldy + col] = s;
 }
 
-int g_spmm_force_rowwise = 0;
-int g_spmm_variant = 0;  // benchmark aid (lb_spmm_benchmark variant 1): time the row-wise kernel
+thread_local int g_spmm_force_rowwise = 0;  // benchmark / self-test aids, per calling thread
+thread_local int g_spmm_variant = 0;  // benchmark aid (lb_spmm_benchmark variant 1): time the row-wise kernel
 
 void spmm(lb_ctx *c, const lb_mat *a, const double *x, int ldx, double *y, int ldy, int m, int mode, const double *b,
           int ldb, const SpmmEpilogue *epi_in) {

@@ -37,7 +37,7 @@ void spmm_f32(lb_ctx *c, const lb_mat *a, const float *x, int ldx, float *y, int
               const float *b = nullptr, int ldb = 0, const SpmmEpilogueT<float> *epi = nullptr);
 bool spmm_f32_supported(lb_ctx *c, const lb_mat *a);
 const float *mat_values_f32(lb_ctx *c, const lb_mat *a);
-extern int g_spmm_force_rowwise, g_spmm_variant;
+extern thread_local int g_spmm_force_rowwise, g_spmm_variant;
 // kernel-level parity of the SpMM forms (lb_spmm_selftest): see blockvec.cu
 void spmm_selftest(lb_ctx *c, const lb_mat *a, int m, double *errs);
 
