@@ -517,7 +517,8 @@ def main():
     def e2e_step():
         return compute_shapedna(hmesh, k=args.k)  # writable arrays: uploads v / t on every call
 
-    e2e_step()
+    for _ in range(3):  # the binding's pool of page-locked result blocks reaches its steady state (two blocks
+        sd = e2e_step()  # alternate while `sd` is rebound) - like the W warm-up steps of the device-timed loop
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):

@@ -70,6 +70,13 @@ int lb_ctx_create(int device, void *stream, lb_ctx **out);
 int lb_ctx_destroy(lb_ctx *ctx);
 int lb_ctx_sync(lb_ctx *ctx);
 const char *lb_last_error(void);
+
+/* Page-locked host memory for large results (the eigenvector array of lb_eigs, the solution block of
+ * lb_solve): a page-locked destination is filled by one DMA, a pageable one through the library's
+ * staging buffers plus a host copy (lapy/solver.py:713 returns a fresh NumPy array per call; the
+ * Python binding keeps a small pool of these blocks behind NumPy arrays).  No context needed. */
+int lb_host_alloc(size_t bytes, void **out);
+int lb_host_free(void *p);
 const char *lb_version(void);
 /* device-time stopwatch on the context's stream (CUDA events) */
 int lb_timer_start(lb_ctx *ctx);

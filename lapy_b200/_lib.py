@@ -71,6 +71,8 @@ SIGNATURES = {
     "lb_block_gram": [_vp, _i64, _i64, _vp, _i64, _vp, _vp],
     "lb_block_update": [_vp, _i64, _i64, _vp, _i64, _vp, _dbl, _dbl, _vp],
     "lb_dense_benchmark": [_vp, _i64, _i64, _i64, _int, _int, _int, C.POINTER(_dbl)],
+    "lb_host_alloc": [C.c_size_t, C.POINTER(C.c_void_p)],
+    "lb_host_free": [_vp],
     "lb_spmm_selftest": [_vp, _vp, _i64, C.POINTER(C.c_double)],
     "lb_eigs": [_vp, _vp, _vp, _int, _dbl, _dbl, _int, _vp, _vp, C.POINTER(Info)],
     "lb_solve": [_vp, _vp, _dbl, _vp, _dbl, _vp, _i64, _vp, _i64, _vp, _dbl, _int, _int, _vp, C.POINTER(Info)],
@@ -126,6 +128,70 @@ def check(status: int):
 
 def ptr(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class _PinnedBlock:
+    """A page-locked host block (lb_host_alloc) that NumPy can wrap (``__array_interface__``)."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.ptr, self.nbytes = ptr, nbytes
+        self.__array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 3}
+
+
+class _PinnedPool:
+    """Large result arrays (eigenvectors: 1 GB at level 9) are NumPy arrays on page-locked blocks: the
+    library fills them with one DMA instead of staging + host copy, and a loop that drops its previous
+    result gets the same block back (no gigabyte of page faults per call).  At most ``max_bytes`` are
+    held (live + free); beyond that, and for small arrays, plain ``np.empty``."""
+
+    max_bytes = 4 << 30
+    min_bytes = 32 << 20
+
+    def __init__(self):
+        import threading
+
+        self.lock = threading.Lock()
+        self.free: dict[int, list[int]] = {}
+        self.total = 0
+
+    def _release(self, ptr: int, nbytes: int):
+        with self.lock:
+            self.free.setdefault(nbytes, []).append(ptr)
+
+    def empty(self, shape, dtype=np.float64) -> np.ndarray:
+        import weakref
+
+        dtype = np.dtype(dtype)
+        nbytes = int(np.prod(shape)) * dtype.itemsize
+        if nbytes < self.min_bytes:
+            return np.empty(shape, dtype)
+        ptr = None
+        with self.lock:
+            if self.free.get(nbytes):
+                ptr = self.free[nbytes].pop()
+            elif self.total + nbytes > self.max_bytes:
+                for size, blocks in list(self.free.items()):  # make room from free blocks of other sizes
+                    while blocks and self.total + nbytes > self.max_bytes:
+                        lib().lb_host_free(C.c_void_p(blocks.pop()))
+                        self.total -= size
+                if self.total + nbytes > self.max_bytes:
+                    return np.empty(shape, dtype)
+            if ptr is None:
+                self.total += nbytes
+        if ptr is None:
+            out = C.c_void_p()
+            if lib().lb_host_alloc(nbytes, C.byref(out)) != 0 or not out.value:
+                with self.lock:
+                    self.total -= nbytes
+                return np.empty(shape, dtype)
+            ptr = out.value
+        block = _PinnedBlock(ptr, nbytes)
+        fin = weakref.finalize(block, self._release, ptr, nbytes)
+        fin.atexit = False
+        return np.asarray(block).view(dtype).reshape(shape)
+
+
+_pinned = _PinnedPool()
 
 
 class Context:
@@ -390,7 +456,7 @@ def eigs(ctx: Context, a: DeviceMatrix, b: DeviceMatrix, k: int, sigma: float, t
                             ptr(evals), None, C.byref(info)))  # fmt: skip
         return evals, None, info.as_dict()
     if out_evecs is None:
-        evecs = np.empty((a.n, k), np.float64)
+        evecs = _pinned.empty((a.n, k), np.float64)
     else:
         evecs = out_evecs
         if evecs.shape != (a.n, k) or evecs.dtype != np.float64 or not evecs.flags.c_contiguous:

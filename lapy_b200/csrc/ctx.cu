@@ -55,8 +55,15 @@ static void hint_huge_pages(void *dst, size_t bytes) {
 #endif
 }
 
+static bool is_page_locked(const void *p) {
+    cudaPointerAttributes attr{};
+    const bool yes = cudaPointerGetAttributes(&attr, p) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+    cudaGetLastError();  // an unregistered pointer is not an error here
+    return yes;
+}
+
 HostPrefault::HostPrefault(void *dst, size_t bytes, int nthreads) {
-    if (!dst || bytes < (32u << 20)) return;
+    if (!dst || bytes < (32u << 20) || is_page_locked(dst)) return;
     hint_huge_pages(dst, bytes);
     const size_t part = ((bytes / nthreads) + 4095) & ~size_t(4095);
     for (int t = 0; t < nthreads; t++) {
@@ -82,14 +89,10 @@ void d2h_large(lb_ctx *c, void *dst, const void *src, size_t bytes) {
         sync(c);
         return;
     }
-    {  // page-locked destination (cudaHostAlloc / cudaHostRegister, e.g. a pinned torch tensor): one DMA, no staging
-        cudaPointerAttributes attr{};
-        if (cudaPointerGetAttributes(&attr, dst) == cudaSuccess && attr.type == cudaMemoryTypeHost) {
-            d2h(c, dst, src, bytes);
-            sync(c);
-            return;
-        }
-        cudaGetLastError();  // an unregistered pointer is not an error here
+    if (is_page_locked(dst)) {  // cudaHostAlloc / cudaHostRegister (lb_host_alloc, a pinned torch tensor): one DMA, no staging
+        d2h(c, dst, src, bytes);
+        sync(c);
+        return;
     }
     hint_huge_pages(dst, bytes);
     for (int i = 0; i < 2; i++) {
@@ -307,6 +310,21 @@ int lb_ctx_create(int device, void *stream, lb_ctx **out) {
     const char *tr = getenv("LAPY_B200_TRACE");
     c->trace = tr && tr[0] == '1';
     *out = c;
+    LB_API_END
+}
+
+int lb_host_alloc(size_t bytes, void **out) {
+    LB_API_BEGIN
+    LB_REQUIRE(out && bytes > 0, "lb_host_alloc: bad argument");
+    *out = nullptr;
+    LB_CUDA(cudaHostAlloc(out, bytes, cudaHostAllocPortable));
+    LB_API_END
+}
+
+int lb_host_free(void *p) {
+    LB_API_BEGIN
+    if (p) cudaFreeHost(p);
+    cudaGetLastError();  // at interpreter exit the driver may already be gone
     LB_API_END
 }
 
