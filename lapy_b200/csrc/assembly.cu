@@ -932,11 +932,28 @@ struct StripLayout {
     int64_t n;
 };
 
+// Single pass (FILL): the row pointers are not an input.  Every thread first sorts its row's neighbour
+// keys (registers) and counts the distinct ones, a block scan turns the counts into offsets inside the
+// strip, and the strip's first output position comes from a DECOUPLED LOOK-BACK over the strips (each CTA
+// publishes its entry count, then its inclusive prefix, in a 64-bit state word; CTAs take their strip
+// from an atomic ticket so that every predecessor is already running).  The kernel writes indptr itself;
+// the output arrays are allocated from the entry count the COUNT pass (FILL = false) measured once at
+// mesh upload (a topological constant of the mesh, like the number of its edges), and the total found
+// here is checked against it.  Round 2: count 106 us + two scans + a host round trip + fill 404 us ->
+// one kernel.
+struct StripFused {
+    unsigned long long *state;  // [nstrips] 0 = nothing yet; bit 63: inclusive prefix, bit 62: aggregate only
+    int32_t *ticket;            // [1] next strip
+    int32_t *indptr_a, *indptr_b;  // (n + 1) outputs (either may be NULL)
+    int32_t *lump_ptr;          // (n + 1) output for a lumped mass (or NULL)
+    int32_t *totals;            // [2] total entries / total rows with entries, written by the last strip
+};
+
 template <bool FILL, class T, int MODE>
-__global__ void __launch_bounds__(kStripThreads) strip_rows_kernel(
+__global__ void __launch_bounds__(kStripThreads, 4) strip_rows_kernel(
     StripLayout L, const typename Ex<T>::V4 *__restrict__ v4m, const double *__restrict__ u1,
-    const double *__restrict__ u2, const double *__restrict__ am, int cap, RowOut out, int32_t *__restrict__ row_nnz,
-    int32_t *__restrict__ row_has, int32_t *__restrict__ flags) {
+    const double *__restrict__ u2, const double *__restrict__ am, int cap, RowOut out, StripFused fz,
+    int32_t *__restrict__ row_nnz, int32_t *__restrict__ row_has, int32_t *__restrict__ flags) {
     constexpr int R = kStripRows;
     extern __shared__ __align__(32) unsigned char smem_raw[];
     // layout: s_rec [E] D4 | s_el [E] int4 | s_a [cap] | s_b [cap] | s_k [cap] | s_cnt [R] | s_inc [8][R] u16 | s_slot [16][R] u8
@@ -948,19 +965,24 @@ __global__ void __launch_bounds__(kStripThreads) strip_rows_kernel(
     int32_t *s_cnt = s_k + (FILL ? cap : 0);
     unsigned short *s_inc = reinterpret_cast<unsigned short *>(s_cnt + R);
     unsigned char *s_slot = reinterpret_cast<unsigned char *>(s_inc + 8 * R);
+    __shared__ int s_strip, s_wsum[2][kStripThreads / 32], s_base[2];
     const int t = threadIdx.x;
-    const int64_t r0 = (int64_t)blockIdx.x * R, r = r0 + t;
+    int strip = blockIdx.x;
+    if (t < R) s_cnt[t] = 0;
+    if (FILL && t == 0) s_strip = atomicAdd(fz.ticket, 1);
+    __syncthreads();
+    if (FILL) strip = s_strip;
+    const int64_t r0 = (int64_t)strip * R, r = r0 + t;
     const int nrows = (int)(min(L.n, r0 + R) - r0);
     const int eb = L.kptr[r0], nown = L.kptr[r0 + nrows] - eb;
-    const int hb = L.hptr[blockIdx.x], ne = nown + (L.hptr[blockIdx.x + 1] - hb);
-    if (ne > kStripElems) {  // uniform
+    const int hb = L.hptr[strip], ne = nown + (L.hptr[strip + 1] - hb);
+    const bool oversized = ne > kStripElems;  // uniform
+    if (oversized) {
         if (t == 0) atomicOr(flags, 1);
-        return;
+        if (!FILL) return;  // (FILL: the strip still has to take part in the look-back chain, with zero entries)
     }
-    if (t < R) s_cnt[t] = 0;
-    __syncthreads();
     // ---- phase 1: elements -> shared memory, strip-local incidence
-    for (int le = t; le < ne; le += kStripThreads) {
+    for (int le = t; le < (oversized ? 0 : ne); le += kStripThreads) {
         const int e = le < nown ? eb + le : __ldg(L.hlist + hb + (le - nown));
         const int4 ti = __ldg(L.t4m + e);
         s_el[le] = ti;
@@ -982,20 +1004,23 @@ __global__ void __launch_bounds__(kStripThreads) strip_rows_kernel(
         }
     }
     __syncthreads();
-    // ---- phase 2: one row per thread out of shared memory
-    const int blk_beg = FILL ? out.indptr[r0] : 0, blk_nnz = FILL ? out.indptr[r0 + nrows] - blk_beg : 0;
+    // ---- phase 2a: every thread sorts the neighbour keys of its row in registers and counts the distinct ones
     const bool want_a = FILL && out.a_val != nullptr, want_b = FILL && out.b_val != nullptr;
     const bool want_pat = want_a || want_b;
-    const bool use_smem = want_pat && blk_nnz <= cap;
-    auto process = [&](int32_t *keys, double *av, double *bv, const int rbeg, const int ninc) {
+    const int ninc = (t < nrows && !oversized) ? s_cnt[t] : 0;
+    const bool fast = ninc > 0 && ninc <= kFastInc;
+    int code[kFastInc], w[16];
+    int cnt = 0, dslot = 0;
+    bool self = false;
+    if (fast) {
         // incidences in the reference's triplet order: (caller's element id, corner)
         int w8[kFastInc];
 #pragma unroll
         for (int u = 0; u < kFastInc; u++) {
             w8[u] = INT_MAX;
             if (u < ninc) {
-                const int code = s_inc[u * R + t];
-                w8[u] = (s_el[code >> 2].w << 5) | ((code & 3) << 3) | u;
+                const int cd = s_inc[u * R + t];
+                w8[u] = (s_el[cd >> 2].w << 5) | ((cd & 3) << 3) | u;
             }
         }
 #define LB_MM8(i, j)                      \
@@ -1008,8 +1033,6 @@ __global__ void __launch_bounds__(kStripThreads) strip_rows_kernel(
         LB_MM8(5, 6) LB_MM8(0, 4) LB_MM8(3, 7) LB_MM8(1, 5) LB_MM8(2, 6) LB_MM8(1, 4) LB_MM8(3, 6) LB_MM8(2, 4) LB_MM8(3, 5)
         LB_MM8(3, 4)
 #undef LB_MM8
-        int code[kFastInc], w[16];
-        bool self = false;
 #pragma unroll
         for (int i = 0; i < kFastInc; i++) {
             code[i] = 0;
@@ -1026,7 +1049,7 @@ __global__ void __launch_bounds__(kStripThreads) strip_rows_kernel(
             }
         }
         LB_NET16(LB_MINMAX)
-        int cnt = 0, dslot = 0, prev = -1;
+        int prev = -1;
         bool dd = false;
 #pragma unroll
         for (int i = 0; i < 16; i++) {
@@ -1038,7 +1061,6 @@ __global__ void __launch_bounds__(kStripThreads) strip_rows_kernel(
                         dslot = cnt++;
                         dd = true;
                     }
-                    if (FILL && want_pat) keys[cnt] = key;
                     cnt++;
                     prev = key;
                 }
@@ -1046,13 +1068,118 @@ __global__ void __launch_bounds__(kStripThreads) strip_rows_kernel(
             }
         }
         if (!dd) dslot = cnt++;
-        if (!FILL) {
-            if (self) atomicOr(flags, 1);
-            row_nnz[r] = cnt;
-            return;
+        if (self) atomicOr(flags, 1);
+    }
+    if (t < nrows && ninc > kFastInc) atomicOr(flags, 1);
+    if (!FILL) {
+        if (t < nrows) {
+            row_has[r] = ninc > 0;
+            row_nnz[r] = fast ? cnt : 0;
         }
-        if (want_pat) keys[dslot] = (int)r;
-        double da = 0.0, db = 0.0, lump = 0.0;
+        return;
+    }
+    // ---- block scan of the row counts (and of "row has entries" for the lumped mass), look-back over the strips
+    const int my_cnt = fast ? cnt : 0, my_has = ninc > 0 ? 1 : 0;
+    int inc_cnt = my_cnt, inc_has = my_has;
+    const int lane = t & 31, wid = t >> 5;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int a = __shfl_up_sync(0xffffffffu, inc_cnt, d), h = __shfl_up_sync(0xffffffffu, inc_has, d);
+        if (lane >= d) {
+            inc_cnt += a;
+            inc_has += h;
+        }
+    }
+    if (lane == 31) {
+        s_wsum[0][wid] = inc_cnt;
+        s_wsum[1][wid] = inc_has;
+    }
+    __syncthreads();
+    int woff_cnt = 0, woff_has = 0, blk_nnz = 0, blk_has = 0;
+#pragma unroll
+    for (int k = 0; k < kStripThreads / 32; k++) {
+        if (k < wid) {
+            woff_cnt += s_wsum[0][k];
+            woff_has += s_wsum[1][k];
+        }
+        blk_nnz += s_wsum[0][k];
+        blk_has += s_wsum[1][k];
+    }
+    const int off = woff_cnt + inc_cnt - my_cnt, off_has = woff_has + inc_has - my_has;
+    // state word: [63] inclusive prefix published, [62] aggregate published, [61:31] rows with entries, [30:0] entries
+    constexpr unsigned long long kP = 1ull << 63, kA = 1ull << 62, kMask = (1ull << 62) - 1;
+    const unsigned long long agg = ((unsigned long long)blk_has << 31) | (unsigned long long)blk_nnz;
+    volatile unsigned long long *st = fz.state;
+    // the strip's entry count is published at once (successors can sum over it), its own look-back runs
+    // AFTER the rows have been merged into shared memory: by then the predecessors have published too
+    if (t == 0) st[strip] = (strip == 0 ? kP : kA) | agg;
+    const bool use_smem = want_pat && blk_nnz <= cap;
+    auto look_back = [&]() {  // warp 0; result in s_base
+        unsigned long long excl = 0;
+        if (strip > 0) {
+            int j = strip - 1;  // predecessor window: lanes look at strips j, j-1, ..., j-31
+            while (true) {
+                const int idx = j - lane;
+                unsigned long long v = 0;
+                do {
+                    v = idx >= 0 ? st[idx] : kP;  // strips before 0 count as a published prefix of zero
+                } while (__any_sync(0xffffffffu, v == 0));
+                const unsigned pmask = __ballot_sync(0xffffffffu, (v & kP) != 0);
+                // sum the window up to and including the first published prefix (lowest lane with P)
+                const int stop = pmask ? __ffs(pmask) - 1 : 31;
+                unsigned long long part = (lane <= stop && idx >= 0) ? (v & kMask) : 0;
+#pragma unroll
+                for (int d = 16; d; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
+                excl += part;
+                if (pmask) break;
+                j -= 32;
+            }
+            if (lane == 0) st[strip] = kP | (excl + agg);
+        }
+        if (lane == 0) {
+            s_base[0] = (int)(excl & 0x7fffffffull);
+            s_base[1] = (int)(excl >> 31);
+            if (r0 + nrows == L.n) {  // the last strip closes the row pointers
+                const int tot = s_base[0] + blk_nnz, toth = s_base[1] + blk_has;
+                if (fz.indptr_a) fz.indptr_a[L.n] = tot;
+                if (fz.indptr_b) fz.indptr_b[L.n] = tot;
+                if (fz.lump_ptr) fz.lump_ptr[L.n] = toth;
+                fz.totals[0] = tot;
+                fz.totals[1] = toth;
+            }
+        }
+    };
+    if (!use_smem) {  // rows go straight to global memory (or only the lumped mass is built): positions needed now
+        if (wid == 0) look_back();
+        __syncthreads();
+    }
+    // ---- phase 2b: keys and values of the row into the shared-memory image of the strip's CSR segment
+    const int rbeg_direct = use_smem ? 0 : s_base[0] + off;
+    double lump = 0.0;
+    if (fast) {
+        int32_t *keys = use_smem ? s_k + off : (want_a ? out.a_idx : out.b_idx) + rbeg_direct;
+        double *av = use_smem ? s_a + off : out.a_val + rbeg_direct;
+        double *bv = use_smem ? s_b + off : out.b_val + rbeg_direct;
+        if (want_pat) {
+            int c2 = 0, prev = -1;
+            bool dd = false;
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+                if (w[i] != INT_MAX) {
+                    const int key = w[i] >> 4;
+                    if (key != prev) {
+                        if (!dd && key > (int)r) {
+                            c2++;
+                            dd = true;
+                        }
+                        keys[c2++] = key;
+                        prev = key;
+                    }
+                }
+            }
+            keys[dslot] = (int)r;
+        }
+        double da = 0.0, db = 0.0;
 #pragma unroll
         for (int i = 0; i < kFastInc; i++) {
             if (i < ninc) {
@@ -1081,33 +1208,28 @@ __global__ void __launch_bounds__(kStripThreads) strip_rows_kernel(
             if (want_a) av[dslot] = da;
             if (want_b) bv[dslot] = db;
             if (!use_smem && want_a && want_b)
-                for (int q = 0; q < cnt; q++) out.b_idx[rbeg + q] = keys[q];
+                for (int q = 0; q < cnt; q++) out.b_idx[rbeg_direct + q] = keys[q];
         }
-        if (out.lump_ptr) {
-            const int lp = out.lump_ptr[r];
-            out.lump_idx[lp] = (int)r;
-            out.lump_val[lp] = lump;
-        }
-    };
+    }
+    if (use_smem) {  // warp 0 looks back once its own rows are merged; one barrier covers both
+        if (wid == 0) look_back();
+        __syncthreads();
+    }
+    const int blk_beg = s_base[0];
     if (t < nrows) {
-        const int ninc = s_cnt[t];
-        if (!FILL) {
-            row_has[r] = ninc > 0;
-            if (ninc > kFastInc) atomicOr(flags, 1);
-            if (ninc == 0 || ninc > kFastInc) row_nnz[r] = 0;
-            else process(nullptr, nullptr, nullptr, 0, ninc);
-        } else if (ninc > 0 && ninc <= kFastInc) {
-            const int rbeg = out.indptr[r];
-            if (use_smem || !want_pat) {
-                const int off = want_pat ? rbeg - blk_beg : 0;
-                process(s_k + off, s_a + off, s_b + off, rbeg, ninc);
-            } else {
-                process((want_a ? out.a_idx : out.b_idx) + rbeg, out.a_val + rbeg, out.b_val + rbeg, rbeg, ninc);
+        const int rbeg = blk_beg + off;
+        if (fz.indptr_a) fz.indptr_a[r] = rbeg;
+        if (fz.indptr_b) fz.indptr_b[r] = rbeg;
+        if (fz.lump_ptr) {
+            const int lp = s_base[1] + off_has;
+            fz.lump_ptr[r] = lp;
+            if (fast) {
+                out.lump_idx[lp] = (int)r;
+                out.lump_val[lp] = lump;
             }
         }
     }
-    if (FILL && use_smem) {
-        __syncthreads();
+    if (use_smem) {
         for (int q = t; q < blk_nnz; q += kStripThreads) {
             const int key = s_k[q];
             if (want_a) {
@@ -1616,6 +1738,27 @@ static void build_layout(lb_mesh *m) {
         LB_LAUNCH(c, halo_list_kernel, cdiv(nt, 256), 256, 0, m->t4m.p, nt, hcnt.p, m->hptr.p, m->hlist.p);
         LB_LAUNCH(c, incidence_sort, cdiv(ns, 128), 128, 0, m->hptr.p, m->hlist.p, (int64_t)ns);  // deterministic order
         m->has_strips = true;
+        // Topological constants of the mesh for the single-pass assembly: the number of stored entries of
+        // its operators (vertices with an element + 2 x edges) and of rows with an element, plus whether
+        // every row qualifies for the strip kernel.  The assembly sizes its outputs with them.
+        {
+            StripLayout L{m->t4m.p, m->kptr.p, m->hptr.p, m->hlist.p, n};
+            DBuf<int32_t> row_nnz(c, n), row_has(c, n), flags(c, 2), scan(c, n + 1);
+            flags.zero();
+            const size_t smem_count = (size_t)kStripElems * 16 + kStripRows * 4 + 8 * kStripRows * 2;
+            LB_LAUNCH(c, (strip_rows_kernel<false, double, MODE_FEM>), ns, kStripThreads, smem_count, L, (const D4 *)nullptr,
+                      (const double *)nullptr, (const double *)nullptr, (const double *)nullptr, 0, RowOut{}, StripFused{},
+                      row_nnz.p, row_has.p, flags.p);
+            int32_t tot[2] = {0, 0}, hflags[2] = {0, 0};
+            exclusive_scan_i32(c, row_nnz.p, scan.p, n);
+            read_back(c, &tot[0], scan.p + n, 1);
+            exclusive_scan_i32(c, row_has.p, scan.p, n);
+            read_back(c, &tot[1], scan.p + n, 1);
+            read_back(c, hflags, flags.p, 2);
+            m->strip_fast = hflags[0] == 0;
+            m->strip_nnz = tot[0];
+            m->strip_nlump = tot[1];
+        }
     }
 }
 
@@ -1801,44 +1944,37 @@ static bool run_strip_rows(lb_mesh *mesh, int kind, const double *u1, const doub
     const typename Ex<T>::V4 *v4;
     if constexpr (sizeof(T) == 4) v4 = mesh->v4fm.p;
     else v4 = mesh->v4m.p;
-    DBuf<int32_t> row_nnz(c, n), row_has(c, n), flags(c, 2), indptr(c, n + 1), lump_ptr;
+    if (!mesh->strip_fast) return false;  // a row / strip the fast path does not cover (measured at upload)
+    const int64_t nnz = mesh->strip_nnz, nlump = mesh->strip_nlump;
+    DBuf<int32_t> flags(c, 2), ticket(c, 1), totals(c, 2);
+    DBuf<unsigned long long> state(c, ns);
     flags.zero();
-    RowOut none{};
-    const size_t smem_count = (size_t)kStripElems * 16 + kStripRows * 4 + 8 * kStripRows * 2;
-    LB_LAUNCH(c, (strip_rows_kernel<false, double, MODE_FEM>), ns, kStripThreads, smem_count, L, (const D4 *)nullptr, u1, u2, am, 0,
-              none, row_nnz.p, row_has.p, flags.p);
-    exclusive_scan_i32(c, row_nnz.p, indptr.p, n);
-    if (lump) {
-        lump_ptr.alloc(c, n + 1);
-        exclusive_scan_i32(c, row_has.p, lump_ptr.p, n);
-    }
-    int32_t hflags[2] = {0, 0}, nnz32 = 0, nlump = 0;
-    read_back(c, hflags, flags.p, 2);
-    if (hflags[0]) return false;
-    read_back(c, &nnz32, indptr.p + n, 1);
-    if (lump) read_back(c, &nlump, lump_ptr.p + n, 1);
-    const int64_t nnz = nnz32;
+    ticket.zero();
+    totals.zero();
+    state.zero();
     const bool full_b = !lump;
     lb_mat *A = nullptr, *B = nullptr;
     try {
         RowOut out{};
-        out.indptr = indptr.p;
+        StripFused fz{};
+        fz.state = state.p;
+        fz.ticket = ticket.p;
+        fz.totals = totals.p;
         if (want_a) {
             A = new_mat(c, n, nnz);
-            d2d(c, A->indptr.p, indptr.p, (n + 1) * sizeof(int32_t));
+            fz.indptr_a = A->indptr.p;
             out.a_idx = A->indices.p;
             out.a_val = A->data.p;
         }
         if (full_b) {
             B = new_mat(c, n, nnz);
-            d2d(c, B->indptr.p, indptr.p, (n + 1) * sizeof(int32_t));
+            fz.indptr_b = B->indptr.p;
             out.b_idx = B->indices.p;
             out.b_val = B->data.p;
         } else {
             B = new_mat(c, n, nlump);
             B->diagonal = true;
-            d2d(c, B->indptr.p, lump_ptr.p, (n + 1) * sizeof(int32_t));
-            out.lump_ptr = lump_ptr.p;
+            fz.lump_ptr = B->indptr.p;
             out.lump_idx = B->indices.p;
             out.lump_val = B->data.p;
         }
@@ -1847,15 +1983,22 @@ static bool run_strip_rows(lb_mesh *mesh, int kind, const double *u1, const doub
 #define LB_STRIP(MODE)                                                                                                   \
     do {                                                                                                                 \
         LB_CUDA(cudaFuncSetAttribute(strip_rows_kernel<true, T, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        LB_LAUNCH(c, (strip_rows_kernel<true, T, MODE>), ns, kStripThreads, smem, L, v4, u1, u2, am, cap, out, (int32_t *)nullptr,  \
-                  (int32_t *)nullptr, flags.p);                                                                          \
+        LB_LAUNCH(c, (strip_rows_kernel<true, T, MODE>), ns, kStripThreads, smem, L, v4, u1, u2, am, cap, out, fz,       \
+                  (int32_t *)nullptr, (int32_t *)nullptr, flags.p);                                                      \
     } while (0)
         if (kind == LB_FEM_TRIA) LB_STRIP(MODE_FEM);
         else if (kind == LB_FEM_TRIA_ANISO) LB_STRIP(MODE_ANISO);
         else LB_STRIP(MODE_MASS);
 #undef LB_STRIP
-        read_back(c, hflags, flags.p, 2);  // a degenerate element: its clamp needs the global mean of vol
-        if (hflags[1]) {
+        // one read-back at the end: flags (a degenerate element needs the global mean of vol -> record
+        // pipeline) and the totals the look-back arrived at (must equal the mesh's constants)
+        int32_t hflags[2] = {0, 0}, htot[2] = {0, 0};
+        d2h(c, c->pinned, flags.p, 2 * sizeof(int32_t));
+        d2h(c, (char *)c->pinned + 8, totals.p, 2 * sizeof(int32_t));
+        sync(c);
+        std::memcpy(hflags, c->pinned, 8);
+        std::memcpy(htot, (char *)c->pinned + 8, 8);
+        if (hflags[0] || hflags[1] || htot[0] != nnz || htot[1] != nlump) {
             delete A;
             delete B;
             return false;

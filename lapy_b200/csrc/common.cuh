@@ -267,6 +267,10 @@ struct lb_mesh {
     lb::DBuf<int32_t> kptr;         // (n_ref + 1) first sorted element whose smallest vertex is >= v
     lb::DBuf<int32_t> hptr, hlist;  // per strip: the elements touching it whose smallest vertex lies in an earlier strip
     bool has_strips = false;
+    // topological constants measured at upload for the single-pass strip assembly: stored entries of the
+    // operators, rows with an element, and whether every row / strip qualifies for the fast path
+    int64_t strip_nnz = -1, strip_nlump = -1;
+    bool strip_fast = false;
 };
 
 struct lb_mat {

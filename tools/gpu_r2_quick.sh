@@ -1,3 +1,5 @@
 #!/bin/bash
 cd "${GRAFT_REPO_ROOT:-/root/repo}"
-for p in 1 0 1 0; do echo "POOL=$p"; POOL=$p timeout 300 python tools/e2e_loop.py 2>&1 | tail -4 | tr '\n' ' '; echo; done
+mkdir -p gpurun_out
+( time timeout 900 python -m pytest tests -m gpu -q -x ) 2>&1 | tail -5
+timeout 300 python tools/time_assembly.py 9 61 2>&1 | tail -4 | cut -c1-200
