@@ -1156,7 +1156,10 @@ __global__ void __launch_bounds__(kStripThreads, 4) strip_rows_kernel(
         __syncthreads();
     }
     // ---- phase 2b: keys and values of the row into the shared-memory image of the strip's CSR segment
-    const int rbeg_direct = use_smem ? 0 : s_base[0] + off;
+    int rbeg_direct = 0;
+    // volatile: keeps the compiler from hoisting the load out of the branch (in the shared-memory case warp 0
+    // writes s_base later, after its look-back; racecheck flags the speculative read although its value is unused)
+    if (!use_smem) rbeg_direct = reinterpret_cast<volatile int *>(s_base)[0] + off;
     double lump = 0.0;
     if (fast) {
         int32_t *keys = use_smem ? s_k + off : (want_a ? out.a_idx : out.b_idx) + rbeg_direct;

@@ -1,5 +1,5 @@
 #!/bin/bash
 cd "${GRAFT_REPO_ROOT:-/root/repo}"
 mkdir -p gpurun_out
-( time timeout 900 python -m pytest tests/test_assembly_gpu.py tests/test_frows_gpu.py -m gpu -q -x ) 2>&1 | tail -5
-timeout 300 python tools/time_assembly.py 9 61 2>&1 | tail -4 | cut -c1-200
+timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python tools/sanitize_small.py > gpurun_out/san_mem.log 2>&1; echo "memcheck rc $?"; grep -E "ERROR SUMMARY|Invalid|tri nnz|selftest|eigs|heat" gpurun_out/san_mem.log | head -12
+timeout 900 compute-sanitizer --tool racecheck --racecheck-report analysis --error-exitcode 9 python tools/sanitize_small.py > gpurun_out/san_race.log 2>&1; echo "racecheck rc $?"; grep -E "RACECHECK SUMMARY|Race reported|hazard" gpurun_out/san_race.log | sort | uniq -c | head -12
