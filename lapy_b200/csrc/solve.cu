@@ -171,8 +171,11 @@ __global__ void __launch_bounds__(256) jacobi_stream_kernel(int64_t n, const int
         __shared__ int s_active;
         if (threadIdx.x == 0) s_active = dep_cnt[blockIdx.x] < 0;
         __syncthreads();
+        // (int): with nd = -1 (too many neighbour strips, always swept) the unsigned comparison was true for every
+        // thread, which then read dependency slots nobody wrote - found by memcheck once the pool handed out memory
+        // with large stale words (level 9; the slots used to hold small stale values, i.e. valid strip ids)
         const int nd = dep_cnt[blockIdx.x];
-        if (threadIdx.x < nd && age_in[dep[(int64_t)blockIdx.x * kJacDepCap + threadIdx.x]] <= 1) s_active = 1;
+        if ((int)threadIdx.x < nd && age_in[dep[(int64_t)blockIdx.x * kJacDepCap + threadIdx.x]] <= 1) s_active = 1;
         __syncthreads();
         if (!s_active) {
             if (threadIdx.x == 0) {
@@ -365,6 +368,7 @@ static SolveStats block_pcg(lb_ctx *c, lb_mat *K, const double *rhs, double *x, 
         LB_CUDA(cudaEventRecord(j0, c->stream));
         DBuf<double> xa(c, (size_t)n * m), xb(c, (size_t)n * m);
         DBuf<unsigned long long> mr(c, 1);
+        mr.zero();  // the unchecked sweeps atomicMax into it too (initcheck)
         DBuf<double> voff(c, (size_t)K->nnz), kdiag(c, n);
         d2d(c, voff.p, K->data.p, (size_t)K->nnz * sizeof(double));
         LB_LAUNCH(c, split_diagonal, cdiv(n, 256), 256, 0, n, K->indptr.p, K->indices.p, voff.p, kdiag.p);

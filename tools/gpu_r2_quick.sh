@@ -1,5 +1,6 @@
 #!/bin/bash
 cd "${GRAFT_REPO_ROOT:-/root/repo}"
-mkdir -p gpurun_out
-timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python tools/sanitize_small.py > gpurun_out/san_mem.log 2>&1; echo "memcheck rc $?"; grep -E "ERROR SUMMARY|Invalid|tri nnz|selftest|eigs|heat" gpurun_out/san_mem.log | head -12
-timeout 900 compute-sanitizer --tool racecheck --racecheck-report analysis --error-exitcode 9 python tools/sanitize_small.py > gpurun_out/san_race.log 2>&1; echo "racecheck rc $?"; grep -E "RACECHECK SUMMARY|Race reported|hazard" gpurun_out/san_race.log | sort | uniq -c | head -12
+for i in 1 2; do CUDA_LAUNCH_BLOCKING=1 LAPY_B200_TRACE=1 timeout 300 python tools/heat_once.py 9 2>&1 | grep -E "heat m=|geodesic|Error|error" | cut -c1-200; done
+timeout 300 python tools/heat_once.py 9 2>&1 | grep -E "heat m=|geodesic|Error|error" | cut -c1-200
+timeout 600 compute-sanitizer --tool memcheck --error-exitcode 9 python tools/heat_once.py 8 2>&1 | grep -E "ERROR SUMMARY|Invalid" | head -3
+timeout 600 python -m pytest tests/test_solvers_gpu.py -m gpu -q -x -k "heat or geodesic or poisson or diffusion" 2>&1 | tail -2
