@@ -18,6 +18,3 @@ except Exception as e:
     print("bench parse failed", e); print(open("gpurun_out/k_bench.json").read()[:2000])
 PY
 timeout 200 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
-timeout 300 ncu --set full --clock-control none -k regex:strip_rows -c 3 -o gpurun_out/asm_strip_r2 -f python tools/asm_once.py ico9 1 > gpurun_out/k3_ncu.log 2>&1
-ncu -i gpurun_out/asm_strip_r2.ncu-rep --page raw --csv > gpurun_out/asm_strip_r2_raw.csv 2>/dev/null
-python tools/ncu_summary.py gpurun_out/asm_strip_r2_raw.csv
