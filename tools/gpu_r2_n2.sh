@@ -13,4 +13,3 @@ try:
 except Exception as e:
     print("bench parse failed", e); print(open("gpurun_out/n2_bench.json").read()[:3000])
 PY
-timeout 600 python bench.py --impl reference --gpus 2 --ref-level 7 2>&1 | tail -1 | cut -c1-600
