@@ -64,3 +64,18 @@ def test_sm100a_only():
     ).stdout  # fmt: skip
     archs = set(re.findall(r"sm_\d+a?", out))
     assert archs == {"sm_100a"}, archs
+
+
+def test_result_pool_falls_back_without_a_gpu():
+    """Large result arrays come from a pool of page-locked blocks (lb_host_alloc); without a usable CUDA device
+    (this suite) or below the size threshold the pool hands out ordinary NumPy arrays of the requested shape."""
+    import numpy as np
+
+    from lapy_b200 import _lib
+
+    small = _lib._pinned.empty((10, 3))
+    assert small.shape == (10, 3) and small.dtype == np.float64 and small.flags.c_contiguous
+    big = _lib._pinned.empty((4_500_000, 1))  # 36 MB: above the threshold
+    assert big.shape == (4_500_000, 1) and big.dtype == np.float64 and big.flags.writeable
+    big[:] = 1.0
+    assert float(big.sum()) == 4_500_000.0
