@@ -77,6 +77,10 @@ const char *lb_last_error(void);
  * Python binding keeps a small pool of these blocks behind NumPy arrays).  No context needed. */
 int lb_host_alloc(size_t bytes, void **out);
 int lb_host_free(void *p);
+
+/* lb_eigs keeps its work blocks ([X P W], A., B.: 24 GB for 2.6M vertices and k = 50) in the context between
+ * calls; this returns them to the device's memory pool.  The next lb_eigs allocates again. */
+int lb_ctx_release_workspace(lb_ctx *ctx);
 const char *lb_version(void);
 /* device-time stopwatch on the context's stream (CUDA events) */
 int lb_timer_start(lb_ctx *ctx);

@@ -328,6 +328,16 @@ int lb_host_free(void *p) {
     LB_API_END
 }
 
+int lb_ctx_release_workspace(lb_ctx *c) {
+    LB_API_BEGIN
+    LB_REQUIRE(c, "ctx is NULL");
+    DeviceGuard g(c->device);
+    if (c->ws) LB_CUDA(cudaFreeAsync(c->ws, c->stream));
+    c->ws = nullptr;
+    c->ws_bytes = 0;
+    LB_API_END
+}
+
 int lb_ctx_destroy(lb_ctx *c) {
     LB_API_BEGIN
     if (!c) return LB_OK;

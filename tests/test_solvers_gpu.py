@@ -174,6 +174,9 @@ def test_k50_lumped_and_small_k():
     ev, vec = fem.eigs(k=50, vectors=False)
     assert vec is None
     check_evals(ev, ref)
+    # the persistent work blocks can be handed back to the pool; the next solve allocates again
+    fem._ctx.release_workspace()
+    check_evals(fem.eigs(k=50)[0], ref)
     tiny = lapy_b200.Solver(M.icosphere(1), lump=True)  # dense path
     ev_t, vec_t = tiny.eigs(k=5, vectors=False)
     assert vec_t is None and np.allclose(ev_t, tiny.eigs(k=5)[0], rtol=0, atol=1e-12)
